@@ -1,0 +1,141 @@
+/* qocvl.h -- C-ABI of the B200 (sm_100a) Van Loan cost + gradient engine.
+ *
+ * This is the drop-in boundary for ONE path of azhutov/optimal-control-rydberg: the
+ * cost / cost-and-gradient evaluation of its two PropagatorVL classes
+ *   ST = code/quantum_optimal_control/state_transfer/propagator_vl.py
+ *   TQ = code/quantum_optimal_control/two_qubit/propagator_vl.py
+ * The reference has no FFI of its own (it is pure Python on JAX); each entry point below
+ * names the reference method(s) it replaces.  All hot-path calls are stream-ordered,
+ * take caller-owned DEVICE pointers, never synchronise and never throw: they return a
+ * status code (0 = ok, see qocvl_strerror).  A plan is bound to one device and is not
+ * thread-safe; use one plan per GPU / rank.
+ *
+ * Complex numbers are interleaved (re, im) doubles.  Matrices are row-major.
+ */
+#ifndef QOCVL_H
+#define QOCVL_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qocvl_plan qocvl_plan;
+
+enum {
+  QOCVL_OK = 0,
+  QOCVL_ERR_ARG = 1,        /* bad argument / shape */
+  QOCVL_ERR_CUDA = 2,       /* a CUDA runtime call failed; qocvl_last_cuda_error() has the text */
+  QOCVL_ERR_STATE = 3,      /* generators / cost / noise not set yet */
+  QOCVL_ERR_NORM = 4,       /* |X_k| bound too large for the Taylor propagator: refine delta_t */
+  QOCVL_ERR_UNSUPPORTED = 5 /* e.g. dense exponentials for n > 32 */
+};
+
+enum { QOCVL_MODEL_STATE_TRANSFER = 0, QOCVL_MODEL_TWO_QUBIT = 1, QOCVL_MODEL_CHAIN = 2 };
+
+/* Problem description.  Mirrors the constructor arguments that reach the hot path:
+ * ST:33-56 and TQ:49-102. */
+typedef struct {
+  int model;        /* QOCVL_MODEL_* : selects the pulse map and auxiliary-amplitude rules */
+  int n;            /* Hilbert-space dimension (5, 16, or the blockade-subspace size) */
+  int n_gen;        /* J: number of Van Loan generators (11 for ST/TQ) */
+  int n_slices;     /* M: time slices = n_basis_pts + 2*pad */
+  int n_basis_pts;  /* nt: points of the Gaussian basis (no_of_steps) */
+  int pad;          /* zero padding on each side (TQ only; 0 otherwise) */
+  int n_gauss;      /* N: Gaussians per channel (input_dim) */
+  int n_chan;       /* C: control channels (5 for ST/TQ, 2 for CHAIN) */
+  int n_vec;        /* number of start kets the cost reads (4 for TQ, 1 for ST) */
+  int adiab_index;  /* which start ket is psi of the adiabaticity term */
+  double dt;        /* delta_t */
+  double duration;  /* ST:46 / TQ:88 */
+  double w_infid, w_adiab; /* ST:310 (0.6/0.4), TQ:574 (0.2/0.8) */
+  double fid_norm;  /* divisor of |sum_v <y_v|U|x_v>|^2: 16 for TQ (TQ:555-556), 1 for ST */
+  double eps;       /* TQ:433 denominator clamp (1e-12); ignored by ST */
+  double scale[4];  /* model scalars: ST {Rabi_1, Rabi_2}; TQ {Rabi_i, Rabi_r}; CHAIN {..} */
+} qocvl_desc;
+
+int qocvl_plan_create(qocvl_plan** out, const qocvl_desc* desc, int device);
+int qocvl_plan_destroy(qocvl_plan* plan);
+
+/* Generators, as built by ST:132-170 / TQ:219-314 but passed as their two distinct blocks:
+ * gens_u[j] = top-left n x n block (== bottom-right), gens_w[j] = top-right n x n block.
+ * HOST pointers, [J][n][n] complex.  coef_const[j] (complex, HOST) is the constant
+ * coefficient of a drift generator (ST:254: 1 for j=0,1; TQ:470: -i for j=0,1) and is
+ * ignored for pulse-driven generators (those get their coefficient from the auxiliary
+ * amplitudes, ST:229-245 / TQ:406-455). */
+int qocvl_set_generators(qocvl_plan* plan, const double* gens_u, const double* gens_w,
+                         const double* coef_const);
+
+/* Real impulse response h[M] of the frequency filter TQ:375-397 (HOST pointer):
+ * wave[k] = sum_t h[(k - t - pad) mod M] * reg[t].  Pass NULL for "no filter" (ST). */
+int qocvl_set_filter(qocvl_plan* plan, const double* taps);
+
+/* What the cost reads (ST:291-302, TQ:549-567): start kets x_v and target kets y_v,
+ * HOST [n_vec][n] complex.  infid = 1 - |sum_v y_v^dag U x_v|^2 / fid_norm,
+ * adiab = Re(1 - (U psi)^dag (W psi) / duration), psi = x_{adiab_index}. */
+int qocvl_set_cost(qocvl_plan* plan, const double* starts, const double* targets);
+
+/* Robustness ensemble: sample s uses coefficients  c_kj * mul[s][j] + add[s][j].
+ * HOST pointers: mul [S][J] real, add [S][J] complex (NULL = zeros).  n_samples = 1 with
+ * mul = NULL restores the single nominal sample.  The cost and gradient are ensemble means. */
+int qocvl_set_noise(qocvl_plan* plan, int n_samples, const double* mul, const double* add);
+
+/* Device bytes held by the plan after the last set_* / evaluation call. */
+size_t qocvl_workspace_bytes(const qocvl_plan* plan);
+
+/* ---- hot path (DEVICE pointers, stream-ordered; stream is a cudaStream_t) ------------ */
+
+/* ST:215-227 / TQ:399-404 return_physical_amplitudes: abc = [3][N][C] (a, b, c) -> wave [M][C]. */
+int qocvl_physical_amplitudes(qocvl_plan* plan, const double* abc, double* wave, void* stream);
+
+/* Reverse of the above (what jax.grad builds for notebook 05 cells 8-12, which differentiates
+ * THROUGH return_physical_amplitudes): gwave [M][C] -> grads [3][N][C] = d/d(a,b,c) of
+ * sum_kc gwave[k][c] * wave[k][c].  Recomputes the forward pulse map internally. */
+int qocvl_physical_amplitudes_vjp(qocvl_plan* plan, const double* abc, const double* gwave,
+                                  double* grads, void* stream);
+
+/* ST:229-245 / TQ:406-455 return_auxiliary_amplitudes: -> aux [M][J-2] complex. */
+int qocvl_auxiliary_amplitudes(qocvl_plan* plan, const double* abc, double* aux, void* stream);
+
+/* ST:247-256 / TQ:460-484 exponentials: -> [M][2n][2n] complex (dense, nominal sample). */
+int qocvl_exponentials(qocvl_plan* plan, const double* abc, double* out, void* stream);
+
+/* ST:258-283 / TQ:489-535 propagate: -> [2n][2n] complex; same product order as the reference. */
+int qocvl_propagate(qocvl_plan* plan, const double* abc, double* out, void* stream);
+
+/* ST:285-310 / TQ:540-574 metrics + target: out3 = {cost, infidelity, adiabaticity}
+ * (ensemble means when a noise ensemble is set). */
+int qocvl_cost(qocvl_plan* plan, const double* abc, double* out3, void* stream);
+
+/* jax.value_and_grad(target, argnums=(0,1,2)) (TQ:592, notebook 01 cell 9):
+ * out = {cost, infid, adiab, ga[N][C], gb[N][C], gc[N][C]}  (3 + 3*N*C doubles).
+ * With sample sharding (qocvl_set_shard) the values are this rank's partial SUMS already
+ * divided by the GLOBAL sample count, so one all-reduce(SUM) over ranks completes them. */
+int qocvl_cost_grad(qocvl_plan* plan, const double* abc, double* out, void* stream);
+
+/* Same two evaluations starting from given physical amplitudes wave [M][C] (device): the
+ * pulse map is skipped; gwave (may be NULL) receives d cost / d wave [M][C].  Used for
+ * stage-wise parity tests and by callers that own their own pulse parametrisation. */
+int qocvl_cost_grad_from_wave(qocvl_plan* plan, const double* wave, double* out3,
+                              double* gwave, void* stream);
+
+/* Multi-GPU: tell the plan that its samples are a shard of a larger ensemble, so means
+ * are normalised by global_samples. */
+int qocvl_set_shard(qocvl_plan* plan, int global_samples);
+
+/* Diagnostics */
+/* Synchronises; returns QOCVL_ERR_NORM if any evaluation since the last check saw a slice whose
+ * norm bound exceeded the Taylor propagator's range (or NaN pulses), QOCVL_OK otherwise. */
+int qocvl_check(qocvl_plan* plan);
+int qocvl_last_taylor_degree(const qocvl_plan* plan); /* max Taylor degree of the last call's plan */
+long long qocvl_launch_count(const qocvl_plan* plan); /* kernels launched so far by this plan */
+double qocvl_flops_per_call(const qocvl_plan* plan, int with_grad); /* executed FP64 flop model */
+const char* qocvl_strerror(int status);
+const char* qocvl_last_cuda_error(void);
+int qocvl_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QOCVL_H */

@@ -1,0 +1,145 @@
+// common.cuh -- shared definitions for the qocvl sm_100a kernels (plan layout, complex helpers).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <complex>
+#include <string>
+
+#include "../../include/qocvl.h"
+
+typedef double2 cplx;  // (re, im)
+
+#define QOCVL_MAX_GEN 16
+#define QOCVL_MAX_CHAN 5
+#define QOCVL_QMAX 40        // hard cap of the Taylor degree
+#define QOCVL_NORM_MAX 4.0   // |X_k|_1 above this -> QOCVL_ERR_NORM
+
+__host__ __device__ __forceinline__ cplx cmake(double re, double im) { cplx r; r.x = re; r.y = im; return r; }
+__host__ __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return cmake(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ cplx csub(cplx a, cplx b) { return cmake(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+  return cmake(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ __forceinline__ cplx cconj(cplx a) { return cmake(a.x, -a.y); }
+__host__ __device__ __forceinline__ cplx cscale(cplx a, double s) { return cmake(a.x * s, a.y * s); }
+// acc + a*b
+__device__ __forceinline__ cplx cfma(cplx a, cplx b, cplx acc) {
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+  return acc;
+}
+// acc + conj(a)*b
+__device__ __forceinline__ cplx cfma_conj(cplx a, cplx b, cplx acc) {
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
+  return acc;
+}
+
+// Smallest q with  nrm^(q+1)/(q+1)! <= 2^-60  (same rule as oracle/vector_model.py::taylor_degree)
+__host__ __device__ inline int qocvl_taylor_degree(double nrm) {
+  const double tol = 8.673617379884035e-19;  // 2^-60
+  double term = 1.0;
+  int q = 0;
+  while (q < QOCVL_QMAX) {
+    ++q;
+    term *= nrm / q;
+    if (q >= 2 && term * nrm / (q + 1) <= tol) return q;
+  }
+  return QOCVL_QMAX;
+}
+
+extern thread_local std::string g_qocvl_cuda_error;
+
+#define QCUDA(call)                                                                      \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      g_qocvl_cuda_error = std::string(#call) + ": " + cudaGetErrorString(e_);           \
+      return QOCVL_ERR_CUDA;                                                             \
+    }                                                                                    \
+  } while (0)
+
+// Sparse layout of one generator block family (u = diagonal blocks, w = top-right blocks),
+// rows distributed one per lane.  "row-owner" slots feed y = A x, "col-owner" slots feed
+// y = A^dag x and the gradient contraction.  Slot 0 of the u family is the diagonal.
+struct BlockLayout {
+  int n_row_slots = 0;  // per-row slots (u: 1 + off-diagonals; w: all entries)
+  int n_col_slots = 0;
+  int kc = 0;           // max generator contributions per slot
+  int nnz = 0;          // true non-zeros of the union pattern
+  // device tables, all [slot][npad] (contribution tables [slot][kc][npad])
+  int* row_col = nullptr;   // column read by row-owner slot (own row when empty)
+  int* col_row = nullptr;   // row read by col-owner slot
+  int* col_src = nullptr;   // index (slot*npad + row) of that entry in the row-owner value table
+  int* rc_gen = nullptr;    // generator id or -1
+  cplx* rc_val = nullptr;
+  int* cc_gen = nullptr;
+  cplx* cc_val = nullptr;
+};
+
+struct qocvl_plan {
+  qocvl_desc d;
+  int device = 0;
+  int npad = 0;            // lanes per vector (8, 16 or 32)
+  int n_samples = 1;
+  int global_samples = 1;
+  bool have_gens = false, have_cost = false, have_filter = false;
+  long long launches = 0;
+  size_t bytes = 0;
+  int qcap = 0;            // a-priori Taylor-degree cap used to size shared memory
+  // generators
+  std::vector<std::complex<double>> h_gu, h_gw, h_coef_const;  // host copies
+  double h_gnorm[QOCVL_MAX_GEN];
+  BlockLayout lu, lw;
+  cplx* d_gdense = nullptr;   // [J][2n][2n] dense generators (for exponentials())
+  cplx* d_coef_const = nullptr;  // [J]
+  double* d_gnorm = nullptr;  // [J] 1-norms (u + w)
+  // cost
+  cplx* d_starts = nullptr;   // [n_vec][npad]
+  cplx* d_targets = nullptr;
+  // noise
+  double* d_mul = nullptr;    // [S][J]
+  cplx* d_add = nullptr;      // [S][J]
+  double* d_mulmax = nullptr; // [J]
+  double* d_addmax = nullptr; // [J]
+  // filter
+  double* d_taps = nullptr;   // [M]
+  // per-call work buffers
+  double* d_raw = nullptr;    // [nt][C]
+  double* d_reg = nullptr;    // [nt][C]
+  double* d_wave = nullptr;   // [M][C]
+  cplx* d_coef = nullptr;     // [M][J]
+  cplx* d_dcoef = nullptr;    // [M][J][C]
+  int* d_qdeg = nullptr;      // [M]
+  int* d_flag = nullptr;      // [1] sticky error flag
+  cplx* d_ckpt = nullptr;     // checkpoints
+  size_t ckpt_bytes = 0;
+  double* d_sample_out = nullptr;  // [S][3]
+  double* d_gw_partial = nullptr;  // [blocks][M][C]
+  size_t gw_partial_elems = 0;
+  double* d_gwave = nullptr;  // [M][C]
+  double* d_greg = nullptr;   // [nt][C]
+  double* d_graw = nullptr;   // [nt][C]
+  double* d_out3 = nullptr;   // [3]
+  cplx* d_dense_a = nullptr;  // [M][2n][2n] ping
+  cplx* d_dense_b = nullptr;  // [M/2+1][2n][2n] pong
+  // chain launch geometry
+  int spb = 1, groups = 0, threads = 0, blocks = 0;
+  size_t chain_smem = 0;
+};
+
+// pulse.cu
+int qocvl_launch_pulse_forward(qocvl_plan* p, const double* abc, cudaStream_t st);
+int qocvl_launch_coefficients(qocvl_plan* p, const double* wave, cudaStream_t st);
+int qocvl_launch_pulse_vjp(qocvl_plan* p, const double* abc, const double* gwave, double* out_grads,
+                           cudaStream_t st);
+int qocvl_launch_aux(qocvl_plan* p, double* aux, cudaStream_t st);
+// chain.cu
+int qocvl_chain_configure(qocvl_plan* p);
+int qocvl_launch_chain(qocvl_plan* p, bool want_grad, double* out3, double* gwave, cudaStream_t st);
+// dense.cu
+int qocvl_launch_dense_expm(qocvl_plan* p, cplx* out, cudaStream_t st);
+int qocvl_launch_dense_tree(qocvl_plan* p, cplx* slices, cplx* out, cudaStream_t st);

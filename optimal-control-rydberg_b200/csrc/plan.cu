@@ -1,0 +1,303 @@
+// plan.cu -- plan lifetime, generator sparsity extraction, constant uploads (host side of the C-ABI).
+#include "common.cuh"
+#include <algorithm>
+#include <cmath>
+
+thread_local std::string g_qocvl_cuda_error;
+
+typedef std::complex<double> zc;
+
+template <typename T>
+static int dev_alloc(qocvl_plan* p, T** ptr, size_t count) {
+  if (*ptr) { cudaFree(*ptr); *ptr = nullptr; }
+  if (count == 0) count = 1;
+  QCUDA(cudaMalloc((void**)ptr, count * sizeof(T)));
+  p->bytes += count * sizeof(T);
+  return QOCVL_OK;
+}
+
+template <typename T>
+static int dev_upload(qocvl_plan* p, T** ptr, const std::vector<T>& host) {
+  int rc = dev_alloc(p, ptr, host.size());
+  if (rc) return rc;
+  if (!host.empty())
+    QCUDA(cudaMemcpy(*ptr, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return QOCVL_OK;
+}
+
+static void free_layout(BlockLayout& l) {
+  cudaFree(l.row_col); cudaFree(l.col_row); cudaFree(l.col_src);
+  cudaFree(l.rc_gen); cudaFree(l.rc_val); cudaFree(l.cc_gen); cudaFree(l.cc_val);
+  l = BlockLayout();
+}
+
+// Build the lane-per-row sparse tables for one block family.
+//   blocks: [J][n][n];  diag_slot: reserve slot 0 for the diagonal entry (u family).
+static int build_layout(qocvl_plan* p, const std::vector<zc>& blocks, bool diag_slot, BlockLayout* out) {
+  const int n = p->d.n, J = p->d.n_gen, np_ = p->npad;
+  auto G = [&](int j, int a, int b) { return blocks[((size_t)j * n + a) * n + b]; };
+  std::vector<char> pat((size_t)n * n, 0);
+  int nnz = 0;
+  for (int a = 0; a < n; ++a)
+    for (int b = 0; b < n; ++b) {
+      bool any = false;
+      for (int j = 0; j < J; ++j) any = any || (std::abs(G(j, a, b)) > 0.0);
+      pat[(size_t)a * n + b] = any;
+      nnz += any;
+    }
+  // per-row and per-column entry lists
+  std::vector<std::vector<int>> rows(n), cols(n);
+  for (int a = 0; a < n; ++a)
+    for (int b = 0; b < n; ++b) {
+      if (!pat[(size_t)a * n + b]) continue;
+      if (diag_slot && a == b) continue;
+      rows[a].push_back(b);
+      cols[b].push_back(a);
+    }
+  int w_row = 0, w_col = 0, kc = 1;
+  for (int r = 0; r < n; ++r) {
+    w_row = std::max(w_row, (int)rows[r].size());
+    w_col = std::max(w_col, (int)cols[r].size());
+  }
+  for (int a = 0; a < n; ++a)
+    for (int b = 0; b < n; ++b) {
+      int c = 0;
+      for (int j = 0; j < J; ++j) c += (std::abs(G(j, a, b)) > 0.0);
+      kc = std::max(kc, c);
+    }
+  const int base = diag_slot ? 1 : 0;
+  const int nrs = std::max(1, base + w_row), ncs = std::max(1, base + w_col);
+  std::vector<int> row_col((size_t)nrs * np_), col_row((size_t)ncs * np_), col_src((size_t)ncs * np_, 0);
+  std::vector<int> rc_gen((size_t)nrs * kc * np_, -1), cc_gen((size_t)ncs * kc * np_, -1);
+  std::vector<cplx> rc_val((size_t)nrs * kc * np_, cmake(0, 0)), cc_val((size_t)ncs * kc * np_, cmake(0, 0));
+  for (int s = 0; s < nrs; ++s) for (int r = 0; r < np_; ++r) row_col[(size_t)s * np_ + r] = r;
+  for (int s = 0; s < ncs; ++s) for (int r = 0; r < np_; ++r) col_row[(size_t)s * np_ + r] = r;
+  auto fill_contrib = [&](std::vector<int>& gen, std::vector<cplx>& val, int slot, int lane, int a, int b) {
+    int c = 0;
+    for (int j = 0; j < J; ++j) {
+      zc v = G(j, a, b);
+      if (std::abs(v) > 0.0) {
+        size_t idx = ((size_t)slot * kc + c) * np_ + lane;
+        gen[idx] = j;
+        val[idx] = cmake(v.real(), v.imag());
+        ++c;
+      }
+    }
+  };
+  for (int r = 0; r < n; ++r) {
+    if (diag_slot) {
+      fill_contrib(rc_gen, rc_val, 0, r, r, r);
+      fill_contrib(cc_gen, cc_val, 0, r, r, r);
+      col_src[r] = r;  // slot 0 * npad + r
+    }
+    for (size_t s = 0; s < rows[r].size(); ++s) {
+      row_col[(base + s) * np_ + r] = rows[r][s];
+      fill_contrib(rc_gen, rc_val, base + (int)s, r, r, rows[r][s]);
+    }
+    for (size_t s = 0; s < cols[r].size(); ++s) {
+      const int a = cols[r][s];  // entry (a, r)
+      col_row[(base + s) * np_ + r] = a;
+      fill_contrib(cc_gen, cc_val, base + (int)s, r, a, r);
+      // where does (a, r) live in row a's slot list?
+      int pos = (int)(std::find(rows[a].begin(), rows[a].end(), r) - rows[a].begin());
+      col_src[(base + s) * np_ + r] = (base + pos) * np_ + a;
+    }
+  }
+  free_layout(*out);
+  out->n_row_slots = nrs; out->n_col_slots = ncs; out->kc = kc; out->nnz = nnz;
+  int rc;
+  if ((rc = dev_upload(p, &out->row_col, row_col))) return rc;
+  if ((rc = dev_upload(p, &out->col_row, col_row))) return rc;
+  if ((rc = dev_upload(p, &out->col_src, col_src))) return rc;
+  if ((rc = dev_upload(p, &out->rc_gen, rc_gen))) return rc;
+  if ((rc = dev_upload(p, &out->rc_val, rc_val))) return rc;
+  if ((rc = dev_upload(p, &out->cc_gen, cc_gen))) return rc;
+  if ((rc = dev_upload(p, &out->cc_val, cc_val))) return rc;
+  return QOCVL_OK;
+}
+
+extern "C" int qocvl_plan_create(qocvl_plan** out, const qocvl_desc* desc, int device) {
+  if (!out || !desc) return QOCVL_ERR_ARG;
+  const qocvl_desc& d = *desc;
+  if (d.n < 1 || d.n_gen < 1 || d.n_gen > QOCVL_MAX_GEN || d.n_chan < 1 || d.n_chan > QOCVL_MAX_CHAN ||
+      d.n_slices < 1 || d.n_basis_pts < 2 || d.n_gauss < 1 || d.n_vec < 1 || d.pad < 0 ||
+      d.adiab_index < 0 || d.adiab_index >= d.n_vec || d.n_slices != d.n_basis_pts + 2 * d.pad ||
+      !(d.dt > 0) || !(d.duration > 0) || !(d.fid_norm > 0))
+    return QOCVL_ERR_ARG;
+  if (d.model != QOCVL_MODEL_STATE_TRANSFER && d.model != QOCVL_MODEL_TWO_QUBIT) return QOCVL_ERR_UNSUPPORTED;
+  if ((d.model == QOCVL_MODEL_STATE_TRANSFER || d.model == QOCVL_MODEL_TWO_QUBIT) &&
+      (d.n_gen != 11 || d.n_chan != 5))
+    return QOCVL_ERR_ARG;
+  if (d.n > 16) return QOCVL_ERR_UNSUPPORTED;  // lane-per-row chain kernel: one vector per half warp
+  QCUDA(cudaSetDevice(device));
+  qocvl_plan* p = new qocvl_plan();
+  p->d = d;
+  p->device = device;
+  p->npad = d.n <= 8 ? 8 : 16;
+  const int M = d.n_slices, nt = d.n_basis_pts, C = d.n_chan, J = d.n_gen;
+  int rc = 0;
+  rc |= dev_alloc(p, &p->d_raw, (size_t)nt * C);
+  rc |= dev_alloc(p, &p->d_reg, (size_t)nt * C);
+  rc |= dev_alloc(p, &p->d_wave, (size_t)M * C);
+  rc |= dev_alloc(p, &p->d_coef, (size_t)M * J);
+  rc |= dev_alloc(p, &p->d_dcoef, (size_t)M * J * C);
+  rc |= dev_alloc(p, &p->d_qdeg, (size_t)M);
+  rc |= dev_alloc(p, &p->d_flag, 1);
+  rc |= dev_alloc(p, &p->d_gwave, (size_t)M * C);
+  rc |= dev_alloc(p, &p->d_greg, (size_t)nt * C);
+  rc |= dev_alloc(p, &p->d_graw, (size_t)nt * C);
+  rc |= dev_alloc(p, &p->d_out3, 4);
+  if (rc) { qocvl_plan_destroy(p); return QOCVL_ERR_CUDA; }
+  cudaMemset(p->d_flag, 0, sizeof(int));
+  // default: one nominal sample
+  rc = qocvl_set_noise(p, 1, nullptr, nullptr);
+  if (rc) { qocvl_plan_destroy(p); return rc; }
+  *out = p;
+  return QOCVL_OK;
+}
+
+extern "C" int qocvl_plan_destroy(qocvl_plan* p) {
+  if (!p) return QOCVL_OK;
+  cudaSetDevice(p->device);
+  free_layout(p->lu); free_layout(p->lw);
+  void* ptrs[] = {p->d_gdense, p->d_coef_const, p->d_gnorm, p->d_starts, p->d_targets, p->d_mul, p->d_add,
+                  p->d_mulmax, p->d_addmax, p->d_taps, p->d_raw, p->d_reg, p->d_wave, p->d_coef, p->d_dcoef,
+                  p->d_qdeg, p->d_flag, p->d_ckpt, p->d_sample_out, p->d_gw_partial, p->d_gwave, p->d_greg,
+                  p->d_graw, p->d_out3, p->d_dense_a, p->d_dense_b};
+  for (void* q : ptrs) if (q) cudaFree(q);
+  delete p;
+  return QOCVL_OK;
+}
+
+extern "C" int qocvl_set_generators(qocvl_plan* p, const double* gens_u, const double* gens_w,
+                                    const double* coef_const) {
+  if (!p || !gens_u || !gens_w || !coef_const) return QOCVL_ERR_ARG;
+  QCUDA(cudaSetDevice(p->device));
+  const int n = p->d.n, J = p->d.n_gen, D = 2 * n;
+  const size_t blk = (size_t)J * n * n;
+  p->h_gu.resize(blk); p->h_gw.resize(blk); p->h_coef_const.resize(J);
+  for (size_t i = 0; i < blk; ++i) {
+    p->h_gu[i] = zc(gens_u[2 * i], gens_u[2 * i + 1]);
+    p->h_gw[i] = zc(gens_w[2 * i], gens_w[2 * i + 1]);
+  }
+  std::vector<cplx> cc(J);
+  for (int j = 0; j < J; ++j) {
+    p->h_coef_const[j] = zc(coef_const[2 * j], coef_const[2 * j + 1]);
+    cc[j] = cmake(coef_const[2 * j], coef_const[2 * j + 1]);
+  }
+  int rc;
+  if ((rc = build_layout(p, p->h_gu, true, &p->lu))) return rc;
+  if ((rc = build_layout(p, p->h_gw, false, &p->lw))) return rc;
+  // induced 1-norms (max column sum) of each generator: |G_u|_1 + |G_w|_1 bounds the 2n x 2n norm
+  std::vector<double> gnorm(J, 0.0);
+  for (int j = 0; j < J; ++j) {
+    double nu = 0, nw = 0;
+    for (int b = 0; b < n; ++b) {
+      double su = 0, sw = 0;
+      for (int a = 0; a < n; ++a) {
+        su += std::abs(p->h_gu[((size_t)j * n + a) * n + b]);
+        sw += std::abs(p->h_gw[((size_t)j * n + a) * n + b]);
+      }
+      nu = std::max(nu, su); nw = std::max(nw, sw);
+    }
+    gnorm[j] = nu + nw;
+    p->h_gnorm[j] = gnorm[j];
+  }
+  if ((rc = dev_upload(p, &p->d_gnorm, gnorm))) return rc;
+  if ((rc = dev_upload(p, &p->d_coef_const, cc))) return rc;
+  // dense 2n x 2n copies for exponentials()/propagate()
+  std::vector<cplx> dense((size_t)J * D * D, cmake(0, 0));
+  for (int j = 0; j < J; ++j)
+    for (int a = 0; a < n; ++a)
+      for (int b = 0; b < n; ++b) {
+        zc u = p->h_gu[((size_t)j * n + a) * n + b], w = p->h_gw[((size_t)j * n + a) * n + b];
+        dense[((size_t)j * D + a) * D + b] = cmake(u.real(), u.imag());
+        dense[((size_t)j * D + n + a) * D + n + b] = cmake(u.real(), u.imag());
+        dense[((size_t)j * D + a) * D + n + b] = cmake(w.real(), w.imag());
+      }
+  if ((rc = dev_upload(p, &p->d_gdense, dense))) return rc;
+  p->have_gens = true;
+  p->groups = 0;  // force re-configuration of the chain launch
+  return QOCVL_OK;
+}
+
+extern "C" int qocvl_set_filter(qocvl_plan* p, const double* taps) {
+  if (!p) return QOCVL_ERR_ARG;
+  QCUDA(cudaSetDevice(p->device));
+  if (!taps) {
+    if (p->d.pad != 0) return QOCVL_ERR_ARG;
+    p->have_filter = false;
+    return QOCVL_OK;
+  }
+  std::vector<double> h(taps, taps + p->d.n_slices);
+  int rc = dev_upload(p, &p->d_taps, h);
+  if (rc) return rc;
+  p->have_filter = true;
+  return QOCVL_OK;
+}
+
+extern "C" int qocvl_set_cost(qocvl_plan* p, const double* starts, const double* targets) {
+  if (!p || !starts || !targets) return QOCVL_ERR_ARG;
+  QCUDA(cudaSetDevice(p->device));
+  const int n = p->d.n, V = p->d.n_vec, np_ = p->npad;
+  std::vector<cplx> s((size_t)V * np_, cmake(0, 0)), t((size_t)V * np_, cmake(0, 0));
+  for (int v = 0; v < V; ++v)
+    for (int r = 0; r < n; ++r) {
+      s[(size_t)v * np_ + r] = cmake(starts[2 * ((size_t)v * n + r)], starts[2 * ((size_t)v * n + r) + 1]);
+      t[(size_t)v * np_ + r] = cmake(targets[2 * ((size_t)v * n + r)], targets[2 * ((size_t)v * n + r) + 1]);
+    }
+  int rc;
+  if ((rc = dev_upload(p, &p->d_starts, s))) return rc;
+  if ((rc = dev_upload(p, &p->d_targets, t))) return rc;
+  p->have_cost = true;
+  return QOCVL_OK;
+}
+
+extern "C" int qocvl_set_noise(qocvl_plan* p, int n_samples, const double* mul, const double* add) {
+  if (!p || n_samples < 1) return QOCVL_ERR_ARG;
+  QCUDA(cudaSetDevice(p->device));
+  const int J = p->d.n_gen;
+  std::vector<double> hm((size_t)n_samples * J, 1.0), mulmax(J, 0.0), addmax(J, 0.0);
+  std::vector<cplx> ha((size_t)n_samples * J, cmake(0, 0));
+  for (size_t i = 0; i < hm.size(); ++i) {
+    if (mul) hm[i] = mul[i];
+    if (add) ha[i] = cmake(add[2 * i], add[2 * i + 1]);
+    const int j = (int)(i % J);
+    mulmax[j] = std::max(mulmax[j], std::fabs(hm[i]));
+    addmax[j] = std::max(addmax[j], std::hypot(ha[i].x, ha[i].y));
+  }
+  int rc;
+  if ((rc = dev_upload(p, &p->d_mul, hm))) return rc;
+  if ((rc = dev_upload(p, &p->d_add, ha))) return rc;
+  if ((rc = dev_upload(p, &p->d_mulmax, mulmax))) return rc;
+  if ((rc = dev_upload(p, &p->d_addmax, addmax))) return rc;
+  if ((rc = dev_alloc(p, &p->d_sample_out, (size_t)n_samples * 3))) return rc;
+  p->n_samples = n_samples;
+  p->global_samples = n_samples;
+  p->groups = 0;
+  return QOCVL_OK;
+}
+
+extern "C" int qocvl_set_shard(qocvl_plan* p, int global_samples) {
+  if (!p || global_samples < p->n_samples) return QOCVL_ERR_ARG;
+  p->global_samples = global_samples;
+  return QOCVL_OK;
+}
+
+extern "C" size_t qocvl_workspace_bytes(const qocvl_plan* p) { return p ? p->bytes : 0; }
+extern "C" long long qocvl_launch_count(const qocvl_plan* p) { return p ? p->launches : 0; }
+extern "C" int qocvl_last_taylor_degree(const qocvl_plan* p) { return p ? p->qcap : 0; }
+extern "C" const char* qocvl_last_cuda_error(void) { return g_qocvl_cuda_error.c_str(); }
+extern "C" int qocvl_version(void) { return 100; }
+
+extern "C" const char* qocvl_strerror(int status) {
+  switch (status) {
+    case QOCVL_OK: return "ok";
+    case QOCVL_ERR_ARG: return "invalid argument";
+    case QOCVL_ERR_CUDA: return "CUDA runtime error";
+    case QOCVL_ERR_STATE: return "plan not fully set up (generators / cost / filter missing)";
+    case QOCVL_ERR_NORM: return "slice generator norm too large for the Taylor propagator (refine delta_t)";
+    case QOCVL_ERR_UNSUPPORTED: return "configuration not supported by this build";
+    default: return "unknown status";
+  }
+}

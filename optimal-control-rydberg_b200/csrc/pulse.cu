@@ -1,0 +1,291 @@
+// pulse.cu -- pulse map (Gaussian basis -> regularisation -> frequency filter), auxiliary
+// amplitudes with their derivatives, and the reverse (VJP) of all of it.
+//   forward : ST:173-245, TQ:319-455        reverse: hand-derived, mirrors oracle/vector_model.py
+#include "common.cuh"
+
+#define PI_D 3.14159265358979323846
+
+__device__ __forceinline__ double basis_time(int t, int nt) {
+  // numpy.linspace(-1, 1, nt): start + t*step, last point forced to the stop value
+  const double step = 2.0 / (double)(nt - 1);
+  return (t == nt - 1) ? 1.0 : (-1.0 + (double)t * step);
+}
+
+// raw[t][c] = sum_n a[n][c] exp(-(tau_t - tanh b)^2 / tanh(c)^2)   (ST:173-202, TQ:319-353)
+// reg = model regularisation (ST:204-227, TQ:355-373)
+__global__ void k_raw_reg(int model, int nt, int N, int C, const double* __restrict__ abc,
+                          double* __restrict__ raw, double* __restrict__ reg) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nt) return;
+  const double* a = abc;
+  const double* b = abc + (size_t)N * C;
+  const double* c = abc + (size_t)2 * N * C;
+  const double tau = basis_time(t, nt);
+  double r[QOCVL_MAX_CHAN];
+  for (int ch = 0; ch < C; ++ch) {
+    double acc = 0.0;
+    for (int n = 0; n < N; ++n) {
+      const double bt = tanh(b[n * C + ch]), ct = tanh(c[n * C + ch]);
+      const double dev = tau - bt;
+      acc += exp(-(dev * dev) / (ct * ct)) * a[n * C + ch];
+    }
+    r[ch] = acc;
+    raw[(size_t)t * C + ch] = acc;
+  }
+  double* o = reg + (size_t)t * C;
+  if (model == QOCVL_MODEL_TWO_QUBIT) {
+    o[0] = 0.0 * r[0] - 1.0;                       // TQ:364
+    o[1] = 1.0 - exp(-(r[1] * r[1]));              // TQ:365
+    o[2] = tanh(r[2]);
+    o[3] = 1.0 - exp(-(r[3] * r[3]));
+    o[4] = tanh(r[4]);
+  } else {
+    o[0] = tanh(r[0]);                             // ST:222
+    for (int p0 = 1; p0 <= 3; p0 += 2) {           // ST:204-213
+      const double rad = sqrt(r[p0] * r[p0] + r[p0 + 1] * r[p0 + 1]);
+      const double sc = (rad == 0.0) ? 1.0 : tanh(rad) / rad;
+      o[p0] = sc * r[p0];
+      o[p0 + 1] = sc * r[p0 + 1];
+    }
+  }
+}
+
+// wave[k][c] = sum_t taps[(k - t - pad) mod M] reg[t][c]      (TQ:375-397 as a real convolution)
+// transpose=1: out[t][c] = sum_k taps[(k - t - pad) mod M] in[k][c]
+__global__ void k_filter(int M, int nt, int pad, int C, int transpose, const double* __restrict__ taps,
+                         const double* __restrict__ in, double* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int n_out = transpose ? nt : M, n_in = transpose ? M : nt;
+  if (warp >= n_out) return;
+  double acc[QOCVL_MAX_CHAN];
+#pragma unroll
+  for (int c = 0; c < QOCVL_MAX_CHAN; ++c) acc[c] = 0.0;
+  for (int i = lane; i < n_in; i += 32) {
+    int idx = transpose ? (i - warp - pad) : (warp - i - pad);
+    idx %= M;
+    if (idx < 0) idx += M;
+    const double h = taps[idx];
+#pragma unroll
+    for (int c = 0; c < QOCVL_MAX_CHAN; ++c)
+      if (c < C) acc[c] = fma(h, in[(size_t)i * C + c], acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < QOCVL_MAX_CHAN; ++c) {
+    double v = acc[c];
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0 && c < C) out[(size_t)warp * C + c] = v;
+  }
+}
+
+// Per-slice generator coefficients and their derivatives with respect to the C real
+// pulse values of that slice; also the Taylor degree for the slice.
+//   TQ:416-476 (drift coefficient -i comes from coef_const), ST:236-255
+__global__ void k_coefficients(int model, int M, int J, int C, double dt, double eps, double s0, double s1,
+                               const double* __restrict__ wave, const cplx* __restrict__ coef_const,
+                               const double* __restrict__ gnorm, const double* __restrict__ mulmax,
+                               const double* __restrict__ addmax, int qcap, cplx* __restrict__ coef,
+                               cplx* __restrict__ dcoef, int* __restrict__ qdeg, int* __restrict__ flag) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= M) return;
+  const double* w = wave + (size_t)k * C;
+  cplx co[QOCVL_MAX_GEN];
+  cplx dc[QOCVL_MAX_GEN][QOCVL_MAX_CHAN];
+  for (int j = 0; j < QOCVL_MAX_GEN; ++j) {
+    co[j] = cmake(0, 0);
+    for (int c = 0; c < QOCVL_MAX_CHAN; ++c) dc[j][c] = cmake(0, 0);
+  }
+  co[0] = coef_const[0];
+  co[1] = coef_const[1];
+  if (model == QOCVL_MODEL_TWO_QUBIT) {
+    const double ri = s0, rr = s1;
+    double si, ci, sr, cr;
+    sincos(PI_D * w[2], &si, &ci);
+    sincos(PI_D * w[4], &sr, &cr);
+    co[2] = cmake(0, -w[0]);              dc[2][0] = cmake(0, -1);
+    co[3] = cmake(0, -w[1] * ci);         dc[3][1] = cmake(0, -ci); dc[3][2] = cmake(0, PI_D * w[1] * si);
+    co[4] = cmake(0, -w[1] * si);         dc[4][1] = cmake(0, -si); dc[4][2] = cmake(0, -PI_D * w[1] * ci);
+    co[5] = cmake(0, -w[3] * cr);         dc[5][3] = cmake(0, -cr); dc[5][4] = cmake(0, PI_D * w[3] * sr);
+    co[6] = cmake(0, -w[3] * sr);         dc[6][3] = cmake(0, -sr); dc[6][4] = cmake(0, -PI_D * w[3] * cr);
+    const double mi = ri * w[1], mr = rr * w[3];
+    const double den_raw = mr * mr + mi * mi;
+    const bool clamped = den_raw < eps;      // TQ:433-434
+    const double den = clamped ? eps : den_raw;
+    const double dd1 = clamped ? 0.0 : 2.0 * mi * ri, dd3 = clamped ? 0.0 : 2.0 * mr * rr;
+    double sp, cp;
+    sincos(PI_D * (w[2] + w[4]), &sp, &cp);
+    const cplx ph = cmake(cp, sp);
+    const double inv = 1.0 / den, inv2 = inv * inv;
+    co[7] = cmake(mr * mr * inv, 0);
+    co[8] = cmake(mi * mi * inv, 0);
+    co[9] = cscale(ph, -mi * mr * inv);
+    co[10] = cconj(co[9]);
+    dc[7][1] = cmake(-mr * mr * dd1 * inv2, 0);
+    dc[7][3] = cmake(2.0 * mr * rr * inv - mr * mr * dd3 * inv2, 0);
+    dc[8][1] = cmake(2.0 * mi * ri * inv - mi * mi * dd1 * inv2, 0);
+    dc[8][3] = cmake(-mi * mi * dd3 * inv2, 0);
+    dc[9][1] = cscale(ph, -(ri * mr * inv - mi * mr * dd1 * inv2));
+    dc[9][3] = cscale(ph, -(mi * rr * inv - mi * mr * dd3 * inv2));
+    dc[9][2] = cmul(cmake(0, PI_D), co[9]);
+    dc[9][4] = dc[9][2];
+    for (int c = 0; c < 5; ++c) dc[10][c] = cconj(dc[9][c]);
+  } else {  // state transfer
+    const double r1 = s0, r2 = s1;
+    for (int c = 0; c < 5; ++c) { co[2 + c] = cmake(0, -w[c]); dc[2 + c][c] = cmake(0, -1); }
+    const cplx o1 = cmake(r1 * w[1], r1 * w[2]), o2 = cmake(r2 * w[3], r2 * w[4]);
+    const double n1 = o1.x * o1.x + o1.y * o1.y, n2 = o2.x * o2.x + o2.y * o2.y;
+    const double den = n1 + n2, inv = 1.0 / den, inv2 = inv * inv;   // ST:242-243: no guard (quirk q7)
+    const cplx o12 = cmul(o1, o2);
+    co[7] = cmake(n2 * inv, 0);
+    co[8] = cmake(n1 * inv, 0);
+    co[9] = cscale(o12, -inv);
+    co[10] = cconj(co[9]);
+    const double dn1[5] = {0, 2 * r1 * r1 * w[1], 2 * r1 * r1 * w[2], 0, 0};
+    const double dn2[5] = {0, 0, 0, 2 * r2 * r2 * w[3], 2 * r2 * r2 * w[4]};
+    const cplx do1[5] = {cmake(0, 0), cmake(r1, 0), cmake(0, r1), cmake(0, 0), cmake(0, 0)};
+    const cplx do2[5] = {cmake(0, 0), cmake(0, 0), cmake(0, 0), cmake(r2, 0), cmake(0, r2)};
+    for (int c = 1; c < 5; ++c) {
+      const double dden = dn1[c] + dn2[c];
+      dc[7][c] = cmake(dn2[c] * inv - n2 * dden * inv2, 0);
+      dc[8][c] = cmake(dn1[c] * inv - n1 * dden * inv2, 0);
+      const cplx num = cadd(cmul(do1[c], o2), cmul(o1, do2[c]));
+      dc[9][c] = cadd(cscale(num, -inv), cscale(o12, dden * inv2));
+      dc[10][c] = cconj(dc[9][c]);
+    }
+  }
+  double nrm = 0.0;
+  for (int j = 0; j < J; ++j) {
+    coef[(size_t)k * J + j] = co[j];
+    for (int c = 0; c < C; ++c) dcoef[((size_t)k * J + j) * C + c] = dc[j][c];
+    const double mag = sqrt(co[j].x * co[j].x + co[j].y * co[j].y);
+    nrm += (mag * mulmax[j] + addmax[j]) * gnorm[j];
+  }
+  nrm *= dt;
+  int q = qocvl_taylor_degree(nrm);
+  if (!(nrm <= QOCVL_NORM_MAX) || q > qcap) {   // also catches NaN pulses
+    atomicOr(flag, 1);
+    q = qcap;
+  }
+  qdeg[k] = q;
+}
+
+// aux[k][0..J-3] = coef[k][2..J-1]   (ST:244-245, TQ:452-455)
+__global__ void k_aux(int M, int J, const cplx* __restrict__ coef, cplx* __restrict__ aux) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * (J - 2)) return;
+  const int k = i / (J - 2), j = i % (J - 2);
+  aux[i] = coef[(size_t)k * J + 2 + j];
+}
+
+// d cost / d raw from d cost / d reg  (reverse of the regularisation)
+__global__ void k_reg_vjp(int model, int nt, int C, const double* __restrict__ raw,
+                          const double* __restrict__ greg, double* __restrict__ graw) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nt) return;
+  const double* r = raw + (size_t)t * C;
+  const double* g = greg + (size_t)t * C;
+  double* o = graw + (size_t)t * C;
+  if (model == QOCVL_MODEL_TWO_QUBIT) {
+    o[0] = 0.0;                                       // TQ:364 -- channel 0 is a constant
+    o[1] = g[1] * 2.0 * r[1] * exp(-(r[1] * r[1]));
+    o[3] = g[3] * 2.0 * r[3] * exp(-(r[3] * r[3]));
+    double th = tanh(r[2]); o[2] = g[2] * (1.0 - th * th);
+    th = tanh(r[4]);        o[4] = g[4] * (1.0 - th * th);
+  } else {
+    const double th0 = tanh(r[0]);
+    o[0] = g[0] * (1.0 - th0 * th0);
+    for (int p0 = 1; p0 <= 3; p0 += 2) {
+      const double x = r[p0], y = r[p0 + 1];
+      const double rad = sqrt(x * x + y * y);
+      double sc = 1.0, dsc = 0.0;
+      if (rad != 0.0) {
+        const double th = tanh(rad);
+        sc = th / rad;
+        dsc = ((1.0 - th * th) * rad - th) / (rad * rad * rad);
+      }
+      const double dot = g[p0] * x + g[p0 + 1] * y;
+      o[p0] = sc * g[p0] + dsc * dot * x;
+      o[p0 + 1] = sc * g[p0 + 1] + dsc * dot * y;
+    }
+  }
+}
+
+// One warp per (n, c): ga, gb, gc from graw (reverse of the Gaussian basis, incl. the tanh clamps)
+__global__ void k_basis_vjp(int nt, int N, int C, const double* __restrict__ abc,
+                            const double* __restrict__ graw, double* __restrict__ grads) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N * C) return;
+  const int n = warp / C, ch = warp % C;
+  const double a = abc[n * C + ch];
+  const double bt = tanh(abc[(size_t)N * C + n * C + ch]);
+  const double ct = tanh(abc[(size_t)2 * N * C + n * C + ch]);
+  const double ic2 = 1.0 / (ct * ct), ic3 = ic2 / ct;
+  double sa = 0, sb = 0, sc = 0;
+  for (int t = lane; t < nt; t += 32) {
+    const double dev = basis_time(t, nt) - bt;
+    const double mode = exp(-(dev * dev) * ic2);
+    const double g = graw[(size_t)t * C + ch] * mode;
+    sa += g;
+    sb += g * 2.0 * dev * ic2;
+    sc += g * 2.0 * dev * dev * ic3;
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, off);
+    sb += __shfl_xor_sync(0xffffffffu, sb, off);
+    sc += __shfl_xor_sync(0xffffffffu, sc, off);
+  }
+  if (lane == 0) {
+    grads[n * C + ch] = sa;
+    grads[(size_t)N * C + n * C + ch] = a * sb * (1.0 - bt * bt);
+    grads[(size_t)2 * N * C + n * C + ch] = a * sc * (1.0 - ct * ct);
+  }
+}
+
+int qocvl_launch_pulse_forward(qocvl_plan* p, const double* abc, cudaStream_t st) {
+  const qocvl_desc& d = p->d;
+  const int nt = d.n_basis_pts, M = d.n_slices, C = d.n_chan;
+  if (d.pad > 0 && !p->have_filter) return QOCVL_ERR_STATE;
+  double* reg_out = p->have_filter ? p->d_reg : p->d_wave;   // no filter: wave == reg (ST)
+  k_raw_reg<<<(nt + 127) / 128, 128, 0, st>>>(d.model, nt, d.n_gauss, C, abc, p->d_raw, reg_out);
+  p->launches++;
+  if (p->have_filter) {
+    k_filter<<<(M * 32 + 255) / 256, 256, 0, st>>>(M, nt, d.pad, C, 0, p->d_taps, p->d_reg, p->d_wave);
+    p->launches++;
+  }
+  QCUDA(cudaGetLastError());
+  return QOCVL_OK;
+}
+
+int qocvl_launch_coefficients(qocvl_plan* p, const double* wave, cudaStream_t st) {
+  const qocvl_desc& d = p->d;
+  k_coefficients<<<(d.n_slices + 127) / 128, 128, 0, st>>>(
+      d.model, d.n_slices, d.n_gen, d.n_chan, d.dt, d.eps, d.scale[0], d.scale[1], wave, p->d_coef_const,
+      p->d_gnorm, p->d_mulmax, p->d_addmax, p->qcap, p->d_coef, p->d_dcoef, p->d_qdeg, p->d_flag);
+  p->launches++;
+  QCUDA(cudaGetLastError());
+  return QOCVL_OK;
+}
+
+int qocvl_launch_aux(qocvl_plan* p, double* aux, cudaStream_t st) {
+  const int total = p->d.n_slices * (p->d.n_gen - 2);
+  k_aux<<<(total + 255) / 256, 256, 0, st>>>(p->d.n_slices, p->d.n_gen, p->d_coef, (cplx*)aux);
+  p->launches++;
+  QCUDA(cudaGetLastError());
+  return QOCVL_OK;
+}
+
+int qocvl_launch_pulse_vjp(qocvl_plan* p, const double* abc, const double* gwave, double* out_grads,
+                           cudaStream_t st) {
+  const qocvl_desc& d = p->d;
+  const int nt = d.n_basis_pts, M = d.n_slices, C = d.n_chan;
+  const double* greg = gwave;
+  if (p->have_filter) {
+    k_filter<<<(nt * 32 + 255) / 256, 256, 0, st>>>(M, nt, d.pad, C, 1, p->d_taps, gwave, p->d_greg);
+    p->launches++;
+    greg = p->d_greg;
+  }
+  k_reg_vjp<<<(nt + 127) / 128, 128, 0, st>>>(d.model, nt, C, p->d_raw, greg, p->d_graw);
+  k_basis_vjp<<<(d.n_gauss * C * 32 + 127) / 128, 128, 0, st>>>(nt, d.n_gauss, C, abc, p->d_graw, out_grads);
+  p->launches += 2;
+  QCUDA(cudaGetLastError());
+  return QOCVL_OK;
+}

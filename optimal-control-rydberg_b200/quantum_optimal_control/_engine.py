@@ -1,0 +1,215 @@
+"""Shared host logic of the two PropagatorVL mirrors: argument packing, the qocvl plan, the
+torch.autograd bridge (stands in for ``jax.value_and_grad``, TQ:592 / notebook 01 cell 9), the
+noise-ensemble and multi-GPU sharding extensions.  All numbers come from libqocvl.so."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+import qocvl
+
+
+def halving_flags(count):
+    """ST:77-87 / TQ:144-154 ``gen_contraction_array``: odd/even flag of each halving level."""
+    flags = []
+    while count > 1:
+        flags.append(bool(count & 1))
+        count >>= 1
+    return flags
+
+
+def block_diag2(m):
+    z = np.zeros_like(m)
+    return np.block([[m, z], [z, m]])
+
+
+def block_upper(m):
+    z = np.zeros_like(m)
+    return np.block([[z, m], [z, z]])
+
+
+class _TargetFn(torch.autograd.Function):
+    """cost(a, b, c) with the engine's analytic gradient."""
+
+    @staticmethod
+    def forward(ctx, prop, a, b, c):
+        out = prop._plan.cost_grad(prop._pack(a, b, c))
+        n, ch = prop.input_dim, prop.num_ctrls
+        ctx.grads = out[3:].view(3, n, ch)
+        ctx.like = (a, b, c)
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        res = []
+        for i, ref in enumerate(ctx.like):
+            g = (ctx.grads[i] * gout).to(device=ref.device, dtype=ref.dtype) if ctx.needs_input_grad[i + 1] else None
+            res.append(g)
+        return (None, *res)
+
+
+class _WaveFn(torch.autograd.Function):
+    """return_physical_amplitudes with its reverse pass (notebook 05 cells 8-12 differentiate it)."""
+
+    @staticmethod
+    def forward(ctx, prop, a, b, c):
+        abc = prop._pack(a, b, c)
+        ctx.prop, ctx.abc, ctx.like = prop, abc, (a, b, c)
+        return prop._plan.physical_amplitudes(abc)
+
+    @staticmethod
+    def backward(ctx, gwave):
+        g = ctx.prop._plan.physical_amplitudes_vjp(ctx.abc, gwave)
+        res = [g[i].to(device=r.device, dtype=r.dtype) if ctx.needs_input_grad[i + 1] else None
+               for i, r in enumerate(ctx.like)]
+        return (None, *res)
+
+
+class EngineBase:
+    """Everything the two models share.  Subclasses fill in the physics in ``_build``."""
+
+    num_ctrls = 5
+
+    # -- set by subclasses --------------------------------------------------------------------
+    _model = None
+    W_INFID = W_ADIAB = None
+
+    def _make_plan(self, *, n, n_slices, n_basis_pts, pad, gens_u, gens_w, coef_const, starts, targets,
+                   adiab_index, fid_norm, scale, taps, eps=1e-12, device=None):
+        self._plan = qocvl.Plan(
+            model=self._model, n=n, n_gen=gens_u.shape[0], n_slices=n_slices, n_basis_pts=n_basis_pts,
+            pad=pad, n_gauss=self.input_dim, n_chan=self.num_ctrls, n_vec=len(starts),
+            adiab_index=adiab_index, dt=self.delta_t, duration=self.duration, w_infid=self.W_INFID,
+            w_adiab=self.W_ADIAB, fid_norm=fid_norm, eps=eps, scale=scale, device=device)
+        self._plan.set_generators(gens_u, gens_w, coef_const)
+        self._plan.set_filter(taps)
+        self._plan.set_cost(starts, targets)
+        self.device = self._plan.device
+        self._world = None
+        self._pin_in = self._pin_out = None
+
+    # -- argument handling ----------------------------------------------------------------------
+    def _pack(self, a, b, c):
+        """(a, b, c) each [input_dim, 5] (numpy / torch, any device) -> float64 [3,N,5] on the GPU."""
+        parts = []
+        for x in (a, b, c):
+            t = x.detach() if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x, dtype=np.float64))
+            if tuple(t.shape) != (self.input_dim, self.num_ctrls):
+                raise ValueError(f"control arrays must have shape ({self.input_dim}, {self.num_ctrls}), "
+                                 f"got {tuple(t.shape)}")
+            parts.append(t.to(device=self.device, dtype=torch.float64))
+        return torch.stack(parts, dim=0).contiguous()
+
+    @staticmethod
+    def _wants_grad(*xs):
+        return torch.is_grad_enabled() and any(isinstance(x, torch.Tensor) and x.requires_grad for x in xs)
+
+    # -- the reference's method surface (ST:215-310, TQ:399-574) ------------------------------------
+    def return_physical_amplitudes(self, ctrl_a, ctrl_b, ctrl_c):
+        if self._wants_grad(ctrl_a, ctrl_b, ctrl_c):
+            return _WaveFn.apply(self, ctrl_a, ctrl_b, ctrl_c)
+        return self._plan.physical_amplitudes(self._pack(ctrl_a, ctrl_b, ctrl_c))
+
+    def return_auxiliary_amplitudes(self, ctrl_a, ctrl_b, ctrl_c):
+        return self._plan.auxiliary_amplitudes(self._pack(ctrl_a, ctrl_b, ctrl_c))
+
+    def exponentials(self, ctrl_a, ctrl_b, ctrl_c):
+        return self._plan.exponentials(self._pack(ctrl_a, ctrl_b, ctrl_c))
+
+    def propagate(self, ctrl_a, ctrl_b, ctrl_c):
+        return self._plan.propagate(self._pack(ctrl_a, ctrl_b, ctrl_c))
+
+    def metrics(self, ctrl_a, ctrl_b, ctrl_c):
+        out = self._plan.cost(self._pack(ctrl_a, ctrl_b, ctrl_c))
+        out = self._allreduce(out)
+        return out[1], out[2]
+
+    def target(self, ctrl_a, ctrl_b, ctrl_c):
+        if self._wants_grad(ctrl_a, ctrl_b, ctrl_c) and self._world is None:
+            return _TargetFn.apply(self, ctrl_a, ctrl_b, ctrl_c)
+        return self._allreduce(self._plan.cost(self._pack(ctrl_a, ctrl_b, ctrl_c)))[0]
+
+    # -- gradient callbacks -----------------------------------------------------------------------
+    def cost_and_grad_packed(self, abc, out=None):
+        """Device in / device out, no host sync: float64 [3+3NC] = cost, infid, adiab, ga, gb, gc."""
+        return self._allreduce(self._plan.cost_grad(abc, out))
+
+    def target_and_grad(self, ctrl_a, ctrl_b, ctrl_c):
+        """Stand-in for ``jax.value_and_grad(target, argnums=(0,1,2))``: -> (cost, (ga, gb, gc)),
+        all CUDA tensors, gradients shaped like the inputs (per-array masks apply, notebook 04 cell 5)."""
+        out = self.cost_and_grad_packed(self._pack(ctrl_a, ctrl_b, ctrl_c))
+        g = out[3:].view(3, self.input_dim, self.num_ctrls)
+        return out[0], (g[0], g[1], g[2])
+
+    def value_and_grad_host(self, ctrl_a, ctrl_b, ctrl_c):
+        """Host optimiser callback (e.g. scipy.optimize.minimize(jac=True)): NumPy in, NumPy out.
+        One pinned host->device copy of the 3*N*C parameters and one device->host copy of
+        3+3*N*C results per call."""
+        n = 3 * self.input_dim * self.num_ctrls
+        if self._pin_in is None:
+            self._pin_in = torch.empty((3, self.input_dim, self.num_ctrls), dtype=torch.float64).pin_memory()
+            self._pin_out = torch.empty(3 + n, dtype=torch.float64).pin_memory()
+            self._dev_in = torch.empty_like(self._pin_in, device=self.device)
+        for i, x in enumerate((ctrl_a, ctrl_b, ctrl_c)):
+            self._pin_in[i].copy_(torch.as_tensor(np.asarray(x, dtype=np.float64)))
+        self._dev_in.copy_(self._pin_in, non_blocking=True)
+        out = self.cost_and_grad_packed(self._dev_in)
+        self._pin_out.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        res = self._pin_out.numpy()
+        g = res[3:].reshape(3, self.input_dim, self.num_ctrls)
+        return float(res[0]), (g[0].copy(), g[1].copy(), g[2].copy())
+
+    # -- extensions: robustness ensemble and multi-GPU sharding ---------------------------------------
+    def _noise_tables(self, del_total, rabi_scale):
+        raise NotImplementedError
+
+    def set_ensemble(self, del_total=None, rabi_scale=None, shard=False):
+        """Robustness ensemble: sample s behaves as if the constructor had been called with
+        ``del_total = del_total[s]`` and both Rabi frequencies multiplied by ``rabi_scale[s]``;
+        ``target`` / ``metrics`` / gradients become ensemble means.  ``shard=True`` keeps only this
+        rank's block of samples (torch.distributed must be initialised) and completes every
+        evaluation with ONE all-reduce of 3+3*N*C doubles."""
+        if del_total is None and rabi_scale is None:
+            self._plan.set_noise(None, None)
+            self._world = None
+            return
+        ref = del_total if del_total is not None else rabi_scale
+        S = len(ref)
+        dl = np.full(S, float(self.del_total)) if del_total is None else np.asarray(del_total, float)
+        rs = np.ones(S) if rabi_scale is None else np.asarray(rabi_scale, float)
+        mul, add = self._noise_tables(dl, rs)
+        if shard:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(), dist.get_rank()
+            lo, hi = shard_bounds(S, world, rank)
+            mul, add = mul[lo:hi], add[lo:hi]
+            self._world = world
+        else:
+            self._world = None
+        self._plan.set_noise(mul, add, global_samples=S)
+
+    def _allreduce(self, out):
+        if self._world is not None and self._world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(out, op=dist.ReduceOp.SUM)
+        return out
+
+
+def shard_bounds(n_items, world, rank):
+    """Contiguous block partition of n_items over world ranks (first ranks get the remainder)."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gradient_step(prop, ctrl_a, ctrl_b, ctrl_c, lr):
+    """TQ:580-600 ``single_optimization_step``: plain gradient descent, returns (cost, a', b', c')."""
+    cost, (ga, gb, gc) = prop.target_and_grad(ctrl_a, ctrl_b, ctrl_c)
+
+    def upd(x, g):
+        if isinstance(x, torch.Tensor):
+            return x.detach() - lr * g.to(device=x.device, dtype=x.dtype)
+        return torch.as_tensor(np.asarray(x, dtype=np.float64), device=g.device) - lr * g
+
+    return cost, upd(ctrl_a, ga), upd(ctrl_b, gb), upd(ctrl_c, gc)

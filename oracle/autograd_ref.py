@@ -128,4 +128,4 @@ def value_and_grad(prop, a, b, c):
     ta, tb, tc = (torch.tensor(np.asarray(x, dtype=np.float64), requires_grad=True) for x in (a, b, c))
     cost, infid, adiab = target_torch(prop, ta, tb, tc, return_parts=True)
     ga, gb, gc = torch.autograd.grad(cost, (ta, tb, tc))
-    return (float(cost), float(infid), float(adiab), ga.numpy(), gb.numpy(), gc.numpy())
+    return (float(cost.detach()), float(infid.detach()), float(adiab.detach()), ga.numpy(), gb.numpy(), gc.numpy())
