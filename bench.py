@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Van Loan cost + 3N-gradient path.
+
+Workload (BASELINE.json configs[2], the one the metric's target is quoted on): robust CZ gate,
+4096 detuning / Rabi-amplitude noise samples x 2000 time slices x N=16 Gaussians per channel,
+complex128.  One "step" = one cost + gradient evaluation of the whole ensemble (what one optimiser
+step needs).  Units = slice-samples.  At N GPUs every rank holds 4096 samples (weak scaling; the
+ensemble is 4096*N samples) and each step ends with ONE all-reduce of 3+3*N*C = 243 doubles.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--samples S] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "optimal-control-rydberg_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "Van Loan cost+3N-gradient evals/sec (slices x samples / s)"
+UNIT = "slice-samples/s"
+N_GAUSS, NT, SEED = 16, 1888, 0          # cfg 3: nt=1888, pad=int(0.03*nt)=56 -> M=2000
+
+
+def workload_config(samples_per_gpu, n_gpus):
+    return {"workload": "robust CZ (BASELINE.json configs[2]): 4096 noise samples x 2000 slices x N=16 Gaussians, "
+                        "two-atom 16-level Van Loan cost + 3N-gradient, complex128",
+            "samples_per_gpu": samples_per_gpu, "samples_total": samples_per_gpu * n_gpus, "slices": 2000,
+            "n_gauss": N_GAUSS, "channels": 5, "hilbert_dim": 16,
+            "l2": "per-step working set (state checkpoints, ~10.7 GB at 4096 samples) exceeds the 126 MB L2; "
+                  "no flush needed",
+            "parallelism": f"samples sharded, {n_gpus} rank(s), one 243-double all-reduce per step"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for i, name in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap")):
+            if any(r[i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+
+
+def oracle_step_seconds(n_samples, repeats=1):
+    """Reference CPU path (oracle port: SciPy/torch-CPU restatement, all host threads): seconds per
+    cost+gradient of `n_samples` members of the SAME workload (M=2000, N=16)."""
+    from oracle import ensemble
+    dl, rs = ensemble.robust_cz_noise(4096)
+    members, (a, b, c) = ensemble.robust_cz_members(dl[:n_samples], rs[:n_samples], seed=SEED, n_gauss=N_GAUSS, nt=NT)
+    ensemble.ensemble_value_and_grad(members[:1], a, b, c)            # warm-up (thread pools, caches)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        ensemble.ensemble_value_and_grad(members, a, b, c)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is JAX-only
+    Python and cannot be installed here (no jax wheel, no network: DESIGN.md), so this arm times the
+    oracle port on the host cores, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_samples = 2
+    times = []
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        oracle_step_seconds(1)
+    for _ in range(args.steps):
+        times.append(oracle_step_seconds(n_samples))
+    total = sum(times)
+    units = 2000 * n_samples * args.steps
+    value = units / total
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128",
+            "data": "synthetic", "config": workload_config(4096, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{n_samples} of 4096 noise samples x 2000 slices per step "
+                                       "(cost is linear in samples); oracle = SciPy/torch-CPU restatement, "
+                                       "torch autograd gradient"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_gpu(args):
+    import torch.distributed as dist
+    from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL
+    import qocvl
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    S_local = args.samples
+    S_total = S_local * world
+
+    # ---- synthetic workload (SURVEY.md 8(d) cfg 3; generation is seed-exact with the oracle) -------
+    pad = int(0.03 * NT)
+    M = NT + 2 * pad
+    dt = 648e-9 / M
+    gammas = [0.1, 1.0 / 118e-9, 1.0 / 1.5e-3, 1.0 / 170e-6]
+    prop = PropagatorVL(N_GAUSS, NT, pad, 50e6, dt, 0.0, 2 * np.pi * 10e6, 2 * np.pi * (-35.7e6),
+                        2 * np.pi * 100e6, 2 * np.pi * 100e6, gammas, device=f"cuda:{local}")
+    rng = np.random.default_rng(SEED)
+    a = rng.uniform(-1, 1, (N_GAUSS, 5)); b = rng.uniform(-1, 1, (N_GAUSS, 5)); c = rng.uniform(0, 0.5, (N_GAUSS, 5))
+    nrng = np.random.default_rng(1234)
+    del_all = nrng.normal(0.0, 2 * np.pi * 0.1e6, S_total) if S_total <= 4096 else None
+    if del_all is None:      # weak scaling beyond 4096: extend the same generator stream
+        nrng = np.random.default_rng(1234)
+        both = nrng.normal(0.0, 1.0, (2, S_total))
+        del_all, eps_all = both[0] * 2 * np.pi * 0.1e6, both[1] * 0.01
+    else:
+        eps_all = nrng.normal(0.0, 0.01, S_total)
+    prop.set_ensemble(del_total=del_all, rabi_scale=1.0 + eps_all, shard=(world > 1))
+    if world == 1:
+        assert prop._plan.n_samples == S_total
+
+    abc = prop._pack(a, b, c)
+    out = torch.empty(3 + 3 * N_GAUSS * 5, dtype=torch.float64, device=abc.device)
+    plan = prop._plan
+    plan.set_timing(True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: K steps, CUDA events, max over ranks ---------------------------
+    for _ in range(args.warmup):
+        prop.cost_and_grad_packed(abc, out)
+    plan.check()
+    launches0 = plan.launches
+    chain_ms = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        for _ in range(args.steps):
+            prop.cost_and_grad_packed(abc, out)
+        ev1.record()
+        barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    chain_ms.append(plan.last_chain_ms())
+    launches = plan.launches - launches0 + (args.steps if world > 1 else 0)   # + NCCL all-reduce kernels
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=abc.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t)
+    units_per_step = M * S_total
+    value = units_per_step * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the public host API: numpy in, numpy out, copies inside the timed region
+    prop.value_and_grad_host(a, b, c)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cost_e2e, grads_e2e = prop.value_and_grad_host(a, b, c)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=abc.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = units_per_step * args.steps / float(t)
+
+    # ---- roofline of the dominant kernel (k_chain) ---------------------------------------------
+    flops = plan.flops_per_call(True)                     # executed useful FP64 flops of one launch
+    k_ms = chain_ms[-1]
+    lib = qocvl.load()
+    peak_tf = float(lib.qocvl_measure_fp64_peak(local, 5))
+    achieved_tf = flops / (k_ms * 1e-3) * 1e-12 if k_ms > 0 else None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    ckpt_bytes = 2.0 * M * S_local * 5 * 16 * 16          # checkpoint write + read: 5 vectors x 16 x c128
+    roofline = {"bound": "fp64", "kernel": "k_chain<16,4,2>", "achieved": achieved_tf, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": (achieved_tf / peak_tf) if achieved_tf and peak_tf > 0 else None,
+                "traffic": None,
+                "peak_source": "live DFMA microbenchmark in this run (qocvl_measure_fp64_peak); "
+                               "MEASURED_PEAKS.json has no FP64 entry",
+                "flops_per_launch": flops, "flops_per_unit": flops / (M * S_local),
+                "kernel_ms": k_ms, "kernel_share_of_step": k_ms * args.steps / elapsed_ms if k_ms > 0 else None,
+                "m1_equivalent_tflops": 840.0 * 16 ** 3 * M * S_local / (k_ms * 1e-3) * 1e-12 if k_ms > 0 else None,
+                "hbm": {"algorithmic_bytes": ckpt_bytes, "achieved_gbs": ckpt_bytes / (k_ms * 1e-3) * 1e-9 if k_ms > 0 else None,
+                        "peak_gbs": peaks.get("hbm_gbs"), "peak_source": "MEASURED_PEAKS.json"}}
+
+    if rank == 0:
+        # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----------------
+        n_cpu = 2
+        cpu_s = oracle_step_seconds(n_cpu)
+        cpu_value = M * n_cpu / cpu_s
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+                "config": workload_config(S_local, world),
+                "clocks": clocks.summary(),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * N_GAUSS * 5 * 8,
+                        "d2h_bytes_per_step": (3 + 3 * N_GAUSS * 5) * 8,
+                        "api": "PropagatorVL.value_and_grad_host(a, b, c): numpy in / numpy out"},
+                "gpu_launches": int(launches),
+                "roofline": roofline,
+                "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                 "sample": f"{n_cpu} of 4096 noise samples x 2000 slices (cost is linear in samples); "
+                                           "oracle = SciPy/torch-CPU restatement, torch autograd gradient",
+                                 "seconds": cpu_s},
+                "result": {"cost": float(cost_e2e), "infidelity": float(out[1]), "adiabaticity": float(out[2]),
+                           "taylor_degree_cap": plan.taylor_cap}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--samples", type=int, default=4096, help="noise samples per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

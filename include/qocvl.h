@@ -131,6 +131,15 @@ int qocvl_check(qocvl_plan* plan);
 int qocvl_last_taylor_degree(const qocvl_plan* plan); /* max Taylor degree of the last call's plan */
 long long qocvl_launch_count(const qocvl_plan* plan); /* kernels launched so far by this plan */
 double qocvl_flops_per_call(const qocvl_plan* plan, int with_grad); /* executed FP64 flop model */
+/* Kernel timing for the roofline report: when enabled, CUDA events bracket the chain kernel on
+ * the launch stream; qocvl_last_chain_ms synchronises on the end event and returns the duration
+ * of the most recent chain-kernel launch in milliseconds (< 0 if none was timed). */
+int qocvl_set_timing(qocvl_plan* plan, int enabled);
+double qocvl_last_chain_ms(qocvl_plan* plan);
+/* Pure-DFMA microbenchmark (no memory traffic): sustained FP64 FMA throughput of `device` in
+ * TFLOP/s, best of `repeats` launches.  This is the FP64 roofline denominator (the driver's
+ * MEASURED_PEAKS.json only has HBM and bf16).  Returns < 0 on error. */
+double qocvl_measure_fp64_peak(int device, int repeats);
 const char* qocvl_strerror(int status);
 const char* qocvl_last_cuda_error(void);
 int qocvl_version(void);

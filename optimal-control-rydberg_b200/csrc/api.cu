@@ -126,3 +126,65 @@ extern "C" double qocvl_flops_per_call(const qocvl_plan* p, int with_grad) {
   }
   return total * 8.0 * (double)p->n_samples;
 }
+
+extern "C" int qocvl_set_timing(qocvl_plan* p, int enabled) {
+  if (!p) return QOCVL_ERR_ARG;
+  QCUDA(cudaSetDevice(p->device));
+  if (enabled && !p->ev0) {
+    QCUDA(cudaEventCreate(&p->ev0));
+    QCUDA(cudaEventCreate(&p->ev1));
+  }
+  p->timing = enabled != 0;
+  p->timed_once = false;
+  return QOCVL_OK;
+}
+
+extern "C" double qocvl_last_chain_ms(qocvl_plan* p) {
+  if (!p || !p->timed_once) return -1.0;
+  float ms = -1.0f;
+  if (cudaEventSynchronize(p->ev1) != cudaSuccess) return -1.0;
+  if (cudaEventElapsedTime(&ms, p->ev0, p->ev1) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+
+// 8 independent FMA chains per thread, operands in registers only.
+__global__ void __launch_bounds__(256) k_dfma_peak(int iters, double seed, double* out) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+         a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 123.456) out[0] = s;   // never true; keeps the chains alive
+}
+
+extern "C" double qocvl_measure_fp64_peak(int device, int repeats) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+  double* d_out = nullptr;
+  if (cudaMalloc((void**)&d_out, sizeof(double)) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+  double best = -1.0;
+  k_dfma_peak<<<blocks, threads>>>(64, 1.0, d_out);   // warm-up
+  for (int r = 0; r < (repeats < 1 ? 1 : repeats); ++r) {
+    cudaEventRecord(e0);
+    k_dfma_peak<<<blocks, threads>>>(iters, 1.0 + r, d_out);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = flops / ((double)ms * 1e-3) * 1e-12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+  return best;
+}

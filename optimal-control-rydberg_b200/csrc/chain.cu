@@ -73,8 +73,23 @@ __global__ void __launch_bounds__(512) k_chain(const ChainArgs P) {
   cplx* s_x = s_bw + spb * nslot_w * LPG;                       // [2][groups][LPG]
   cplx* s_dpart = s_x + 2 * P.groups * LPG;                     // [groups]  overlap partials
   cplx* s_T = s_dpart + P.groups;                               // [qcap][nthreads]
-  double* s_mul = (double*)(s_T + (size_t)P.qcap * nthreads);   // [spb][J]
+  // generator-contribution tables (constant over the chain, shared by every sample of the CTA)
+  const int n_urc = nslot_u * P.kc_u * LPG, n_ucc = (P.wc_u + 1) * P.kc_u * LPG;
+  const int n_wrc = P.w_w * P.kc_w * LPG, n_wcc = P.wc_w * P.kc_w * LPG;
+  cplx* s_urcv = s_T + (size_t)P.qcap * nthreads;               // [nslot_u][kc_u][LPG]
+  cplx* s_uccv = s_urcv + n_urc;                                // [wc_u+1][kc_u][LPG]
+  cplx* s_wrcv = s_uccv + n_ucc;                                // [w_w][kc_w][LPG]
+  cplx* s_wccv = s_wrcv + n_wrc;                                // [wc_w][kc_w][LPG]
+  double* s_mul = (double*)(s_wccv + n_wcc);                    // [spb][J]
   double* s_red = s_mul + spb * J;                              // [nwarps][C]
+  int* s_urcg = (int*)(s_red + ((nthreads + 31) >> 5) * C);
+  int* s_uccg = s_urcg + n_urc;
+  int* s_wrcg = s_uccg + n_ucc;
+  int* s_wccg = s_wrcg + n_wrc;
+  for (int i = tid; i < n_urc; i += nthreads) { s_urcv[i] = P.u_rc_val[i]; s_urcg[i] = P.u_rc_gen[i]; }
+  for (int i = tid; i < n_ucc; i += nthreads) { s_uccv[i] = P.u_cc_val[i]; s_uccg[i] = P.u_cc_gen[i]; }
+  for (int i = tid; i < n_wrc; i += nthreads) { s_wrcv[i] = P.w_rc_val[i]; s_wrcg[i] = P.w_rc_gen[i]; }
+  for (int i = tid; i < n_wcc; i += nthreads) { s_wccv[i] = P.w_cc_val[i]; s_wccg[i] = P.w_cc_gen[i]; }
 
   // ---- who am I ----------------------------------------------------------------------
   int role, s_l, v;
@@ -149,16 +164,16 @@ __global__ void __launch_bounds__(512) k_chain(const ChainArgs P) {
       for (int slot = 0; slot < nslot_u; ++slot) {
         cplx acc = czero;
         for (int kc = 0; kc < P.kc_u; ++kc) {
-          const int gi = P.u_rc_gen[(slot * P.kc_u + kc) * LPG + r];
-          if (gi >= 0) acc = cfma(s_cs[s_l * J + gi], P.u_rc_val[(slot * P.kc_u + kc) * LPG + r], acc);
+          const int gi = s_urcg[(slot * P.kc_u + kc) * LPG + r];
+          if (gi >= 0) acc = cfma(s_cs[s_l * J + gi], s_urcv[(slot * P.kc_u + kc) * LPG + r], acc);
         }
         s_au[(s_l * nslot_u + slot) * LPG + r] = cscale(acc, P.dt);
       }
       for (int slot = 0; slot < P.w_w; ++slot) {
         cplx acc = czero;
         for (int kc = 0; kc < P.kc_w; ++kc) {
-          const int gi = P.w_rc_gen[(slot * P.kc_w + kc) * LPG + r];
-          if (gi >= 0) acc = cfma(s_cs[s_l * J + gi], P.w_rc_val[(slot * P.kc_w + kc) * LPG + r], acc);
+          const int gi = s_wrcg[(slot * P.kc_w + kc) * LPG + r];
+          if (gi >= 0) acc = cfma(s_cs[s_l * J + gi], s_wrcv[(slot * P.kc_w + kc) * LPG + r], acc);
         }
         s_bw[(s_l * nslot_w + slot) * LPG + r] = cscale(acc, P.dt);
       }
@@ -337,9 +352,9 @@ __global__ void __launch_bounds__(512) k_chain(const ChainArgs P) {
         for (int s = 0; s < WMAX; ++s)
           if (slot == s + 1) xval = xc[s];
         for (int kc = 0; kc < P.kc_u; ++kc) {
-          const int gi = P.u_cc_gen[(slot * P.kc_u + kc) * LPG + r];
+          const int gi = s_uccg[(slot * P.kc_u + kc) * LPG + r];
           if (gi >= 0) {
-            const cplx tmp = cscale(cmul(P.u_cc_val[(slot * P.kc_u + kc) * LPG + r], xval),
+            const cplx tmp = cscale(cmul(s_uccv[(slot * P.kc_u + kc) * LPG + r], xval),
                                     two_dt * s_mul[s_l * J + gi]);
 #pragma unroll
             for (int c = 0; c < QOCVL_MAX_CHAN; ++c)
@@ -354,9 +369,9 @@ __global__ void __launch_bounds__(512) k_chain(const ChainArgs P) {
           for (int s = 0; s < WBMAX; ++s)
             if (slot == s) xval = xcb[s];
           for (int kc = 0; kc < P.kc_w; ++kc) {
-            const int gi = P.w_cc_gen[(slot * P.kc_w + kc) * LPG + r];
+            const int gi = s_wccg[(slot * P.kc_w + kc) * LPG + r];
             if (gi >= 0) {
-              const cplx tmp = cscale(cmul(P.w_cc_val[(slot * P.kc_w + kc) * LPG + r], xval),
+              const cplx tmp = cscale(cmul(s_wccv[(slot * P.kc_w + kc) * LPG + r], xval),
                                       two_dt * s_mul[s_l * J + gi]);
 #pragma unroll
               for (int c = 0; c < QOCVL_MAX_CHAN; ++c)
@@ -417,7 +432,10 @@ static size_t chain_smem_bytes(const qocvl_plan* p, int spb, int groups, int thr
   size_t cplx_count = (size_t)2 * J + (size_t)2 * J * C + (size_t)2 * spb * J + (size_t)spb * nslot_u * L +
                       (size_t)spb * nslot_w * L + (size_t)2 * groups * L + groups + (size_t)qcap * threads;
   size_t dbl_count = (size_t)spb * J + (size_t)((threads + 31) / 32) * C;
-  return cplx_count * sizeof(cplx) + dbl_count * sizeof(double);
+  // generator-contribution tables: value (cplx) + generator id (int) per (slot, contribution, lane)
+  const size_t w_w = p->lw.nnz ? p->lw.n_row_slots : 0, wc_w = p->lw.nnz ? p->lw.n_col_slots : 0;
+  const size_t tab = ((size_t)(p->lu.n_row_slots + p->lu.n_col_slots) * p->lu.kc + (w_w + wc_w) * p->lw.kc) * L;
+  return (cplx_count + tab) * sizeof(cplx) + dbl_count * sizeof(double) + tab * sizeof(int);
 }
 
 typedef void (*chain_fn)(const ChainArgs);
@@ -436,13 +454,19 @@ int qocvl_chain_configure(qocvl_plan* p) {
   std::vector<double> mulmax(J), addmax(J);
   cudaMemcpy(mulmax.data(), p->d_mulmax, J * sizeof(double), cudaMemcpyDeviceToHost);
   cudaMemcpy(addmax.data(), p->d_addmax, J * sizeof(double), cudaMemcpyDeviceToHost);
+  // |c_j| <= 1 for every pulse-driven coefficient (tanh / 1-exp regularisation, filter taps >= 0 with
+  // sum < 1, projector weights are ratios <= 1); 1e-3 relative margin for filter round-off.
   double bound = 0.0;
-  for (int j = 0; j < J; ++j) {
-    const double cmax = j < 2 ? std::abs(p->h_coef_const[j]) : 1.5;
-    bound += (cmax * mulmax[j] + addmax[j]) * p->h_gnorm[j];
+  for (int b = 0; b < d.n; ++b) {
+    double s = 0.0;
+    for (int j = 0; j < J; ++j) {
+      const double cmax = j < 2 ? std::abs(p->h_coef_const[j]) : 1.001;
+      s += (cmax * mulmax[j] + addmax[j]) * p->h_gcol[(size_t)j * d.n + b];
+    }
+    bound = std::max(bound, s);
   }
   bound *= d.dt;
-  if (!(bound <= QOCVL_NORM_MAX)) return QOCVL_ERR_NORM;
+  if (!(bound == bound)) return QOCVL_ERR_ARG;
   p->qcap = qocvl_taylor_degree(bound);
   // samples per CTA: aim for ~192 threads
   int spb = 192 / (R * L);
@@ -494,7 +518,9 @@ int qocvl_launch_chain(qocvl_plan* p, bool want_grad, double* out3, double* gwav
   a.coef = p->d_coef; a.dcoef = p->d_dcoef; a.qdeg = p->d_qdeg; a.mul = p->d_mul; a.add = p->d_add;
   a.starts = p->d_starts; a.targets = p->d_targets; a.ckpt = p->d_ckpt; a.sample_out = p->d_sample_out;
   a.gw_partial = p->d_gw_partial;
+  if (p->timing) QCUDA(cudaEventRecord(p->ev0, st));
   pick_kernel(p->npad)<<<p->blocks, p->threads, p->chain_smem, st>>>(a);
+  if (p->timing) { QCUDA(cudaEventRecord(p->ev1, st)); p->timed_once = true; }
   k_reduce_samples<<<1, 256, 0, st>>>(p->n_samples, a.inv_samples, p->d_sample_out, out3);
   p->launches += 2;
   if (want_grad) {

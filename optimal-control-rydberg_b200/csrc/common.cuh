@@ -92,11 +92,11 @@ struct qocvl_plan {
   int qcap = 0;            // a-priori Taylor-degree cap used to size shared memory
   // generators
   std::vector<std::complex<double>> h_gu, h_gw, h_coef_const;  // host copies
-  double h_gnorm[QOCVL_MAX_GEN];
+  std::vector<double> h_gcol;   // [J][n] column sums of |G_u| + |G_w| (entrywise-abs norm bound)
   BlockLayout lu, lw;
   cplx* d_gdense = nullptr;   // [J][2n][2n] dense generators (for exponentials())
   cplx* d_coef_const = nullptr;  // [J]
-  double* d_gnorm = nullptr;  // [J] 1-norms (u + w)
+  double* d_gnorm = nullptr;  // [J][n] column sums of |G_u| + |G_w|
   // cost
   cplx* d_starts = nullptr;   // [n_vec][npad]
   cplx* d_targets = nullptr;
@@ -126,6 +126,9 @@ struct qocvl_plan {
   double* d_out3 = nullptr;   // [3]
   cplx* d_dense_a = nullptr;  // [M][2n][2n] ping
   cplx* d_dense_b = nullptr;  // [M/2+1][2n][2n] pong
+  // optional kernel timing
+  bool timing = false, timed_once = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // chain launch geometry
   int spb = 1, groups = 0, threads = 0, blocks = 0;
   size_t chain_smem = 0;

@@ -188,21 +188,17 @@ extern "C" int qocvl_set_generators(qocvl_plan* p, const double* gens_u, const d
   int rc;
   if ((rc = build_layout(p, p->h_gu, true, &p->lu))) return rc;
   if ((rc = build_layout(p, p->h_gw, false, &p->lw))) return rc;
-  // induced 1-norms (max column sum) of each generator: |G_u|_1 + |G_w|_1 bounds the 2n x 2n norm
-  std::vector<double> gnorm(J, 0.0);
-  for (int j = 0; j < J; ++j) {
-    double nu = 0, nw = 0;
+  // column sums of |G_u| + |G_w| per generator: |X|_1 <= dt * max_b sum_j |c_j| * gcol[j][b]
+  // (entrywise triangle inequality; the 2n x 2n block matrix has column sums |A| and |B|+|A|)
+  std::vector<double> gnorm((size_t)J * n, 0.0);
+  for (int j = 0; j < J; ++j)
     for (int b = 0; b < n; ++b) {
-      double su = 0, sw = 0;
-      for (int a = 0; a < n; ++a) {
-        su += std::abs(p->h_gu[((size_t)j * n + a) * n + b]);
-        sw += std::abs(p->h_gw[((size_t)j * n + a) * n + b]);
-      }
-      nu = std::max(nu, su); nw = std::max(nw, sw);
+      double s = 0;
+      for (int a = 0; a < n; ++a)
+        s += std::abs(p->h_gu[((size_t)j * n + a) * n + b]) + std::abs(p->h_gw[((size_t)j * n + a) * n + b]);
+      gnorm[(size_t)j * n + b] = s;
     }
-    gnorm[j] = nu + nw;
-    p->h_gnorm[j] = gnorm[j];
-  }
+  p->h_gcol = gnorm;
   if ((rc = dev_upload(p, &p->d_gnorm, gnorm))) return rc;
   if ((rc = dev_upload(p, &p->d_coef_const, cc))) return rc;
   // dense 2n x 2n copies for exponentials()/propagate()

@@ -80,7 +80,7 @@ __global__ void k_filter(int M, int nt, int pad, int C, int transpose, const dou
 // Per-slice generator coefficients and their derivatives with respect to the C real
 // pulse values of that slice; also the Taylor degree for the slice.
 //   TQ:416-476 (drift coefficient -i comes from coef_const), ST:236-255
-__global__ void k_coefficients(int model, int M, int J, int C, double dt, double eps, double s0, double s1,
+__global__ void k_coefficients(int model, int n, int M, int J, int C, double dt, double eps, double s0, double s1,
                                const double* __restrict__ wave, const cplx* __restrict__ coef_const,
                                const double* __restrict__ gnorm, const double* __restrict__ mulmax,
                                const double* __restrict__ addmax, int qcap, cplx* __restrict__ coef,
@@ -152,18 +152,25 @@ __global__ void k_coefficients(int model, int M, int J, int C, double dt, double
       dc[10][c] = cconj(dc[9][c]);
     }
   }
-  double nrm = 0.0;
+  double wgt[QOCVL_MAX_GEN];
   for (int j = 0; j < J; ++j) {
     coef[(size_t)k * J + j] = co[j];
     for (int c = 0; c < C; ++c) dcoef[((size_t)k * J + j) * C + c] = dc[j][c];
-    const double mag = sqrt(co[j].x * co[j].x + co[j].y * co[j].y);
-    nrm += (mag * mulmax[j] + addmax[j]) * gnorm[j];
+    wgt[j] = sqrt(co[j].x * co[j].x + co[j].y * co[j].y) * mulmax[j] + addmax[j];
+  }
+  double nrm = 0.0;   // entrywise-abs bound on |X_k|_1 over every noise sample
+  for (int b = 0; b < n; ++b) {
+    double s = 0.0;
+    for (int j = 0; j < J; ++j) s += wgt[j] * gnorm[j * n + b];
+    nrm = fmax(nrm, s);
   }
   nrm *= dt;
   int q = qocvl_taylor_degree(nrm);
   if (!(nrm <= QOCVL_NORM_MAX) || q > qcap) {   // also catches NaN pulses
     atomicOr(flag, 1);
-    q = qcap;
+    q = 2;
+    // fail loudly: poison the slice so the cost and gradient come out NaN instead of silently wrong
+    coef[(size_t)k * J] = cmake(nan(""), nan(""));
   }
   qdeg[k] = q;
 }
@@ -258,7 +265,7 @@ int qocvl_launch_pulse_forward(qocvl_plan* p, const double* abc, cudaStream_t st
 int qocvl_launch_coefficients(qocvl_plan* p, const double* wave, cudaStream_t st) {
   const qocvl_desc& d = p->d;
   k_coefficients<<<(d.n_slices + 127) / 128, 128, 0, st>>>(
-      d.model, d.n_slices, d.n_gen, d.n_chan, d.dt, d.eps, d.scale[0], d.scale[1], wave, p->d_coef_const,
+      d.model, d.n, d.n_slices, d.n_gen, d.n_chan, d.dt, d.eps, d.scale[0], d.scale[1], wave, p->d_coef_const,
       p->d_gnorm, p->d_mulmax, p->d_addmax, p->qcap, p->d_coef, p->d_dcoef, p->d_qdeg, p->d_flag);
   p->launches++;
   QCUDA(cudaGetLastError());

@@ -44,6 +44,9 @@ SIGNATURES = {
     "qocvl_last_taylor_degree": (C.c_int, [_P]),
     "qocvl_launch_count": (C.c_longlong, [_P]),
     "qocvl_flops_per_call": (C.c_double, [_P, C.c_int]),
+    "qocvl_set_timing": (C.c_int, [_P, C.c_int]),
+    "qocvl_last_chain_ms": (C.c_double, [_P]),
+    "qocvl_measure_fp64_peak": (C.c_double, [C.c_int, C.c_int]),
     "qocvl_strerror": (C.c_char_p, [C.c_int]),
     "qocvl_last_cuda_error": (C.c_char_p, []),
     "qocvl_version": (C.c_int, []),

@@ -188,5 +188,11 @@ class Plan:
     def workspace_bytes(self):
         return int(self._lib.qocvl_workspace_bytes(self._h))
 
+    def set_timing(self, enabled=True):
+        _lib.check(self._lib.qocvl_set_timing(self._h, 1 if enabled else 0), "set_timing")
+
+    def last_chain_ms(self):
+        return float(self._lib.qocvl_last_chain_ms(self._h))
+
     def flops_per_call(self, with_grad=True):
         return float(self._lib.qocvl_flops_per_call(self._h, 1 if with_grad else 0))

@@ -183,11 +183,13 @@ class PropagatorVL:
 GAMMAS_CZ = [0.1, 1.0 / 118e-9, 1.0 / 1.5e-3, 1.0 / 170e-6]
 
 
-def notebook02_setup(seed=0, n_gauss=10, nt=500, del_total=0.0, rabi_scale=1.0, total_time=648e-9):
+def notebook02_setup(seed=0, n_gauss=10, nt=500, del_total=0.0, rabi_scale=1.0, total_time=None):
     """cfg 2 of SURVEY.md 8(d): notebook 02 cell 4 parameters; a,b,c from default_rng(seed)
     (the notebook's jax.random.PRNGKey(6) draw is not reproducible without jax).
     With nt=1888, n_gauss=16 this is the per-sample problem of cfg 3."""
     pad = int(0.03 * nt)
+    if total_time is None:   # reduced-size test grids keep the notebook's time step (648 ns / 530)
+        total_time = 648e-9 if nt >= 500 else 648e-9 * (nt + 2 * pad) / 530
     dt = total_time / (nt + 2 * pad)
     prop = PropagatorVL(n_gauss, nt, pad, 50e6, dt, del_total, 2 * np.pi * 10e6,
                         2 * np.pi * (-35.7e6), 2 * np.pi * 100e6 * rabi_scale,

