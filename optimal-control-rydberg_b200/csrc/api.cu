@@ -118,7 +118,8 @@ extern "C" double qocvl_flops_per_call(const qocvl_plan* p, int with_grad) {
   cudaSetDevice(p->device);
   cudaDeviceSynchronize();
   if (cudaMemcpy(q.data(), p->d_qdeg, M * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 0.0;
-  const double macs = (double)(p->d.n_vec + 1) * p->lu.nnz + p->lw.nnz;
+  // vectors that are actually propagated: the moving start kets plus p = W psi
+  const double macs = (double)(p->n_live + 1) * p->lu.nnz + p->lw.nnz;
   double total = 0.0;
   for (int k = 0; k < M; ++k) {
     total += q[k] * macs;

@@ -97,9 +97,13 @@ struct qocvl_plan {
   cplx* d_gdense = nullptr;   // [J][2n][2n] dense generators (for exponentials())
   cplx* d_coef_const = nullptr;  // [J]
   double* d_gnorm = nullptr;  // [J][n] column sums of |G_u| + |G_w|
-  // cost
-  cplx* d_starts = nullptr;   // [n_vec][npad]
+  // cost: host copies of all kets [n_vec][npad]; device copies only of the "live" kets (start kets
+  // annihilated by every generator never move: their overlap is the constant d_const)
+  std::vector<cplx> h_starts, h_targets;
+  cplx* d_starts = nullptr;   // [n_live][npad]
   cplx* d_targets = nullptr;
+  int n_live = 0, adiab_live = 0;
+  cplx d_const = {0.0, 0.0};
   // noise
   double* d_mul = nullptr;    // [S][J]
   cplx* d_add = nullptr;      // [S][J]

@@ -242,9 +242,9 @@ extern "C" int qocvl_set_cost(qocvl_plan* p, const double* starts, const double*
       s[(size_t)v * np_ + r] = cmake(starts[2 * ((size_t)v * n + r)], starts[2 * ((size_t)v * n + r) + 1]);
       t[(size_t)v * np_ + r] = cmake(targets[2 * ((size_t)v * n + r)], targets[2 * ((size_t)v * n + r) + 1]);
     }
-  int rc;
-  if ((rc = dev_upload(p, &p->d_starts, s))) return rc;
-  if ((rc = dev_upload(p, &p->d_targets, t))) return rc;
+  p->h_starts = s;     // the chain configuration compacts these to the kets that actually move
+  p->h_targets = t;
+  p->groups = 0;
   p->have_cost = true;
   return QOCVL_OK;
 }
