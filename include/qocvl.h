@@ -76,6 +76,14 @@ int qocvl_set_filter(qocvl_plan* plan, const double* taps);
  * adiab = Re(1 - (U psi)^dag (W psi) / duration), psi = x_{adiab_index}. */
 int qocvl_set_cost(qocvl_plan* plan, const double* starts, const double* targets);
 
+/* Optional symmetry hint: perm[n] (HOST) is a permutation of the basis states under which every
+ * generator's diagonal block is invariant, G^u_j[perm[a]][perm[b]] == G^u_j[a][b] (e.g. exchange of
+ * the two identical atoms of the TQ model, TQ:201-207).  The engine VERIFIES the invariance
+ * (QOCVL_ERR_ARG if it does not hold) and then propagates only one of any two start kets that the
+ * permutation maps onto each other (with their target kets), counting its overlap twice.  Results
+ * are unchanged; NULL clears the hint. */
+int qocvl_set_symmetry(qocvl_plan* plan, const int* perm);
+
 /* Robustness ensemble: sample s uses coefficients  c_kj * mul[s][j] + add[s][j].
  * HOST pointers: mul [S][J] real, add [S][J] complex (NULL = zeros).  n_samples = 1 with
  * mul = NULL restores the single nominal sample.  The cost and gradient are ensemble means. */

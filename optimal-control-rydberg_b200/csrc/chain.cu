@@ -511,24 +511,61 @@ int qocvl_chain_configure(qocvl_plan* p) {
   p->d_const = cmake(0, 0);
   p->n_live = 0;
   p->adiab_live = 0;
+  std::vector<int> weight(d.n_vec, 1);          // how many start kets this one stands for
+  std::vector<char> moves(d.n_vec, 0);
   for (int v = 0; v < d.n_vec; ++v) {
-    bool moves = (v == d.adiab_index);
-    for (int j = 0; j < J && !moves; ++j)
-      for (int a = 0; a < n && !moves; ++a) {
+    bool mv = (v == d.adiab_index);
+    for (int j = 0; j < J && !mv; ++j)
+      for (int a = 0; a < n && !mv; ++a) {
         std::complex<double> acc(0, 0);
         for (int b = 0; b < n; ++b)
           acc += p->h_gu[((size_t)j * n + a) * n + b] *
                  std::complex<double>(p->h_starts[(size_t)v * L + b].x, p->h_starts[(size_t)v * L + b].y);
-        moves = std::abs(acc) > 0.0;
+        mv = std::abs(acc) > 0.0;
       }
-    if (moves) {
+    moves[v] = mv;
+  }
+  // ---- symmetry hint: verify G^u invariance, then merge start kets that are images of each other
+  if (!p->h_perm.empty()) {
+    const std::vector<int>& pm = p->h_perm;
+    for (int j = 0; j < J; ++j)
+      for (int a = 0; a < n; ++a)
+        for (int b = 0; b < n; ++b)
+          if (p->h_gu[((size_t)j * n + pm[a]) * n + pm[b]] != p->h_gu[((size_t)j * n + a) * n + b])
+            return QOCVL_ERR_ARG;
+    auto is_image = [&](const std::vector<cplx>& kets, int v, int w) {   // kets[w] == P kets[v] ?
+      for (int i = 0; i < n; ++i) {
+        const cplx x = kets[(size_t)v * L + i], y = kets[(size_t)w * L + pm[i]];
+        if (x.x != y.x || x.y != y.y) return false;
+      }
+      return true;
+    };
+    std::vector<int> order;                     // representatives: the adiabatic ket first
+    order.push_back(d.adiab_index);
+    for (int v = 0; v < d.n_vec; ++v) if (v != d.adiab_index) order.push_back(v);
+    for (size_t i = 0; i < order.size(); ++i) {
+      const int v = order[i];
+      if (!moves[v] || weight[v] == 0) continue;
+      for (size_t k2 = i + 1; k2 < order.size(); ++k2) {
+        const int w = order[k2];
+        if (!moves[w] || weight[w] == 0 || w == d.adiab_index) continue;
+        if (is_image(p->h_starts, v, w) && is_image(p->h_targets, v, w)) {
+          weight[v] += weight[w];
+          weight[w] = 0;
+        }
+      }
+    }
+  }
+  for (int v = 0; v < d.n_vec; ++v) {
+    if (moves[v] && weight[v] > 0) {
       if (v == d.adiab_index) p->adiab_live = p->n_live;
       for (int r = 0; r < L; ++r) {
         live_s.push_back(p->h_starts[(size_t)v * L + r]);
-        live_t.push_back(p->h_targets[(size_t)v * L + r]);
+        // the weight rides on the target ket: overlap and terminal cotangent are both linear in it
+        live_t.push_back(cscale(p->h_targets[(size_t)v * L + r], (double)weight[v]));
       }
       p->n_live++;
-    } else {
+    } else if (!moves[v]) {
       for (int r = 0; r < n; ++r) {   // y_v^dag x_v
         const cplx y = p->h_targets[(size_t)v * L + r], x = p->h_starts[(size_t)v * L + r];
         p->d_const.x += y.x * x.x + y.y * x.y;

@@ -100,6 +100,7 @@ struct qocvl_plan {
   // cost: host copies of all kets [n_vec][npad]; device copies only of the "live" kets (start kets
   // annihilated by every generator never move: their overlap is the constant d_const)
   std::vector<cplx> h_starts, h_targets;
+  std::vector<int> h_perm;    // optional symmetry hint (qocvl_set_symmetry)
   cplx* d_starts = nullptr;   // [n_live][npad]
   cplx* d_targets = nullptr;
   int n_live = 0, adiab_live = 0;

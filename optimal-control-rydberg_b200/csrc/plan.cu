@@ -253,13 +253,15 @@ extern "C" int qocvl_set_noise(qocvl_plan* p, int n_samples, const double* mul, 
   if (!p || n_samples < 1) return QOCVL_ERR_ARG;
   QCUDA(cudaSetDevice(p->device));
   const int J = p->d.n_gen;
-  std::vector<double> hm((size_t)n_samples * J, 1.0), mulmax(J, 0.0), addmax(J, 0.0);
+  // mulmax = [ max_s |mul_sj| (J entries) , max_s |mul_sj - 1| (J entries) ]
+  std::vector<double> hm((size_t)n_samples * J, 1.0), mulmax(2 * (size_t)J, 0.0), addmax(J, 0.0);
   std::vector<cplx> ha((size_t)n_samples * J, cmake(0, 0));
   for (size_t i = 0; i < hm.size(); ++i) {
     if (mul) hm[i] = mul[i];
     if (add) ha[i] = cmake(add[2 * i], add[2 * i + 1]);
     const int j = (int)(i % J);
     mulmax[j] = std::max(mulmax[j], std::fabs(hm[i]));
+    mulmax[J + j] = std::max(mulmax[J + j], std::fabs(hm[i] - 1.0));
     addmax[j] = std::max(addmax[j], std::hypot(ha[i].x, ha[i].y));
   }
   int rc;
@@ -271,6 +273,19 @@ extern "C" int qocvl_set_noise(qocvl_plan* p, int n_samples, const double* mul, 
   p->n_samples = n_samples;
   p->global_samples = n_samples;
   p->groups = 0;
+  return QOCVL_OK;
+}
+
+extern "C" int qocvl_set_symmetry(qocvl_plan* p, const int* perm) {
+  if (!p) return QOCVL_ERR_ARG;
+  p->groups = 0;
+  if (!perm) { p->h_perm.clear(); return QOCVL_OK; }
+  const int n = p->d.n;
+  std::vector<int> seen(n, 0);
+  for (int i = 0; i < n; ++i) {
+    if (perm[i] < 0 || perm[i] >= n || seen[perm[i]]++) return QOCVL_ERR_ARG;
+  }
+  p->h_perm.assign(perm, perm + n);
   return QOCVL_OK;
 }
 

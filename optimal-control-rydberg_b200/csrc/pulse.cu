@@ -82,7 +82,7 @@ __global__ void k_filter(int M, int nt, int pad, int C, int transpose, const dou
 //   TQ:416-476 (drift coefficient -i comes from coef_const), ST:236-255
 __global__ void k_coefficients(int model, int n, int M, int J, int C, double dt, double eps, double s0, double s1,
                                const double* __restrict__ wave, const cplx* __restrict__ coef_const,
-                               const double* __restrict__ gnorm, const double* __restrict__ mulmax,
+                               const cplx* __restrict__ gdense, const double* __restrict__ gnorm, const double* __restrict__ mulmax,
                                const double* __restrict__ addmax, int qcap, cplx* __restrict__ coef,
                                cplx* __restrict__ dcoef, int* __restrict__ qdeg, int* __restrict__ flag) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -156,12 +156,24 @@ __global__ void k_coefficients(int model, int n, int M, int J, int C, double dt,
   for (int j = 0; j < J; ++j) {
     coef[(size_t)k * J + j] = co[j];
     for (int c = 0; c < C; ++c) dcoef[((size_t)k * J + j) * C + c] = dc[j][c];
-    wgt[j] = sqrt(co[j].x * co[j].x + co[j].y * co[j].y) * mulmax[j] + addmax[j];
+    // deviation of any noise sample from the nominal coefficient: |c| * max|mul-1| + max|add|
+    wgt[j] = sqrt(co[j].x * co[j].x + co[j].y * co[j].y) * mulmax[J + j] + addmax[j];
   }
-  double nrm = 0.0;   // entrywise-abs bound on |X_k|_1 over every noise sample
+  // |X_k|_1 over every noise sample <= exact 1-norm of the nominal 2n x 2n generator
+  //   (column b: sum_a |A_ab|, column n+b: sum_a |B_ab| + |A_ab|)  +  entrywise bound of the deviation
+  const int D = 2 * n;
+  double nrm = 0.0;
   for (int b = 0; b < n; ++b) {
     double s = 0.0;
     for (int j = 0; j < J; ++j) s += wgt[j] * gnorm[j * n + b];
+    for (int a = 0; a < n; ++a) {
+      cplx ea = cmake(0, 0), eb = cmake(0, 0);
+      for (int j = 0; j < J; ++j) {
+        ea = cfma(co[j], gdense[((size_t)j * D + a) * D + b], ea);
+        eb = cfma(co[j], gdense[((size_t)j * D + a) * D + n + b], eb);
+      }
+      s += sqrt(ea.x * ea.x + ea.y * ea.y) + sqrt(eb.x * eb.x + eb.y * eb.y);
+    }
     nrm = fmax(nrm, s);
   }
   nrm *= dt;
@@ -266,7 +278,7 @@ int qocvl_launch_coefficients(qocvl_plan* p, const double* wave, cudaStream_t st
   const qocvl_desc& d = p->d;
   k_coefficients<<<(d.n_slices + 127) / 128, 128, 0, st>>>(
       d.model, d.n, d.n_slices, d.n_gen, d.n_chan, d.dt, d.eps, d.scale[0], d.scale[1], wave, p->d_coef_const,
-      p->d_gnorm, p->d_mulmax, p->d_addmax, p->qcap, p->d_coef, p->d_dcoef, p->d_qdeg, p->d_flag);
+      p->d_gdense, p->d_gnorm, p->d_mulmax, p->d_addmax, p->qcap, p->d_coef, p->d_dcoef, p->d_qdeg, p->d_flag);
   p->launches++;
   QCUDA(cudaGetLastError());
   return QOCVL_OK;

@@ -30,6 +30,7 @@ SIGNATURES = {
     "qocvl_set_filter": (C.c_int, [_P, _D]),
     "qocvl_set_cost": (C.c_int, [_P, _D, _D]),
     "qocvl_set_noise": (C.c_int, [_P, C.c_int, _D, _D]),
+    "qocvl_set_symmetry": (C.c_int, [_P, _D]),
     "qocvl_workspace_bytes": (C.c_size_t, [_P]),
     "qocvl_physical_amplitudes": (C.c_int, [_P, _D, _D, _V]),
     "qocvl_physical_amplitudes_vjp": (C.c_int, [_P, _D, _D, _D, _V]),

@@ -80,6 +80,17 @@ class Plan:
             raise ValueError("start / target kets must be [n_vec, n]")
         _lib.check(self._lib.qocvl_set_cost(self._h, ps, pt), "set_cost")
 
+    def set_symmetry(self, perm):
+        """Basis permutation that leaves every generator's diagonal block invariant (verified by the
+        engine); start kets it maps onto each other are propagated once.  None clears the hint."""
+        if perm is None:
+            _lib.check(self._lib.qocvl_set_symmetry(self._h, None), "set_symmetry")
+            return
+        arr = np.ascontiguousarray(np.asarray(perm, dtype=np.int32))
+        if arr.shape != (self.desc.n,):
+            raise ValueError("perm must have n entries")
+        _lib.check(self._lib.qocvl_set_symmetry(self._h, arr.ctypes.data_as(C.c_void_p)), "set_symmetry")
+
     def set_noise(self, mul=None, add=None, global_samples=None):
         """mul [S,J] real, add [S,J] complex (per-sample coefficient c*mul+add); None = nominal."""
         if mul is None and add is None:

@@ -75,7 +75,7 @@ class EngineBase:
     W_INFID = W_ADIAB = None
 
     def _make_plan(self, *, n, n_slices, n_basis_pts, pad, gens_u, gens_w, coef_const, starts, targets,
-                   adiab_index, fid_norm, scale, taps, eps=1e-12, device=None):
+                   adiab_index, fid_norm, scale, taps, eps=1e-12, device=None, symmetry=None):
         self._plan = qocvl.Plan(
             model=self._model, n=n, n_gen=gens_u.shape[0], n_slices=n_slices, n_basis_pts=n_basis_pts,
             pad=pad, n_gauss=self.input_dim, n_chan=self.num_ctrls, n_vec=len(starts),
@@ -84,6 +84,8 @@ class EngineBase:
         self._plan.set_generators(gens_u, gens_w, coef_const)
         self._plan.set_filter(taps)
         self._plan.set_cost(starts, targets)
+        if symmetry is not None:
+            self._plan.set_symmetry(symmetry)
         self.device = self._plan.device
         self._world = None
         self._pin_in = self._pin_out = None

@@ -86,7 +86,10 @@ class PropagatorVL(EngineBase):
                         coef_const=coef_const, starts=[eye16[c] for c in cols],
                         targets=[self.U_target[:, c] for c in cols], adiab_index=cols.index(4),
                         fid_norm=float(np.sum(np.abs(signs)) ** 2),          # (Tr Ut^dag Ut)^2 = 16, TQ:555
-                        scale=(Rabi_i, Rabi_r, 0, 0), taps=taps, device=device)
+                        scale=(Rabi_i, Rabi_r, 0, 0), taps=taps, device=device,
+                        # both atoms see the same global drive (TQ:201-207): exchanging them is a symmetry of
+                        # every Hamiltonian piece, so U|01> is the mirror image of U|10> (engine-verified hint)
+                        symmetry=[4 * (s % 4) + s // 4 for s in range(16)])
 
     gen_contraction_array = staticmethod(halving_flags)
 

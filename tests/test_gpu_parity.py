@@ -199,6 +199,24 @@ def test_alias_modules_and_errors():
     assert np.array_equal(prop.VL_Generators_ansatz, po.VL_Generators_ansatz)
 
 
+def test_symmetry_hint_changes_nothing_and_is_verified():
+    """The atom-exchange hint only removes redundant work: same numbers with and without it; a
+    permutation that is not a symmetry of the generators is rejected."""
+    import qocvl
+    po, a, b, c = otq.notebook02_setup(seed=3, n_gauss=6, nt=77)
+    prop = make_tq(po)
+    with_hint = np_(prop.cost_and_grad_packed(prop._pack(a, b, c))).copy()
+    prop._plan.set_symmetry(None)
+    without = np_(prop.cost_and_grad_packed(prop._pack(a, b, c))).copy()
+    assert np.abs(with_hint[:3] - without[:3]).max() < 1e-14
+    assert rel(with_hint[3:], without[3:]) < 1e-12
+    prop._plan.set_symmetry(np.roll(np.arange(16), 1))          # cyclic shift: not a symmetry
+    with pytest.raises(qocvl.QocvlError):
+        prop.target(a, b, c)
+    with pytest.raises(qocvl.QocvlError):
+        prop._plan.set_symmetry(np.zeros(16, dtype=int))        # not a permutation
+
+
 def test_norm_guard_fails_loudly():
     """A time step so coarse that |X_k| leaves the Taylor range must be reported, not mis-computed."""
     import qocvl
