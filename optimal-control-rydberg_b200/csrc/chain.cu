@@ -11,44 +11,40 @@
 // Reverse sweep of the same recurrence:  tb_q = lam', tb_{j-1} = lam' + X^dag tb_j / j,
 //   Xbar += conj(tb_j) t_{j-1}^T / j, contracted on the fly with the generators' sparsity.
 //
-// Mapping: one vector per group of LPG lanes (row r of the vector on lane r), vectors of a
-// sample in the same CTA.  Sparse rows of A_k live in registers (WMAX off-diagonals),
-// gathers go through a double-buffered shared-memory exchange, Taylor terms t_j of the
-// reverse sweep are parked in shared memory [j][thread].  The (q, p) pair of a sample sits in
-// adjacent groups of one warp so the B_k coupling needs only __syncwarp.
-// Pipeline: ONE __syncthreads per slice.  While slice k is being propagated, the rows of
-// A_{k+1}, B_{k+1} are assembled into the other half of a double buffer (work split over all
-// groups of the sample) and the coefficients of slice k+2 are already in flight from global memory.
+// Mapping (v3): ONE NOISE SAMPLE PER GROUP OF LPG LANES.  Lane r owns row r of A_k (diagonal +
+// WMAX off-diagonals, in registers) and element r of ALL NV+1 vectors of its sample, so the
+// NV+1 Taylor chains of a lane are independent instruction streams (ILP) that share the row
+// values, and the q -> p coupling through B_k is local to the group.  Gathers of the other rows'
+// elements go through a double-buffered shared-memory exchange guarded by __syncwarp only: there
+// is no CTA-wide barrier inside the sweeps.  Taylor terms of the reverse sweep are parked in
+// shared memory [j][v][lane]; state checkpoints z_k go to HBM, coalesced, once per slice.
 #include "common.cuh"
+#include "model.cuh"
 #include <algorithm>
-
-#define ROLE_Q 0  // U psi: couples INTO p (forward), receives from p (reverse)
-#define ROLE_P 1  // W psi
-#define ROLE_Z 2  // any other start ket
 
 __constant__ double c_inv[QOCVL_QMAX + 2];   // 1/j
 
 struct ChainArgs {
-  int n, J, M, C, S, R, adiab_index, spb, groups;
-  int w_u, wc_u, kc_u;   // off-diagonal row slots / col slots / contributions (u family)
-  int w_w, wc_w, kc_w;   // (w family, no diagonal slot)
-  int qcap, want_grad, nblocks;
+  int n, J, M, C, S, nv, va;   // nv = moving start kets, va = which of them is psi
+  int w_u, wc_u, kc_u;         // off-diagonal row slots / col slots / contributions (u family)
+  int w_w, wc_w, kc_w;         // (w family, no diagonal slot)
+  int qcap, want_grad, nwarps_total;
   double dt, inv_duration, w_infid, w_adiab, inv_fid_norm, inv_samples;
-  cplx d_const;          // overlap contribution of the start kets that never move
-  const int *u_row_col, *u_col_row, *u_col_src, *u_rc_gen, *u_cc_gen;
+  cplx d_const;                // overlap contribution of the start kets that never move
+  const int *u_row_col, *u_col_row, *u_rc_gen, *u_cc_gen;
   const cplx *u_rc_val, *u_cc_val;
-  const int *w_row_col, *w_col_row, *w_col_src, *w_rc_gen, *w_cc_gen;
+  const int *w_row_col, *w_col_row, *w_rc_gen, *w_cc_gen;
   const cplx *w_rc_val, *w_cc_val;
   const cplx* coef;    // [M][J]
   const cplx* dcoef;   // [M][J][C]
   const int* qdeg;     // [M]
   const double* mul;   // [S][J]
   const cplx* add;     // [S][J]
-  const cplx* starts;  // [R-1][LPG]
-  const cplx* targets;
-  cplx* ckpt;          // [M][nblocks][threads]
+  const cplx* starts;  // [nv][LPG]
+  const cplx* targets; // [nv][LPG] (symmetry weight folded in)
+  cplx* ckpt;          // [M][nv+1][total threads]
   double* sample_out;  // [S][3]
-  double* gw_partial;  // [nblocks][M][C]
+  double* gw_partial;  // [total warps][M][C]
 };
 
 template <int LPG>
@@ -61,289 +57,245 @@ __device__ __forceinline__ cplx group_sum(cplx v) {
   return v;
 }
 
-template <int LPG, int WMAX, int WBMAX>
-__global__ void __launch_bounds__(512) k_chain(const ChainArgs P) {
+template <int LPG, int NV, int WMAX, int WBMAX>
+__global__ void __launch_bounds__(256) k_chain(const ChainArgs P) {
+  constexpr int NVP = NV + 1;                      // the NV columns of U plus p = W psi (index NV)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nthreads = blockDim.x;
-  const int g = tid / LPG, r = tid % LPG;
-  const int J = P.J, C = P.C, spb = P.spb, JC = P.J * P.C;
-  const int nslot_u = P.w_u + 1;             // row-owner slots incl. diagonal
-  const int nslot_w = P.w_w > 0 ? P.w_w : 1;
-  const int nwarps = (nthreads + 31) >> 5, warp = tid >> 5, lane = tid & 31;
+  const int grp = tid / LPG, r = tid % LPG, ngroups = nthreads / LPG;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+  const int J = P.J, C = P.C, JC = P.J * P.C, va = P.va;
+  const size_t gtid = (size_t)blockIdx.x * nthreads + tid, gthreads = (size_t)gridDim.x * nthreads;
+  const int sample = blockIdx.x * ngroups + grp;
+  const bool live = sample < P.S && r < P.n;
+  const int sm = sample < P.S ? sample : P.S - 1;
 
   // ---- shared memory carve-up -------------------------------------------------------
-  cplx* s_coef = (cplx*)smem_raw;                               // [3][J]      stage ring
-  cplx* s_dcoef = s_coef + 3 * J;                               // [3][J][C]
-  cplx* s_add = s_dcoef + 3 * JC;                               // [spb][J]
-  cplx* s_au = s_add + spb * J;                                 // [2][spb][nslot_u][LPG]
-  cplx* s_bw = s_au + 2 * spb * nslot_u * LPG;                  // [2][spb][nslot_w][LPG]
-  cplx* s_x = s_bw + 2 * spb * nslot_w * LPG;                   // [2][groups][LPG]
-  cplx* s_dpart = s_x + 2 * P.groups * LPG;                     // [groups]  overlap partials
-  cplx* s_T = s_dpart + P.groups;                               // [qcap][nthreads]
-  // generator-contribution tables (constant over the chain, shared by every sample of the CTA)
-  const int n_urc = nslot_u * P.kc_u * LPG, n_ucc = (P.wc_u + 1) * P.kc_u * LPG;
+  const int n_urc = (P.w_u + 1) * P.kc_u * LPG, n_ucc = (P.wc_u + 1) * P.kc_u * LPG;
   const int n_wrc = P.w_w * P.kc_w * LPG, n_wcc = P.wc_w * P.kc_w * LPG;
-  cplx* s_urcv = s_T + (size_t)P.qcap * nthreads;               // [nslot_u][kc_u][LPG]
-  cplx* s_uccv = s_urcv + n_urc;                                // [wc_u+1][kc_u][LPG]
-  cplx* s_wrcv = s_uccv + n_ucc;                                // [w_w][kc_w][LPG]
-  cplx* s_wccv = s_wrcv + n_wrc;                                // [wc_w][kc_w][LPG]
-  double* s_mul = (double*)(s_wccv + n_wcc);                    // [spb][J]
-  double* s_red = s_mul + spb * J;                              // [2][nwarps][C]
-  int* s_urcg = (int*)(s_red + 2 * nwarps * C);
+  cplx* carve = (cplx*)smem_raw;
+  cplx* s_urcv = carve; carve += n_urc;                        // [w_u+1][kc_u][LPG]  row-owner contributions
+  cplx* s_uccv = carve; carve += n_ucc;                        // [wc_u+1][kc_u][LPG] col-owner contributions
+  cplx* s_wrcv = carve; carve += n_wrc;
+  cplx* s_wccv = carve; carve += n_wcc;
+  cplx* s_cs = carve + (size_t)grp * J; carve += (size_t)ngroups * J;          // [ngroups][J] slice coefficients
+  cplx* s_dco = carve + (size_t)warp * JC; carve += (size_t)nwarps * JC;       // [nwarps][J][C]
+  cplx* s_x = carve + (size_t)grp * 2 * NVP * LPG; carve += (size_t)ngroups * 2 * NVP * LPG;   // [ngroups][2][NVP][LPG]
+  cplx* s_T = carve + (size_t)grp * P.qcap * NVP * LPG; carve += (size_t)ngroups * P.qcap * NVP * LPG;  // [ngroups][qcap][NVP][LPG]
+  double* s_mul = (double*)carve + (size_t)grp * J;                            // [ngroups][J]
+  int* s_urcg = (int*)((double*)carve + (size_t)ngroups * J);
   int* s_uccg = s_urcg + n_urc;
   int* s_wrcg = s_uccg + n_ucc;
   int* s_wccg = s_wrcg + n_wrc;
-  int* s_q = s_wccg + n_wcc;                                    // [3] Taylor degree ring
   for (int i = tid; i < n_urc; i += nthreads) { s_urcv[i] = P.u_rc_val[i]; s_urcg[i] = P.u_rc_gen[i]; }
   for (int i = tid; i < n_ucc; i += nthreads) { s_uccv[i] = P.u_cc_val[i]; s_uccg[i] = P.u_cc_gen[i]; }
   for (int i = tid; i < n_wrc; i += nthreads) { s_wrcv[i] = P.w_rc_val[i]; s_wrcg[i] = P.w_rc_gen[i]; }
   for (int i = tid; i < n_wcc; i += nthreads) { s_wccv[i] = P.w_cc_val[i]; s_wccg[i] = P.w_cc_gen[i]; }
-
-  // ---- who am I ----------------------------------------------------------------------
-  const int nz = P.R - 2;                    // plain start kets per sample
-  int role, s_l, v, grank;
-  bool pad_group = false;
-  if (g < 2 * spb) {
-    s_l = g >> 1;
-    role = (g & 1) ? ROLE_P : ROLE_Q;
-    grank = g & 1;
-    v = P.adiab_index;
-  } else {
-    const int gz = g - 2 * spb;
-    role = ROLE_Z;
-    if (nz > 0 && gz < spb * nz) {
-      s_l = gz / nz;
-      const int zi = gz % nz;
-      v = zi < P.adiab_index ? zi : zi + 1;
-      grank = 2 + zi;
-    } else {  // padding group (only to fill the last warp)
-      s_l = 0; v = 0; grank = 0; pad_group = true;
-    }
-  }
-  const int sample = blockIdx.x * spb + s_l;
-  const bool live = !pad_group && sample < P.S && r < P.n;
-
-  // per-sample noise tables
-  for (int i = tid; i < spb * J; i += nthreads) {
-    const int sl = i / J, j = i % J;
-    int sm = blockIdx.x * spb + sl;
-    if (sm >= P.S) sm = P.S - 1;
-    s_mul[i] = P.mul[(size_t)sm * J + j];
-    s_add[i] = P.add[(size_t)sm * J + j];
-  }
+  for (int j = r; j < J; j += LPG) s_mul[j] = P.mul[(size_t)sm * J + j];
+  __syncthreads();                                             // the only CTA-wide barrier
 
   // static pattern indices of my row / column (empty slots point at my own row and carry a zero value)
-  int rcol[WMAX], crow[WMAX], csrc[WMAX];
+  int rcol[WMAX], crow[WMAX];
 #pragma unroll
   for (int s = 0; s < WMAX; ++s) {
-    rcol[s] = r; crow[s] = r; csrc[s] = r;
-    if (s < P.w_u) rcol[s] = P.u_row_col[(1 + s) * LPG + r];
-    if (s < P.wc_u) { crow[s] = P.u_col_row[(1 + s) * LPG + r]; csrc[s] = P.u_col_src[(1 + s) * LPG + r]; }
+    rcol[s] = (s < P.w_u) ? P.u_row_col[(1 + s) * LPG + r] : r;
+    crow[s] = (s < P.wc_u) ? P.u_col_row[(1 + s) * LPG + r] : r;
   }
-  int brcol[WBMAX], bcrow[WBMAX], bcsrc[WBMAX];
+  int brcol[WBMAX], bcrow[WBMAX];
 #pragma unroll
   for (int s = 0; s < WBMAX; ++s) {
-    brcol[s] = r; bcrow[s] = r; bcsrc[s] = r;
-    if (s < P.w_w) brcol[s] = P.w_row_col[s * LPG + r];
-    if (s < P.wc_w) { bcrow[s] = P.w_col_row[s * LPG + r]; bcsrc[s] = P.w_col_src[s * LPG + r]; }
+    brcol[s] = (s < P.w_w) ? P.w_row_col[s * LPG + r] : r;
+    bcrow[s] = (s < P.wc_w) ? P.w_col_row[s * LPG + r] : r;
+  }
+  // my share of the per-sample noise table: lane r prepares coefficient j = r (+LPG)
+  double mymul[(QOCVL_MAX_GEN + LPG - 1) / LPG];
+  cplx myadd[(QOCVL_MAX_GEN + LPG - 1) / LPG];
+#pragma unroll
+  for (int i = 0; i < (QOCVL_MAX_GEN + LPG - 1) / LPG; ++i) {
+    const int j = r + i * LPG;
+    mymul[i] = (j < J) ? P.mul[(size_t)sm * J + j] : 0.0;
+    myadd[i] = (j < J) ? P.add[(size_t)sm * J + j] : cmake(0, 0);
   }
 
   const cplx czero = cmake(0.0, 0.0);
-  cplx z = czero;
-  if (live && role != ROLE_P) z = P.starts[v * LPG + r];
-  const cplx ytgt = (live && role != ROLE_P) ? P.targets[v * LPG + r] : czero;
-
-  // exchange buffers: [phase][group][lane]; ph is the phase offset (0 or groups*LPG)
-  cplx* const xme0 = s_x + (size_t)g * LPG;
-  // partner group of the (q,p) pair: q = g-1 for p, p = g+1 for q (unused for ROLE_Z)
-  const int gp = role == ROLE_P ? g - 1 : (role == ROLE_Q ? g + 1 : g);
-  cplx* const xpa0 = s_x + (size_t)gp * LPG;
-  const int ph_stride = P.groups * LPG;
-  int ph = 0;
+  cplx z[NVP], ytgt[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    z[v] = live ? P.starts[v * LPG + r] : czero;
+    ytgt[v] = live ? P.targets[v * LPG + r] : czero;
+  }
+  z[NV] = czero;
+  int ph = 0;                                                   // exchange phase offset: 0 or NVP*LPG
 
   cplx a_d, a_row[WMAX], b_row[WBMAX];
 
-  // Stage s of a sweep handles slice k(s); rings: coefficients s%3, assembled rows s&1.
-  // Assemble the sparse rows of A, B for stage `st` (all groups of a sample share the slots).
-  auto assemble = [&](int st) {
-    if (pad_group) return;
-    const cplx* co = s_coef + (st % 3) * J;
-    const cplx* ad = s_add + s_l * J;
-    const double* mu = s_mul + s_l * J;
-    cplx* au = s_au + (size_t)((st & 1) * spb + s_l) * nslot_u * LPG;
-    cplx* bw = s_bw + (size_t)((st & 1) * spb + s_l) * nslot_w * LPG;
-    for (int slot = grank; slot < nslot_u + P.w_w; slot += P.R) {
-      cplx acc = czero;
-      if (slot < nslot_u) {
-        for (int kc = 0; kc < P.kc_u; ++kc) {
-          const int gi = s_urcg[(slot * P.kc_u + kc) * LPG + r];
-          if (gi >= 0) {
-            const cplx cs = cadd(cscale(co[gi], mu[gi]), ad[gi]);
-            acc = cfma(cs, s_urcv[(slot * P.kc_u + kc) * LPG + r], acc);
-          }
-        }
-        au[slot * LPG + r] = cscale(acc, P.dt);
-      } else {
-        const int sw = slot - nslot_u;
-        for (int kc = 0; kc < P.kc_w; ++kc) {
-          const int gi = s_wrcg[(sw * P.kc_w + kc) * LPG + r];
-          if (gi >= 0) {
-            const cplx cs = cadd(cscale(co[gi], mu[gi]), ad[gi]);
-            acc = cfma(cs, s_wrcv[(sw * P.kc_w + kc) * LPG + r], acc);
-          }
-        }
-        bw[sw * LPG + r] = cscale(acc, P.dt);
-      }
+  // cs[j] = coef_kj * mul_sj + add_sj for slice kk, written to the group's shared slot
+  auto load_coef = [&](int kk, cplx* creg) {
+#pragma unroll
+    for (int i = 0; i < (QOCVL_MAX_GEN + LPG - 1) / LPG; ++i) {
+      const int j = r + i * LPG;
+      creg[i] = (j < J) ? P.coef[(size_t)kk * J + j] : czero;
     }
   };
-  auto load_rows = [&](int st) {
-    const cplx* au = s_au + (size_t)((st & 1) * spb + s_l) * nslot_u * LPG;
-    a_d = au[r];
+  auto store_cs = [&](const cplx* creg) {
 #pragma unroll
-    for (int s = 0; s < WMAX; ++s) a_row[s] = (s < P.w_u) ? au[(1 + s) * LPG + r] : czero;
-    const cplx* bw = s_bw + (size_t)((st & 1) * spb + s_l) * nslot_w * LPG;
-#pragma unroll
-    for (int s = 0; s < WBMAX; ++s) b_row[s] = (s < P.w_w && role == ROLE_P) ? bw[s * LPG + r] : czero;
+    for (int i = 0; i < (QOCVL_MAX_GEN + LPG - 1) / LPG; ++i) {
+      const int j = r + i * LPG;
+      if (j < J) s_cs[j] = cadd(cscale(creg[i], mymul[i]), myadd[i]);
+    }
   };
-  // one forward Taylor step: returns X t / j
-  auto step_fwd = [&](cplx t, double invj) -> cplx {
-    xme0[ph + r] = t;
+  auto slot_value = [&](const int* gen, const cplx* val, int kcn, int slot) -> cplx {
+    cplx acc = czero;
+    for (int kc = 0; kc < kcn; ++kc) {
+      const int gi = gen[(slot * kcn + kc) * LPG + r];
+      if (gi >= 0) acc = cfma(s_cs[gi], val[(slot * kcn + kc) * LPG + r], acc);
+    }
+    return cscale(acc, P.dt);
+  };
+  auto assemble_rows = [&]() {
+    a_d = slot_value(s_urcg, s_urcv, P.kc_u, 0);
+#pragma unroll
+    for (int s = 0; s < WMAX; ++s) a_row[s] = (s < P.w_u) ? slot_value(s_urcg, s_urcv, P.kc_u, 1 + s) : czero;
+#pragma unroll
+    for (int s = 0; s < WBMAX; ++s) b_row[s] = (s < P.w_w) ? slot_value(s_wrcg, s_wrcv, P.kc_w, s) : czero;
+  };
+  // one forward Taylor step on all vectors of the sample: t <- X t / j
+  auto step_fwd = [&](cplx* t, double invj) {
+    cplx* xs = s_x + ph;
+#pragma unroll
+    for (int v = 0; v < NVP; ++v) xs[v * LPG + r] = t[v];
     __syncwarp();
-    const cplx* xv = xme0 + ph;
-    cplx acc0 = cmul(a_d, t), acc1 = czero;
+    cplx tq_b[WBMAX];
 #pragma unroll
-    for (int s = 0; s < WMAX; s += 2) {
-      acc0 = cfma(a_row[s], xv[rcol[s]], acc0);
-      if (s + 1 < WMAX) acc1 = cfma(a_row[s + 1], xv[rcol[s + 1]], acc1);
-    }
-    if (role == ROLE_P) {
-      const cplx* xq = xpa0 + ph;
+    for (int s = 0; s < WBMAX; ++s) tq_b[s] = xs[va * LPG + brcol[s]];
 #pragma unroll
-      for (int s = 0; s < WBMAX; ++s) acc1 = cfma(b_row[s], xq[brcol[s]], acc1);
+    for (int v = 0; v < NVP; ++v) {
+      cplx acc0 = cmul(a_d, t[v]), acc1 = czero;
+#pragma unroll
+      for (int s = 0; s < WMAX; ++s) {
+        const cplx xv = xs[v * LPG + rcol[s]];
+        if (s & 1) acc1 = cfma(a_row[s], xv, acc1); else acc0 = cfma(a_row[s], xv, acc0);
+      }
+      if (v == NV) {
+#pragma unroll
+        for (int s = 0; s < WBMAX; ++s) acc1 = cfma(b_row[s], tq_b[s], acc1);
+      }
+      t[v] = cscale(cadd(acc0, acc1), invj);
     }
-    ph = ph_stride - ph;
-    return cscale(cadd(acc0, acc1), invj);
+    ph = NVP * LPG - ph;
   };
 
-  // ---- prologue of the forward sweep: coefficients of stages 0 and 1, rows of stage 0
-  if (tid < J) {
-    s_coef[tid] = P.coef[tid];
-    if (P.M > 1) s_coef[J + tid] = P.coef[(size_t)J + tid];
+  // ---- prologue: coefficients of slice 0
+  {
+    cplx creg[(QOCVL_MAX_GEN + LPG - 1) / LPG];
+    load_coef(0, creg);
+    store_cs(creg);
+    __syncwarp();
   }
-  if (tid < 2) s_q[tid] = P.qdeg[tid < P.M ? tid : 0];
-  __syncthreads();
-  assemble(0);
 
   // =================================== forward sweep ===================================
   for (int k = 0; k < P.M; ++k) {
-    __syncthreads();
-    const int q = s_q[k % 3];
-    load_rows(k);
-    // coefficients of slice k+2: in flight while this slice is propagated
-    cplx cnext = czero;
-    int qnext = 0;
-    const bool pf = (k + 2 < P.M);
-    if (pf && tid < J) cnext = P.coef[(size_t)(k + 2) * J + tid];
-    if (pf && tid == 0) qnext = P.qdeg[k + 2];
-    if (P.want_grad) P.ckpt[((size_t)k * P.nblocks + blockIdx.x) * nthreads + tid] = z;
-    cplx t = z;
-    for (int j = 1; j <= q; ++j) {
-      t = step_fwd(t, c_inv[j]);
-      z = cadd(z, t);
+    const int q = P.qdeg[k];
+    assemble_rows();
+    __syncwarp();                                   // everyone has read cs of slice k
+    cplx creg[(QOCVL_MAX_GEN + LPG - 1) / LPG];
+    if (k + 1 < P.M) load_coef(k + 1, creg);        // in flight while this slice is propagated
+    if (P.want_grad) {
+#pragma unroll
+      for (int v = 0; v < NVP; ++v) P.ckpt[((size_t)k * NVP + v) * gthreads + gtid] = z[v];
     }
-    if (k + 1 < P.M) assemble(k + 1);
-    if (pf && tid < J) s_coef[((k + 2) % 3) * J + tid] = cnext;
-    if (pf && tid == 0) s_q[(k + 2) % 3] = qnext;
+    cplx t[NVP];
+#pragma unroll
+    for (int v = 0; v < NVP; ++v) t[v] = z[v];
+    for (int j = 1; j <= q; ++j) {
+      step_fwd(t, c_inv[j]);
+#pragma unroll
+      for (int v = 0; v < NVP; ++v) z[v] = cadd(z[v], t[v]);
+    }
+    if (k + 1 < P.M) store_cs(creg);
+    __syncwarp();
   }
 
   // =================================== cost ============================================
-  // overlap partials  y_v^dag z_v  (q and z groups), and  q^dag p  (p groups)
-  xme0[ph + r] = z;
-  __syncwarp();
-  cplx part = czero;
-  if (role == ROLE_P) part = cfma_conj(xpa0[ph + r], z, czero);   // conj(q_r) p_r
-  else part = cfma_conj(ytgt, z, czero);                          // conj(y_r) z_r
-  const cplx zpartner = xpa0[ph + r];                             // q sees p, p sees q
-  ph = ph_stride - ph;
-  part = group_sum<LPG>(part);
-  if (r == 0) s_dpart[g] = part;
-  __syncthreads();
-  cplx dsum = cadd(P.d_const, s_dpart[2 * s_l]);                  // constant kets + the q group
-  for (int i = 0; i < nz; ++i) dsum = cadd(dsum, s_dpart[2 * spb + s_l * nz + i]);
-  const cplx qp = s_dpart[2 * s_l + 1];
-  if (role == ROLE_Q && r == 0 && sample < P.S) {
-    const double infid = 1.0 - (dsum.x * dsum.x + dsum.y * dsum.y) * P.inv_fid_norm;
-    const double adiab = 1.0 - qp.x * P.inv_duration;
-    P.sample_out[(size_t)sample * 3 + 0] = P.w_infid * infid + P.w_adiab * adiab;
-    P.sample_out[(size_t)sample * 3 + 1] = infid;
-    P.sample_out[(size_t)sample * 3 + 2] = adiab;
+  cplx dsum = czero, qp = czero;
+  {
+    cplx part = czero;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) part = cfma_conj(ytgt[v], z[v], part);     // sum_v conj(y_v[r]) z_v[r]
+    cplx zq = czero;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) if (v == va) zq = z[v];
+    dsum = cadd(P.d_const, group_sum<LPG>(part));
+    qp = group_sum<LPG>(cfma_conj(zq, z[NV], czero));                        // q^dag p
+    if (r == 0 && sample < P.S) {
+      const double infid = 1.0 - (dsum.x * dsum.x + dsum.y * dsum.y) * P.inv_fid_norm;
+      const double adiab = 1.0 - qp.x * P.inv_duration;
+      P.sample_out[(size_t)sample * 3 + 0] = P.w_infid * infid + P.w_adiab * adiab;
+      P.sample_out[(size_t)sample * 3 + 1] = infid;
+      P.sample_out[(size_t)sample * 3 + 2] = adiab;
+    }
   }
   if (!P.want_grad) return;
 
   // terminal cotangents lam = d cost / d conj(z), scaled by 1/S_global (ensemble mean)
-  cplx lam = czero;
+  cplx lam[NVP];
   {
-    const double ws = (sample < P.S && !pad_group) ? P.inv_samples : 0.0;
+    const double ws = live ? P.inv_samples : 0.0;
     const double ca = -0.5 * P.w_adiab * P.inv_duration * ws;
-    if (role == ROLE_P) {
-      lam = cscale(zpartner, ca);                                 // -(wa/2T) q
-    } else {
-      lam = cscale(cmul(dsum, ytgt), -P.w_infid * P.inv_fid_norm * ws);
-      if (role == ROLE_Q) lam = cadd(lam, cscale(zpartner, ca));  // -(wa/2T) p
+    cplx zq = czero;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) if (v == va) zq = z[v];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      lam[v] = cscale(cmul(dsum, ytgt[v]), -P.w_infid * P.inv_fid_norm * ws);
+      if (v == va) lam[v] = cadd(lam[v], cscale(z[NV], ca));                 // -(wa/2T) p
     }
-    if (!live) lam = czero;
+    lam[NV] = cscale(zq, ca);                                                // -(wa/2T) q
   }
 
-  // ---- prologue of the reverse sweep: stage s handles slice M-1-s
-  __syncthreads();
-  for (int st = 0; st < 2 && st < P.M; ++st) {
-    const int kk = P.M - 1 - st;
-    if (tid < J) s_coef[st * J + tid] = P.coef[(size_t)kk * J + tid];
-    for (int i = tid; i < JC; i += nthreads) s_dcoef[st * JC + i] = P.dcoef[(size_t)kk * JC + i];
-    if (tid == 0) s_q[st] = P.qdeg[kk];
+  // ---- prologue of the reverse sweep
+  __syncwarp();
+  {
+    cplx creg[(QOCVL_MAX_GEN + LPG - 1) / LPG];
+    load_coef(P.M - 1, creg);
+    store_cs(creg);
+    __syncwarp();
   }
-  __syncthreads();
-  assemble(0);
 
   // =================================== reverse sweep ===================================
-  for (int st = 0; st < P.M; ++st) {
-    const int k = P.M - 1 - st;
-    __syncthreads();
-    const int q = s_q[st % 3];
-    // flush the previous stage's per-warp gradient sums (slice k+1)
-    if (st > 0 && tid < C) {
-      double acc = 0.0;
-      const double* red = s_red + ((st - 1) & 1) * nwarps * C;
-      for (int w = 0; w < nwarps; ++w) acc += red[w * C + tid];
-      P.gw_partial[((size_t)blockIdx.x * P.M + (k + 1)) * C + tid] = acc;
-    }
-    load_rows(st);
-    // column-owner values: A[a][r] for the rows a of my column (and B[a][r] for the q group)
+  const size_t gwarp = (size_t)blockIdx.x * nwarps + warp;
+  for (int k = P.M - 1; k >= 0; --k) {
+    const int q = P.qdeg[k];
+    assemble_rows();
+    // column-owner values: A[a][r] for the rows a of my column, B[a][r] for the q <- p coupling
     cplx a_col[WMAX], b_col[WBMAX];
-    {
-      const cplx* au = s_au + (size_t)((st & 1) * spb + s_l) * nslot_u * LPG;
 #pragma unroll
-      for (int s = 0; s < WMAX; ++s) a_col[s] = (s < P.wc_u) ? au[csrc[s]] : czero;
-      const cplx* bw = s_bw + (size_t)((st & 1) * spb + s_l) * nslot_w * LPG;
+    for (int s = 0; s < WMAX; ++s) a_col[s] = (s < P.wc_u) ? slot_value(s_uccg, s_uccv, P.kc_u, 1 + s) : czero;
 #pragma unroll
-      for (int s = 0; s < WBMAX; ++s) b_col[s] = (s < P.wc_w && role == ROLE_Q) ? bw[bcsrc[s]] : czero;
-    }
-    // coefficients of stage st+2 (slice k-2): in flight during this slice
-    const bool pf = (st + 2 < P.M);
-    cplx cnext = czero, dnext = czero;
-    int qnext = 0;
-    if (pf && tid < J) cnext = P.coef[(size_t)(k - 2) * J + tid];
-    if (pf && tid < JC) dnext = P.dcoef[(size_t)(k - 2) * JC + tid];
-    if (pf && tid == 0) qnext = P.qdeg[k - 2];
+    for (int s = 0; s < WBMAX; ++s) b_col[s] = (s < P.wc_w) ? slot_value(s_wccg, s_wccv, P.kc_w, s) : czero;
+    __syncwarp();                                   // everyone has read cs of slice k
+    cplx creg[(QOCVL_MAX_GEN + LPG - 1) / LPG];
+    if (k > 0) load_coef(k - 1, creg);
+    // d coef / d wave of this slice: needed only by the contraction at the end of the slice
+    cplx dreg[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) dreg[i] = (lane + 32 * i < JC) ? P.dcoef[(size_t)k * JC + lane + 32 * i] : czero;
     // ---- recompute forward Taylor terms t_0 .. t_{q-1}
-    cplx t = P.ckpt[((size_t)k * P.nblocks + blockIdx.x) * nthreads + tid];
-    s_T[tid] = t;
+    cplx t[NVP];
+#pragma unroll
+    for (int v = 0; v < NVP; ++v) {
+      t[v] = P.ckpt[((size_t)k * NVP + v) * gthreads + gtid];
+      s_T[v * LPG + r] = t[v];
+    }
     for (int j = 1; j < q; ++j) {
-      t = step_fwd(t, c_inv[j]);
-      s_T[(size_t)j * nthreads + tid] = t;
+      step_fwd(t, c_inv[j]);
+#pragma unroll
+      for (int v = 0; v < NVP; ++v) s_T[((size_t)j * NVP + v) * LPG + r] = t[v];
     }
     // ---- descending adjoint recurrence with on-the-fly contraction
-    cplx tb = lam;
+    cplx tb[NVP];
+#pragma unroll
+    for (int v = 0; v < NVP; ++v) tb[v] = lam[v];
     cplx xc_d = czero, xc[WMAX], xcb[WBMAX];
 #pragma unroll
     for (int s = 0; s < WMAX; ++s) xc[s] = czero;
@@ -351,38 +303,44 @@ __global__ void __launch_bounds__(512) k_chain(const ChainArgs P) {
     for (int s = 0; s < WBMAX; ++s) xcb[s] = czero;
     for (int j = q; j >= 1; --j) {
       const double invj = c_inv[j];
-      xme0[ph + r] = tb;
+      cplx* xs = s_x + ph;
+#pragma unroll
+      for (int v = 0; v < NVP; ++v) xs[v * LPG + r] = tb[v];
       __syncwarp();
-      const cplx tprev = cscale(s_T[(size_t)(j - 1) * nthreads + tid], invj);
-      cplx acc0 = cfma_conj(a_d, tb, czero), acc1 = czero;
-      xc_d = cfma_conj(tb, tprev, xc_d);
-      const cplx* xv = xme0 + ph;
+      const cplx* tp = s_T + (size_t)(j - 1) * NVP * LPG + r;
 #pragma unroll
-      for (int s = 0; s < WMAX; ++s) {
-        const cplx ta = xv[crow[s]];
-        if (s & 1) acc1 = cfma_conj(a_col[s], ta, acc1);
-        else acc0 = cfma_conj(a_col[s], ta, acc0);
-        xc[s] = cfma_conj(ta, tprev, xc[s]);
-      }
-      if (role == ROLE_Q) {
-        const cplx* xp = xpa0 + ph;
+      for (int v = 0; v < NVP; ++v) {
+        const cplx tprev = cscale(tp[v * LPG], invj);
+        cplx acc0 = cfma_conj(a_d, tb[v], czero), acc1 = czero;
+        xc_d = cfma_conj(tb[v], tprev, xc_d);
 #pragma unroll
-        for (int s = 0; s < WBMAX; ++s) {
-          const cplx ta = xp[bcrow[s]];
-          acc1 = cfma_conj(b_col[s], ta, acc1);
-          xcb[s] = cfma_conj(ta, tprev, xcb[s]);
+        for (int s = 0; s < WMAX; ++s) {
+          const cplx ta = xs[v * LPG + crow[s]];
+          if (s & 1) acc1 = cfma_conj(a_col[s], ta, acc1); else acc0 = cfma_conj(a_col[s], ta, acc0);
+          xc[s] = cfma_conj(ta, tprev, xc[s]);
         }
+        if (v == va) {                              // q receives B^dag tb_p; Bbar pairs tb_p with t_q
+#pragma unroll
+          for (int s = 0; s < WBMAX; ++s) {
+            const cplx ta = xs[NV * LPG + bcrow[s]];
+            acc1 = cfma_conj(b_col[s], ta, acc1);
+            xcb[s] = cfma_conj(ta, tprev, xcb[s]);
+          }
+        }
+        tb[v] = cadd(lam[v], cscale(cadd(acc0, acc1), invj));
       }
-      ph = ph_stride - ph;
-      tb = cadd(lam, cscale(cadd(acc0, acc1), invj));
+      ph = NVP * LPG - ph;
     }
-    lam = tb;
+#pragma unroll
+    for (int v = 0; v < NVP; ++v) lam[v] = tb[v];
     // ---- contract Xbar with the generators: d cost / d wave[k][c]
+#pragma unroll
+    for (int i = 0; i < 3; ++i) if (lane + 32 * i < JC) s_dco[lane + 32 * i] = dreg[i];
+    __syncwarp();
     double gw[QOCVL_MAX_CHAN];
 #pragma unroll
     for (int c = 0; c < QOCVL_MAX_CHAN; ++c) gw[c] = 0.0;
     if (live) {
-      const cplx* dco = s_dcoef + (st % 3) * JC;
       const double two_dt = 2.0 * P.dt;
       for (int slot = 0; slot <= P.wc_u; ++slot) {
         cplx xval = xc_d;
@@ -392,53 +350,37 @@ __global__ void __launch_bounds__(512) k_chain(const ChainArgs P) {
         for (int kc = 0; kc < P.kc_u; ++kc) {
           const int gi = s_uccg[(slot * P.kc_u + kc) * LPG + r];
           if (gi >= 0) {
-            const cplx tmp = cscale(cmul(s_uccv[(slot * P.kc_u + kc) * LPG + r], xval),
-                                    two_dt * s_mul[s_l * J + gi]);
+            const cplx tmp = cscale(cmul(s_uccv[(slot * P.kc_u + kc) * LPG + r], xval), two_dt * s_mul[gi]);
 #pragma unroll
             for (int c = 0; c < QOCVL_MAX_CHAN; ++c)
-              if (c < C) gw[c] += tmp.x * dco[gi * C + c].x - tmp.y * dco[gi * C + c].y;
+              if (c < C) gw[c] += tmp.x * s_dco[gi * C + c].x - tmp.y * s_dco[gi * C + c].y;
           }
         }
       }
-      if (role == ROLE_Q) {
-        for (int slot = 0; slot < P.wc_w; ++slot) {
-          cplx xval = czero;
+      for (int slot = 0; slot < P.wc_w; ++slot) {
+        cplx xval = czero;
 #pragma unroll
-          for (int s = 0; s < WBMAX; ++s)
-            if (slot == s) xval = xcb[s];
-          for (int kc = 0; kc < P.kc_w; ++kc) {
-            const int gi = s_wccg[(slot * P.kc_w + kc) * LPG + r];
-            if (gi >= 0) {
-              const cplx tmp = cscale(cmul(s_wccv[(slot * P.kc_w + kc) * LPG + r], xval),
-                                      two_dt * s_mul[s_l * J + gi]);
+        for (int s = 0; s < WBMAX; ++s)
+          if (slot == s) xval = xcb[s];
+        for (int kc = 0; kc < P.kc_w; ++kc) {
+          const int gi = s_wccg[(slot * P.kc_w + kc) * LPG + r];
+          if (gi >= 0) {
+            const cplx tmp = cscale(cmul(s_wccv[(slot * P.kc_w + kc) * LPG + r], xval), two_dt * s_mul[gi]);
 #pragma unroll
-              for (int c = 0; c < QOCVL_MAX_CHAN; ++c)
-                if (c < C) gw[c] += tmp.x * dco[gi * C + c].x - tmp.y * dco[gi * C + c].y;
-            }
+            for (int c = 0; c < QOCVL_MAX_CHAN; ++c)
+              if (c < C) gw[c] += tmp.x * s_dco[gi * C + c].x - tmp.y * s_dco[gi * C + c].y;
           }
         }
       }
     }
-    {
-      double* red = s_red + (st & 1) * nwarps * C;
 #pragma unroll
-      for (int c = 0; c < QOCVL_MAX_CHAN; ++c) {
-        double vsum = gw[c];
-        for (int off = 16; off > 0; off >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, off);
-        if (lane == 0 && c < C) red[warp * C + c] = vsum;
-      }
+    for (int c = 0; c < QOCVL_MAX_CHAN; ++c) {
+      double vsum = gw[c];
+      for (int off = 16; off > 0; off >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, off);
+      if (lane == 0 && c < C) P.gw_partial[(gwarp * P.M + k) * C + c] = vsum;
     }
-    if (st + 1 < P.M) assemble(st + 1);
-    if (pf && tid < J) s_coef[((st + 2) % 3) * J + tid] = cnext;
-    if (pf && tid < JC) s_dcoef[((st + 2) % 3) * JC + tid] = dnext;
-    if (pf && tid == 0) s_q[(st + 2) % 3] = qnext;
-  }
-  __syncthreads();
-  if (tid < C) {
-    double acc = 0.0;
-    const double* red = s_red + ((P.M - 1) & 1) * nwarps * C;
-    for (int w = 0; w < nwarps; ++w) acc += red[w * C + tid];
-    P.gw_partial[((size_t)blockIdx.x * P.M + 0) * C + tid] = acc;
+    if (k > 0) store_cs(creg);
+    __syncwarp();
   }
 }
 
@@ -462,33 +404,84 @@ __global__ void k_reduce_samples(int S, double inv_samples, const double* __rest
   if (tid < 3) out3[tid] = sh[tid][0] * inv_samples;
 }
 
-// gwave[k][c] = sum over CTAs of their partial sums
-__global__ void k_reduce_gwave(int nblocks, int MC, const double* __restrict__ partial,
+// gwave[k][c] = sum over warps of their partial sums (fixed order: deterministic)
+__global__ void k_reduce_gwave(int nparts, int MC, const double* __restrict__ partial,
                                double* __restrict__ gwave) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= MC) return;
   double acc = 0.0;
-  for (int b = 0; b < nblocks; ++b) acc += partial[(size_t)b * MC + i];
+  for (int b = 0; b < nparts; ++b) acc += partial[(size_t)b * MC + i];
   gwave[i] = acc;
 }
 
-static size_t chain_smem_bytes(const qocvl_plan* p, int spb, int groups, int threads, int qcap) {
-  const int J = p->d.n_gen, C = p->d.n_chan, L = p->npad;
-  const int nslot_u = p->lu.n_row_slots, nslot_w = p->lw.n_row_slots;
-  size_t cplx_count = (size_t)3 * J + (size_t)3 * J * C + (size_t)spb * J + (size_t)2 * spb * nslot_u * L +
-                      (size_t)2 * spb * nslot_w * L + (size_t)2 * groups * L + groups + (size_t)qcap * threads;
-  size_t dbl_count = (size_t)spb * J + (size_t)2 * ((threads + 31) / 32) * C;
-  // generator-contribution tables: value (cplx) + generator id (int) per (slot, contribution, lane)
+static size_t chain_smem_bytes(const qocvl_plan* p, int ngroups, int qcap) {
+  const int J = p->d.n_gen, C = p->d.n_chan, L = p->npad, nvp = p->n_live + 1;
+  const int nwarps = ngroups * L / 32;
   const size_t w_w = p->lw.nnz ? p->lw.n_row_slots : 0, wc_w = p->lw.nnz ? p->lw.n_col_slots : 0;
   const size_t tab = ((size_t)(p->lu.n_row_slots + p->lu.n_col_slots) * p->lu.kc + (w_w + wc_w) * p->lw.kc) * L;
-  return (cplx_count + tab) * sizeof(cplx) + dbl_count * sizeof(double) + (tab + 4) * sizeof(int);
+  const size_t cplx_count = tab + (size_t)ngroups * J + (size_t)nwarps * J * C + (size_t)ngroups * 2 * nvp * L +
+                            (size_t)ngroups * qcap * nvp * L;
+  return cplx_count * sizeof(cplx) + (size_t)ngroups * J * sizeof(double) + tab * sizeof(int);
 }
 
 typedef void (*chain_fn)(const ChainArgs);
+template <int LPG, int W>
+static chain_fn pick_nv(int nv) {
+  switch (nv) {
+    case 1: return k_chain<LPG, 1, W, 2>;
+    case 2: return k_chain<LPG, 2, W, 2>;
+    case 3: return k_chain<LPG, 3, W, 2>;
+    case 4: return k_chain<LPG, 4, W, 2>;
+    default: return nullptr;
+  }
+}
 static chain_fn pick_kernel(const qocvl_plan* p) {
-  const bool narrow = p->lu.n_row_slots - 1 <= 2 && p->lu.n_col_slots - 1 <= 2;
-  if (p->npad == 8) return narrow ? k_chain<8, 2, 2> : k_chain<8, 4, 2>;
-  return narrow ? k_chain<16, 2, 2> : k_chain<16, 4, 2>;
+  return p->npad == 8 ? pick_nv<8, 4>(p->n_live) : pick_nv<16, 4>(p->n_live);
+}
+
+// Host-side a-priori bound on |X_k|_1: maximum of the exact slice norm over a grid of admissible
+// physical amplitudes (the regularisation keeps every amplitude in [-1, 1], ST:204-227 / TQ:355-373,
+// and the filter taps are >= 0 with sum < 1), with a 5 % margin for the grid spacing.  It only sizes
+// the shared-memory ring of Taylor terms: the device computes the per-slice degree from the actual
+// amplitudes and poisons + flags a slice that would exceed this cap (never silently wrong).
+static double apriori_norm_bound(const qocvl_plan* p, const std::vector<double>& mulmax,
+                                 const std::vector<double>& addmax) {
+  const qocvl_desc& d = p->d;
+  ModelParams mp = {d.model, d.n, d.n_gen, d.n_chan, d.dt, d.eps, d.scale[0], d.scale[1]};
+  const int J = d.n_gen, D = 2 * d.n;
+  std::vector<cplx> gdense((size_t)J * D * D, cmake(0, 0)), cc(J);
+  for (int j = 0; j < J; ++j) {
+    cc[j] = cmake(p->h_coef_const[j].real(), p->h_coef_const[j].imag());
+    for (int a = 0; a < d.n; ++a)
+      for (int b = 0; b < d.n; ++b) {
+        const std::complex<double> u = p->h_gu[((size_t)j * d.n + a) * d.n + b], w = p->h_gw[((size_t)j * d.n + a) * d.n + b];
+        gdense[((size_t)j * D + a) * D + b] = cmake(u.real(), u.imag());
+        gdense[((size_t)j * D + a) * D + d.n + b] = cmake(w.real(), w.imag());
+      }
+  }
+  cplx co[QOCVL_MAX_GEN];
+  cplx dc[QOCVL_MAX_GEN][QOCVL_MAX_CHAN];
+  double worst = 0.0;
+  const int NA = 8;   // angles
+  for (int i0 = 0; i0 < 2; ++i0)
+    for (int r1 = 1; r1 <= 2; ++r1)
+      for (int a1 = 0; a1 < NA; ++a1)
+        for (int r3 = 1; r3 <= 2; ++r3)
+          for (int a3 = 0; a3 < NA; ++a3) {
+            double w[5];
+            if (d.model == QOCVL_MODEL_TWO_QUBIT) {   // (magnitude, phase) pairs
+              w[0] = i0 ? -1.0 : 0.0;
+              w[1] = 0.5 * r1; w[2] = -1.0 + 2.0 * a1 / NA;
+              w[3] = 0.5 * r3; w[4] = -1.0 + 2.0 * a3 / NA;
+            } else {                                  // (re, im) pairs inside the unit disk
+              w[0] = i0 ? -1.0 : 1.0;
+              w[1] = 0.5 * r1 * cos(2 * PI_D * a1 / NA); w[2] = 0.5 * r1 * sin(2 * PI_D * a1 / NA);
+              w[3] = 0.5 * r3 * cos(2 * PI_D * a3 / NA); w[4] = 0.5 * r3 * sin(2 * PI_D * a3 / NA);
+            }
+            qocvl_model_coefficients(mp, w, cc.data(), co, dc);
+            worst = std::max(worst, qocvl_slice_norm(mp, co, gdense.data(), p->h_gcol.data(), mulmax.data(), addmax.data()));
+          }
+  return 1.05 * worst;
 }
 
 // Decide the launch geometry, size the a-priori Taylor cap and (re)allocate per-sample buffers.
@@ -499,6 +492,7 @@ int qocvl_chain_configure(qocvl_plan* p) {
   const int L = p->npad, S = p->n_samples, J = d.n_gen, n = d.n;
   if (p->lu.n_row_slots - 1 > 4 || p->lu.n_col_slots - 1 > 4 || p->lw.n_row_slots > 2 || p->lw.n_col_slots > 2)
     return QOCVL_ERR_UNSUPPORTED;
+  if (J * d.n_chan > 96) return QOCVL_ERR_UNSUPPORTED;   // dcoef staging: 3 entries per lane
   {
     double inv[QOCVL_QMAX + 2];
     inv[0] = 0.0;
@@ -573,64 +567,42 @@ int qocvl_chain_configure(qocvl_plan* p) {
       }
     }
   }
+  if (p->n_live > 4) return QOCVL_ERR_UNSUPPORTED;
   if (p->d_starts) { cudaFree(p->d_starts); p->d_starts = nullptr; }
   if (p->d_targets) { cudaFree(p->d_targets); p->d_targets = nullptr; }
   QCUDA(cudaMalloc((void**)&p->d_starts, live_s.size() * sizeof(cplx)));
   QCUDA(cudaMalloc((void**)&p->d_targets, live_t.size() * sizeof(cplx)));
   QCUDA(cudaMemcpy(p->d_starts, live_s.data(), live_s.size() * sizeof(cplx), cudaMemcpyHostToDevice));
   QCUDA(cudaMemcpy(p->d_targets, live_t.data(), live_t.size() * sizeof(cplx), cudaMemcpyHostToDevice));
-  const int R = p->n_live + 1;
-  // ---- a-priori bound on |X_k|_1 (sizes the shared-memory ring of Taylor terms).
-  // |c_j| <= 1 for every pulse-driven coefficient (tanh / 1-exp regularisation, filter taps >= 0 with
-  // sum < 1, projector weights are ratios <= 1); 1e-3 relative margin for filter round-off.
-  std::vector<double> mulmax(J), addmax(J);
-  QCUDA(cudaMemcpy(mulmax.data(), p->d_mulmax, J * sizeof(double), cudaMemcpyDeviceToHost));
+  // ---- a-priori Taylor cap (sizes the shared-memory ring of Taylor terms)
+  std::vector<double> mulmax(2 * (size_t)J), addmax(J);
+  QCUDA(cudaMemcpy(mulmax.data(), p->d_mulmax, 2 * J * sizeof(double), cudaMemcpyDeviceToHost));
   QCUDA(cudaMemcpy(addmax.data(), p->d_addmax, J * sizeof(double), cudaMemcpyDeviceToHost));
-  double bound = 0.0;
-  for (int b = 0; b < n; ++b) {
-    double s = 0.0;
-    for (int j = 0; j < J; ++j) {
-      const double cmax = j < 2 ? std::abs(p->h_coef_const[j]) : 1.001;
-      s += (cmax * mulmax[j] + addmax[j]) * p->h_gcol[(size_t)j * n + b];
-    }
-    bound = std::max(bound, s);
-  }
-  bound *= d.dt;
+  const double bound = apriori_norm_bound(p, mulmax, addmax);
   if (!(bound == bound)) return QOCVL_ERR_ARG;
   p->qcap = qocvl_taylor_degree(bound);
-  // ---- samples per CTA: aim for ~128-192 threads
-  int spb = 160 / (R * L);
-  if (const char* e = getenv("QOCVL_SPB")) spb = atoi(e);
-  if (spb < 1) spb = 1;
-  if (spb > S) spb = S;
+  if (const char* e = getenv("QOCVL_QCAP")) p->qcap = std::max(2, std::min(QOCVL_QMAX, atoi(e)));
+  // ---- samples per CTA: a CTA is only a container of independent groups; keep it small so the
+  //      tail of the grid balances, but a multiple of the warp size
   const int gpw = 32 / L;
-  for (;;) {
-    int groups = ((spb * R + gpw - 1) / gpw) * gpw;
-    int threads = groups * L;
-    size_t smem = chain_smem_bytes(p, spb, groups, threads, p->qcap);
-    if ((smem <= 200 * 1024 && threads <= 512) || spb == 1) {
-      p->spb = spb; p->groups = groups; p->threads = threads; p->chain_smem = smem;
-      break;
-    }
-    --spb;
-  }
-  if (p->chain_smem > 227 * 1024 || p->threads < J * d.n_chan) {
-    // the coefficient prefetch uses one thread per (generator, channel) entry
-    if (p->chain_smem > 227 * 1024) return QOCVL_ERR_UNSUPPORTED;
-    const int need = ((J * d.n_chan + L - 1) / L + gpw - 1) / gpw * gpw;   // pad with idle groups
-    p->groups = std::max(p->groups, need);
-    p->threads = p->groups * L;
-    p->chain_smem = chain_smem_bytes(p, p->spb, p->groups, p->threads, p->qcap);
-  }
-  p->blocks = (S + p->spb - 1) / p->spb;
-  QCUDA(cudaFuncSetAttribute(pick_kernel(p), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->chain_smem));
+  int ngroups = 2 * gpw;                                   // 2 warps
+  if (const char* e = getenv("QOCVL_SPB")) ngroups = std::max(gpw, (atoi(e) + gpw - 1) / gpw * gpw);
+  while (ngroups > gpw && chain_smem_bytes(p, ngroups, p->qcap) > 100 * 1024) ngroups -= gpw;
+  p->spb = ngroups; p->groups = ngroups; p->threads = ngroups * L;
+  p->chain_smem = chain_smem_bytes(p, ngroups, p->qcap);
+  if (p->chain_smem > 227 * 1024) return QOCVL_ERR_UNSUPPORTED;
+  p->blocks = (S + ngroups - 1) / ngroups;
+  chain_fn fn = pick_kernel(p);
+  if (!fn) return QOCVL_ERR_UNSUPPORTED;
+  QCUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->chain_smem));
   // ---- per-sample buffers
-  const size_t ck = (size_t)d.n_slices * p->blocks * p->threads;
+  const size_t total_threads = (size_t)p->blocks * p->threads, total_warps = total_threads / 32;
+  const size_t ck = (size_t)d.n_slices * (p->n_live + 1) * total_threads;
   if (p->d_ckpt) { cudaFree(p->d_ckpt); p->d_ckpt = nullptr; p->bytes -= p->ckpt_bytes; }
   QCUDA(cudaMalloc((void**)&p->d_ckpt, ck * sizeof(cplx)));
   p->ckpt_bytes = ck * sizeof(cplx);
   if (p->d_gw_partial) { cudaFree(p->d_gw_partial); p->d_gw_partial = nullptr; p->bytes -= p->gw_partial_elems * sizeof(double); }
-  p->gw_partial_elems = (size_t)p->blocks * d.n_slices * d.n_chan;
+  p->gw_partial_elems = total_warps * d.n_slices * d.n_chan;
   QCUDA(cudaMalloc((void**)&p->d_gw_partial, p->gw_partial_elems * sizeof(double)));
   p->bytes += p->ckpt_bytes + p->gw_partial_elems * sizeof(double);
   return QOCVL_OK;
@@ -641,17 +613,18 @@ int qocvl_launch_chain(qocvl_plan* p, bool want_grad, double* out3, double* gwav
   if (rc) return rc;
   const qocvl_desc& d = p->d;
   ChainArgs a;
-  a.n = d.n; a.J = d.n_gen; a.M = d.n_slices; a.C = d.n_chan; a.S = p->n_samples; a.R = p->n_live + 1;
-  a.adiab_index = p->adiab_live; a.spb = p->spb; a.groups = p->groups;
+  a.n = d.n; a.J = d.n_gen; a.M = d.n_slices; a.C = d.n_chan; a.S = p->n_samples;
+  a.nv = p->n_live; a.va = p->adiab_live;
   a.w_u = p->lu.n_row_slots - 1; a.wc_u = p->lu.n_col_slots - 1; a.kc_u = p->lu.kc;
   a.w_w = p->lw.nnz ? p->lw.n_row_slots : 0; a.wc_w = p->lw.nnz ? p->lw.n_col_slots : 0; a.kc_w = p->lw.kc;
-  a.qcap = p->qcap; a.want_grad = want_grad ? 1 : 0; a.nblocks = p->blocks;
+  a.qcap = p->qcap; a.want_grad = want_grad ? 1 : 0;
+  a.nwarps_total = p->blocks * p->threads / 32;
   a.dt = d.dt; a.inv_duration = 1.0 / d.duration; a.w_infid = d.w_infid; a.w_adiab = d.w_adiab;
   a.inv_fid_norm = 1.0 / d.fid_norm; a.inv_samples = 1.0 / (double)p->global_samples;
   a.d_const = p->d_const;
-  a.u_row_col = p->lu.row_col; a.u_col_row = p->lu.col_row; a.u_col_src = p->lu.col_src;
+  a.u_row_col = p->lu.row_col; a.u_col_row = p->lu.col_row;
   a.u_rc_gen = p->lu.rc_gen; a.u_cc_gen = p->lu.cc_gen; a.u_rc_val = p->lu.rc_val; a.u_cc_val = p->lu.cc_val;
-  a.w_row_col = p->lw.row_col; a.w_col_row = p->lw.col_row; a.w_col_src = p->lw.col_src;
+  a.w_row_col = p->lw.row_col; a.w_col_row = p->lw.col_row;
   a.w_rc_gen = p->lw.rc_gen; a.w_cc_gen = p->lw.cc_gen; a.w_rc_val = p->lw.rc_val; a.w_cc_val = p->lw.cc_val;
   a.coef = p->d_coef; a.dcoef = p->d_dcoef; a.qdeg = p->d_qdeg; a.mul = p->d_mul; a.add = p->d_add;
   a.starts = p->d_starts; a.targets = p->d_targets; a.ckpt = p->d_ckpt; a.sample_out = p->d_sample_out;
@@ -663,7 +636,7 @@ int qocvl_launch_chain(qocvl_plan* p, bool want_grad, double* out3, double* gwav
   p->launches += 2;
   if (want_grad) {
     const int MC = d.n_slices * d.n_chan;
-    k_reduce_gwave<<<(MC + 255) / 256, 256, 0, st>>>(p->blocks, MC, p->d_gw_partial, gwave);
+    k_reduce_gwave<<<(MC + 255) / 256, 256, 0, st>>>(a.nwarps_total, MC, p->d_gw_partial, gwave);
     p->launches++;
   }
   QCUDA(cudaGetLastError());

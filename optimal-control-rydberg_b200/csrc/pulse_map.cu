@@ -2,8 +2,7 @@
 // amplitudes with their derivatives, and the reverse (VJP) of all of it.
 //   forward : ST:173-245, TQ:319-455        reverse: hand-derived, mirrors oracle/vector_model.py
 #include "common.cuh"
-
-#define PI_D 3.14159265358979323846
+#include "model.cuh"
 
 __device__ __forceinline__ double basis_time(int t, int nt) {
   // numpy.linspace(-1, 1, nt): start + t*step, last point forced to the stop value
@@ -77,106 +76,24 @@ __global__ void k_filter(int M, int nt, int pad, int C, int transpose, const dou
   }
 }
 
-// Per-slice generator coefficients and their derivatives with respect to the C real
-// pulse values of that slice; also the Taylor degree for the slice.
-//   TQ:416-476 (drift coefficient -i comes from coef_const), ST:236-255
-__global__ void k_coefficients(int model, int n, int M, int J, int C, double dt, double eps, double s0, double s1,
-                               const double* __restrict__ wave, const cplx* __restrict__ coef_const,
-                               const cplx* __restrict__ gdense, const double* __restrict__ gnorm, const double* __restrict__ mulmax,
+// Per-slice generator coefficients and their derivatives with respect to the C real pulse values
+// of that slice (model.cuh), plus the Taylor degree for the slice from the norm bound.
+__global__ void k_coefficients(ModelParams mp, int M, const double* __restrict__ wave,
+                               const cplx* __restrict__ coef_const, const cplx* __restrict__ gdense,
+                               const double* __restrict__ gcol, const double* __restrict__ mulmax,
                                const double* __restrict__ addmax, int qcap, cplx* __restrict__ coef,
                                cplx* __restrict__ dcoef, int* __restrict__ qdeg, int* __restrict__ flag) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= M) return;
-  const double* w = wave + (size_t)k * C;
+  const int J = mp.J, C = mp.C;
   cplx co[QOCVL_MAX_GEN];
   cplx dc[QOCVL_MAX_GEN][QOCVL_MAX_CHAN];
-  for (int j = 0; j < QOCVL_MAX_GEN; ++j) {
-    co[j] = cmake(0, 0);
-    for (int c = 0; c < QOCVL_MAX_CHAN; ++c) dc[j][c] = cmake(0, 0);
-  }
-  co[0] = coef_const[0];
-  co[1] = coef_const[1];
-  if (model == QOCVL_MODEL_TWO_QUBIT) {
-    const double ri = s0, rr = s1;
-    double si, ci, sr, cr;
-    sincos(PI_D * w[2], &si, &ci);
-    sincos(PI_D * w[4], &sr, &cr);
-    co[2] = cmake(0, -w[0]);              dc[2][0] = cmake(0, -1);
-    co[3] = cmake(0, -w[1] * ci);         dc[3][1] = cmake(0, -ci); dc[3][2] = cmake(0, PI_D * w[1] * si);
-    co[4] = cmake(0, -w[1] * si);         dc[4][1] = cmake(0, -si); dc[4][2] = cmake(0, -PI_D * w[1] * ci);
-    co[5] = cmake(0, -w[3] * cr);         dc[5][3] = cmake(0, -cr); dc[5][4] = cmake(0, PI_D * w[3] * sr);
-    co[6] = cmake(0, -w[3] * sr);         dc[6][3] = cmake(0, -sr); dc[6][4] = cmake(0, -PI_D * w[3] * cr);
-    const double mi = ri * w[1], mr = rr * w[3];
-    const double den_raw = mr * mr + mi * mi;
-    const bool clamped = den_raw < eps;      // TQ:433-434
-    const double den = clamped ? eps : den_raw;
-    const double dd1 = clamped ? 0.0 : 2.0 * mi * ri, dd3 = clamped ? 0.0 : 2.0 * mr * rr;
-    double sp, cp;
-    sincos(PI_D * (w[2] + w[4]), &sp, &cp);
-    const cplx ph = cmake(cp, sp);
-    const double inv = 1.0 / den, inv2 = inv * inv;
-    co[7] = cmake(mr * mr * inv, 0);
-    co[8] = cmake(mi * mi * inv, 0);
-    co[9] = cscale(ph, -mi * mr * inv);
-    co[10] = cconj(co[9]);
-    dc[7][1] = cmake(-mr * mr * dd1 * inv2, 0);
-    dc[7][3] = cmake(2.0 * mr * rr * inv - mr * mr * dd3 * inv2, 0);
-    dc[8][1] = cmake(2.0 * mi * ri * inv - mi * mi * dd1 * inv2, 0);
-    dc[8][3] = cmake(-mi * mi * dd3 * inv2, 0);
-    dc[9][1] = cscale(ph, -(ri * mr * inv - mi * mr * dd1 * inv2));
-    dc[9][3] = cscale(ph, -(mi * rr * inv - mi * mr * dd3 * inv2));
-    dc[9][2] = cmul(cmake(0, PI_D), co[9]);
-    dc[9][4] = dc[9][2];
-    for (int c = 0; c < 5; ++c) dc[10][c] = cconj(dc[9][c]);
-  } else {  // state transfer
-    const double r1 = s0, r2 = s1;
-    for (int c = 0; c < 5; ++c) { co[2 + c] = cmake(0, -w[c]); dc[2 + c][c] = cmake(0, -1); }
-    const cplx o1 = cmake(r1 * w[1], r1 * w[2]), o2 = cmake(r2 * w[3], r2 * w[4]);
-    const double n1 = o1.x * o1.x + o1.y * o1.y, n2 = o2.x * o2.x + o2.y * o2.y;
-    const double den = n1 + n2, inv = 1.0 / den, inv2 = inv * inv;   // ST:242-243: no guard (quirk q7)
-    const cplx o12 = cmul(o1, o2);
-    co[7] = cmake(n2 * inv, 0);
-    co[8] = cmake(n1 * inv, 0);
-    co[9] = cscale(o12, -inv);
-    co[10] = cconj(co[9]);
-    const double dn1[5] = {0, 2 * r1 * r1 * w[1], 2 * r1 * r1 * w[2], 0, 0};
-    const double dn2[5] = {0, 0, 0, 2 * r2 * r2 * w[3], 2 * r2 * r2 * w[4]};
-    const cplx do1[5] = {cmake(0, 0), cmake(r1, 0), cmake(0, r1), cmake(0, 0), cmake(0, 0)};
-    const cplx do2[5] = {cmake(0, 0), cmake(0, 0), cmake(0, 0), cmake(r2, 0), cmake(0, r2)};
-    for (int c = 1; c < 5; ++c) {
-      const double dden = dn1[c] + dn2[c];
-      dc[7][c] = cmake(dn2[c] * inv - n2 * dden * inv2, 0);
-      dc[8][c] = cmake(dn1[c] * inv - n1 * dden * inv2, 0);
-      const cplx num = cadd(cmul(do1[c], o2), cmul(o1, do2[c]));
-      dc[9][c] = cadd(cscale(num, -inv), cscale(o12, dden * inv2));
-      dc[10][c] = cconj(dc[9][c]);
-    }
-  }
-  double wgt[QOCVL_MAX_GEN];
+  qocvl_model_coefficients(mp, wave + (size_t)k * C, coef_const, co, dc);
   for (int j = 0; j < J; ++j) {
     coef[(size_t)k * J + j] = co[j];
     for (int c = 0; c < C; ++c) dcoef[((size_t)k * J + j) * C + c] = dc[j][c];
-    // deviation of any noise sample from the nominal coefficient: |c| * max|mul-1| + max|add|
-    wgt[j] = sqrt(co[j].x * co[j].x + co[j].y * co[j].y) * mulmax[J + j] + addmax[j];
   }
-  // |X_k|_1 over every noise sample <= exact 1-norm of the nominal 2n x 2n generator
-  //   (column b: sum_a |A_ab|, column n+b: sum_a |B_ab| + |A_ab|)  +  entrywise bound of the deviation
-  const int D = 2 * n;
-  double nrm = 0.0;
-  for (int b = 0; b < n; ++b) {
-    double s = 0.0;
-    for (int j = 0; j < J; ++j) s += wgt[j] * gnorm[j * n + b];
-    for (int a = 0; a < n; ++a) {
-      cplx ea = cmake(0, 0), eb = cmake(0, 0);
-      for (int j = 0; j < J; ++j) {
-        ea = cfma(co[j], gdense[((size_t)j * D + a) * D + b], ea);
-        eb = cfma(co[j], gdense[((size_t)j * D + a) * D + n + b], eb);
-      }
-      s += sqrt(ea.x * ea.x + ea.y * ea.y) + sqrt(eb.x * eb.x + eb.y * eb.y);
-    }
-    nrm = fmax(nrm, s);
-  }
-  nrm *= dt;
+  const double nrm = qocvl_slice_norm(mp, co, gdense, gcol, mulmax, addmax);
   int q = qocvl_taylor_degree(nrm);
   if (!(nrm <= QOCVL_NORM_MAX) || q > qcap) {   // also catches NaN pulses
     atomicOr(flag, 1);
@@ -276,9 +193,10 @@ int qocvl_launch_pulse_forward(qocvl_plan* p, const double* abc, cudaStream_t st
 
 int qocvl_launch_coefficients(qocvl_plan* p, const double* wave, cudaStream_t st) {
   const qocvl_desc& d = p->d;
+  ModelParams mp = {d.model, d.n, d.n_gen, d.n_chan, d.dt, d.eps, d.scale[0], d.scale[1]};
   k_coefficients<<<(d.n_slices + 127) / 128, 128, 0, st>>>(
-      d.model, d.n, d.n_slices, d.n_gen, d.n_chan, d.dt, d.eps, d.scale[0], d.scale[1], wave, p->d_coef_const,
-      p->d_gdense, p->d_gnorm, p->d_mulmax, p->d_addmax, p->qcap, p->d_coef, p->d_dcoef, p->d_qdeg, p->d_flag);
+      mp, d.n_slices, wave, p->d_coef_const, p->d_gdense, p->d_gnorm, p->d_mulmax, p->d_addmax, p->qcap,
+      p->d_coef, p->d_dcoef, p->d_qdeg, p->d_flag);
   p->launches++;
   QCUDA(cudaGetLastError());
   return QOCVL_OK;
