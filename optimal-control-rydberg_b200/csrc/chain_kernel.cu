@@ -57,7 +57,9 @@ __device__ __forceinline__ cplx group_sum(cplx v) {
   return v;
 }
 
-template <int LPG, int NV, int WMAX, int WBMAX>
+// TLOCAL = 1 parks the Taylor terms of the reverse sweep in thread-local memory (L1-cached, write-back,
+// lane-interleaved by the hardware) instead of shared memory: occupancy is then bounded by registers only.
+template <int LPG, int NV, int WMAX, int WBMAX, int TLOCAL>
 __global__ void __launch_bounds__(256) k_chain(const ChainArgs P) {
   constexpr int NVP = NV + 1;                      // the NV columns of U plus p = W psi (index NV)
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -81,7 +83,9 @@ __global__ void __launch_bounds__(256) k_chain(const ChainArgs P) {
   cplx* s_cs = carve + (size_t)grp * J; carve += (size_t)ngroups * J;          // [ngroups][J] slice coefficients
   cplx* s_dco = carve + (size_t)warp * JC; carve += (size_t)nwarps * JC;       // [nwarps][J][C]
   cplx* s_x = carve + (size_t)grp * 2 * NVP * LPG; carve += (size_t)ngroups * 2 * NVP * LPG;   // [ngroups][2][NVP][LPG]
-  cplx* s_T = carve + (size_t)grp * P.qcap * NVP * LPG; carve += (size_t)ngroups * P.qcap * NVP * LPG;  // [ngroups][qcap][NVP][LPG]
+  cplx* s_T = carve + (TLOCAL ? 0 : (size_t)grp * P.qcap * NVP * LPG);      // [ngroups][qcap][NVP][LPG] (TLOCAL=0)
+  carve += TLOCAL ? 0 : (size_t)ngroups * P.qcap * NVP * LPG;
+  cplx t_loc[TLOCAL ? QOCVL_QMAX * NVP : 1];                                // [QMAX][NVP] (TLOCAL=1)
   double* s_mul = (double*)carve + (size_t)grp * J;                            // [ngroups][J]
   int* s_urcg = (int*)((double*)carve + (size_t)ngroups * J);
   int* s_uccg = s_urcg + n_urc;
@@ -107,6 +111,13 @@ __global__ void __launch_bounds__(256) k_chain(const ChainArgs P) {
     brcol[s] = (s < P.w_w) ? P.w_row_col[s * LPG + r] : r;
     bcrow[s] = (s < P.wc_w) ? P.w_col_row[s * LPG + r] : r;
   }
+  // how many of my slots are real entries (they form a prefix): gathers of empty slots are predicated
+  // off, which saves shared-memory wavefronts -- the sweeps are bound by the shared-memory pipe
+  int rcnt = 0, ccnt = 0, brcnt = 0, bccnt = 0;
+  for (int s = 0; s < P.w_u; ++s) rcnt += s_urcg[((1 + s) * P.kc_u) * LPG + r] >= 0;
+  for (int s = 0; s < P.wc_u; ++s) ccnt += s_uccg[((1 + s) * P.kc_u) * LPG + r] >= 0;
+  for (int s = 0; s < P.w_w; ++s) brcnt += s_wrcg[(s * P.kc_w) * LPG + r] >= 0;
+  for (int s = 0; s < P.wc_w; ++s) bccnt += s_wccg[(s * P.kc_w) * LPG + r] >= 0;
   // my share of the per-sample noise table: lane r prepares coefficient j = r (+LPG)
   double mymul[(QOCVL_MAX_GEN + LPG - 1) / LPG];
   cplx myadd[(QOCVL_MAX_GEN + LPG - 1) / LPG];
@@ -167,13 +178,13 @@ __global__ void __launch_bounds__(256) k_chain(const ChainArgs P) {
     __syncwarp();
     cplx tq_b[WBMAX];
 #pragma unroll
-    for (int s = 0; s < WBMAX; ++s) tq_b[s] = xs[va * LPG + brcol[s]];
+    for (int s = 0; s < WBMAX; ++s) tq_b[s] = (s < brcnt) ? xs[va * LPG + brcol[s]] : czero;
 #pragma unroll
     for (int v = 0; v < NVP; ++v) {
       cplx acc0 = cmul(a_d, t[v]), acc1 = czero;
 #pragma unroll
       for (int s = 0; s < WMAX; ++s) {
-        const cplx xv = xs[v * LPG + rcol[s]];
+        const cplx xv = (s < rcnt) ? xs[v * LPG + rcol[s]] : czero;
         if (s & 1) acc1 = cfma(a_row[s], xv, acc1); else acc0 = cfma(a_row[s], xv, acc0);
       }
       if (v == NV) {
@@ -285,12 +296,14 @@ __global__ void __launch_bounds__(256) k_chain(const ChainArgs P) {
 #pragma unroll
     for (int v = 0; v < NVP; ++v) {
       t[v] = P.ckpt[((size_t)k * NVP + v) * gthreads + gtid];
-      s_T[v * LPG + r] = t[v];
+      if (TLOCAL) t_loc[v] = t[v]; else s_T[v * LPG + r] = t[v];
     }
     for (int j = 1; j < q; ++j) {
       step_fwd(t, c_inv[j]);
 #pragma unroll
-      for (int v = 0; v < NVP; ++v) s_T[((size_t)j * NVP + v) * LPG + r] = t[v];
+      for (int v = 0; v < NVP; ++v) {
+        if (TLOCAL) t_loc[j * NVP + v] = t[v]; else s_T[((size_t)j * NVP + v) * LPG + r] = t[v];
+      }
     }
     // ---- descending adjoint recurrence with on-the-fly contraction
     cplx tb[NVP];
@@ -307,22 +320,21 @@ __global__ void __launch_bounds__(256) k_chain(const ChainArgs P) {
 #pragma unroll
       for (int v = 0; v < NVP; ++v) xs[v * LPG + r] = tb[v];
       __syncwarp();
-      const cplx* tp = s_T + (size_t)(j - 1) * NVP * LPG + r;
 #pragma unroll
       for (int v = 0; v < NVP; ++v) {
-        const cplx tprev = cscale(tp[v * LPG], invj);
+        const cplx tprev = cscale(TLOCAL ? t_loc[(j - 1) * NVP + v] : s_T[((size_t)(j - 1) * NVP + v) * LPG + r], invj);
         cplx acc0 = cfma_conj(a_d, tb[v], czero), acc1 = czero;
         xc_d = cfma_conj(tb[v], tprev, xc_d);
 #pragma unroll
         for (int s = 0; s < WMAX; ++s) {
-          const cplx ta = xs[v * LPG + crow[s]];
+          const cplx ta = (s < ccnt) ? xs[v * LPG + crow[s]] : czero;
           if (s & 1) acc1 = cfma_conj(a_col[s], ta, acc1); else acc0 = cfma_conj(a_col[s], ta, acc0);
           xc[s] = cfma_conj(ta, tprev, xc[s]);
         }
         if (v == va) {                              // q receives B^dag tb_p; Bbar pairs tb_p with t_q
 #pragma unroll
           for (int s = 0; s < WBMAX; ++s) {
-            const cplx ta = xs[NV * LPG + bcrow[s]];
+            const cplx ta = (s < bccnt) ? xs[NV * LPG + bcrow[s]] : czero;
             acc1 = cfma_conj(b_col[s], ta, acc1);
             xcb[s] = cfma_conj(ta, tprev, xcb[s]);
           }
@@ -414,7 +426,7 @@ __global__ void k_reduce_gwave(int nparts, int MC, const double* __restrict__ pa
   gwave[i] = acc;
 }
 
-static size_t chain_smem_bytes(const qocvl_plan* p, int ngroups, int qcap) {
+static size_t chain_smem_bytes(const qocvl_plan* p, int ngroups, int qcap) {   // qcap = 0: Taylor terms not in smem
   const int J = p->d.n_gen, C = p->d.n_chan, L = p->npad, nvp = p->n_live + 1;
   const int nwarps = ngroups * L / 32;
   const size_t w_w = p->lw.nnz ? p->lw.n_row_slots : 0, wc_w = p->lw.nnz ? p->lw.n_col_slots : 0;
@@ -425,18 +437,19 @@ static size_t chain_smem_bytes(const qocvl_plan* p, int ngroups, int qcap) {
 }
 
 typedef void (*chain_fn)(const ChainArgs);
-template <int LPG, int W>
+template <int LPG, int TL>
 static chain_fn pick_nv(int nv) {
   switch (nv) {
-    case 1: return k_chain<LPG, 1, W, 2>;
-    case 2: return k_chain<LPG, 2, W, 2>;
-    case 3: return k_chain<LPG, 3, W, 2>;
-    case 4: return k_chain<LPG, 4, W, 2>;
+    case 1: return k_chain<LPG, 1, 4, 2, TL>;
+    case 2: return k_chain<LPG, 2, 4, 2, TL>;
+    case 3: return LPG == 16 ? k_chain<16, 3, 4, 2, TL> : nullptr;
+    case 4: return LPG == 16 ? k_chain<16, 4, 4, 2, TL> : nullptr;
     default: return nullptr;
   }
 }
 static chain_fn pick_kernel(const qocvl_plan* p) {
-  return p->npad == 8 ? pick_nv<8, 4>(p->n_live) : pick_nv<16, 4>(p->n_live);
+  if (p->tlocal) return p->npad == 8 ? pick_nv<8, 1>(p->n_live) : pick_nv<16, 1>(p->n_live);
+  return p->npad == 8 ? pick_nv<8, 0>(p->n_live) : pick_nv<16, 0>(p->n_live);
 }
 
 // Host-side a-priori bound on |X_k|_1: maximum of the exact slice norm over a grid of admissible
@@ -585,11 +598,18 @@ int qocvl_chain_configure(qocvl_plan* p) {
   // ---- samples per CTA: a CTA is only a container of independent groups; keep it small so the
   //      tail of the grid balances, but a multiple of the warp size
   const int gpw = 32 / L;
-  int ngroups = 2 * gpw;                                   // 2 warps
+  p->tlocal = true;                                        // Taylor terms in thread-local memory (L1)
+  if (const char* e = getenv("QOCVL_TLOCAL")) p->tlocal = atoi(e) != 0;
+  // warps per CTA: 8 with thread-local Taylor terms (one 256-thread CTA per SM keeps the L1 working
+  // set of those terms resident; measured best on cfg 3), 2 with the shared-memory ring
+  int ngroups = (p->tlocal ? 8 : 2) * gpw;
   if (const char* e = getenv("QOCVL_SPB")) ngroups = std::max(gpw, (atoi(e) + gpw - 1) / gpw * gpw);
-  while (ngroups > gpw && chain_smem_bytes(p, ngroups, p->qcap) > 100 * 1024) ngroups -= gpw;
+  ngroups = std::min(ngroups, (S + gpw - 1) / gpw * gpw);  // small ensembles: do not launch idle warps
+  const int q_smem = p->tlocal ? 0 : p->qcap;
+  while (ngroups > gpw && chain_smem_bytes(p, ngroups, q_smem) > 100 * 1024) ngroups -= gpw;
   p->spb = ngroups; p->groups = ngroups; p->threads = ngroups * L;
-  p->chain_smem = chain_smem_bytes(p, ngroups, p->qcap);
+  p->chain_smem = chain_smem_bytes(p, ngroups, q_smem);
+  if (p->tlocal) p->qcap = QOCVL_QMAX;                    // no shared-memory limit on the degree any more
   if (p->chain_smem > 227 * 1024) return QOCVL_ERR_UNSUPPORTED;
   p->blocks = (S + ngroups - 1) / ngroups;
   chain_fn fn = pick_kernel(p);

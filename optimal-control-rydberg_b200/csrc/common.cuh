@@ -136,6 +136,7 @@ struct qocvl_plan {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // chain launch geometry
   int spb = 1, groups = 0, threads = 0, blocks = 0;
+  bool tlocal = true;      // Taylor terms of the reverse sweep in thread-local (L1) instead of shared memory
   size_t chain_smem = 0;
 };
 
