@@ -222,8 +222,9 @@ def run_gpu(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    ckpt_bytes = 2.0 * M * S_local * 5 * 16 * 16          # checkpoint write + read: 5 vectors x 16 x c128
-    roofline = {"bound": "fp64", "kernel": "k_chain<16,4,2>", "achieved": achieved_tf, "peak": peak_tf,
+    nvec = plan.vectors_propagated                        # 3 for CZ: U|10>, U|11>, W|10>
+    ckpt_bytes = 2.0 * M * S_local * nvec * 16 * 16       # checkpoint write + read: nvec vectors x 16 rows x c128
+    roofline = {"bound": "fp64", "kernel": f"k_chain<16,{nvec - 1},4,2,1>", "achieved": achieved_tf, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": (achieved_tf / peak_tf) if achieved_tf and peak_tf > 0 else None,
                 "traffic": None,
                 "peak_source": "live DFMA microbenchmark in this run (qocvl_measure_fp64_peak); "

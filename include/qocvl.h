@@ -136,7 +136,10 @@ int qocvl_set_shard(qocvl_plan* plan, int global_samples);
 /* Synchronises; returns QOCVL_ERR_NORM if any evaluation since the last check saw a slice whose
  * norm bound exceeded the Taylor propagator's range (or NaN pulses), QOCVL_OK otherwise. */
 int qocvl_check(qocvl_plan* plan);
-int qocvl_last_taylor_degree(const qocvl_plan* plan); /* max Taylor degree of the last call's plan */
+int qocvl_last_taylor_degree(const qocvl_plan* plan); /* cap on the per-slice Taylor degree for this plan */
+/* Vectors the chain kernel propagates per sample after dropping inert start kets and merging
+ * symmetric ones (moving start kets + the W psi vector); 0 before the first evaluation. */
+int qocvl_vectors_propagated(const qocvl_plan* plan);
 long long qocvl_launch_count(const qocvl_plan* plan); /* kernels launched so far by this plan */
 double qocvl_flops_per_call(const qocvl_plan* plan, int with_grad); /* executed FP64 flop model */
 /* Kernel timing for the roofline report: when enabled, CUDA events bracket the chain kernel on

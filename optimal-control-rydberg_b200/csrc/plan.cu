@@ -298,6 +298,7 @@ extern "C" int qocvl_set_shard(qocvl_plan* p, int global_samples) {
 extern "C" size_t qocvl_workspace_bytes(const qocvl_plan* p) { return p ? p->bytes : 0; }
 extern "C" long long qocvl_launch_count(const qocvl_plan* p) { return p ? p->launches : 0; }
 extern "C" int qocvl_last_taylor_degree(const qocvl_plan* p) { return p ? p->qcap : 0; }
+extern "C" int qocvl_vectors_propagated(const qocvl_plan* p) { return (p && p->groups > 0) ? p->n_live + 1 : 0; }
 extern "C" const char* qocvl_last_cuda_error(void) { return g_qocvl_cuda_error.c_str(); }
 extern "C" int qocvl_version(void) { return 100; }
 

@@ -196,6 +196,10 @@ class Plan:
         return int(self._lib.qocvl_last_taylor_degree(self._h))
 
     @property
+    def vectors_propagated(self):
+        return int(self._lib.qocvl_vectors_propagated(self._h))
+
+    @property
     def workspace_bytes(self):
         return int(self._lib.qocvl_workspace_bytes(self._h))
 
