@@ -6,7 +6,7 @@
 // twin): the Van Loan slice generator is X_k = [[A_k, B_k],[0, A_k]] with
 //   A_k = dt * sum_j c_kj G^u_j,   B_k = dt * sum_j c_kj G^w_j,   c_kj = coef_kj*mul_sj + add_sj.
 // exp(X_k) is applied to vectors by a truncated Taylor series (degree q_k chosen from |X_k|_1
-// so the remainder is < 2^-60): t_0 = z, t_j = X t_{j-1}/j, z' = sum t_j.  The columns needed are
+// so the remainder is < 2^-55): t_0 = z, t_j = X t_{j-1}/j, z' = sum t_j.  The columns needed are
 //   z_v = U x_v (one per start ket that moves) and p = W psi (coupled to q = U psi through B_k).
 // Reverse sweep of the same recurrence:  tb_q = lam', tb_{j-1} = lam' + X^dag tb_j / j,
 //   Xbar += conj(tb_j) t_{j-1}^T / j, contracted on the fly with the generators' sparsity.
@@ -23,6 +23,10 @@
 #include <algorithm>
 
 __constant__ double c_inv[QOCVL_QMAX + 2];   // 1/j
+
+#ifndef QOCVL_MINB
+#define QOCVL_MINB 1   // min CTAs of 256 threads per SM the register allocation must allow (tuning knob)
+#endif
 
 struct ChainArgs {
   int n, J, M, C, S, nv, va;   // nv = moving start kets, va = which of them is psi
@@ -60,7 +64,7 @@ __device__ __forceinline__ cplx group_sum(cplx v) {
 // TLOCAL = 1 parks the Taylor terms of the reverse sweep in thread-local memory (L1-cached, write-back,
 // lane-interleaved by the hardware) instead of shared memory: occupancy is then bounded by registers only.
 template <int LPG, int NV, int WMAX, int WBMAX, int TLOCAL>
-__global__ void __launch_bounds__(256) k_chain(const ChainArgs P) {
+__global__ void __launch_bounds__(256, QOCVL_MINB) k_chain(const ChainArgs P) {
   constexpr int NVP = NV + 1;                      // the NV columns of U plus p = W psi (index NV)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -140,6 +144,16 @@ __global__ void __launch_bounds__(256) k_chain(const ChainArgs P) {
 
   cplx a_d, a_row[WMAX], b_row[WBMAX];
 
+  // exchange layout per vector: re[LPG] then im[LPG] (8-byte accesses: the 16 lanes of a sample hit 16
+  // distinct bank pairs whatever the gather pattern -> no shared-memory bank conflicts)
+  auto xput = [&](double* xs, int v, cplx val) {
+    xs[v * 2 * LPG + r] = val.x;
+    xs[v * 2 * LPG + LPG + r] = val.y;
+  };
+  auto xget = [&](const double* xs, int v, int idx) -> cplx {
+    return cmake(xs[v * 2 * LPG + idx], xs[v * 2 * LPG + LPG + idx]);
+  };
+
   // cs[j] = coef_kj * mul_sj + add_sj for slice kk, written to the group's shared slot
   auto load_coef = [&](int kk, cplx* creg) {
 #pragma unroll
@@ -172,19 +186,19 @@ __global__ void __launch_bounds__(256) k_chain(const ChainArgs P) {
   };
   // one forward Taylor step on all vectors of the sample: t <- X t / j
   auto step_fwd = [&](cplx* t, double invj) {
-    cplx* xs = s_x + ph;
+    double* xs = (double*)(s_x + ph);
 #pragma unroll
-    for (int v = 0; v < NVP; ++v) xs[v * LPG + r] = t[v];
+    for (int v = 0; v < NVP; ++v) xput(xs, v, t[v]);
     __syncwarp();
     cplx tq_b[WBMAX];
 #pragma unroll
-    for (int s = 0; s < WBMAX; ++s) tq_b[s] = (s < brcnt) ? xs[va * LPG + brcol[s]] : czero;
+    for (int s = 0; s < WBMAX; ++s) tq_b[s] = (s < brcnt) ? xget(xs, va, brcol[s]) : czero;
 #pragma unroll
     for (int v = 0; v < NVP; ++v) {
       cplx acc0 = cmul(a_d, t[v]), acc1 = czero;
 #pragma unroll
       for (int s = 0; s < WMAX; ++s) {
-        const cplx xv = (s < rcnt) ? xs[v * LPG + rcol[s]] : czero;
+        const cplx xv = (s < rcnt) ? xget(xs, v, rcol[s]) : czero;
         if (s & 1) acc1 = cfma(a_row[s], xv, acc1); else acc0 = cfma(a_row[s], xv, acc0);
       }
       if (v == NV) {
@@ -316,9 +330,9 @@ __global__ void __launch_bounds__(256) k_chain(const ChainArgs P) {
     for (int s = 0; s < WBMAX; ++s) xcb[s] = czero;
     for (int j = q; j >= 1; --j) {
       const double invj = c_inv[j];
-      cplx* xs = s_x + ph;
+      double* xs = (double*)(s_x + ph);
 #pragma unroll
-      for (int v = 0; v < NVP; ++v) xs[v * LPG + r] = tb[v];
+      for (int v = 0; v < NVP; ++v) xput(xs, v, tb[v]);
       __syncwarp();
 #pragma unroll
       for (int v = 0; v < NVP; ++v) {
@@ -327,14 +341,14 @@ __global__ void __launch_bounds__(256) k_chain(const ChainArgs P) {
         xc_d = cfma_conj(tb[v], tprev, xc_d);
 #pragma unroll
         for (int s = 0; s < WMAX; ++s) {
-          const cplx ta = (s < ccnt) ? xs[v * LPG + crow[s]] : czero;
+          const cplx ta = (s < ccnt) ? xget(xs, v, crow[s]) : czero;
           if (s & 1) acc1 = cfma_conj(a_col[s], ta, acc1); else acc0 = cfma_conj(a_col[s], ta, acc0);
           xc[s] = cfma_conj(ta, tprev, xc[s]);
         }
         if (v == va) {                              // q receives B^dag tb_p; Bbar pairs tb_p with t_q
 #pragma unroll
           for (int s = 0; s < WBMAX; ++s) {
-            const cplx ta = (s < bccnt) ? xs[NV * LPG + bcrow[s]] : czero;
+            const cplx ta = (s < bccnt) ? xget(xs, NV, bcrow[s]) : czero;
             acc1 = cfma_conj(b_col[s], ta, acc1);
             xcb[s] = cfma_conj(ta, tprev, xcb[s]);
           }

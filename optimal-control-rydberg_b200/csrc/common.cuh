@@ -38,9 +38,11 @@ __device__ __forceinline__ cplx cfma_conj(cplx a, cplx b, cplx acc) {
   return acc;
 }
 
-// Smallest q with  nrm^(q+1)/(q+1)! <= 2^-60  (same rule as oracle/vector_model.py::taylor_degree)
+// Smallest q with  nrm^(q+1)/(q+1)! <= 2^-55 = u/4 (u = fp64 unit round-off: a smaller remainder is not
+// representable next to the O(1) state; the oracle's twin rule, oracle/vector_model.py::taylor_degree,
+// uses the stricter 2^-60)
 __host__ __device__ inline int qocvl_taylor_degree(double nrm) {
-  const double tol = 8.673617379884035e-19;  // 2^-60
+  const double tol = 2.7755575615628914e-17;  // 2^-55
   double term = 1.0;
   int q = 0;
   while (q < QOCVL_QMAX) {
