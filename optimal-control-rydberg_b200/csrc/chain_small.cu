@@ -1,4 +1,4 @@
-// chain.cu -- the hot kernel: time-ordered propagation of the columns the cost reads, through
+// chain_small.cu -- the hot kernel (n <= 16): time-ordered propagation of the columns the cost reads, through
 // every slice of every noise sample, and the exact reverse sweep that yields d cost / d wave.
 //
 // Replaces (numerically, not structurally) ST:247-302 / TQ:460-567 plus the reverse pass
@@ -410,36 +410,6 @@ __global__ void __launch_bounds__(256, QOCVL_MINB) k_chain(const ChainArgs P) {
   }
 }
 
-// out3 = ensemble sums of (cost, infid, adiab) / global sample count; deterministic order.
-__global__ void k_reduce_samples(int S, double inv_samples, const double* __restrict__ sample_out,
-                                 double* __restrict__ out3) {
-  __shared__ double sh[3][256];
-  const int tid = threadIdx.x;
-  double a0 = 0, a1 = 0, a2 = 0;
-  for (int s = tid; s < S; s += 256) {
-    a0 += sample_out[(size_t)s * 3 + 0];
-    a1 += sample_out[(size_t)s * 3 + 1];
-    a2 += sample_out[(size_t)s * 3 + 2];
-  }
-  sh[0][tid] = a0; sh[1][tid] = a1; sh[2][tid] = a2;
-  __syncthreads();
-  for (int off = 128; off > 0; off >>= 1) {
-    if (tid < off) { sh[0][tid] += sh[0][tid + off]; sh[1][tid] += sh[1][tid + off]; sh[2][tid] += sh[2][tid + off]; }
-    __syncthreads();
-  }
-  if (tid < 3) out3[tid] = sh[tid][0] * inv_samples;
-}
-
-// gwave[k][c] = sum over warps of their partial sums (fixed order: deterministic)
-__global__ void k_reduce_gwave(int nparts, int MC, const double* __restrict__ partial,
-                               double* __restrict__ gwave) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= MC) return;
-  double acc = 0.0;
-  for (int b = 0; b < nparts; ++b) acc += partial[(size_t)b * MC + i];
-  gwave[i] = acc;
-}
-
 static size_t chain_smem_bytes(const qocvl_plan* p, int ngroups, int qcap) {   // qcap = 0: Taylor terms not in smem
   const int J = p->d.n_gen, C = p->d.n_chan, L = p->npad, nvp = p->n_live + 1;
   const int nwarps = ngroups * L / 32;
@@ -466,151 +436,21 @@ static chain_fn pick_kernel(const qocvl_plan* p) {
   return p->npad == 8 ? pick_nv<8, 0>(p->n_live) : pick_nv<16, 0>(p->n_live);
 }
 
-// Host-side a-priori bound on |X_k|_1: maximum of the exact slice norm over a grid of admissible
-// physical amplitudes (the regularisation keeps every amplitude in [-1, 1], ST:204-227 / TQ:355-373,
-// and the filter taps are >= 0 with sum < 1), with a 5 % margin for the grid spacing.  It only sizes
-// the shared-memory ring of Taylor terms: the device computes the per-slice degree from the actual
-// amplitudes and poisons + flags a slice that would exceed this cap (never silently wrong).
-static double apriori_norm_bound(const qocvl_plan* p, const std::vector<double>& mulmax,
-                                 const std::vector<double>& addmax) {
+// Launch geometry and per-sample buffers of the lane-per-row kernel (called by qocvl_chain_configure
+// once the live start kets and the a-priori Taylor cap are known).
+int qocvl_small_configure(qocvl_plan* p) {
   const qocvl_desc& d = p->d;
-  ModelParams mp = {d.model, d.n, d.n_gen, d.n_chan, d.dt, d.eps, d.scale[0], d.scale[1]};
-  const int J = d.n_gen, D = 2 * d.n;
-  std::vector<cplx> gdense((size_t)J * D * D, cmake(0, 0)), cc(J);
-  for (int j = 0; j < J; ++j) {
-    cc[j] = cmake(p->h_coef_const[j].real(), p->h_coef_const[j].imag());
-    for (int a = 0; a < d.n; ++a)
-      for (int b = 0; b < d.n; ++b) {
-        const std::complex<double> u = p->h_gu[((size_t)j * d.n + a) * d.n + b], w = p->h_gw[((size_t)j * d.n + a) * d.n + b];
-        gdense[((size_t)j * D + a) * D + b] = cmake(u.real(), u.imag());
-        gdense[((size_t)j * D + a) * D + d.n + b] = cmake(w.real(), w.imag());
-      }
-  }
-  cplx co[QOCVL_MAX_GEN];
-  cplx dc[QOCVL_MAX_GEN][QOCVL_MAX_CHAN];
-  double worst = 0.0;
-  const int NA = 8;   // angles
-  for (int i0 = 0; i0 < 2; ++i0)
-    for (int r1 = 1; r1 <= 2; ++r1)
-      for (int a1 = 0; a1 < NA; ++a1)
-        for (int r3 = 1; r3 <= 2; ++r3)
-          for (int a3 = 0; a3 < NA; ++a3) {
-            double w[5];
-            if (d.model == QOCVL_MODEL_TWO_QUBIT) {   // (magnitude, phase) pairs
-              w[0] = i0 ? -1.0 : 0.0;
-              w[1] = 0.5 * r1; w[2] = -1.0 + 2.0 * a1 / NA;
-              w[3] = 0.5 * r3; w[4] = -1.0 + 2.0 * a3 / NA;
-            } else {                                  // (re, im) pairs inside the unit disk
-              w[0] = i0 ? -1.0 : 1.0;
-              w[1] = 0.5 * r1 * cos(2 * PI_D * a1 / NA); w[2] = 0.5 * r1 * sin(2 * PI_D * a1 / NA);
-              w[3] = 0.5 * r3 * cos(2 * PI_D * a3 / NA); w[4] = 0.5 * r3 * sin(2 * PI_D * a3 / NA);
-            }
-            qocvl_model_coefficients(mp, w, cc.data(), co, dc);
-            worst = std::max(worst, qocvl_slice_norm(mp, co, gdense.data(), p->h_gcol.data(), mulmax.data(), addmax.data()));
-          }
-  return 1.05 * worst;
-}
-
-// Decide the launch geometry, size the a-priori Taylor cap and (re)allocate per-sample buffers.
-int qocvl_chain_configure(qocvl_plan* p) {
-  if (!p->have_gens || !p->have_cost) return QOCVL_ERR_STATE;
-  if (p->groups > 0) return QOCVL_OK;
-  const qocvl_desc& d = p->d;
-  const int L = p->npad, S = p->n_samples, J = d.n_gen, n = d.n;
-  if (p->lu.n_row_slots - 1 > 4 || p->lu.n_col_slots - 1 > 4 || p->lw.n_row_slots > 2 || p->lw.n_col_slots > 2)
+  const int L = p->npad, S = p->n_samples;
+  if (L == 0 || p->lu.n_row_slots - 1 > 4 || p->lu.n_col_slots - 1 > 4 || p->lw.n_row_slots > 2 ||
+      p->lw.n_col_slots > 2 || d.n_gen * d.n_chan > 96 || p->n_live > 4)
     return QOCVL_ERR_UNSUPPORTED;
-  if (J * d.n_chan > 96) return QOCVL_ERR_UNSUPPORTED;   // dcoef staging: 3 entries per lane
   {
     double inv[QOCVL_QMAX + 2];
     inv[0] = 0.0;
     for (int j = 1; j < QOCVL_QMAX + 2; ++j) inv[j] = 1.0 / (double)j;
     QCUDA(cudaMemcpyToSymbol(c_inv, inv, sizeof(inv)));
   }
-  // ---- start kets annihilated by every generator block never move (e.g. |00> of the CZ model):
-  //      drop them from the propagation and keep their overlap as a constant.
-  std::vector<cplx> live_s, live_t;
-  p->d_const = cmake(0, 0);
-  p->n_live = 0;
-  p->adiab_live = 0;
-  std::vector<int> weight(d.n_vec, 1);          // how many start kets this one stands for
-  std::vector<char> moves(d.n_vec, 0);
-  for (int v = 0; v < d.n_vec; ++v) {
-    bool mv = (v == d.adiab_index);
-    for (int j = 0; j < J && !mv; ++j)
-      for (int a = 0; a < n && !mv; ++a) {
-        std::complex<double> acc(0, 0);
-        for (int b = 0; b < n; ++b)
-          acc += p->h_gu[((size_t)j * n + a) * n + b] *
-                 std::complex<double>(p->h_starts[(size_t)v * L + b].x, p->h_starts[(size_t)v * L + b].y);
-        mv = std::abs(acc) > 0.0;
-      }
-    moves[v] = mv;
-  }
-  // ---- symmetry hint: verify G^u invariance, then merge start kets that are images of each other
-  if (!p->h_perm.empty()) {
-    const std::vector<int>& pm = p->h_perm;
-    for (int j = 0; j < J; ++j)
-      for (int a = 0; a < n; ++a)
-        for (int b = 0; b < n; ++b)
-          if (p->h_gu[((size_t)j * n + pm[a]) * n + pm[b]] != p->h_gu[((size_t)j * n + a) * n + b])
-            return QOCVL_ERR_ARG;
-    auto is_image = [&](const std::vector<cplx>& kets, int v, int w) {   // kets[w] == P kets[v] ?
-      for (int i = 0; i < n; ++i) {
-        const cplx x = kets[(size_t)v * L + i], y = kets[(size_t)w * L + pm[i]];
-        if (x.x != y.x || x.y != y.y) return false;
-      }
-      return true;
-    };
-    std::vector<int> order;                     // representatives: the adiabatic ket first
-    order.push_back(d.adiab_index);
-    for (int v = 0; v < d.n_vec; ++v) if (v != d.adiab_index) order.push_back(v);
-    for (size_t i = 0; i < order.size(); ++i) {
-      const int v = order[i];
-      if (!moves[v] || weight[v] == 0) continue;
-      for (size_t k2 = i + 1; k2 < order.size(); ++k2) {
-        const int w = order[k2];
-        if (!moves[w] || weight[w] == 0 || w == d.adiab_index) continue;
-        if (is_image(p->h_starts, v, w) && is_image(p->h_targets, v, w)) {
-          weight[v] += weight[w];
-          weight[w] = 0;
-        }
-      }
-    }
-  }
-  for (int v = 0; v < d.n_vec; ++v) {
-    if (moves[v] && weight[v] > 0) {
-      if (v == d.adiab_index) p->adiab_live = p->n_live;
-      for (int r = 0; r < L; ++r) {
-        live_s.push_back(p->h_starts[(size_t)v * L + r]);
-        // the weight rides on the target ket: overlap and terminal cotangent are both linear in it
-        live_t.push_back(cscale(p->h_targets[(size_t)v * L + r], (double)weight[v]));
-      }
-      p->n_live++;
-    } else if (!moves[v]) {
-      for (int r = 0; r < n; ++r) {   // y_v^dag x_v
-        const cplx y = p->h_targets[(size_t)v * L + r], x = p->h_starts[(size_t)v * L + r];
-        p->d_const.x += y.x * x.x + y.y * x.y;
-        p->d_const.y += y.x * x.y - y.y * x.x;
-      }
-    }
-  }
-  if (p->n_live > 4) return QOCVL_ERR_UNSUPPORTED;
-  if (p->d_starts) { cudaFree(p->d_starts); p->d_starts = nullptr; }
-  if (p->d_targets) { cudaFree(p->d_targets); p->d_targets = nullptr; }
-  QCUDA(cudaMalloc((void**)&p->d_starts, live_s.size() * sizeof(cplx)));
-  QCUDA(cudaMalloc((void**)&p->d_targets, live_t.size() * sizeof(cplx)));
-  QCUDA(cudaMemcpy(p->d_starts, live_s.data(), live_s.size() * sizeof(cplx), cudaMemcpyHostToDevice));
-  QCUDA(cudaMemcpy(p->d_targets, live_t.data(), live_t.size() * sizeof(cplx), cudaMemcpyHostToDevice));
-  // ---- a-priori Taylor cap (sizes the shared-memory ring of Taylor terms)
-  std::vector<double> mulmax(2 * (size_t)J), addmax(J);
-  QCUDA(cudaMemcpy(mulmax.data(), p->d_mulmax, 2 * J * sizeof(double), cudaMemcpyDeviceToHost));
-  QCUDA(cudaMemcpy(addmax.data(), p->d_addmax, J * sizeof(double), cudaMemcpyDeviceToHost));
-  const double bound = apriori_norm_bound(p, mulmax, addmax);
-  if (!(bound == bound)) return QOCVL_ERR_ARG;
-  p->qcap = qocvl_taylor_degree(bound);
-  if (const char* e = getenv("QOCVL_QCAP")) p->qcap = std::max(2, std::min(QOCVL_QMAX, atoi(e)));
-  // ---- samples per CTA: a CTA is only a container of independent groups; keep it small so the
-  //      tail of the grid balances, but a multiple of the warp size
+  // a CTA is only a container of independent groups (no barrier inside the sweeps)
   const int gpw = 32 / L;
   p->tlocal = true;                                        // Taylor terms in thread-local memory (L1)
   if (const char* e = getenv("QOCVL_TLOCAL")) p->tlocal = atoi(e) != 0;
@@ -629,22 +469,17 @@ int qocvl_chain_configure(qocvl_plan* p) {
   chain_fn fn = pick_kernel(p);
   if (!fn) return QOCVL_ERR_UNSUPPORTED;
   QCUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->chain_smem));
-  // ---- per-sample buffers
-  const size_t total_threads = (size_t)p->blocks * p->threads, total_warps = total_threads / 32;
+  const size_t total_threads = (size_t)p->blocks * p->threads;
+  p->n_parts = total_threads / 32;                         // one partial gradient per warp
   const size_t ck = (size_t)d.n_slices * (p->n_live + 1) * total_threads;
   if (p->d_ckpt) { cudaFree(p->d_ckpt); p->d_ckpt = nullptr; p->bytes -= p->ckpt_bytes; }
   QCUDA(cudaMalloc((void**)&p->d_ckpt, ck * sizeof(cplx)));
   p->ckpt_bytes = ck * sizeof(cplx);
-  if (p->d_gw_partial) { cudaFree(p->d_gw_partial); p->d_gw_partial = nullptr; p->bytes -= p->gw_partial_elems * sizeof(double); }
-  p->gw_partial_elems = total_warps * d.n_slices * d.n_chan;
-  QCUDA(cudaMalloc((void**)&p->d_gw_partial, p->gw_partial_elems * sizeof(double)));
-  p->bytes += p->ckpt_bytes + p->gw_partial_elems * sizeof(double);
+  p->bytes += p->ckpt_bytes;
   return QOCVL_OK;
 }
 
-int qocvl_launch_chain(qocvl_plan* p, bool want_grad, double* out3, double* gwave, cudaStream_t st) {
-  int rc = qocvl_chain_configure(p);
-  if (rc) return rc;
+int qocvl_small_launch(qocvl_plan* p, bool want_grad, cudaStream_t st) {
   const qocvl_desc& d = p->d;
   ChainArgs a;
   a.n = d.n; a.J = d.n_gen; a.M = d.n_slices; a.C = d.n_chan; a.S = p->n_samples;
@@ -652,7 +487,7 @@ int qocvl_launch_chain(qocvl_plan* p, bool want_grad, double* out3, double* gwav
   a.w_u = p->lu.n_row_slots - 1; a.wc_u = p->lu.n_col_slots - 1; a.kc_u = p->lu.kc;
   a.w_w = p->lw.nnz ? p->lw.n_row_slots : 0; a.wc_w = p->lw.nnz ? p->lw.n_col_slots : 0; a.kc_w = p->lw.kc;
   a.qcap = p->qcap; a.want_grad = want_grad ? 1 : 0;
-  a.nwarps_total = p->blocks * p->threads / 32;
+  a.nwarps_total = (int)p->n_parts;
   a.dt = d.dt; a.inv_duration = 1.0 / d.duration; a.w_infid = d.w_infid; a.w_adiab = d.w_adiab;
   a.inv_fid_norm = 1.0 / d.fid_norm; a.inv_samples = 1.0 / (double)p->global_samples;
   a.d_const = p->d_const;
@@ -663,16 +498,8 @@ int qocvl_launch_chain(qocvl_plan* p, bool want_grad, double* out3, double* gwav
   a.coef = p->d_coef; a.dcoef = p->d_dcoef; a.qdeg = p->d_qdeg; a.mul = p->d_mul; a.add = p->d_add;
   a.starts = p->d_starts; a.targets = p->d_targets; a.ckpt = p->d_ckpt; a.sample_out = p->d_sample_out;
   a.gw_partial = p->d_gw_partial;
-  if (p->timing) QCUDA(cudaEventRecord(p->ev0, st));
   pick_kernel(p)<<<p->blocks, p->threads, p->chain_smem, st>>>(a);
-  if (p->timing) { QCUDA(cudaEventRecord(p->ev1, st)); p->timed_once = true; }
-  k_reduce_samples<<<1, 256, 0, st>>>(p->n_samples, a.inv_samples, p->d_sample_out, out3);
-  p->launches += 2;
-  if (want_grad) {
-    const int MC = d.n_slices * d.n_chan;
-    k_reduce_gwave<<<(MC + 255) / 256, 256, 0, st>>>(a.nwarps_total, MC, p->d_gw_partial, gwave);
-    p->launches++;
-  }
+  p->launches++;
   QCUDA(cudaGetLastError());
   return QOCVL_OK;
 }

@@ -82,6 +82,24 @@ struct BlockLayout {
   cplx* cc_val = nullptr;
 };
 
+// CSR (row-owner) and CSC (column-owner) view of the union sparsity pattern of one block family,
+// with up to kc generator contributions per entry:  value_e = dt * sum_c coef[gen[e][c]] * val[e][c].
+struct CsrLayout {
+  int n = 0, nnz = 0, kc = 1;
+  // device
+  int* rowptr = nullptr;   // [n+1]
+  int* col = nullptr;      // [nnz]   column of entry e
+  int* erow = nullptr;     // [nnz]   row of entry e
+  int* colptr = nullptr;   // [n+1]
+  int* crow = nullptr;     // [nnz]   row of the i-th entry in column order
+  int* ceid = nullptr;     // [nnz]   its entry id e (row order)
+  int* egen = nullptr;     // [nnz][kc] generator id or -1
+  cplx* eval = nullptr;    // [nnz][kc]
+  // host copies (a-priori norm bound)
+  std::vector<int> h_colptr, h_ceid, h_egen;
+  std::vector<cplx> h_eval;
+};
+
 struct qocvl_plan {
   qocvl_desc d;
   int device = 0;
@@ -95,7 +113,8 @@ struct qocvl_plan {
   // generators
   std::vector<std::complex<double>> h_gu, h_gw, h_coef_const;  // host copies
   std::vector<double> h_gcol;   // [J][n] column sums of |G_u| + |G_w| (entrywise-abs norm bound)
-  BlockLayout lu, lw;
+  BlockLayout lu, lw;      // lane-per-row tables (n <= 16 only)
+  CsrLayout cu, cw;        // CSR / CSC tables (any n): big-n kernel, norm bounds
   cplx* d_gdense = nullptr;   // [J][2n][2n] dense generators (for exponentials())
   cplx* d_coef_const = nullptr;  // [J]
   double* d_gnorm = nullptr;  // [J][n] column sums of |G_u| + |G_w|
@@ -139,6 +158,10 @@ struct qocvl_plan {
   // chain launch geometry
   int spb = 1, groups = 0, threads = 0, blocks = 0;
   bool tlocal = true;      // Taylor terms of the reverse sweep in thread-local (L1) instead of shared memory
+  bool use_big = false;    // rows-strided-over-a-CTA kernel (n > 16, or forced with QOCVL_FORCE_BIG=1)
+  size_t n_parts = 0;      // number of per-warp / per-CTA partial gradients in d_gw_partial
+  cplx* d_tring = nullptr; // big kernel: Taylor-term ring [S][qcap][nvp][n] in global memory (L2-resident)
+  size_t tring_bytes = 0;
   size_t chain_smem = 0;
 };
 
@@ -148,9 +171,14 @@ int qocvl_launch_coefficients(qocvl_plan* p, const double* wave, cudaStream_t st
 int qocvl_launch_pulse_vjp(qocvl_plan* p, const double* abc, const double* gwave, double* out_grads,
                            cudaStream_t st);
 int qocvl_launch_aux(qocvl_plan* p, double* aux, cudaStream_t st);
-// chain.cu
+// chain_setup.cu (common host logic + dispatch), chain_small.cu (n <= 16), chain_big.cu (any n)
 int qocvl_chain_configure(qocvl_plan* p);
 int qocvl_launch_chain(qocvl_plan* p, bool want_grad, double* out3, double* gwave, cudaStream_t st);
+int qocvl_small_configure(qocvl_plan* p);
+int qocvl_small_launch(qocvl_plan* p, bool want_grad, cudaStream_t st);
+int qocvl_big_configure(qocvl_plan* p);
+int qocvl_big_launch(qocvl_plan* p, bool want_grad, cudaStream_t st);
+int qocvl_build_csr(qocvl_plan* p, const std::vector<std::complex<double>>& blocks, CsrLayout* out);
 // dense.cu
 int qocvl_launch_dense_expm(qocvl_plan* p, cplx* out, cudaStream_t st);
 int qocvl_launch_dense_tree(qocvl_plan* p, cplx* slices, cplx* out, cudaStream_t st);

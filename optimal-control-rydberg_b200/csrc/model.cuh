@@ -10,15 +10,27 @@
 struct ModelParams {
   int model, n, J, C;
   double dt, eps, s0, s1;   // s0, s1: the two Rabi scales of the model
+  int M;                    // number of slices (time-dependent penalty weights of the CHAIN model)
 };
 
 // co[j]: coefficient of generator j for this slice; dc[j][c] = d co[j] / d wave[c]
-__host__ __device__ inline void qocvl_model_coefficients(const ModelParams& mp, const double* w,
+__host__ __device__ inline void qocvl_model_coefficients(const ModelParams& mp, int k, const double* w,
                                                          const cplx* coef_const, cplx* co,
                                                          cplx (*dc)[QOCVL_MAX_CHAN]) {
   for (int j = 0; j < QOCVL_MAX_GEN; ++j) {
     co[j] = cmake(0, 0);
     for (int c = 0; c < QOCVL_MAX_CHAN; ++c) dc[j][c] = cmake(0, 0);
+  }
+  if (mp.model == QOCVL_MODEL_CHAIN) {
+    // Blockade (PXP) chain, SURVEY.md 8(d) cfg 4/5 (no reference counterpart): two pulse-driven
+    // Hamiltonian pieces  -i*Omega(t)/Omega_max * G0,  -i*Delta(t)/Delta_max * G1  and two penalty
+    // pieces in the top-right block with the time ramp  (1 - k/M) * G2 + (k/M) * G3.  No drift.
+    co[0] = cmake(0, -w[0]);  dc[0][0] = cmake(0, -1);
+    co[1] = cmake(0, -w[1]);  dc[1][1] = cmake(0, -1);
+    const double ramp = (double)k / (double)mp.M;
+    co[2] = cmake(1.0 - ramp, 0);
+    co[3] = cmake(ramp, 0);
+    return;
   }
   co[0] = coef_const[0];   // drift pieces: ST:254 (+1), TQ:470 (-i)
   co[1] = coef_const[1];
@@ -76,6 +88,52 @@ __host__ __device__ inline void qocvl_model_coefficients(const ModelParams& mp, 
       dc[10][c] = cconj(dc[9][c]);
     }
   }
+}
+
+// Sparse twin of qocvl_slice_norm below (same bound, O(nnz) instead of O(n^2 J)): column sums through
+// the CSC views of the two block families.  *_colptr [n+1], *_ceid [nnz] (entry id in row order),
+// *_egen / *_eval [nnz][kc].
+__host__ __device__ inline double qocvl_slice_norm_csr(const ModelParams& mp, const cplx* co,
+                                                      const int* u_colptr, const int* u_ceid, const int* u_egen,
+                                                      const cplx* u_eval, int u_kc, const int* w_colptr,
+                                                      const int* w_ceid, const int* w_egen, const cplx* w_eval,
+                                                      int w_kc, const double* gcol, const double* mulmax,
+                                                      const double* addmax) {
+  const int n = mp.n, J = mp.J;
+  double wgt[QOCVL_MAX_GEN];
+  for (int j = 0; j < J; ++j)
+    wgt[j] = sqrt(co[j].x * co[j].x + co[j].y * co[j].y) * mulmax[J + j] + addmax[j];
+  double nrm = 0.0;
+  for (int b = 0; b < n; ++b) {
+    double s = 0.0;
+    for (int j = 0; j < J; ++j) s += wgt[j] * gcol[j * n + b];
+    for (int i = u_colptr[b]; i < u_colptr[b + 1]; ++i) {
+      const int e = u_ceid[i];
+      double re = 0, im = 0;
+      for (int c = 0; c < u_kc; ++c) {
+        const int g = u_egen[e * u_kc + c];
+        if (g >= 0) {
+          const cplx v = u_eval[e * u_kc + c];
+          re += co[g].x * v.x - co[g].y * v.y; im += co[g].x * v.y + co[g].y * v.x;
+        }
+      }
+      s += sqrt(re * re + im * im);
+    }
+    for (int i = w_colptr[b]; i < w_colptr[b + 1]; ++i) {
+      const int e = w_ceid[i];
+      double re = 0, im = 0;
+      for (int c = 0; c < w_kc; ++c) {
+        const int g = w_egen[e * w_kc + c];
+        if (g >= 0) {
+          const cplx v = w_eval[e * w_kc + c];
+          re += co[g].x * v.x - co[g].y * v.y; im += co[g].x * v.y + co[g].y * v.x;
+        }
+      }
+      s += sqrt(re * re + im * im);
+    }
+    nrm = fmax(nrm, s);
+  }
+  return nrm * mp.dt;
 }
 
 // Bound on |X|_1 of the 2n x 2n slice generator over every noise sample:

@@ -124,16 +124,18 @@ extern "C" int qocvl_plan_create(qocvl_plan** out, const qocvl_desc* desc, int d
       d.adiab_index < 0 || d.adiab_index >= d.n_vec || d.n_slices != d.n_basis_pts + 2 * d.pad ||
       !(d.dt > 0) || !(d.duration > 0) || !(d.fid_norm > 0))
     return QOCVL_ERR_ARG;
-  if (d.model != QOCVL_MODEL_STATE_TRANSFER && d.model != QOCVL_MODEL_TWO_QUBIT) return QOCVL_ERR_UNSUPPORTED;
+  if (d.model != QOCVL_MODEL_STATE_TRANSFER && d.model != QOCVL_MODEL_TWO_QUBIT && d.model != QOCVL_MODEL_CHAIN)
+    return QOCVL_ERR_UNSUPPORTED;
   if ((d.model == QOCVL_MODEL_STATE_TRANSFER || d.model == QOCVL_MODEL_TWO_QUBIT) &&
       (d.n_gen != 11 || d.n_chan != 5))
     return QOCVL_ERR_ARG;
-  if (d.n > 16) return QOCVL_ERR_UNSUPPORTED;  // lane-per-row chain kernel: one vector per half warp
+  if (d.model == QOCVL_MODEL_CHAIN && (d.n_gen != 4 || d.n_chan != 2 || d.pad != 0)) return QOCVL_ERR_ARG;
+  if (d.n > 1024) return QOCVL_ERR_UNSUPPORTED;
   QCUDA(cudaSetDevice(device));
   qocvl_plan* p = new qocvl_plan();
   p->d = d;
   p->device = device;
-  p->npad = d.n <= 8 ? 8 : 16;
+  p->npad = d.n <= 8 ? 8 : (d.n <= 16 ? 16 : 0);   // 0: no lane-per-row tables, big-n kernel only
   const int M = d.n_slices, nt = d.n_basis_pts, C = d.n_chan, J = d.n_gen;
   int rc = 0;
   rc |= dev_alloc(p, &p->d_raw, (size_t)nt * C);
@@ -160,6 +162,11 @@ extern "C" int qocvl_plan_destroy(qocvl_plan* p) {
   if (!p) return QOCVL_OK;
   cudaSetDevice(p->device);
   free_layout(p->lu); free_layout(p->lw);
+  for (CsrLayout* c : {&p->cu, &p->cw}) {
+    cudaFree(c->rowptr); cudaFree(c->col); cudaFree(c->erow); cudaFree(c->colptr);
+    cudaFree(c->crow); cudaFree(c->ceid); cudaFree(c->egen); cudaFree(c->eval);
+  }
+  if (p->d_tring) cudaFree(p->d_tring);
   void* ptrs[] = {p->d_gdense, p->d_coef_const, p->d_gnorm, p->d_starts, p->d_targets, p->d_mul, p->d_add,
                   p->d_mulmax, p->d_addmax, p->d_taps, p->d_raw, p->d_reg, p->d_wave, p->d_coef, p->d_dcoef,
                   p->d_qdeg, p->d_flag, p->d_ckpt, p->d_sample_out, p->d_gw_partial, p->d_gwave, p->d_greg,
@@ -186,8 +193,12 @@ extern "C" int qocvl_set_generators(qocvl_plan* p, const double* gens_u, const d
     cc[j] = cmake(coef_const[2 * j], coef_const[2 * j + 1]);
   }
   int rc;
-  if ((rc = build_layout(p, p->h_gu, true, &p->lu))) return rc;
-  if ((rc = build_layout(p, p->h_gw, false, &p->lw))) return rc;
+  if ((rc = qocvl_build_csr(p, p->h_gu, &p->cu))) return rc;
+  if ((rc = qocvl_build_csr(p, p->h_gw, &p->cw))) return rc;
+  if (p->npad > 0) {
+    if ((rc = build_layout(p, p->h_gu, true, &p->lu))) return rc;
+    if ((rc = build_layout(p, p->h_gw, false, &p->lw))) return rc;
+  }
   // column sums of |G_u| + |G_w| per generator: |X|_1 <= dt * max_b sum_j |c_j| * gcol[j][b]
   // (entrywise triangle inequality; the 2n x 2n block matrix has column sums |A| and |B|+|A|)
   std::vector<double> gnorm((size_t)J * n, 0.0);
@@ -201,17 +212,19 @@ extern "C" int qocvl_set_generators(qocvl_plan* p, const double* gens_u, const d
   p->h_gcol = gnorm;
   if ((rc = dev_upload(p, &p->d_gnorm, gnorm))) return rc;
   if ((rc = dev_upload(p, &p->d_coef_const, cc))) return rc;
-  // dense 2n x 2n copies for exponentials()/propagate()
-  std::vector<cplx> dense((size_t)J * D * D, cmake(0, 0));
-  for (int j = 0; j < J; ++j)
-    for (int a = 0; a < n; ++a)
-      for (int b = 0; b < n; ++b) {
-        zc u = p->h_gu[((size_t)j * n + a) * n + b], w = p->h_gw[((size_t)j * n + a) * n + b];
-        dense[((size_t)j * D + a) * D + b] = cmake(u.real(), u.imag());
-        dense[((size_t)j * D + n + a) * D + n + b] = cmake(u.real(), u.imag());
-        dense[((size_t)j * D + a) * D + n + b] = cmake(w.real(), w.imag());
-      }
-  if ((rc = dev_upload(p, &p->d_gdense, dense))) return rc;
+  // dense 2n x 2n copies for exponentials()/propagate() (shared-memory dense path: 2n <= 32 only)
+  if (n <= 16) {
+    std::vector<cplx> dense((size_t)J * D * D, cmake(0, 0));
+    for (int j = 0; j < J; ++j)
+      for (int a = 0; a < n; ++a)
+        for (int b = 0; b < n; ++b) {
+          zc u = p->h_gu[((size_t)j * n + a) * n + b], w = p->h_gw[((size_t)j * n + a) * n + b];
+          dense[((size_t)j * D + a) * D + b] = cmake(u.real(), u.imag());
+          dense[((size_t)j * D + n + a) * D + n + b] = cmake(u.real(), u.imag());
+          dense[((size_t)j * D + a) * D + n + b] = cmake(w.real(), w.imag());
+        }
+    if ((rc = dev_upload(p, &p->d_gdense, dense))) return rc;
+  }
   p->have_gens = true;
   p->groups = 0;  // force re-configuration of the chain launch
   return QOCVL_OK;
@@ -235,7 +248,7 @@ extern "C" int qocvl_set_filter(qocvl_plan* p, const double* taps) {
 extern "C" int qocvl_set_cost(qocvl_plan* p, const double* starts, const double* targets) {
   if (!p || !starts || !targets) return QOCVL_ERR_ARG;
   QCUDA(cudaSetDevice(p->device));
-  const int n = p->d.n, V = p->d.n_vec, np_ = p->npad;
+  const int n = p->d.n, V = p->d.n_vec, np_ = n;   // host copies are unpadded [n_vec][n]
   std::vector<cplx> s((size_t)V * np_, cmake(0, 0)), t((size_t)V * np_, cmake(0, 0));
   for (int v = 0; v < V; ++v)
     for (int r = 0; r < n; ++r) {

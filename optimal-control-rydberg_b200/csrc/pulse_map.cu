@@ -32,7 +32,10 @@ __global__ void k_raw_reg(int model, int nt, int N, int C, const double* __restr
     raw[(size_t)t * C + ch] = acc;
   }
   double* o = reg + (size_t)t * C;
-  if (model == QOCVL_MODEL_TWO_QUBIT) {
+  if (model == QOCVL_MODEL_CHAIN) {                // Omega: 1 - exp(-x^2) in [0,1);  Delta: tanh(x) in (-1,1)
+    o[0] = 1.0 - exp(-(r[0] * r[0]));
+    o[1] = tanh(r[1]);
+  } else if (model == QOCVL_MODEL_TWO_QUBIT) {
     o[0] = 0.0 * r[0] - 1.0;                       // TQ:364
     o[1] = 1.0 - exp(-(r[1] * r[1]));              // TQ:365
     o[2] = tanh(r[2]);
@@ -78,22 +81,30 @@ __global__ void k_filter(int M, int nt, int pad, int C, int transpose, const dou
 
 // Per-slice generator coefficients and their derivatives with respect to the C real pulse values
 // of that slice (model.cuh), plus the Taylor degree for the slice from the norm bound.
+struct NormTables {   // CSC views of the two block families (plan.cu / chain_big.cu::qocvl_build_csr)
+  const int *u_colptr, *u_ceid, *u_egen; const cplx* u_eval; int u_kc;
+  const int *w_colptr, *w_ceid, *w_egen; const cplx* w_eval; int w_kc;
+  const double* gcol;
+};
+
 __global__ void k_coefficients(ModelParams mp, int M, const double* __restrict__ wave,
-                               const cplx* __restrict__ coef_const, const cplx* __restrict__ gdense,
-                               const double* __restrict__ gcol, const double* __restrict__ mulmax,
-                               const double* __restrict__ addmax, int qcap, cplx* __restrict__ coef,
-                               cplx* __restrict__ dcoef, int* __restrict__ qdeg, int* __restrict__ flag) {
+                               const cplx* __restrict__ coef_const, NormTables nt,
+                               const double* __restrict__ mulmax, const double* __restrict__ addmax, int qcap,
+                               cplx* __restrict__ coef, cplx* __restrict__ dcoef, int* __restrict__ qdeg,
+                               int* __restrict__ flag) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= M) return;
   const int J = mp.J, C = mp.C;
   cplx co[QOCVL_MAX_GEN];
   cplx dc[QOCVL_MAX_GEN][QOCVL_MAX_CHAN];
-  qocvl_model_coefficients(mp, wave + (size_t)k * C, coef_const, co, dc);
+  qocvl_model_coefficients(mp, k, wave + (size_t)k * C, coef_const, co, dc);
   for (int j = 0; j < J; ++j) {
     coef[(size_t)k * J + j] = co[j];
     for (int c = 0; c < C; ++c) dcoef[((size_t)k * J + j) * C + c] = dc[j][c];
   }
-  const double nrm = qocvl_slice_norm(mp, co, gdense, gcol, mulmax, addmax);
+  const double nrm = qocvl_slice_norm_csr(mp, co, nt.u_colptr, nt.u_ceid, nt.u_egen, nt.u_eval, nt.u_kc,
+                                          nt.w_colptr, nt.w_ceid, nt.w_egen, nt.w_eval, nt.w_kc, nt.gcol,
+                                          mulmax, addmax);
   int q = qocvl_taylor_degree(nrm);
   if (!(nrm <= QOCVL_NORM_MAX) || q > qcap) {   // also catches NaN pulses
     atomicOr(flag, 1);
@@ -120,7 +131,11 @@ __global__ void k_reg_vjp(int model, int nt, int C, const double* __restrict__ r
   const double* r = raw + (size_t)t * C;
   const double* g = greg + (size_t)t * C;
   double* o = graw + (size_t)t * C;
-  if (model == QOCVL_MODEL_TWO_QUBIT) {
+  if (model == QOCVL_MODEL_CHAIN) {
+    o[0] = g[0] * 2.0 * r[0] * exp(-(r[0] * r[0]));
+    const double th = tanh(r[1]);
+    o[1] = g[1] * (1.0 - th * th);
+  } else if (model == QOCVL_MODEL_TWO_QUBIT) {
     o[0] = 0.0;                                       // TQ:364 -- channel 0 is a constant
     o[1] = g[1] * 2.0 * r[1] * exp(-(r[1] * r[1]));
     o[3] = g[3] * 2.0 * r[3] * exp(-(r[3] * r[3]));
@@ -193,10 +208,12 @@ int qocvl_launch_pulse_forward(qocvl_plan* p, const double* abc, cudaStream_t st
 
 int qocvl_launch_coefficients(qocvl_plan* p, const double* wave, cudaStream_t st) {
   const qocvl_desc& d = p->d;
-  ModelParams mp = {d.model, d.n, d.n_gen, d.n_chan, d.dt, d.eps, d.scale[0], d.scale[1]};
-  k_coefficients<<<(d.n_slices + 127) / 128, 128, 0, st>>>(
-      mp, d.n_slices, wave, p->d_coef_const, p->d_gdense, p->d_gnorm, p->d_mulmax, p->d_addmax, p->qcap,
-      p->d_coef, p->d_dcoef, p->d_qdeg, p->d_flag);
+  ModelParams mp = {d.model, d.n, d.n_gen, d.n_chan, d.dt, d.eps, d.scale[0], d.scale[1], d.n_slices};
+  NormTables nt = {p->cu.colptr, p->cu.ceid, p->cu.egen, p->cu.eval, p->cu.kc,
+                   p->cw.colptr, p->cw.ceid, p->cw.egen, p->cw.eval, p->cw.kc, p->d_gnorm};
+  k_coefficients<<<(d.n_slices + 63) / 64, 64, 0, st>>>(mp, d.n_slices, wave, p->d_coef_const, nt, p->d_mulmax,
+                                                       p->d_addmax, p->qcap, p->d_coef, p->d_dcoef, p->d_qdeg,
+                                                       p->d_flag);
   p->launches++;
   QCUDA(cudaGetLastError());
   return QOCVL_OK;

@@ -8,4 +8,4 @@ so the package imports without matplotlib / qutip / arc.
 """
 __version__ = "0.1.0"   # reference __init__.py:5
 
-from . import state_transfer, two_qubit, single_qubit  # noqa: E402,F401
+from . import state_transfer, two_qubit, single_qubit, blockade_chain  # noqa: E402,F401

@@ -1,0 +1,112 @@
+"""GPU parity tests of (i) the rows-strided big-n chain kernel and (ii) the blockade-chain (PXP) model of
+BASELINE.json configs 4-5, against the dense torch oracle (oracle/blockade_chain.py) and against the
+lane-per-row kernel."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore", category=UserWarning)
+
+from oracle import blockade_chain as obc, ensemble, two_qubit as otq  # noqa: E402
+
+
+def rel(x, y):
+    x, y = np.asarray(x), np.asarray(y)
+    return np.abs(x - y).max() / max(np.abs(y).max(), 1e-300)
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+def make_chain(po):
+    from quantum_optimal_control.blockade_chain.propagator_vl import PropagatorVL
+    return PropagatorVL(po.input_dim, po.no_of_steps, po.delta_t, po.n_atoms, po.Rabi_max, po.Delta_max)
+
+
+class force_big:
+    """QOCVL_FORCE_BIG is read when the plan configures its launch (first evaluation)."""
+
+    def __enter__(self):
+        os.environ["QOCVL_FORCE_BIG"] = "1"
+
+    def __exit__(self, *exc):
+        os.environ.pop("QOCVL_FORCE_BIG", None)
+
+
+@pytest.mark.parametrize("n_atoms,expect_dim", [(4, 8), (5, 13), (7, 34)])
+def test_chain_cost_and_gradient_match_dense_oracle(n_atoms, expect_dim):
+    po, a, b, c = obc.chain_setup(n_atoms=n_atoms, n_gauss=6, nt=64)
+    prop = make_chain(po)
+    assert prop.dim == po.dim == expect_dim
+    ref = po.value_and_grad(a, b, c)
+    cost, (ga, gb, gc) = prop.target_and_grad(a, b, c)
+    infid, adiab = prop.metrics(a, b, c)
+    prop._plan.check()
+    assert abs(float(infid) - ref[1]) < 1e-10 and abs(float(adiab) - ref[2]) < 1e-10
+    assert abs(float(cost) - ref[0]) < 1e-10
+    for mine, r in ((ga, ref[3]), (gb, ref[4]), (gc, ref[5])):
+        assert tuple(mine.shape) == (6, 2) and rel(np_(mine), r) < 1e-8
+    wave = np_(prop.return_physical_amplitudes(a, b, c))
+    assert np.abs(wave - po.waves(*(torch.tensor(x) for x in (a, b, c))).numpy()).max() < 1e-13
+
+
+def test_chain_dim144_matches_dense_oracle():
+    """cfg 4 Hilbert space (10 atoms, blockade subspace of dimension 144) at a reduced slice count."""
+    po, a, b, c = obc.chain_setup(n_atoms=10, n_gauss=16, nt=40, seed=7)
+    prop = make_chain(po)
+    assert prop.dim == 144
+    ref = po.value_and_grad(a, b, c)
+    cost, (ga, gb, gc) = prop.target_and_grad(a, b, c)
+    prop._plan.check()
+    assert abs(float(cost) - ref[0]) < 1e-10
+    for mine, r in ((ga, ref[3]), (gb, ref[4]), (gc, ref[5])):
+        assert rel(np_(mine), r) < 1e-8
+
+
+def test_chain_ensemble_mean():
+    po, a, b, c = obc.chain_setup(n_atoms=5, n_gauss=5, nt=48)
+    rng = np.random.default_rng(3)
+    dl, rs = rng.normal(0, 2 * np.pi * 0.1e6, 3), 1 + rng.normal(0, 0.01, 3)
+    acc = None
+    for d, s in zip(dl, rs):
+        member, *_ = obc.chain_setup(n_atoms=5, n_gauss=5, nt=48, del_offset=float(d), rabi_scale=float(s))
+        vals = [np.asarray(x, float) for x in member.value_and_grad(a, b, c)]
+        acc = vals if acc is None else [x + y for x, y in zip(acc, vals)]
+    ref = [x / 3 for x in acc]
+    prop = make_chain(po)
+    prop.set_ensemble(del_total=dl, rabi_scale=rs)
+    out = np_(prop.cost_and_grad_packed(prop._pack(a, b, c)))
+    prop._plan.check()
+    assert np.abs(out[:3] - np.array(ref[:3])).max() < 1e-10
+    assert rel(out[3:13], ref[3].ravel()) < 1e-8
+
+
+def test_big_kernel_equals_lane_kernel_on_cz():
+    """Same CZ problem through both chain kernels (the big one forced): independent data layouts, same numbers."""
+    from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL
+    po, a, b, c = otq.notebook02_setup(seed=3, n_gauss=6, nt=77)
+    args = (6, 77, po.padding, 50e6, po.delta_t, 0.0, po.Vint, po.Delta_i_val, po.Rabi_i_val, po.Rabi_r_val, otq.GAMMAS_CZ)
+    dl, rs = ensemble.robust_cz_noise(5)
+    small = PropagatorVL(*args)
+    small.set_ensemble(del_total=dl, rabi_scale=rs)
+    out_small = np_(small.cost_and_grad_packed(small._pack(a, b, c))).copy()
+    with force_big():
+        big = PropagatorVL(*args)
+        big.set_ensemble(del_total=dl, rabi_scale=rs)
+        out_big = np_(big.cost_and_grad_packed(big._pack(a, b, c))).copy()
+        big._plan.check()
+    assert np.abs(out_big[:3] - out_small[:3]).max() < 1e-13
+    assert rel(out_big[3:], out_small[3:]) < 1e-10
+
+
+def test_dense_api_is_unsupported_for_large_n():
+    import qocvl
+    po, a, b, c = obc.chain_setup(n_atoms=7, n_gauss=4, nt=16)
+    prop = make_chain(po)
+    with pytest.raises(qocvl.QocvlError, match="not supported"):
+        prop.exponentials(a, b, c)
