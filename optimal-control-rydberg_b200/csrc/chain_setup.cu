@@ -186,6 +186,10 @@ int qocvl_chain_configure(qocvl_plan* p) {
   // ---- kernel-specific geometry and buffers
   int rc = p->use_big ? qocvl_big_configure(p) : qocvl_small_configure(p);
   if (rc) { p->groups = 0; return rc; }
+  // a single sample has no ensemble parallelism: cut the slice axis into concurrent chunks instead
+  p->use_tp = !p->use_big && p->n_samples == 1 && d.n_slices >= 32;
+  if (const char* e = getenv("QOCVL_TP")) p->use_tp = p->use_tp && atoi(e) != 0;
+  if (p->use_tp && (rc = qocvl_tp_configure(p))) { p->groups = 0; return rc; }
   if (p->d_gw_partial) { cudaFree(p->d_gw_partial); p->d_gw_partial = nullptr; p->bytes -= p->gw_partial_elems * sizeof(double); }
   p->gw_partial_elems = p->n_parts * d.n_slices * d.n_chan;
   QCUDA(cudaMalloc((void**)&p->d_gw_partial, p->gw_partial_elems * sizeof(double)));
@@ -198,12 +202,13 @@ int qocvl_launch_chain(qocvl_plan* p, bool want_grad, double* out3, double* gwav
   if (rc) return rc;
   const qocvl_desc& d = p->d;
   if (p->timing) QCUDA(cudaEventRecord(p->ev0, st));
-  rc = p->use_big ? qocvl_big_launch(p, want_grad, st) : qocvl_small_launch(p, want_grad, st);
+  if (p->use_tp) rc = qocvl_tp_launch(p, want_grad, gwave, st);
+  else rc = p->use_big ? qocvl_big_launch(p, want_grad, st) : qocvl_small_launch(p, want_grad, st);
   if (rc) return rc;
   if (p->timing) { QCUDA(cudaEventRecord(p->ev1, st)); p->timed_once = true; }
   k_reduce_samples<<<1, 256, 0, st>>>(p->n_samples, 1.0 / (double)p->global_samples, p->d_sample_out, out3);
   p->launches++;
-  if (want_grad) {
+  if (want_grad && !p->use_tp) {
     const int MC = d.n_slices * d.n_chan;
     k_reduce_gwave<<<(MC + 255) / 256, 256, 0, st>>>((int)p->n_parts, MC, p->d_gw_partial, gwave);
     p->launches++;

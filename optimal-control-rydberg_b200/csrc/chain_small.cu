@@ -46,9 +46,16 @@ struct ChainArgs {
   const cplx* add;     // [S][J]
   const cplx* starts;  // [nv][LPG]
   const cplx* targets; // [nv][LPG] (symmetry weight folded in)
-  cplx* ckpt;          // [M][nv+1][total threads]
+  cplx* ckpt;          // [M][nv+1][total threads]   (TP=2: [chunk_len][nv+1][total threads])
   double* sample_out;  // [S][3]
   double* gw_partial;  // [total warps][M][C]
+  // ---- time-parallel single-sample mode (TP != 0): the M slices are cut into chunks that run concurrently
+  int chunk_len, n_chunks, ncol_pad;
+  cplx* tp_uc;         // [n_chunks][n][LPG]  column i of the chunk propagator block U_c
+  cplx* tp_wc;         // [n_chunks][n][LPG]  column i of W_c
+  const cplx* tp_zc;   // [n_chunks+1][nv+1][LPG]  states at the chunk boundaries (k_tp_combine)
+  const cplx* tp_lc;   // [n_chunks+1][nv+1][LPG]  cotangents at the chunk boundaries
+  double* tp_gwave;    // [M][C]  written directly (every slice belongs to exactly one chunk)
 };
 
 template <int LPG>
@@ -63,7 +70,12 @@ __device__ __forceinline__ cplx group_sum(cplx v) {
 
 // TLOCAL = 1 parks the Taylor terms of the reverse sweep in thread-local memory (L1-cached, write-back,
 // lane-interleaved by the hardware) instead of shared memory: occupancy is then bounded by registers only.
-template <int LPG, int NV, int WMAX, int WBMAX, int TLOCAL>
+// TP = 0: one noise sample per lane group, all M slices (the ensemble hot path).
+// TP = 1: single sample, work item = (chunk, basis column): forward sweep over the chunk's slices only, result =
+//         one column of the chunk's Van Loan propagator blocks (U_c e_i, W_c e_i).
+// TP = 2: single sample, work item = chunk: forward + reverse sweep over the chunk's slices between the boundary
+//         states / cotangents that k_tp_combine stitched together from the chunk propagators.
+template <int LPG, int NV, int WMAX, int WBMAX, int TLOCAL, int TP>
 __global__ void __launch_bounds__(256, QOCVL_MINB) k_chain(const ChainArgs P) {
   constexpr int NVP = NV + 1;                      // the NV columns of U plus p = W psi (index NV)
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -72,9 +84,18 @@ __global__ void __launch_bounds__(256, QOCVL_MINB) k_chain(const ChainArgs P) {
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
   const int J = P.J, C = P.C, JC = P.J * P.C, va = P.va;
   const size_t gtid = (size_t)blockIdx.x * nthreads + tid, gthreads = (size_t)gridDim.x * nthreads;
-  const int sample = blockIdx.x * ngroups + grp;
-  const bool live = sample < P.S && r < P.n;
-  const int sm = sample < P.S ? sample : P.S - 1;
+  const int wid = blockIdx.x * ngroups + grp;        // work item of my lane group
+  const int sample = TP ? 0 : wid;
+  int chunk = 0, colid = 0;
+  if (TP == 1) { chunk = wid / P.ncol_pad; colid = wid % P.ncol_pad; }
+  if (TP == 2) chunk = wid;
+  const bool item_ok = TP == 0 ? (wid < P.S) : (TP == 1 ? (chunk < P.n_chunks && colid < P.n) : (chunk < P.n_chunks));
+  const bool live = item_ok && r < P.n;
+  const int sm = (TP == 0 && wid < P.S) ? wid : (TP ? 0 : P.S - 1);
+  // slice range of my work item; every group of the launch runs the same number of local slices (nloc)
+  const int k0 = TP ? (chunk < P.n_chunks ? chunk : P.n_chunks - 1) * P.chunk_len : 0;
+  const int k1 = TP ? (k0 + P.chunk_len < P.M ? k0 + P.chunk_len : P.M) : P.M;
+  const int nloc = TP ? P.chunk_len : P.M;
 
   // ---- shared memory carve-up -------------------------------------------------------
   const int n_urc = (P.w_u + 1) * P.kc_u * LPG, n_ucc = (P.wc_u + 1) * P.kc_u * LPG;
@@ -85,7 +106,8 @@ __global__ void __launch_bounds__(256, QOCVL_MINB) k_chain(const ChainArgs P) {
   cplx* s_wrcv = carve; carve += n_wrc;
   cplx* s_wccv = carve; carve += n_wcc;
   cplx* s_cs = carve + (size_t)grp * J; carve += (size_t)ngroups * J;          // [ngroups][J] slice coefficients
-  cplx* s_dco = carve + (size_t)warp * JC; carve += (size_t)nwarps * JC;       // [nwarps][J][C]
+  // d coef / d wave of the current slice: one table per warp (TP = 0: its groups share the slice) or per group
+  cplx* s_dco = carve + (size_t)(TP ? grp : warp) * JC; carve += (size_t)ngroups * JC;   // [ngroups][J][C]
   cplx* s_x = carve + (size_t)grp * 2 * NVP * LPG; carve += (size_t)ngroups * 2 * NVP * LPG;   // [ngroups][2][NVP][LPG]
   cplx* s_T = carve + (TLOCAL ? 0 : (size_t)grp * P.qcap * NVP * LPG);      // [ngroups][qcap][NVP][LPG] (TLOCAL=0)
   carve += TLOCAL ? 0 : (size_t)ngroups * P.qcap * NVP * LPG;
@@ -140,6 +162,11 @@ __global__ void __launch_bounds__(256, QOCVL_MINB) k_chain(const ChainArgs P) {
     ytgt[v] = live ? P.targets[v * LPG + r] : czero;
   }
   z[NV] = czero;
+  if (TP == 1) z[0] = (live && r == colid) ? cmake(1.0, 0.0) : czero;            // basis column e_colid
+  if (TP == 2) {
+#pragma unroll
+    for (int v = 0; v < NVP; ++v) z[v] = live ? P.tp_zc[((size_t)chunk * NVP + v) * LPG + r] : czero;
+  }
   int ph = 0;                                                   // exchange phase offset: 0 or NVP*LPG
 
   cplx a_d, a_row[WMAX], b_row[WBMAX];
@@ -213,21 +240,42 @@ __global__ void __launch_bounds__(256, QOCVL_MINB) k_chain(const ChainArgs P) {
   // ---- prologue: coefficients of slice 0
   {
     cplx creg[(QOCVL_MAX_GEN + LPG - 1) / LPG];
-    load_coef(0, creg);
+    load_coef(k0, creg);
     store_cs(creg);
     __syncwarp();
   }
+  // Taylor degree of local slice kk: in the time-parallel modes the groups of a warp sit on different slices,
+  // so the warp runs the largest degree any of them needs (extra terms are below the truncation tolerance)
+  auto slice_degree = [&](int k, bool act) -> int {
+    int q = act ? P.qdeg[k] : 0;
+    if (TP) {
+#pragma unroll
+      for (int off = LPG; off < 32; off <<= 1) q = max(q, __shfl_xor_sync(0xffffffffu, q, off));
+    }
+    return q;
+  };
+  auto clear_rows = [&]() {                          // a local slice beyond the end of the last chunk: X = 0
+    a_d = czero;
+#pragma unroll
+    for (int s = 0; s < WMAX; ++s) a_row[s] = czero;
+#pragma unroll
+    for (int s = 0; s < WBMAX; ++s) b_row[s] = czero;
+  };
 
   // =================================== forward sweep ===================================
-  for (int k = 0; k < P.M; ++k) {
-    const int q = P.qdeg[k];
+  for (int kk = 0; kk < nloc; ++kk) {
+    const int k = (k0 + kk < P.M) ? k0 + kk : P.M - 1;
+    const bool act = (TP == 0) || (k0 + kk < k1);
+    const int q = slice_degree(k, act);
     assemble_rows();
+    if (TP && !act) clear_rows();
     __syncwarp();                                   // everyone has read cs of slice k
     cplx creg[(QOCVL_MAX_GEN + LPG - 1) / LPG];
-    if (k + 1 < P.M) load_coef(k + 1, creg);        // in flight while this slice is propagated
-    if (P.want_grad) {
+    const bool more = kk + 1 < nloc;
+    if (more) load_coef((k0 + kk + 1 < P.M) ? k0 + kk + 1 : P.M - 1, creg);   // in flight during this slice
+    if (P.want_grad && TP != 1) {
 #pragma unroll
-      for (int v = 0; v < NVP; ++v) P.ckpt[((size_t)k * NVP + v) * gthreads + gtid] = z[v];
+      for (int v = 0; v < NVP; ++v) P.ckpt[((size_t)(TP ? kk : k) * NVP + v) * gthreads + gtid] = z[v];
     }
     cplx t[NVP];
 #pragma unroll
@@ -237,13 +285,20 @@ __global__ void __launch_bounds__(256, QOCVL_MINB) k_chain(const ChainArgs P) {
 #pragma unroll
       for (int v = 0; v < NVP; ++v) z[v] = cadd(z[v], t[v]);
     }
-    if (k + 1 < P.M) store_cs(creg);
+    if (more) store_cs(creg);
     __syncwarp();
+  }
+  if (TP == 1) {                                    // one column of the chunk propagator blocks
+    if (live) {
+      P.tp_uc[((size_t)chunk * P.n + colid) * LPG + r] = z[0];
+      P.tp_wc[((size_t)chunk * P.n + colid) * LPG + r] = z[NV];
+    }
+    return;
   }
 
   // =================================== cost ============================================
   cplx dsum = czero, qp = czero;
-  {
+  if (TP == 0) {
     cplx part = czero;
 #pragma unroll
     for (int v = 0; v < NV; ++v) part = cfma_conj(ytgt[v], z[v], part);     // sum_v conj(y_v[r]) z_v[r]
@@ -277,39 +332,54 @@ __global__ void __launch_bounds__(256, QOCVL_MINB) k_chain(const ChainArgs P) {
     }
     lam[NV] = cscale(zq, ca);                                                // -(wa/2T) q
   }
+  if (TP == 2) {                                    // cotangents at the end of my chunk (k_tp_combine)
+#pragma unroll
+    for (int v = 0; v < NVP; ++v) lam[v] = live ? P.tp_lc[((size_t)(chunk + 1) * NVP + v) * LPG + r] : czero;
+  }
 
   // ---- prologue of the reverse sweep
   __syncwarp();
   {
     cplx creg[(QOCVL_MAX_GEN + LPG - 1) / LPG];
-    load_coef(P.M - 1, creg);
+    load_coef((k0 + nloc - 1 < P.M) ? k0 + nloc - 1 : P.M - 1, creg);
     store_cs(creg);
     __syncwarp();
   }
 
   // =================================== reverse sweep ===================================
   const size_t gwarp = (size_t)blockIdx.x * nwarps + warp;
-  for (int k = P.M - 1; k >= 0; --k) {
-    const int q = P.qdeg[k];
+  for (int kk = nloc - 1; kk >= 0; --kk) {
+    const int k = (k0 + kk < P.M) ? k0 + kk : P.M - 1;
+    const bool act = (TP == 0) || (k0 + kk < k1);
+    const int q = slice_degree(k, act);
     assemble_rows();
+    if (TP && !act) clear_rows();
     // column-owner values: A[a][r] for the rows a of my column, B[a][r] for the q <- p coupling
     cplx a_col[WMAX], b_col[WBMAX];
 #pragma unroll
     for (int s = 0; s < WMAX; ++s) a_col[s] = (s < P.wc_u) ? slot_value(s_uccg, s_uccv, P.kc_u, 1 + s) : czero;
 #pragma unroll
     for (int s = 0; s < WBMAX; ++s) b_col[s] = (s < P.wc_w) ? slot_value(s_wccg, s_wccv, P.kc_w, s) : czero;
+    if (TP && !act) {                               // beyond the end of the last chunk: X^dag = 0 as well
+#pragma unroll
+      for (int s = 0; s < WMAX; ++s) a_col[s] = czero;
+#pragma unroll
+      for (int s = 0; s < WBMAX; ++s) b_col[s] = czero;
+    }
     __syncwarp();                                   // everyone has read cs of slice k
     cplx creg[(QOCVL_MAX_GEN + LPG - 1) / LPG];
-    if (k > 0) load_coef(k - 1, creg);
+    if (kk > 0) load_coef((k0 + kk - 1 < P.M) ? k0 + kk - 1 : P.M - 1, creg);
     // d coef / d wave of this slice: needed only by the contraction at the end of the slice
     cplx dreg[3];
+    if (TP == 0) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) dreg[i] = (lane + 32 * i < JC) ? P.dcoef[(size_t)k * JC + lane + 32 * i] : czero;
+      for (int i = 0; i < 3; ++i) dreg[i] = (lane + 32 * i < JC) ? P.dcoef[(size_t)k * JC + lane + 32 * i] : czero;
+    }
     // ---- recompute forward Taylor terms t_0 .. t_{q-1}
     cplx t[NVP];
 #pragma unroll
     for (int v = 0; v < NVP; ++v) {
-      t[v] = P.ckpt[((size_t)k * NVP + v) * gthreads + gtid];
+      t[v] = P.ckpt[((size_t)(TP ? kk : k) * NVP + v) * gthreads + gtid];
       if (TLOCAL) t_loc[v] = t[v]; else s_T[v * LPG + r] = t[v];
     }
     for (int j = 1; j < q; ++j) {
@@ -360,13 +430,17 @@ __global__ void __launch_bounds__(256, QOCVL_MINB) k_chain(const ChainArgs P) {
 #pragma unroll
     for (int v = 0; v < NVP; ++v) lam[v] = tb[v];
     // ---- contract Xbar with the generators: d cost / d wave[k][c]
+    if (TP == 0) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) if (lane + 32 * i < JC) s_dco[lane + 32 * i] = dreg[i];
+      for (int i = 0; i < 3; ++i) if (lane + 32 * i < JC) s_dco[lane + 32 * i] = dreg[i];
+    } else {                                        // groups of a warp sit on different slices
+      for (int i = r; i < JC; i += LPG) s_dco[i] = P.dcoef[(size_t)k * JC + i];
+    }
     __syncwarp();
     double gw[QOCVL_MAX_CHAN];
 #pragma unroll
     for (int c = 0; c < QOCVL_MAX_CHAN; ++c) gw[c] = 0.0;
-    if (live) {
+    if (live && act) {
       const double two_dt = 2.0 * P.dt;
       for (int slot = 0; slot <= P.wc_u; ++slot) {
         cplx xval = xc_d;
@@ -402,10 +476,16 @@ __global__ void __launch_bounds__(256, QOCVL_MINB) k_chain(const ChainArgs P) {
 #pragma unroll
     for (int c = 0; c < QOCVL_MAX_CHAN; ++c) {
       double vsum = gw[c];
-      for (int off = 16; off > 0; off >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, off);
-      if (lane == 0 && c < C) P.gw_partial[(gwarp * P.M + k) * C + c] = vsum;
+      if (TP == 0) {
+        for (int off = 16; off > 0; off >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, off);
+        if (lane == 0 && c < C) P.gw_partial[(gwarp * P.M + k) * C + c] = vsum;
+      } else {                                      // my chunk owns slice k: reduce over my group only
+#pragma unroll
+        for (int off = LPG / 2; off > 0; off >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, off);
+        if (r == 0 && c < C && act && item_ok) P.tp_gwave[(size_t)k * C + c] = vsum;
+      }
     }
-    if (k > 0) store_cs(creg);
+    if (kk > 0) store_cs(creg);
     __syncwarp();
   }
 }
@@ -415,25 +495,31 @@ static size_t chain_smem_bytes(const qocvl_plan* p, int ngroups, int qcap) {   /
   const int nwarps = ngroups * L / 32;
   const size_t w_w = p->lw.nnz ? p->lw.n_row_slots : 0, wc_w = p->lw.nnz ? p->lw.n_col_slots : 0;
   const size_t tab = ((size_t)(p->lu.n_row_slots + p->lu.n_col_slots) * p->lu.kc + (w_w + wc_w) * p->lw.kc) * L;
-  const size_t cplx_count = tab + (size_t)ngroups * J + (size_t)nwarps * J * C + (size_t)ngroups * 2 * nvp * L +
+  const size_t cplx_count = tab + (size_t)ngroups * J + (size_t)ngroups * J * C + (size_t)ngroups * 2 * nvp * L +
                             (size_t)ngroups * qcap * nvp * L;
   return cplx_count * sizeof(cplx) + (size_t)ngroups * J * sizeof(double) + tab * sizeof(int);
 }
 
 typedef void (*chain_fn)(const ChainArgs);
-template <int LPG, int TL>
+template <int LPG, int TL, int TP>
 static chain_fn pick_nv(int nv) {
   switch (nv) {
-    case 1: return k_chain<LPG, 1, 4, 2, TL>;
-    case 2: return k_chain<LPG, 2, 4, 2, TL>;
-    case 3: return LPG == 16 ? k_chain<16, 3, 4, 2, TL> : nullptr;
-    case 4: return LPG == 16 ? k_chain<16, 4, 4, 2, TL> : nullptr;
+    case 1: return k_chain<LPG, 1, 4, 2, TL, TP>;
+    case 2: return k_chain<LPG, 2, 4, 2, TL, TP>;
+    case 3: return LPG == 16 ? k_chain<16, 3, 4, 2, TL, TP> : nullptr;
+    case 4: return LPG == 16 ? k_chain<16, 4, 4, 2, TL, TP> : nullptr;
     default: return nullptr;
   }
 }
 static chain_fn pick_kernel(const qocvl_plan* p) {
-  if (p->tlocal) return p->npad == 8 ? pick_nv<8, 1>(p->n_live) : pick_nv<16, 1>(p->n_live);
-  return p->npad == 8 ? pick_nv<8, 0>(p->n_live) : pick_nv<16, 0>(p->n_live);
+  if (p->tlocal) return p->npad == 8 ? pick_nv<8, 1, 0>(p->n_live) : pick_nv<16, 1, 0>(p->n_live);
+  return p->npad == 8 ? pick_nv<8, 0, 0>(p->n_live) : pick_nv<16, 0, 0>(p->n_live);
+}
+static chain_fn pick_tp_sweep(const qocvl_plan* p) {
+  return p->npad == 8 ? pick_nv<8, 1, 2>(p->n_live) : pick_nv<16, 1, 2>(p->n_live);
+}
+static chain_fn pick_tp_prop(const qocvl_plan* p) {
+  return p->npad == 8 ? k_chain<8, 1, 4, 2, 1, 1> : k_chain<16, 1, 4, 2, 1, 1>;
 }
 
 // Launch geometry and per-sample buffers of the lane-per-row kernel (called by qocvl_chain_configure
@@ -463,6 +549,7 @@ int qocvl_small_configure(qocvl_plan* p) {
   while (ngroups > gpw && chain_smem_bytes(p, ngroups, q_smem) > 100 * 1024) ngroups -= gpw;
   p->spb = ngroups; p->groups = ngroups; p->threads = ngroups * L;
   p->chain_smem = chain_smem_bytes(p, ngroups, q_smem);
+  p->qcap_apriori = p->qcap;
   if (p->tlocal) p->qcap = QOCVL_QMAX;                    // no shared-memory limit on the degree any more
   if (p->chain_smem > 227 * 1024) return QOCVL_ERR_UNSUPPORTED;
   p->blocks = (S + ngroups - 1) / ngroups;
@@ -479,9 +566,199 @@ int qocvl_small_configure(qocvl_plan* p) {
   return QOCVL_OK;
 }
 
+static void fill_common_args(qocvl_plan* p, ChainArgs& a, bool want_grad);
+
 int qocvl_small_launch(qocvl_plan* p, bool want_grad, cudaStream_t st) {
-  const qocvl_desc& d = p->d;
   ChainArgs a;
+  fill_common_args(p, a, want_grad);
+  pick_kernel(p)<<<p->blocks, p->threads, p->chain_smem, st>>>(a);
+  p->launches++;
+  QCUDA(cudaGetLastError());
+  return QOCVL_OK;
+}
+
+// ===================================================================================================
+// Time-parallel single-sample path (cfg 1 / cfg 2: the reference's own notebook workloads).
+// A single sample exposes no ensemble parallelism and the slices are sequentially dependent, so the
+// plain sweep would run on one warp.  Instead:
+//   A. k_chain<.., TP=1>: every (chunk, basis column) pair propagates one column through its chunk:
+//      the chunk's Van Loan propagator blocks U_c, W_c (n_chunks * n independent work items);
+//   B. k_tp_combine: one small CTA walks the chunks once forward (boundary states, cost, terminal
+//      cotangents) and once backward (boundary cotangents) with dense n x n mat-vecs;
+//   C. k_chain<.., TP=2>: every chunk runs the usual forward + reverse sweep between its boundaries.
+// Sequential depth drops from M slices to ~2 chunk_len slices + n_chunks small mat-vecs.
+// ===================================================================================================
+struct CombineArgs {
+  int n, nv, va, n_chunks, lpg;
+  double inv_duration, w_infid, w_adiab, inv_fid_norm, inv_samples;
+  cplx d_const;
+  const cplx *uc, *wc, *starts, *targets;
+  cplx *zc, *lc;
+  double* sample_out;
+  int want_grad;
+};
+
+__global__ void __launch_bounds__(128) k_tp_combine(const CombineArgs A) {
+  // Sequential over the chunks, so latency is everything: the propagator blocks of the NEXT chunk are
+  // staged global -> registers -> shared memory while the current chunk (already in shared memory) is applied.
+  __shared__ cplx z[5][16], y[5][16];
+  __shared__ cplx s_u[2][256], s_w[2][256];       // [buffer][column i][row r] of U_c / W_c  (n, L <= 16)
+  __shared__ cplx s_d;
+  const int tid = threadIdx.x, L = A.lpg, n = A.n, NV = A.nv, NVP = A.nv + 1, va = A.va;
+  const int v = tid / L, r = tid % L, nL = n * L;
+  const bool mine = v < NVP;
+  const cplx czero = cmake(0, 0);
+  cplx stage[4];                                   // 2 * nL <= 512 elements over 128 threads
+  auto fetch = [&](int c) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + 128 * i;                 // element of [U_c | W_c]
+      stage[i] = e < nL ? A.uc[(size_t)c * nL + e] : (e - nL < nL && e >= nL ? A.wc[(size_t)c * nL + e - nL] : czero);
+    }
+  };
+  auto commit = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + 128 * i;
+      if (e < nL) s_u[buf][e] = stage[i];
+      else if (e - nL < nL) s_w[buf][e - nL] = stage[i];
+    }
+  };
+  if (mine) {
+    z[v][r] = (v < NV && r < n) ? A.starts[v * L + r] : czero;
+    A.zc[(size_t)v * L + r] = z[v][r];
+  }
+  fetch(0);
+  commit(0);
+  __syncthreads();
+  for (int c = 0; c < A.n_chunks; ++c) {
+    const int buf = c & 1;
+    if (c + 1 < A.n_chunks) fetch(c + 1);
+    cplx acc0 = czero, acc1 = czero;
+    if (mine && r < n) {
+      for (int i = 0; i + 1 < n; i += 2) {
+        acc0 = cfma(s_u[buf][i * L + r], z[v][i], acc0);
+        acc1 = cfma(s_u[buf][(i + 1) * L + r], z[v][i + 1], acc1);
+      }
+      if (n & 1) acc0 = cfma(s_u[buf][(n - 1) * L + r], z[v][n - 1], acc0);
+      if (v == NV) {
+        for (int i = 0; i + 1 < n; i += 2) {
+          acc0 = cfma(s_w[buf][i * L + r], z[va][i], acc0);
+          acc1 = cfma(s_w[buf][(i + 1) * L + r], z[va][i + 1], acc1);
+        }
+        if (n & 1) acc0 = cfma(s_w[buf][(n - 1) * L + r], z[va][n - 1], acc0);
+      }
+    }
+    const cplx acc = cadd(acc0, acc1);
+    __syncthreads();                               // everyone has read z and buffer `buf`
+    if (mine) {
+      z[v][r] = acc;
+      A.zc[((size_t)(c + 1) * NVP + v) * L + r] = acc;
+    }
+    if (c + 1 < A.n_chunks) commit(buf ^ 1);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    cplx d = A.d_const, qp = czero;
+    for (int vv = 0; vv < NV; ++vv)
+      for (int i = 0; i < n; ++i) d = cfma_conj(A.targets[vv * L + i], z[vv][i], d);
+    for (int i = 0; i < n; ++i) qp = cfma_conj(z[va][i], z[NV][i], qp);
+    const double infid = 1.0 - (d.x * d.x + d.y * d.y) * A.inv_fid_norm;
+    const double adiab = 1.0 - qp.x * A.inv_duration;
+    A.sample_out[0] = A.w_infid * infid + A.w_adiab * adiab;
+    A.sample_out[1] = infid;
+    A.sample_out[2] = adiab;
+    s_d = d;
+  }
+  __syncthreads();
+  if (!A.want_grad) return;
+  // terminal cotangents (same expressions as the TP = 0 kernel)
+  if (mine) {
+    const double ca = -0.5 * A.w_adiab * A.inv_duration * A.inv_samples;
+    cplx lam = czero;
+    if (r < n) {
+      if (v == NV) lam = cscale(z[va][r], ca);
+      else {
+        lam = cscale(cmul(s_d, A.targets[v * L + r]), -A.w_infid * A.inv_fid_norm * A.inv_samples);
+        if (v == va) lam = cadd(lam, cscale(z[NV][r], ca));
+      }
+    }
+    y[v][r] = lam;
+    A.lc[((size_t)A.n_chunks * NVP + v) * L + r] = lam;
+  }
+  // backward walk: lam_c = P_c^dag lam_{c+1}; thread (v, r) uses COLUMN r of U_c (and of W_c for the q vector);
+  // the last chunk's blocks are still in buffer (n_chunks-1)&1
+  __syncthreads();
+  for (int c = A.n_chunks - 1; c >= 0; --c) {
+    const int buf = c & 1;
+    if (c > 0) fetch(c - 1);
+    cplx acc0 = czero, acc1 = czero;
+    if (mine && r < n) {
+      for (int a = 0; a + 1 < n; a += 2) {
+        acc0 = cfma_conj(s_u[buf][r * L + a], y[v][a], acc0);
+        acc1 = cfma_conj(s_u[buf][r * L + a + 1], y[v][a + 1], acc1);
+      }
+      if (n & 1) acc0 = cfma_conj(s_u[buf][r * L + n - 1], y[v][n - 1], acc0);
+      if (v == va) {
+        for (int a = 0; a + 1 < n; a += 2) {
+          acc0 = cfma_conj(s_w[buf][r * L + a], y[NV][a], acc0);
+          acc1 = cfma_conj(s_w[buf][r * L + a + 1], y[NV][a + 1], acc1);
+        }
+        if (n & 1) acc0 = cfma_conj(s_w[buf][r * L + n - 1], y[NV][n - 1], acc0);
+      }
+    }
+    const cplx acc = cadd(acc0, acc1);
+    __syncthreads();
+    if (mine) {
+      y[v][r] = acc;
+      A.lc[((size_t)c * NVP + v) * L + r] = acc;
+    }
+    if (c > 0) commit(buf ^ 1);
+    __syncthreads();
+  }
+}
+
+int qocvl_tp_configure(qocvl_plan* p) {
+  const qocvl_desc& d = p->d;
+  const int L = p->npad, n = d.n, M = d.n_slices, nvp = p->n_live + 1;
+  // depth ~ chunk_len * 4 q Taylor steps (A + C) + 2 * n_chunks combine steps: balance the two
+  int lc = (int)lround(sqrt(2.0 * (double)M / (double)std::max(4, p->qcap_apriori)));   // measured optimum on cfg 2
+  if (const char* e = getenv("QOCVL_TP_CHUNK")) lc = atoi(e);
+  lc = std::max(2, std::min(lc, M));
+  p->tp_chunk = lc;
+  p->tp_nchunks = (M + lc - 1) / lc;
+  const int gpw = 32 / L;
+  p->tp_ncol_pad = (n + gpw - 1) / gpw * gpw;      // columns of one chunk fill whole warps
+  const size_t blk = (size_t)p->tp_nchunks * n * L, bnd = (size_t)(p->tp_nchunks + 1) * nvp * L;
+  for (cplx** q : {&p->d_tp_uc, &p->d_tp_wc, &p->d_tp_zc, &p->d_tp_lc}) if (*q) { cudaFree(*q); *q = nullptr; }
+  QCUDA(cudaMalloc((void**)&p->d_tp_uc, blk * sizeof(cplx)));
+  QCUDA(cudaMalloc((void**)&p->d_tp_wc, blk * sizeof(cplx)));
+  QCUDA(cudaMalloc((void**)&p->d_tp_zc, bnd * sizeof(cplx)));
+  QCUDA(cudaMalloc((void**)&p->d_tp_lc, bnd * sizeof(cplx)));
+  // launch geometry: 4 warps per CTA for both sweeps
+  const int ngroups = 4 * gpw;
+  p->tp_threads = ngroups * L;
+  p->tp_blocks_a = (p->tp_nchunks * p->tp_ncol_pad + ngroups - 1) / ngroups;
+  p->tp_blocks_c = (p->tp_nchunks + ngroups - 1) / ngroups;
+  qocvl_plan tmp_geom = *p;                         // smem sizes depend on nv: A uses nv = 1, C uses n_live
+  tmp_geom.n_live = 1;
+  p->tp_smem_a = chain_smem_bytes(&tmp_geom, ngroups, 0);
+  p->tp_smem_c = chain_smem_bytes(p, ngroups, 0);
+  chain_fn fa = pick_tp_prop(p), fc = pick_tp_sweep(p);
+  if (!fa || !fc) return QOCVL_ERR_UNSUPPORTED;
+  QCUDA(cudaFuncSetAttribute(fa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tp_smem_a));
+  QCUDA(cudaFuncSetAttribute(fc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tp_smem_c));
+  const size_t ck = (size_t)lc * nvp * p->tp_blocks_c * p->tp_threads;
+  if (p->d_ckpt) { cudaFree(p->d_ckpt); p->d_ckpt = nullptr; p->bytes -= p->ckpt_bytes; }
+  QCUDA(cudaMalloc((void**)&p->d_ckpt, ck * sizeof(cplx)));
+  p->ckpt_bytes = ck * sizeof(cplx);
+  p->bytes += p->ckpt_bytes + (2 * blk + 2 * bnd) * sizeof(cplx);
+  p->n_parts = 1;
+  return QOCVL_OK;
+}
+
+static void fill_common_args(qocvl_plan* p, ChainArgs& a, bool want_grad) {
+  const qocvl_desc& d = p->d;
   a.n = d.n; a.J = d.n_gen; a.M = d.n_slices; a.C = d.n_chan; a.S = p->n_samples;
   a.nv = p->n_live; a.va = p->adiab_live;
   a.w_u = p->lu.n_row_slots - 1; a.wc_u = p->lu.n_col_slots - 1; a.kc_u = p->lu.kc;
@@ -498,8 +775,32 @@ int qocvl_small_launch(qocvl_plan* p, bool want_grad, cudaStream_t st) {
   a.coef = p->d_coef; a.dcoef = p->d_dcoef; a.qdeg = p->d_qdeg; a.mul = p->d_mul; a.add = p->d_add;
   a.starts = p->d_starts; a.targets = p->d_targets; a.ckpt = p->d_ckpt; a.sample_out = p->d_sample_out;
   a.gw_partial = p->d_gw_partial;
-  pick_kernel(p)<<<p->blocks, p->threads, p->chain_smem, st>>>(a);
-  p->launches++;
+  a.chunk_len = p->tp_chunk; a.n_chunks = p->tp_nchunks; a.ncol_pad = p->tp_ncol_pad;
+  a.tp_uc = p->d_tp_uc; a.tp_wc = p->d_tp_wc; a.tp_zc = p->d_tp_zc; a.tp_lc = p->d_tp_lc;
+  a.tp_gwave = nullptr;
+}
+
+// gwave: [M][C] device buffer that receives d cost / d wave directly (no partial reduction needed)
+int qocvl_tp_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t st) {
+  const qocvl_desc& d = p->d;
+  ChainArgs a;
+  fill_common_args(p, a, want_grad);
+  ChainArgs pa = a;                                 // A: one column per work item, q = the column, p = W column
+  pa.nv = 1; pa.va = 0; pa.want_grad = 0;
+  pick_tp_prop(p)<<<p->tp_blocks_a, p->tp_threads, p->tp_smem_a, st>>>(pa);
+  CombineArgs c;
+  c.n = d.n; c.nv = p->n_live; c.va = p->adiab_live; c.n_chunks = p->tp_nchunks; c.lpg = p->npad;
+  c.inv_duration = a.inv_duration; c.w_infid = a.w_infid; c.w_adiab = a.w_adiab; c.inv_fid_norm = a.inv_fid_norm;
+  c.inv_samples = a.inv_samples; c.d_const = a.d_const;
+  c.uc = p->d_tp_uc; c.wc = p->d_tp_wc; c.starts = p->d_starts; c.targets = p->d_targets;
+  c.zc = p->d_tp_zc; c.lc = p->d_tp_lc; c.sample_out = p->d_sample_out; c.want_grad = want_grad ? 1 : 0;
+  k_tp_combine<<<1, 128, 0, st>>>(c);
+  p->launches += 2;
+  if (want_grad) {
+    a.tp_gwave = gwave;
+    pick_tp_sweep(p)<<<p->tp_blocks_c, p->tp_threads, p->tp_smem_c, st>>>(a);
+    p->launches++;
+  }
   QCUDA(cudaGetLastError());
   return QOCVL_OK;
 }

@@ -110,6 +110,7 @@ struct qocvl_plan {
   long long launches = 0;
   size_t bytes = 0;
   int qcap = 0;            // a-priori Taylor-degree cap used to size shared memory
+  int qcap_apriori = 0;    // the same before the thread-local ring lifts it to QOCVL_QMAX
   // generators
   std::vector<std::complex<double>> h_gu, h_gw, h_coef_const;  // host copies
   std::vector<double> h_gcol;   // [J][n] column sums of |G_u| + |G_w| (entrywise-abs norm bound)
@@ -159,6 +160,11 @@ struct qocvl_plan {
   int spb = 1, groups = 0, threads = 0, blocks = 0;
   bool tlocal = true;      // Taylor terms of the reverse sweep in thread-local (L1) instead of shared memory
   bool use_big = false;    // rows-strided-over-a-CTA kernel (n > 16, or forced with QOCVL_FORCE_BIG=1)
+  // time-parallel single-sample path (chain_small.cu): chunk propagators -> combine -> per-chunk sweeps
+  bool use_tp = false;
+  int tp_chunk = 0, tp_nchunks = 0, tp_ncol_pad = 0, tp_threads = 0, tp_blocks_a = 0, tp_blocks_c = 0;
+  size_t tp_smem_a = 0, tp_smem_c = 0;
+  cplx *d_tp_uc = nullptr, *d_tp_wc = nullptr, *d_tp_zc = nullptr, *d_tp_lc = nullptr;
   size_t n_parts = 0;      // number of per-warp / per-CTA partial gradients in d_gw_partial
   cplx* d_tring = nullptr; // big kernel: Taylor-term ring [S][qcap][nvp][n] in global memory (L2-resident)
   size_t tring_bytes = 0;
@@ -176,6 +182,8 @@ int qocvl_chain_configure(qocvl_plan* p);
 int qocvl_launch_chain(qocvl_plan* p, bool want_grad, double* out3, double* gwave, cudaStream_t st);
 int qocvl_small_configure(qocvl_plan* p);
 int qocvl_small_launch(qocvl_plan* p, bool want_grad, cudaStream_t st);
+int qocvl_tp_configure(qocvl_plan* p);
+int qocvl_tp_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t st);
 int qocvl_big_configure(qocvl_plan* p);
 int qocvl_big_launch(qocvl_plan* p, bool want_grad, cudaStream_t st);
 int qocvl_build_csr(qocvl_plan* p, const std::vector<std::complex<double>>& blocks, CsrLayout* out);

@@ -110,3 +110,51 @@ def test_dense_api_is_unsupported_for_large_n():
     prop = make_chain(po)
     with pytest.raises(qocvl.QocvlError, match="not supported"):
         prop.exponentials(a, b, c)
+
+
+class env:
+    def __init__(self, **kv):
+        self.kv = kv
+
+    def __enter__(self):
+        os.environ.update({k: str(v) for k, v in self.kv.items()})
+
+    def __exit__(self, *exc):
+        for k in self.kv:
+            os.environ.pop(k, None)
+
+
+@pytest.mark.parametrize("chunk", [None, 2, 7, 64])
+def test_time_parallel_path_equals_sequential_sweep(chunk):
+    """Single-sample evaluations cut the slice axis into concurrent chunks (chunk propagators -> combine ->
+    per-chunk sweeps); the result must equal the plain sequential sweep (QOCVL_TP=0) for any chunk length,
+    including one that does not divide M (M = 81) and one larger than M/2."""
+    from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL
+    po, a, b, c = otq.notebook02_setup(seed=3, n_gauss=6, nt=77)
+    args = (6, 77, po.padding, 50e6, po.delta_t, 0.0, po.Vint, po.Delta_i_val, po.Rabi_i_val, po.Rabi_r_val, otq.GAMMAS_CZ)
+    with env(QOCVL_TP=0):
+        seq = PropagatorVL(*args)
+        out_seq = np_(seq.cost_and_grad_packed(seq._pack(a, b, c))).copy()
+        cost_seq = float(seq.target(a, b, c))
+    kv = {} if chunk is None else {"QOCVL_TP_CHUNK": chunk}
+    with env(**kv):
+        tp = PropagatorVL(*args)
+        out_tp = np_(tp.cost_and_grad_packed(tp._pack(a, b, c))).copy()
+        cost_tp = float(tp.target(a, b, c))           # cost-only path (propagators + combine)
+        tp._plan.check()
+    assert np.abs(out_tp[:3] - out_seq[:3]).max() < 1e-13 and abs(cost_tp - cost_seq) < 1e-13
+    assert rel(out_tp[3:], out_seq[3:]) < 1e-10
+
+
+def test_time_parallel_state_transfer():
+    from oracle import state_transfer as ost
+    from quantum_optimal_control.state_transfer.propagator_vl import PropagatorVL
+    po, a, b, c = ost.notebook01_setup()
+    args = (po.input_dim, po.no_of_steps, po.delta_t, po.del_total, po.Delta_1, po.Rabi_1, po.Rabi_2, po.Gamma_r, po.Gamma_i)
+    with env(QOCVL_TP=0):
+        seq = PropagatorVL(*args)
+        out_seq = np_(seq.cost_and_grad_packed(seq._pack(a, b, c))).copy()
+    tp = PropagatorVL(*args)
+    out_tp = np_(tp.cost_and_grad_packed(tp._pack(a, b, c))).copy()
+    assert np.abs(out_tp[:3] - out_seq[:3]).max() < 1e-13
+    assert rel(out_tp[3:], out_seq[3:]) < 1e-9
