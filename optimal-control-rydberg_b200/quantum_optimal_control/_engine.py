@@ -197,6 +197,50 @@ class EngineBase:
             dist.all_reduce(out, op=dist.ReduceOp.SUM)
         return out
 
+    # -- the optimiser loop of the notebooks, kept on the device ------------------------------------------
+    def optimize(self, ctrl_a, ctrl_b, ctrl_c, num_iters, lr, masks=None, use_graph=True):
+        """``num_iters`` plain gradient-descent steps (notebook 01 cell 9, notebook 02 cell 13:
+        ``ctrl -= lr * grad`` with the cost recorded BEFORE each update, TQ:580-600) without a host
+        synchronisation per step.  ``masks`` = optional (mask_a, mask_b, mask_c) multiplied into the
+        gradients (notebook 04 cells 5, 12: frozen columns).  One step is captured in a CUDA graph and
+        replayed; the cost history stays on the device.
+
+        Returns (cost_history [num_iters] CUDA tensor, a, b, c) with a, b, c CUDA tensors [input_dim, C]."""
+        dev = self.device
+        abc = self._pack(ctrl_a, ctrl_b, ctrl_c).clone()
+        n = 3 * self.input_dim * self.num_ctrls
+        out = torch.empty(3 + n, dtype=torch.float64, device=dev)
+        hist = torch.zeros(max(1, num_iters), dtype=torch.float64, device=dev)
+        step_idx = torch.zeros(1, dtype=torch.long, device=dev)
+        if masks is None:
+            scale = torch.full((3, self.input_dim, self.num_ctrls), float(lr), dtype=torch.float64, device=dev)
+        else:
+            scale = float(lr) * torch.stack([torch.as_tensor(np.asarray(m, dtype=np.float64)) for m in masks]).to(dev)
+            scale = scale.expand(3, self.input_dim, self.num_ctrls).contiguous()
+
+        def one_step():
+            self.cost_and_grad_packed(abc, out)
+            hist.index_copy_(0, step_idx, out[0:1])
+            abc.sub_(scale * out[3:].view_as(abc))
+            step_idx.add_(1)
+
+        graph_ok = use_graph and self._world is None and num_iters > 2
+        if graph_ok:
+            self.cost_and_grad_packed(abc, out)             # configure the plan outside of the capture
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    one_step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            for _ in range(num_iters):
+                graph.replay()
+        else:
+            for _ in range(num_iters):
+                one_step()
+        return hist[:num_iters], abc[0], abc[1], abc[2]
+
 
 def shard_bounds(n_items, world, rank):
     """Contiguous block partition of n_items over world ranks (first ranks get the remainder)."""

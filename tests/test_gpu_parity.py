@@ -294,3 +294,33 @@ def test_full_size_properties_cfg3_slice():
     assert np.abs(0.5 * (halves[0][:3] + halves[1][:3]) - full[:3]).max() < 1e-13
     assert rel(0.5 * (halves[0][3:] + halves[1][3:]), full[3:]) < 1e-11
     assert 0.0 <= full[1] <= 1.0
+
+
+def test_device_side_optimiser_loop_matches_manual_steps():
+    """prop.optimize (CUDA-graph replay, no host sync per step) == the notebooks' Python loop over
+    single_optimization_step, including notebook 04's frozen-column masks."""
+    from quantum_optimal_control.two_qubit.propagator_vl import single_optimization_step
+    po, a, b, c = otq.notebook02_setup(seed=3, n_gauss=6, nt=77)
+    prop = make_tq(po)
+    mask = np.ones((6, 5))
+    mask[:, 2] = 0.0                                             # freeze the Rabi_i phase channel
+    masks = (mask, mask, np.ones((6, 5)))
+    steps, lr = 6, 2e-3
+    ta, tb, tc = (torch.tensor(x, device="cuda") for x in (a, b, c))
+    manual = []
+    for _ in range(steps):
+        cost, (ga, gb, gc) = prop.target_and_grad(ta, tb, tc)
+        manual.append(float(cost))
+        ta = ta - lr * torch.tensor(mask, device="cuda") * ga
+        tb = tb - lr * torch.tensor(mask, device="cuda") * gb
+        tc = tc - lr * gc
+    for use_graph in (True, False):
+        hist, a2, b2, c2 = prop.optimize(a, b, c, steps, lr, masks=masks, use_graph=use_graph)
+        assert np.abs(np_(hist) - np.array(manual)).max() < 1e-13
+        assert np.abs(np_(a2) - np_(ta)).max() < 1e-13 and np.abs(np_(c2) - np_(tc)).max() < 1e-13
+        assert np.array_equal(np_(a2)[:, 2], a[:, 2])            # frozen column untouched
+    assert manual[-1] < manual[0]
+    # unmasked loop == single_optimization_step
+    cost0, a1, b1, c1 = single_optimization_step(prop, a, b, c, lr=lr)
+    hist, a3, b3, c3 = prop.optimize(a, b, c, 3, lr)
+    assert abs(float(hist[0]) - float(cost0)) < 1e-14
