@@ -25,7 +25,7 @@
 __constant__ double c_inv[QOCVL_QMAX + 2];   // 1/j
 
 #ifndef QOCVL_MINB
-#define QOCVL_MINB 1   // min CTAs of 256 threads per SM the register allocation must allow (tuning knob)
+#define QOCVL_MINB 1   // min CTAs of 512 threads per SM the register allocation must allow (tuning knob)
 #endif
 
 struct ChainArgs {
@@ -76,7 +76,7 @@ __device__ __forceinline__ cplx group_sum(cplx v) {
 // TP = 2: single sample, work item = chunk: forward + reverse sweep over the chunk's slices between the boundary
 //         states / cotangents that k_tp_combine stitched together from the chunk propagators.
 template <int LPG, int NV, int WMAX, int WBMAX, int TLOCAL, int TP>
-__global__ void __launch_bounds__(256, QOCVL_MINB) k_chain(const ChainArgs P) {
+__global__ void __launch_bounds__(512, QOCVL_MINB) k_chain(const ChainArgs P) {
   constexpr int NVP = NV + 1;                      // the NV columns of U plus p = W psi (index NV)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -540,9 +540,25 @@ int qocvl_small_configure(qocvl_plan* p) {
   const int gpw = 32 / L;
   p->tlocal = true;                                        // Taylor terms in thread-local memory (L1)
   if (const char* e = getenv("QOCVL_TLOCAL")) p->tlocal = atoi(e) != 0;
-  // warps per CTA: 8 with thread-local Taylor terms (one 256-thread CTA per SM keeps the L1 working
-  // set of those terms resident; measured best on cfg 3), 2 with the shared-memory ring
-  int ngroups = (p->tlocal ? 8 : 2) * gpw;
+  // Samples per CTA.  The kernel is compiled for <= 128 registers (512 threads / SM); beyond ~8 resident
+  // warps an SM's throughput is flat, so the makespan is the number of samples the busiest SM has to process.
+  // Pick the CTA size that minimises it (wave quantisation was worth 20 % on cfg 3: 4096 samples / 148 SMs ->
+  // 28 samples per CTA = 147 CTAs = one even wave, instead of 256 CTAs of 16 = 1.73 waves).
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+  const int gmax = 512 / L / gpw * gpw;
+  int ngroups = gpw;
+  {
+    long best_load = -1;
+    for (int g = gpw; g <= gmax; g += gpw) {
+      const long n_ctas = (S + g - 1) / g;
+      const long load = (n_ctas + sms - 1) / sms * g;
+      if (best_load < 0 || load < best_load || (load == best_load && g <= 32 && g > ngroups)) {
+        best_load = load; ngroups = g;
+      }
+    }
+  }
+  if (!p->tlocal) ngroups = std::min(ngroups, 2 * gpw);
   if (const char* e = getenv("QOCVL_SPB")) ngroups = std::max(gpw, (atoi(e) + gpw - 1) / gpw * gpw);
   ngroups = std::min(ngroups, (S + gpw - 1) / gpw * gpw);  // small ensembles: do not launch idle warps
   const int q_smem = p->tlocal ? 0 : p->qcap;
