@@ -36,8 +36,8 @@ def workload_config(samples_per_gpu, n_gpus):
                         "two-atom 16-level Van Loan cost + 3N-gradient, complex128",
             "samples_per_gpu": samples_per_gpu, "samples_total": samples_per_gpu * n_gpus, "slices": 2000,
             "n_gauss": N_GAUSS, "channels": 5, "hilbert_dim": 16,
-            "l2": "per-step working set (state checkpoints, ~10.7 GB at 4096 samples) exceeds the 126 MB L2; "
-                  "no flush needed",
+            "l2": "per-step working set (state checkpoints, 6.3 GB at 4096 samples, written then read once) "
+                  "exceeds the 126 MB L2; no flush needed",
             "parallelism": f"samples sharded, {n_gpus} rank(s), one 243-double all-reduce per step"}
 
 
@@ -216,6 +216,7 @@ def run_gpu(args):
     k_ms = chain_ms[-1]
     lib = qocvl.load()
     peak_tf = float(lib.qocvl_measure_fp64_peak(local, 5))
+    peak_reg_tf = float(lib.qocvl_measure_fp64_peak_reg(local, 5))
     achieved_tf = flops / (k_ms * 1e-3) * 1e-12 if k_ms > 0 else None
     peaks = {}
     try:
@@ -229,6 +230,11 @@ def run_gpu(args):
                 "traffic": None,
                 "peak_source": "live DFMA microbenchmark in this run (qocvl_measure_fp64_peak); "
                                "MEASURED_PEAKS.json has no FP64 entry",
+                "peak_register_operands": peak_reg_tf,
+                "frac_of_register_operand_peak": (achieved_tf / peak_reg_tf) if achieved_tf and peak_reg_tf > 0 else None,
+                "peak_note": "peak = DFMA with one register operand (issue peak, 64 lanes/clk/SM); "
+                             "peak_register_operands = a=fma(a,b,c) with three register operands, the form every "
+                             "real kernel issues: the SM register file sustains only ~2/3 of the issue peak",
                 "flops_per_launch": flops, "flops_per_unit": flops / (M * S_local),
                 "kernel_ms": k_ms, "kernel_share_of_step": k_ms * args.steps / elapsed_ms if k_ms > 0 else None,
                 "m1_equivalent_tflops": 840.0 * 16 ** 3 * M * S_local / (k_ms * 1e-3) * 1e-12 if k_ms > 0 else None,

@@ -151,6 +151,9 @@ double qocvl_last_chain_ms(qocvl_plan* plan);
  * TFLOP/s, best of `repeats` launches.  This is the FP64 roofline denominator (the driver's
  * MEASURED_PEAKS.json only has HBM and bf16).  Returns < 0 on error. */
 double qocvl_measure_fp64_peak(int device, int repeats);
+/* Same loop with three REGISTER operands per FMA (a = fma(a, b, c)), which is what real kernels issue:
+ * the register file of the B200 SM sustains ~25 TFLOP/s of these, 2/3 of the issue peak above. */
+double qocvl_measure_fp64_peak_reg(int device, int repeats);
 const char* qocvl_strerror(int status);
 const char* qocvl_last_cuda_error(void);
 int qocvl_version(void);

@@ -148,23 +148,34 @@ extern "C" double qocvl_last_chain_ms(qocvl_plan* p) {
   return (double)ms;
 }
 
-// 8 independent FMA chains per thread, operands in registers only.
+// FP64 FMA peak microbenchmarks: 8 independent chains per thread, no memory traffic.
+//   REG = 0: a = fma(a, const, const)  -- one register operand: the pipe's issue peak (64 lanes/clk/SM)
+//   REG = 1: a = fma(a, b, c) with b, c per-thread registers -- three 64-bit register operands, which is
+//            what real kernels issue; the register file then sustains only ~2/3 of the issue peak on B200.
+template <int REG>
 __global__ void __launch_bounds__(256) k_dfma_peak(int iters, double seed, double* out) {
-  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
-         a6 = a0 + 6, a7 = a0 + 7;
-  const double m = 0.999999, c = 1e-9;
-  for (int i = 0; i < iters; ++i) {
+  double a[8], b[8], c[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = seed + threadIdx.x + i;
+    b[i] = 0.999999 + 1e-9 * (threadIdx.x + i);
+    c[i] = 1e-9 * (i + 1 + threadIdx.x);
+  }
+  for (int it = 0; it < iters; ++it) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
-      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = REG ? fma(a[i], b[i], c[i]) : fma(a[i], 0.999999, 1e-9);
     }
   }
-  const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
   if (s == 123.456) out[0] = s;   // never true; keeps the chains alive
 }
 
-extern "C" double qocvl_measure_fp64_peak(int device, int repeats) {
+template <int REG>
+static double measure_peak(int device, int repeats) {
   if (cudaSetDevice(device) != cudaSuccess) return -1.0;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
@@ -175,10 +186,10 @@ extern "C" double qocvl_measure_fp64_peak(int device, int repeats) {
   const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
   const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
   double best = -1.0;
-  k_dfma_peak<<<blocks, threads>>>(64, 1.0, d_out);   // warm-up
+  k_dfma_peak<REG><<<blocks, threads>>>(64, 1.0, d_out);   // warm-up
   for (int r = 0; r < (repeats < 1 ? 1 : repeats); ++r) {
     cudaEventRecord(e0);
-    k_dfma_peak<<<blocks, threads>>>(iters, 1.0 + r, d_out);
+    k_dfma_peak<REG><<<blocks, threads>>>(iters, 1.0 + r, d_out);
     cudaEventRecord(e1);
     if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
     float ms = 0.f;
@@ -189,3 +200,6 @@ extern "C" double qocvl_measure_fp64_peak(int device, int repeats) {
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
   return best;
 }
+
+extern "C" double qocvl_measure_fp64_peak(int device, int repeats) { return measure_peak<0>(device, repeats); }
+extern "C" double qocvl_measure_fp64_peak_reg(int device, int repeats) { return measure_peak<1>(device, repeats); }

@@ -222,17 +222,19 @@ __global__ void __launch_bounds__(512, QOCVL_MINB) k_chain(const ChainArgs P) {
     for (int s = 0; s < WBMAX; ++s) tq_b[s] = (s < brcnt) ? xget(xs, va, brcol[s]) : czero;
 #pragma unroll
     for (int v = 0; v < NVP; ++v) {
-      cplx acc0 = cmul(a_d, t[v]), acc1 = czero;
+      // one accumulator per vector: with >= 3 resident warps per scheduler the dependent chain is hidden,
+      // and the FP64 pipe (not latency) is what the sweep is bound by -- fewer instructions win
+      cplx acc0 = cmul(a_d, t[v]);
 #pragma unroll
       for (int s = 0; s < WMAX; ++s) {
         const cplx xv = (s < rcnt) ? xget(xs, v, rcol[s]) : czero;
-        if (s & 1) acc1 = cfma(a_row[s], xv, acc1); else acc0 = cfma(a_row[s], xv, acc0);
+        acc0 = cfma(a_row[s], xv, acc0);
       }
       if (v == NV) {
 #pragma unroll
-        for (int s = 0; s < WBMAX; ++s) acc1 = cfma(b_row[s], tq_b[s], acc1);
+        for (int s = 0; s < WBMAX; ++s) acc0 = cfma(b_row[s], tq_b[s], acc0);
       }
-      t[v] = cscale(cadd(acc0, acc1), invj);
+      t[v] = cscale(acc0, invj);
     }
     ph = NVP * LPG - ph;
   };
@@ -407,23 +409,23 @@ __global__ void __launch_bounds__(512, QOCVL_MINB) k_chain(const ChainArgs P) {
 #pragma unroll
       for (int v = 0; v < NVP; ++v) {
         const cplx tprev = cscale(TLOCAL ? t_loc[(j - 1) * NVP + v] : s_T[((size_t)(j - 1) * NVP + v) * LPG + r], invj);
-        cplx acc0 = cfma_conj(a_d, tb[v], czero), acc1 = czero;
+        cplx acc0 = cfma_conj(a_d, tb[v], czero);
         xc_d = cfma_conj(tb[v], tprev, xc_d);
 #pragma unroll
         for (int s = 0; s < WMAX; ++s) {
           const cplx ta = (s < ccnt) ? xget(xs, v, crow[s]) : czero;
-          if (s & 1) acc1 = cfma_conj(a_col[s], ta, acc1); else acc0 = cfma_conj(a_col[s], ta, acc0);
+          acc0 = cfma_conj(a_col[s], ta, acc0);
           xc[s] = cfma_conj(ta, tprev, xc[s]);
         }
         if (v == va) {                              // q receives B^dag tb_p; Bbar pairs tb_p with t_q
 #pragma unroll
           for (int s = 0; s < WBMAX; ++s) {
             const cplx ta = (s < bccnt) ? xget(xs, NV, bcrow[s]) : czero;
-            acc1 = cfma_conj(b_col[s], ta, acc1);
+            acc0 = cfma_conj(b_col[s], ta, acc0);
             xcb[s] = cfma_conj(ta, tprev, xcb[s]);
           }
         }
-        tb[v] = cadd(lam[v], cscale(cadd(acc0, acc1), invj));
+        tb[v] = cadd(lam[v], cscale(acc0, invj));
       }
       ph = NVP * LPG - ph;
     }
