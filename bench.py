@@ -106,7 +106,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_samples = 2
+    n_samples = 4                                             # per step; K steps stay within a few minutes
     times = []
     for _ in range(args.warmup if args.warmup < 1 else 1):
         oracle_step_seconds(1)
@@ -243,7 +243,7 @@ def run_gpu(args):
 
     if rank == 0:
         # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----------------
-        n_cpu = 2
+        n_cpu = 16                                            # ~10-15 s of oracle work on the box's host cores
         cpu_s = oracle_step_seconds(n_cpu)
         cpu_value = M * n_cpu / cpu_s
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -104,3 +104,17 @@ def test_plan_needs_cuda():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         pst.PropagatorVL(10, 500, 4e-10, 0, 0, 1e9, 1e9, 1e4, 1e7)
+
+
+def test_blockade_chain_generators_match_oracle():
+    """Product-side generator builder of the (non-reference) blockade-chain model vs the oracle's own enumeration."""
+    from oracle import blockade_chain as obc
+    from quantum_optimal_control.blockade_chain.propagator_vl import blockade_basis, chain_generators
+    assert [len(blockade_basis(k)) for k in (1, 2, 3, 4, 5, 10, 12)] == [2, 3, 5, 8, 13, 144, 377]   # Fibonacci F(n+2)
+    for n_atoms in (3, 5, 6):
+        po = obc.BlockadeChain(4, 8, 1e-9, n_atoms, 3.0, 7.0)
+        states, gu, gw, i_g, i_z = chain_generators(n_atoms, 3.0, 7.0)
+        assert states == obc.basis_states(n_atoms) and (i_g, i_z) == (po.i_g, po.i_z)
+        assert np.array_equal(gu[0], 3.0 * po.h_drive) and np.array_equal(gu[1], -7.0 * po.h_number)
+        assert gw[2][i_g, i_g] == 1 and gw[3][i_z, i_z] == 1 and np.count_nonzero(gw) == 2
+        assert np.array_equal(gu[0], gu[0].conj().T)
