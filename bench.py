@@ -83,10 +83,26 @@ class ClockSampler:
                 "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
 
 
+_THREADPOOL_GUARD = []
+
+
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU baseline is meant to use all host cores."""
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    try:
+        from threadpoolctl import threadpool_limits
+        _THREADPOOL_GUARD.append(threadpool_limits(limits=n))      # numpy / scipy BLAS pools
+    except Exception:
+        pass
+    return n
+
+
 def oracle_step_seconds(n_samples, repeats=1):
     """Reference CPU path (oracle port: SciPy/torch-CPU restatement, all host threads): seconds per
     cost+gradient of `n_samples` members of the SAME workload (M=2000, N=16)."""
     from oracle import ensemble
+    use_all_host_threads()
     dl, rs = ensemble.robust_cz_noise(4096)
     members, (a, b, c) = ensemble.robust_cz_members(dl[:n_samples], rs[:n_samples], seed=SEED, n_gauss=N_GAUSS, nt=NT)
     ensemble.ensemble_value_and_grad(members[:1], a, b, c)            # warm-up (thread pools, caches)
