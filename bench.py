@@ -259,9 +259,15 @@ def run_gpu(args):
 
     if rank == 0:
         # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----------------
+        # (N = 1 only: with more ranks the other processes' NCCL polling competes for the host cores)
         n_cpu = 16                                            # ~10-15 s of oracle work on the box's host cores
-        cpu_s = oracle_step_seconds(n_cpu)
-        cpu_value = M * n_cpu / cpu_s
+        cpu_baseline = None
+        if world == 1:
+            cpu_s = oracle_step_seconds(n_cpu)
+            cpu_baseline = {"value": M * n_cpu / cpu_s, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                            "sample": f"{n_cpu} of 4096 noise samples x 2000 slices (cost is linear in samples); "
+                                      "oracle = SciPy/torch-CPU restatement, torch autograd gradient",
+                            "seconds": cpu_s}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
@@ -272,10 +278,7 @@ def run_gpu(args):
                         "api": "PropagatorVL.value_and_grad_host(a, b, c): numpy in / numpy out"},
                 "gpu_launches": int(launches),
                 "roofline": roofline,
-                "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                 "sample": f"{n_cpu} of 4096 noise samples x 2000 slices (cost is linear in samples); "
-                                           "oracle = SciPy/torch-CPU restatement, torch autograd gradient",
-                                 "seconds": cpu_s},
+                "cpu_baseline": cpu_baseline,
                 "result": {"cost": float(cost_e2e), "infidelity": float(out[1]), "adiabaticity": float(out[2]),
                            "taylor_degree_cap": plan.taylor_cap}}
         print(json.dumps(line), flush=True)
