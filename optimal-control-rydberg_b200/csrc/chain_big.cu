@@ -48,7 +48,7 @@ __device__ __forceinline__ void block_sum(double* vals, int count, double* s_scr
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) k_chain_big(const BigArgs P) {
+__global__ void __launch_bounds__(512) k_chain_big(const BigArgs P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int n = P.n, J = P.J, C = P.C, JC = P.J * P.C, nvp = P.nv + 1, va = P.va, NV = P.nv;
@@ -321,7 +321,7 @@ int qocvl_big_configure(qocvl_plan* p) {
   if (smem > 227 * 1024) return QOCVL_ERR_UNSUPPORTED;
   QCUDA(cudaFuncSetAttribute(k_chain_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   p->chain_smem = smem;
-  p->threads = std::min(256, std::max(64, (vn + 31) / 32 * 32));
+  p->threads = std::min(512, std::max(64, (vn + 31) / 32 * 32));   // one (vector, row) output per thread when it fits
   p->blocks = S;
   p->spb = 1; p->groups = 1;
   p->n_parts = (size_t)S;
