@@ -140,6 +140,11 @@ int qocvl_last_taylor_degree(const qocvl_plan* plan); /* cap on the per-slice Ta
 /* Vectors the chain kernel propagates per sample after dropping inert start kets and merging
  * symmetric ones (moving start kets + the W psi vector); 0 before the first evaluation. */
 int qocvl_vectors_propagated(const qocvl_plan* plan);
+/* Rows per sample of the reduced stacked system the ensemble kernel runs on (every propagated vector restricted
+ * to the basis states it can reach, symmetric sectors folded onto orbit representatives; CZ: 12 instead of
+ * 3 x 16), or 0 when the evaluation does not use it (single-sample time-parallel path, large Hilbert spaces,
+ * QOCVL_AUG=0).  Results are identical either way: only structural zeros are skipped. */
+int qocvl_reduced_rows(const qocvl_plan* plan);
 long long qocvl_launch_count(const qocvl_plan* plan); /* kernels launched so far by this plan */
 double qocvl_flops_per_call(const qocvl_plan* plan, int with_grad); /* executed FP64 flop model */
 /* Kernel timing for the roofline report: when enabled, CUDA events bracket the chain kernel on

@@ -119,7 +119,8 @@ extern "C" double qocvl_flops_per_call(const qocvl_plan* p, int with_grad) {
   cudaDeviceSynchronize();
   if (cudaMemcpy(q.data(), p->d_qdeg, M * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 0.0;
   // vectors that are actually propagated: the moving start kets plus p = W psi
-  const double macs = (double)(p->n_live + 1) * p->cu.nnz + p->cw.nnz;
+  // (reduced stacked system of chain_aug.cu: only the entries that meet a populated vector element)
+  const double macs = p->use_aug ? (double)p->aug_nnz : (double)(p->n_live + 1) * p->cu.nnz + p->cw.nnz;
   double total = 0.0;
   for (int k = 0; k < M; ++k) {
     total += q[k] * macs;

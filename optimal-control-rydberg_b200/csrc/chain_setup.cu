@@ -152,9 +152,14 @@ int qocvl_chain_configure(qocvl_plan* p) {
   }
   const int stride = p->use_big ? n : p->npad;  // device layout of the live kets: [n_live][stride]
   std::vector<cplx> live_s, live_t;
+  p->h_live_s.clear(); p->h_live_t.clear();
   for (int v = 0; v < d.n_vec; ++v) {
     if (moves[v] && weight[v] > 0) {
       if (v == d.adiab_index) p->adiab_live = p->n_live;
+      for (int r = 0; r < n; ++r) {          // unpadded host copies for the reduced-system builder (chain_aug.cu)
+        p->h_live_s.push_back(ket(p->h_starts, v, r));
+        p->h_live_t.push_back(cscale(ket(p->h_targets, v, r), (double)weight[v]));
+      }
       for (int r = 0; r < stride; ++r) {
         live_s.push_back(r < n ? ket(p->h_starts, v, r) : cmake(0, 0));
         // the weight rides on the target ket: overlap and terminal cotangent are both linear in it
@@ -184,11 +189,22 @@ int qocvl_chain_configure(qocvl_plan* p) {
   p->qcap = qocvl_taylor_degree(bound);
   if (const char* e = getenv("QOCVL_QCAP")) p->qcap = std::max(2, std::min(QOCVL_QMAX, atoi(e)));
   // ---- kernel-specific geometry and buffers
-  int rc = p->use_big ? qocvl_big_configure(p) : qocvl_small_configure(p);
-  if (rc) { p->groups = 0; return rc; }
   // a single sample has no ensemble parallelism: cut the slice axis into concurrent chunks instead
   p->use_tp = !p->use_big && p->n_samples == 1 && d.n_slices >= 32;
   if (const char* e = getenv("QOCVL_TP")) p->use_tp = p->use_tp && atoi(e) != 0;
+  // ensembles: the reduced stacked system (chain_aug.cu) whenever it fits its kernel
+  p->use_aug = false;
+  int rc = QOCVL_ERR_UNSUPPORTED;
+  bool try_aug = !p->use_tp && !getenv("QOCVL_FORCE_BIG");
+  if (const char* e = getenv("QOCVL_AUG")) try_aug = try_aug && atoi(e) != 0;
+  if (try_aug) {
+    rc = qocvl_aug_configure(p);
+    if (rc != QOCVL_OK && rc != QOCVL_ERR_UNSUPPORTED) { p->groups = 0; return rc; }
+  }
+  if (!p->use_aug) {
+    rc = p->use_big ? qocvl_big_configure(p) : qocvl_small_configure(p);
+    if (rc) { p->groups = 0; return rc; }
+  }
   if (p->use_tp && (rc = qocvl_tp_configure(p))) { p->groups = 0; return rc; }
   if (p->d_gw_partial) { cudaFree(p->d_gw_partial); p->d_gw_partial = nullptr; p->bytes -= p->gw_partial_elems * sizeof(double); }
   p->gw_partial_elems = p->n_parts * d.n_slices * d.n_chan;
@@ -203,6 +219,7 @@ int qocvl_launch_chain(qocvl_plan* p, bool want_grad, double* out3, double* gwav
   const qocvl_desc& d = p->d;
   if (p->timing) QCUDA(cudaEventRecord(p->ev0, st));
   if (p->use_tp) rc = qocvl_tp_launch(p, want_grad, gwave, st);
+  else if (p->use_aug) rc = qocvl_aug_launch(p, want_grad, st);
   else rc = p->use_big ? qocvl_big_launch(p, want_grad, st) : qocvl_small_launch(p, want_grad, st);
   if (rc) return rc;
   if (p->timing) { QCUDA(cudaEventRecord(p->ev1, st)); p->timed_once = true; }

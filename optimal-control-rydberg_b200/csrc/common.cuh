@@ -169,6 +169,15 @@ struct qocvl_plan {
   cplx* d_tring = nullptr; // big kernel: Taylor-term ring [S][qcap][nvp][n] in global memory (L2-resident)
   size_t tring_bytes = 0;
   size_t chain_smem = 0;
+  // reduced ensemble path (chain_aug.cu): every propagated vector restricted to the basis states it can reach,
+  // symmetric sectors folded onto orbit representatives, all of it stacked into ONE sparse system of aug_n rows
+  bool use_aug = false;
+  int aug_n = 0, aug_lpg = 0, aug_nnz = 0, aug_wmax = 0;
+  BlockLayout la;          // lane-per-row tables of the stacked system (u-family conventions, diagonal in slot 0)
+  std::vector<cplx> h_live_s, h_live_t;   // [n_live][n] live start / (weighted) target kets, unpadded
+  cplx *d_aug_starts = nullptr, *d_aug_targets = nullptr;   // [aug_lpg]
+  int* d_aug_pair = nullptr;      // [aug_lpg] row of the partner (q row <-> p row) in the adiabaticity term, or -1
+  double* d_aug_wq = nullptr;     // [aug_lpg] orbit size of the row (weight of its term in q^dag p)
 };
 
 // pulse.cu
@@ -186,6 +195,10 @@ int qocvl_tp_configure(qocvl_plan* p);
 int qocvl_tp_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t st);
 int qocvl_big_configure(qocvl_plan* p);
 int qocvl_big_launch(qocvl_plan* p, bool want_grad, cudaStream_t st);
+int qocvl_aug_configure(qocvl_plan* p);
+int qocvl_aug_launch(qocvl_plan* p, bool want_grad, cudaStream_t st);
+int qocvl_build_lane_layout(qocvl_plan* p, const std::vector<std::complex<double>>& blocks, int n, int npad,
+                            bool diag_slot, BlockLayout* out);
 int qocvl_build_csr(qocvl_plan* p, const std::vector<std::complex<double>>& blocks, CsrLayout* out);
 // dense.cu
 int qocvl_launch_dense_expm(qocvl_plan* p, cplx* out, cudaStream_t st);

@@ -32,9 +32,10 @@ static void free_layout(BlockLayout& l) {
 }
 
 // Build the lane-per-row sparse tables for one block family.
-//   blocks: [J][n][n];  diag_slot: reserve slot 0 for the diagonal entry (u family).
-static int build_layout(qocvl_plan* p, const std::vector<zc>& blocks, bool diag_slot, BlockLayout* out) {
-  const int n = p->d.n, J = p->d.n_gen, np_ = p->npad;
+//   blocks: [J][n][n], np_ lanes per vector;  diag_slot: reserve slot 0 for the diagonal entry (u family).
+int qocvl_build_lane_layout(qocvl_plan* p, const std::vector<zc>& blocks, int n, int np_, bool diag_slot,
+                            BlockLayout* out) {
+  const int J = p->d.n_gen;
   auto G = [&](int j, int a, int b) { return blocks[((size_t)j * n + a) * n + b]; };
   std::vector<char> pat((size_t)n * n, 0);
   int nnz = 0;
@@ -161,7 +162,7 @@ extern "C" int qocvl_plan_create(qocvl_plan** out, const qocvl_desc* desc, int d
 extern "C" int qocvl_plan_destroy(qocvl_plan* p) {
   if (!p) return QOCVL_OK;
   cudaSetDevice(p->device);
-  free_layout(p->lu); free_layout(p->lw);
+  free_layout(p->lu); free_layout(p->lw); free_layout(p->la);
   for (CsrLayout* c : {&p->cu, &p->cw}) {
     cudaFree(c->rowptr); cudaFree(c->col); cudaFree(c->erow); cudaFree(c->colptr);
     cudaFree(c->crow); cudaFree(c->ceid); cudaFree(c->egen); cudaFree(c->eval);
@@ -170,7 +171,8 @@ extern "C" int qocvl_plan_destroy(qocvl_plan* p) {
   void* ptrs[] = {p->d_gdense, p->d_coef_const, p->d_gnorm, p->d_starts, p->d_targets, p->d_mul, p->d_add,
                   p->d_mulmax, p->d_addmax, p->d_taps, p->d_raw, p->d_reg, p->d_wave, p->d_coef, p->d_dcoef,
                   p->d_qdeg, p->d_flag, p->d_ckpt, p->d_sample_out, p->d_gw_partial, p->d_gwave, p->d_greg,
-                  p->d_graw, p->d_out3, p->d_dense_a, p->d_dense_b};
+                  p->d_graw, p->d_out3, p->d_dense_a, p->d_dense_b, p->d_aug_starts, p->d_aug_targets,
+                  p->d_aug_pair, p->d_aug_wq};
   for (void* q : ptrs) if (q) cudaFree(q);
   delete p;
   return QOCVL_OK;
@@ -196,8 +198,8 @@ extern "C" int qocvl_set_generators(qocvl_plan* p, const double* gens_u, const d
   if ((rc = qocvl_build_csr(p, p->h_gu, &p->cu))) return rc;
   if ((rc = qocvl_build_csr(p, p->h_gw, &p->cw))) return rc;
   if (p->npad > 0) {
-    if ((rc = build_layout(p, p->h_gu, true, &p->lu))) return rc;
-    if ((rc = build_layout(p, p->h_gw, false, &p->lw))) return rc;
+    if ((rc = qocvl_build_lane_layout(p, p->h_gu, p->d.n, p->npad, true, &p->lu))) return rc;
+    if ((rc = qocvl_build_lane_layout(p, p->h_gw, p->d.n, p->npad, false, &p->lw))) return rc;
   }
   // column sums of |G_u| + |G_w| per generator: |X|_1 <= dt * max_b sum_j |c_j| * gcol[j][b]
   // (entrywise triangle inequality; the 2n x 2n block matrix has column sums |A| and |B|+|A|)
@@ -312,6 +314,7 @@ extern "C" size_t qocvl_workspace_bytes(const qocvl_plan* p) { return p ? p->byt
 extern "C" long long qocvl_launch_count(const qocvl_plan* p) { return p ? p->launches : 0; }
 extern "C" int qocvl_last_taylor_degree(const qocvl_plan* p) { return p ? p->qcap : 0; }
 extern "C" int qocvl_vectors_propagated(const qocvl_plan* p) { return (p && p->groups > 0) ? p->n_live + 1 : 0; }
+extern "C" int qocvl_reduced_rows(const qocvl_plan* p) { return (p && p->groups > 0 && p->use_aug) ? p->aug_n : 0; }
 extern "C" const char* qocvl_last_cuda_error(void) { return g_qocvl_cuda_error.c_str(); }
 extern "C" int qocvl_version(void) { return 100; }
 

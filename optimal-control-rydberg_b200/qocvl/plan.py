@@ -196,6 +196,11 @@ class Plan:
         return int(self._lib.qocvl_last_taylor_degree(self._h))
 
     @property
+    def reduced_rows(self):
+        """Rows per sample of the reduced stacked system (chain_aug.cu), 0 if the last configuration does not use it."""
+        return int(self._lib.qocvl_reduced_rows(self._h))
+
+    @property
     def vectors_propagated(self):
         return int(self._lib.qocvl_vectors_propagated(self._h))
 

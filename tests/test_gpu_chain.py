@@ -158,3 +158,48 @@ def test_time_parallel_state_transfer():
     out_tp = np_(tp.cost_and_grad_packed(tp._pack(a, b, c))).copy()
     assert np.abs(out_tp[:3] - out_seq[:3]).max() < 1e-13
     assert rel(out_tp[3:], out_seq[3:]) < 1e-9
+
+
+@pytest.mark.parametrize("nofold", [False, True])
+def test_reduced_system_equals_lane_kernel_on_cz(nofold):
+    """chain_aug.cu (reachable sectors + orbit folding, 12 rows per sample; 15 without folding) against the
+    full lane-per-row kernel (3 vectors x 16 rows) on a small CZ ensemble, with a ragged sample count."""
+    from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL
+    po, a, b, c = otq.notebook02_setup(seed=3, n_gauss=6, nt=77)
+    args = (6, 77, po.padding, 50e6, po.delta_t, 0.0, po.Vint, po.Delta_i_val, po.Rabi_i_val, po.Rabi_r_val, otq.GAMMAS_CZ)
+    dl, rs = ensemble.robust_cz_noise(37)
+    with env(QOCVL_AUG=0):
+        full = PropagatorVL(*args)
+        full.set_ensemble(del_total=dl, rabi_scale=rs)
+        out_full = np_(full.cost_and_grad_packed(full._pack(a, b, c))).copy()
+        assert not full._plan.reduced_rows
+    kv = {"QOCVL_NOFOLD": 1} if nofold else {}
+    with env(**kv):
+        red = PropagatorVL(*args)
+        red.set_ensemble(del_total=dl, rabi_scale=rs)
+        out_red = np_(red.cost_and_grad_packed(red._pack(a, b, c))).copy()
+        cost_only = float(red.target(a, b, c))
+        red._plan.check()
+        assert red._plan.reduced_rows == (15 if nofold else 12)
+    assert np.abs(out_red[:3] - out_full[:3]).max() < 1e-13 and abs(cost_only - out_full[0]) < 1e-13
+    assert rel(out_red[3:], out_full[3:]) < 1e-10
+
+
+def test_reduced_system_state_transfer_ensemble():
+    """Same check on the 5-level state-transfer model (one start ket, its W psi partner, no symmetry hint)."""
+    from oracle import state_transfer as ost
+    from quantum_optimal_control.state_transfer.propagator_vl import PropagatorVL
+    po, a, b, c = ost.notebook01_setup()
+    args = (po.input_dim, po.no_of_steps, po.delta_t, po.del_total, po.Delta_1, po.Rabi_1, po.Rabi_2, po.Gamma_r, po.Gamma_i)
+    rng = np.random.default_rng(5)
+    dl, rs = rng.normal(0, 2 * np.pi * 1e5, 9), 1 + rng.normal(0, 0.01, 9)
+    outs = []
+    for flag in (0, 1):
+        with env(QOCVL_AUG=flag):
+            prop = PropagatorVL(*args)
+            prop.set_ensemble(del_total=dl, rabi_scale=rs)
+            outs.append(np_(prop.cost_and_grad_packed(prop._pack(a, b, c))).copy())
+            prop._plan.check()
+            assert bool(prop._plan.reduced_rows) == bool(flag)
+    assert np.abs(outs[1][:3] - outs[0][:3]).max() < 1e-13
+    assert rel(outs[1][3:], outs[0][3:]) < 1e-10
