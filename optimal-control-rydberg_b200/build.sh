@@ -1,11 +1,26 @@
 #!/usr/bin/env bash
 # Builds libqocvl.so (the C-ABI library, include/qocvl.h) for sm_100a, in-tree.
+# Every translation unit is compiled on its own (in parallel), then linked; no relocatable device code needed.
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 OUT="$HERE/libqocvl.so"
-SRCS=("$HERE"/csrc/plan.cu "$HERE"/csrc/pulse_map.cu "$HERE"/csrc/chain_small.cu "$HERE"/csrc/chain_aug.cu "$HERE"/csrc/chain_big.cu "$HERE"/csrc/chain_setup.cu "$HERE"/csrc/dense.cu "$HERE"/csrc/api.cu)
-"$NVCC" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
-  -Xcompiler -fPIC -shared ${QOCVL_PTXAS_V:+-Xptxas -v} \
-  -o "$OUT" "${SRCS[@]}" -lcudart
+OBJ="$HERE/build"
+mkdir -p "$OBJ"
+UNITS=(plan pulse_map chain_small chain_aug chain_big chain_setup dense api)
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC ${QOCVL_PTXAS_V:+-Xptxas -v})
+pids=()
+for u in "${UNITS[@]}"; do
+  "$NVCC" "${FLAGS[@]}" -c "$HERE/csrc/$u.cu" -o "$OBJ/$u.o" > "$OBJ/$u.log" 2>&1 &
+  pids+=($!)
+done
+fail=0
+for i in "${!pids[@]}"; do
+  if ! wait "${pids[$i]}"; then fail=1; echo "nvcc failed on ${UNITS[$i]}.cu:" >&2; fi
+  cat "$OBJ/${UNITS[$i]}.log" >&2
+done
+[ "$fail" -eq 0 ] || exit 1
+objs=()
+for u in "${UNITS[@]}"; do objs+=("$OBJ/$u.o"); done
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC -o "$OUT" "${objs[@]}" -lcudart
 echo "built $OUT"

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cmath>
+#include <map>
 
 typedef std::complex<double> zc;
 
@@ -28,65 +29,69 @@ __constant__ double c_ainv[QOCVL_QMAX + 2];   // 1/j
 
 struct AugArgs {
   int N, J, M, C, S;
-  int w, wc, kc;             // off-diagonal row slots / column slots / generator contributions per slot
+  int w, wc;                 // off-diagonal row slots / column slots in use
+  int ncr, ncc;              // contribution slots per lane: (1+w)*KC, (1+wc)*KC
+  int KA, KG, ncls, nparts;
+  unsigned add_row_mask, add_col_mask;
   int want_grad;
   double dt, inv_duration, w_infid, w_adiab, inv_fid_norm, inv_samples;
   cplx d_const;              // overlap contribution of the start kets that never move
-  const int *row_col, *col_row, *rc_gen, *cc_gen;
-  const cplx *rc_val, *cc_val;
-  const cplx* coef;    // [M][J]
-  const cplx* dcoef;   // [M][J][C]
-  const int* qdeg;     // [M]
-  const double* mul;   // [S][J]
-  const cplx* add;     // [S][J]
-  const cplx* starts;  // [LPG]
-  const cplx* targets; // [LPG] (symmetry / orbit weights folded in)
-  const int* pair;     // [LPG] partner row in q^dag p, or -1
-  const double* wq;    // [2][LPG]: weight of the row's term in q^dag p (q rows only) / in the cotangent (q and p rows)
-  cplx* ckpt;          // [M][total threads]
-  double* sample_out;  // [S][3]
-  double* gw_partial;  // [total warps][M][C]
+  const int *row_col, *col_row, *r_cls, *c_cls, *r_gen, *c_gen, *ra_gen, *ca_gen;
+  const cplx *r_val, *c_val, *ra_val, *ca_val;
+  cplx *p_row, *p_col;       // per-slice entry tables (written by k_aug_tables, read by k_chain_aug)
+  const cplx* coef;          // [M][J]
+  const cplx* dcoef;         // [M][J][C]
+  const int* qdeg;           // [M]
+  const double* mcls;        // [S][ncls]
+  const cplx* add;           // [S][J]
+  const cplx* starts;        // [LPG]
+  const cplx* targets;       // [LPG] (symmetry / orbit weights folded in)
+  const int* pair;           // [LPG] partner row in q^dag p, or -1
+  const double* wq;          // [2][LPG]: weight of the row's term in q^dag p (q rows only) / in the cotangent
+  cplx* ckpt;                // [M][total threads]
+  double* sample_out;        // [S][3]
+  cplx* y_partial;           // [warps][M][ncc][LPG]  per-warp sums of m * Xbar
+  double* gwave;             // [M][C]
 };
 
-template <int LPG>
-__device__ __forceinline__ cplx aug_group_sum(cplx v) {
-#pragma unroll
-  for (int off = LPG / 2; off > 0; off >>= 1) {
-    v.x += __shfl_xor_sync(0xffffffffu, v.x, off);
-    v.y += __shfl_xor_sync(0xffffffffu, v.y, off);
+// P_i(k) = dt * sum_{g in contribution i} coef_kg * val_ig for every row-owner and column-owner contribution:
+// the sample-independent part of the slice generators, computed once per evaluation (M * (ncr+ncc) * L values).
+__global__ void k_aug_tables(const AugArgs P, int L) {
+  const int k = blockIdx.x;
+  for (int t = threadIdx.x; t < (P.ncr + P.ncc) * L; t += blockDim.x) {
+    const bool rowtab = t < P.ncr * L;
+    const int u = rowtab ? t : t - P.ncr * L;
+    const int c = u / L, lane = u % L;
+    const int* gen = rowtab ? P.r_gen : P.c_gen;
+    const cplx* val = rowtab ? P.r_val : P.c_val;
+    cplx acc = cmake(0, 0);
+    for (int i = 0; i < P.KG; ++i) {
+      const int g = gen[((size_t)c * P.KG + i) * L + lane];
+      if (g >= 0) acc = cfma(P.coef[(size_t)k * P.J + g], val[((size_t)c * P.KG + i) * L + lane], acc);
+    }
+    acc = cscale(acc, P.dt);
+    if (rowtab) P.p_row[((size_t)k * P.ncr + c) * L + lane] = acc;
+    else P.p_col[((size_t)k * P.ncc + c) * L + lane] = acc;
   }
-  return v;
 }
 
-template <int LPG, int WMAX>
+template <int LPG, int WMAX, int KC>
 __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int NCO = (QOCVL_MAX_GEN + LPG - 1) / LPG;   // coefficients a lane prepares per slice
+  constexpr int NSL = 1 + WMAX;                  // slots per lane (diagonal + off-diagonals)
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int grp = tid / LPG, r = tid % LPG, ngroups = nthreads / LPG;
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
-  const int J = P.J, C = P.C, JC = P.J * P.C;
   const size_t gtid = (size_t)blockIdx.x * nthreads + tid, gthreads = (size_t)gridDim.x * nthreads;
   const int sample = blockIdx.x * ngroups + grp;
   const bool item_ok = sample < P.S;
   const bool live = item_ok && r < P.N;
   const int sm = item_ok ? sample : P.S - 1;
 
-  // ---- shared memory carve-up
-  const int n_rc = (P.w + 1) * P.kc * LPG, n_cc = (P.wc + 1) * P.kc * LPG;
+  // ---- shared memory: exchange buffers and (only with additive noise) the per-sample constant terms
   cplx* carve = (cplx*)smem_raw;
-  cplx* s_rcv = carve; carve += n_rc;                               // [w+1][kc][LPG]  row-owner contributions
-  cplx* s_ccv = carve; carve += n_cc;                               // [wc+1][kc][LPG] column-owner contributions
-  cplx* s_cs = carve + (size_t)grp * J; carve += (size_t)ngroups * J;      // [ngroups][J] slice coefficients
-  cplx* s_dco = carve + (size_t)warp * JC; carve += (size_t)nwarps * JC;   // [nwarps][J][C] d coef / d wave
   cplx* s_x = carve + (size_t)grp * 2 * LPG; carve += (size_t)ngroups * 2 * LPG;   // [ngroups][2 buffers][LPG]
-  double* s_mul = (double*)carve + (size_t)grp * J;                 // [ngroups][J]
-  int* s_rcg = (int*)((double*)carve + (size_t)ngroups * J);
-  int* s_ccg = s_rcg + n_rc;
-  for (int i = tid; i < n_rc; i += nthreads) { s_rcv[i] = P.rc_val[i]; s_rcg[i] = P.rc_gen[i]; }
-  for (int i = tid; i < n_cc; i += nthreads) { s_ccv[i] = P.cc_val[i]; s_ccg[i] = P.cc_gen[i]; }
-  for (int j = r; j < J; j += LPG) s_mul[j] = P.mul[(size_t)sm * J + j];
-  __syncthreads();                                                  // the only CTA-wide barrier
+  cplx* s_A = carve + (size_t)grp * 2 * NSL * LPG;                                 // [ngroups][2][NSL][LPG]
 
   int rcol[WMAX], crow[WMAX];
 #pragma unroll
@@ -94,18 +99,37 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
     rcol[s] = (s < P.w) ? P.row_col[(1 + s) * LPG + r] : r;
     crow[s] = (s < P.wc) ? P.col_row[(1 + s) * LPG + r] : r;
   }
-  int rcnt = 0, ccnt = 0;     // real entries of my row / column (they form a prefix of the slots)
-  for (int s = 0; s < P.w; ++s) rcnt += s_rcg[((1 + s) * P.kc) * LPG + r] >= 0;
-  for (int s = 0; s < P.wc; ++s) ccnt += s_ccg[((1 + s) * P.kc) * LPG + r] >= 0;
-  double mymul[NCO];
-  cplx myadd[NCO];
+  // per-sample multiplier of each of my contributions (0 = no contribution); real entries form a slot prefix
+  double m_row[NSL * KC], m_col[NSL * KC];
+  int rcnt = 0, ccnt = 0;
 #pragma unroll
-  for (int i = 0; i < NCO; ++i) {
-    const int j = r + i * LPG;
-    mymul[i] = (j < J) ? P.mul[(size_t)sm * J + j] : 0.0;
-    myadd[i] = (j < J) ? P.add[(size_t)sm * J + j] : cmake(0, 0);
+  for (int s = 0; s < NSL; ++s) {
+    bool any_r = false, any_c = false;
+#pragma unroll
+    for (int i = 0; i < KC; ++i) {
+      const int cr = (s <= P.w) ? P.r_cls[(s * KC + i) * LPG + r] : -1;
+      const int cc = (s <= P.wc) ? P.c_cls[(s * KC + i) * LPG + r] : -1;
+      m_row[s * KC + i] = (cr >= 0 && live) ? P.mcls[(size_t)sm * P.ncls + cr] : 0.0;
+      m_col[s * KC + i] = (cc >= 0 && live) ? P.mcls[(size_t)sm * P.ncls + cc] : 0.0;
+      any_r = any_r || cr >= 0;
+      any_c = any_c || cc >= 0;
+    }
+    if (s > 0) { rcnt += any_r; ccnt += any_c; }
   }
   const cplx czero = cmake(0.0, 0.0);
+  if (P.KA > 0) {   // A_e = dt * sum_g add_sg * val_eg for my row-owner and column-owner slots
+    for (int s = 0; s < NSL; ++s) {
+      cplx ar = czero, ac = czero;
+      for (int i = 0; i < P.KA; ++i) {
+        const int gr = (s <= P.w) ? P.ra_gen[(s * P.KA + i) * LPG + r] : -1;
+        const int gc = (s <= P.wc) ? P.ca_gen[(s * P.KA + i) * LPG + r] : -1;
+        if (gr >= 0 && live) ar = cfma(P.add[(size_t)sm * P.J + gr], P.ra_val[(s * P.KA + i) * LPG + r], ar);
+        if (gc >= 0 && live) ac = cfma(P.add[(size_t)sm * P.J + gc], P.ca_val[(s * P.KA + i) * LPG + r], ac);
+      }
+      s_A[s * LPG + r] = cscale(ar, P.dt);
+      s_A[(NSL + s) * LPG + r] = cscale(ac, P.dt);
+    }
+  }
   cplx z = live ? P.starts[r] : czero;
   const cplx ytgt = live ? P.targets[r] : czero;
   const int pr = live ? P.pair[r] : -1;
@@ -113,36 +137,28 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
   int ph = 0;                                                       // exchange buffer offset: 0 or LPG
   cplx t_loc[QOCVL_QMAX];
   cplx a_d, a_row[WMAX];
+  __syncwarp();
 
   // exchange layout: re[LPG] then im[LPG]; 8-byte accesses of the LPG lanes of a sample hit distinct banks
   auto xput = [&](double* xs, cplx val) { xs[r] = val.x; xs[LPG + r] = val.y; };
   auto xget = [&](const double* xs, int idx) -> cplx { return cmake(xs[idx], xs[LPG + idx]); };
-  auto load_coef = [&](int kk, cplx* creg) {
-#pragma unroll
-    for (int i = 0; i < NCO; ++i) {
-      const int j = r + i * LPG;
-      creg[i] = (j < J) ? P.coef[(size_t)kk * J + j] : czero;
-    }
-  };
-  auto store_cs = [&](const cplx* creg) {
-#pragma unroll
-    for (int i = 0; i < NCO; ++i) {
-      const int j = r + i * LPG;
-      if (j < J) s_cs[j] = cadd(cscale(creg[i], mymul[i]), myadd[i]);
-    }
-  };
-  auto slot_value = [&](const int* gen, const cplx* val, int slot) -> cplx {
+  // entry of slot s: A + sum_i m_i * P_i(k)   (row-owner tables: col = 0, column-owner tables: col = 1)
+  auto slot_value = [&](const cplx* tab, const double* m, unsigned mask, int col, int s) -> cplx {
     cplx acc = czero;
-    for (int kc = 0; kc < P.kc; ++kc) {
-      const int gi = gen[(slot * P.kc + kc) * LPG + r];
-      if (gi >= 0) acc = cfma(s_cs[gi], val[(slot * P.kc + kc) * LPG + r], acc);
-    }
-    return cscale(acc, P.dt);
-  };
-  auto assemble_rows = [&]() {
-    a_d = slot_value(s_rcg, s_rcv, 0);
 #pragma unroll
-    for (int s = 0; s < WMAX; ++s) a_row[s] = (s < P.w) ? slot_value(s_rcg, s_rcv, 1 + s) : czero;
+    for (int i = 0; i < KC; ++i) {
+      const cplx pv = __ldg(tab + (size_t)(s * KC + i) * LPG);
+      acc.x = fma(m[s * KC + i], pv.x, acc.x);
+      acc.y = fma(m[s * KC + i], pv.y, acc.y);
+    }
+    if ((mask >> s) & 1u) acc = cadd(acc, s_A[(col * NSL + s) * LPG + r]);
+    return acc;
+  };
+  auto assemble_rows = [&](int k) {
+    const cplx* tab = P.p_row + (size_t)k * P.ncr * LPG + r;
+    a_d = slot_value(tab, m_row, P.add_row_mask, 0, 0);
+#pragma unroll
+    for (int s = 0; s < WMAX; ++s) a_row[s] = (s < P.w) ? slot_value(tab, m_row, P.add_row_mask, 0, 1 + s) : czero;
   };
   // one forward Taylor step: t <- Xaug t / j
   auto step_fwd = [&](cplx t, double invj) -> cplx {
@@ -159,28 +175,16 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
     return cscale(acc, invj);
   };
 
-  {
-    cplx creg[NCO];
-    load_coef(0, creg);
-    store_cs(creg);
-    __syncwarp();
-  }
   // =================================== forward sweep ===================================
   for (int k = 0; k < P.M; ++k) {
     const int q = P.qdeg[k];
-    assemble_rows();
-    __syncwarp();                                   // everyone has read cs of slice k
-    cplx creg[NCO];
-    const bool more = k + 1 < P.M;
-    if (more) load_coef(k + 1, creg);               // in flight during this slice
+    assemble_rows(k);
     if (P.want_grad && live) P.ckpt[(size_t)k * gthreads + gtid] = z;
     cplx t = z;
     for (int j = 1; j <= q; ++j) {
       t = step_fwd(t, c_ainv[j]);
       z = cadd(z, t);
     }
-    if (more) store_cs(creg);
-    __syncwarp();
   }
 
   // =================================== cost ============================================
@@ -192,16 +196,21 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
     zp = (pr >= 0) ? xget(xs, pr) : czero;
     ph = LPG - ph;
   }
-  const cplx dsum = cadd(P.d_const, aug_group_sum<LPG>(cfma_conj(ytgt, z, czero)));   // sum_r conj(y_r) z_r
-  {
-    const cplx qp = aug_group_sum<LPG>(cscale(cfma_conj(z, zp, czero), w_qp));         // q^dag p
-    if (r == 0 && item_ok) {
-      const double infid = 1.0 - (dsum.x * dsum.x + dsum.y * dsum.y) * P.inv_fid_norm;
-      const double adiab = 1.0 - qp.x * P.inv_duration;
-      P.sample_out[(size_t)sample * 3 + 0] = P.w_infid * infid + P.w_adiab * adiab;
-      P.sample_out[(size_t)sample * 3 + 1] = infid;
-      P.sample_out[(size_t)sample * 3 + 2] = adiab;
-    }
+  cplx dsum = cfma_conj(ytgt, z, czero);                            // sum_r conj(y_r) z_r
+  cplx qp = cscale(cfma_conj(z, zp, czero), w_qp);                  // q^dag p
+#pragma unroll
+  for (int off = LPG / 2; off > 0; off >>= 1) {
+    dsum.x += __shfl_xor_sync(0xffffffffu, dsum.x, off);
+    dsum.y += __shfl_xor_sync(0xffffffffu, dsum.y, off);
+    qp.x += __shfl_xor_sync(0xffffffffu, qp.x, off);
+  }
+  dsum = cadd(P.d_const, dsum);
+  if (r == 0 && item_ok) {
+    const double infid = 1.0 - (dsum.x * dsum.x + dsum.y * dsum.y) * P.inv_fid_norm;
+    const double adiab = 1.0 - qp.x * P.inv_duration;
+    P.sample_out[(size_t)sample * 3 + 0] = P.w_infid * infid + P.w_adiab * adiab;
+    P.sample_out[(size_t)sample * 3 + 1] = infid;
+    P.sample_out[(size_t)sample * 3 + 2] = adiab;
   }
   if (!P.want_grad) return;
 
@@ -213,28 +222,18 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
     lam = cscale(cmul(dsum, ytgt), -P.w_infid * P.inv_fid_norm * ws);
     lam = cadd(lam, cscale(zp, ca * w_lam));        // q rows receive -(wa/2T) p, p rows -(wa/2T) q
   }
-  __syncwarp();
-  {
-    cplx creg[NCO];
-    load_coef(P.M - 1, creg);
-    store_cs(creg);
-    __syncwarp();
-  }
 
   // =================================== reverse sweep ===================================
   const size_t gwarp = (size_t)blockIdx.x * nwarps + warp;
   for (int k = P.M - 1; k >= 0; --k) {
     const int q = P.qdeg[k];
-    assemble_rows();
+    assemble_rows(k);
     cplx a_col[WMAX];                               // column-owner values Xaug[a][r] for the rows a of my column
+    {
+      const cplx* tab = P.p_col + (size_t)k * P.ncc * LPG + r;
 #pragma unroll
-    for (int s = 0; s < WMAX; ++s) a_col[s] = (s < P.wc) ? slot_value(s_ccg, s_ccv, 1 + s) : czero;
-    __syncwarp();                                   // everyone has read cs of slice k
-    cplx creg[NCO];
-    if (k > 0) load_coef(k - 1, creg);
-    cplx dreg[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) dreg[i] = (lane + 32 * i < JC) ? P.dcoef[(size_t)k * JC + lane + 32 * i] : czero;
+      for (int s = 0; s < WMAX; ++s) a_col[s] = (s < P.wc) ? slot_value(tab, m_col, P.add_col_mask, 1, 1 + s) : czero;
+    }
     // ---- recompute the forward Taylor terms t_0 .. t_{q-1}
     cplx t = live ? P.ckpt[(size_t)k * gthreads + gtid] : czero;
     t_loc[0] = t;
@@ -242,7 +241,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
       t = step_fwd(t, c_ainv[j]);
       t_loc[j] = t;
     }
-    // ---- descending adjoint recurrence with on-the-fly contraction
+    // ---- descending adjoint recurrence, Xbar accumulated on my column's entries
     cplx tb = lam;
     cplx xc_d = czero, xc[WMAX];
 #pragma unroll
@@ -265,68 +264,100 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
       ph = LPG - ph;
     }
     lam = tb;
-    // ---- contract Xbar with the generators: d cost / d wave[k][c]
+    // ---- Ybar_e = sum over the warp's samples of m_s * Xbar_e: the generators' d coef / d wave is the same for
+    //      every sample, so the contraction with it happens once per slice in k_aug_reduce, not here
+    cplx* yout = P.y_partial + ((gwarp * P.M + k) * P.ncc) * LPG + r;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) if (lane + 32 * i < JC) s_dco[lane + 32 * i] = dreg[i];
-    __syncwarp();
-    double gw[QOCVL_MAX_CHAN];
+    for (int s = 0; s < NSL; ++s) {
+      if (s <= P.wc) {
+        const cplx xval = (s == 0) ? xc_d : xc[s > 0 ? s - 1 : 0];
 #pragma unroll
-    for (int c = 0; c < QOCVL_MAX_CHAN; ++c) gw[c] = 0.0;
-    if (live) {
-      const double two_dt = 2.0 * P.dt;
-      for (int slot = 0; slot <= P.wc; ++slot) {
-        cplx xval = xc_d;
+        for (int i = 0; i < KC; ++i) {
+          cplx y = cscale(xval, m_col[s * KC + i]);
 #pragma unroll
-        for (int s = 0; s < WMAX; ++s)
-          if (slot == s + 1) xval = xc[s];
-        for (int kc = 0; kc < P.kc; ++kc) {
-          const int gi = s_ccg[(slot * P.kc + kc) * LPG + r];
-          if (gi >= 0) {
-            const cplx tmp = cscale(cmul(s_ccv[(slot * P.kc + kc) * LPG + r], xval), two_dt * s_mul[gi]);
-#pragma unroll
-            for (int c = 0; c < QOCVL_MAX_CHAN; ++c)
-              if (c < C) gw[c] += tmp.x * s_dco[gi * C + c].x - tmp.y * s_dco[gi * C + c].y;
+          for (int off = LPG; off < 32; off <<= 1) {
+            y.x += __shfl_xor_sync(0xffffffffu, y.x, off);
+            y.y += __shfl_xor_sync(0xffffffffu, y.y, off);
           }
+          if (lane < LPG) yout[(size_t)(s * KC + i) * LPG] = y;
         }
       }
     }
-#pragma unroll
-    for (int c = 0; c < QOCVL_MAX_CHAN; ++c) {
-      double vsum = gw[c];
-      for (int off = 16; off > 0; off >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, off);
-      if (lane == 0 && c < C) P.gw_partial[(gwarp * P.M + k) * C + c] = vsum;
-    }
-    if (k > 0) store_cs(creg);
-    __syncwarp();
   }
 }
 
+// gwave[k][c] = 2 dt Re sum_{e,i} Ybar_{e,i}(k) * sum_{g in (e,i)} val_eg * dcoef_kgc, with Ybar summed over the
+// per-warp partials in a fixed order (deterministic).  One block per slice, one thread per (contribution, lane).
+__global__ void __launch_bounds__(1024) k_aug_reduce(const AugArgs P, int L) {
+  __shared__ double red[QOCVL_MAX_CHAN][1024];
+  const int k = blockIdx.x, t = threadIdx.x, nt = P.ncc * L;
+  double term[QOCVL_MAX_CHAN];
+#pragma unroll
+  for (int c = 0; c < QOCVL_MAX_CHAN; ++c) term[c] = 0.0;
+  if (t < nt) {
+    cplx y0 = cmake(0, 0), y1 = cmake(0, 0), y2 = cmake(0, 0), y3 = cmake(0, 0);
+    const cplx* src = P.y_partial + (size_t)k * nt + t;
+    const size_t stride = (size_t)P.M * nt;
+    int wv = 0;
+    for (; wv + 4 <= P.nparts; wv += 4) {          // 4 independent chains (fixed association: still deterministic)
+      y0 = cadd(y0, src[(size_t)wv * stride]);
+      y1 = cadd(y1, src[(size_t)(wv + 1) * stride]);
+      y2 = cadd(y2, src[(size_t)(wv + 2) * stride]);
+      y3 = cadd(y3, src[(size_t)(wv + 3) * stride]);
+    }
+    for (; wv < P.nparts; ++wv) y0 = cadd(y0, src[(size_t)wv * stride]);
+    const cplx y = cadd(cadd(y0, y1), cadd(y2, y3));
+    const int c = t / L, lane = t % L;
+    for (int i = 0; i < P.KG; ++i) {
+      const int g = P.c_gen[((size_t)c * P.KG + i) * L + lane];
+      if (g < 0) continue;
+      const cplx yv = cmul(y, P.c_val[((size_t)c * P.KG + i) * L + lane]);
+#pragma unroll
+      for (int ch = 0; ch < QOCVL_MAX_CHAN; ++ch)
+        if (ch < P.C) {
+          const cplx d = P.dcoef[((size_t)k * P.J + g) * P.C + ch];
+          term[ch] += yv.x * d.x - yv.y * d.y;
+        }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < QOCVL_MAX_CHAN; ++c) red[c][t] = term[c];
+  __syncthreads();
+  for (int off = blockDim.x >> 1; off > 0; off >>= 1) {
+    if (t < off) {
+#pragma unroll
+      for (int c = 0; c < QOCVL_MAX_CHAN; ++c) red[c][t] += red[c][t + off];
+    }
+    __syncthreads();
+  }
+  if (t < P.C) P.gwave[(size_t)k * P.C + t] = 2.0 * P.dt * red[t][0];
+}
+
 typedef void (*aug_fn)(const AugArgs);
-static aug_fn pick_aug(int lpg, int wmax) {
+template <int KC>
+static aug_fn pick_aug_kc(int lpg, int wmax) {
   if (wmax <= 3) {
     switch (lpg) {
-      case 4: return k_chain_aug<4, 3>;
-      case 8: return k_chain_aug<8, 3>;
-      case 16: return k_chain_aug<16, 3>;
-      case 32: return k_chain_aug<32, 3>;
+      case 8: return k_chain_aug<8, 3, KC>;
+      case 16: return k_chain_aug<16, 3, KC>;
+      case 32: return k_chain_aug<32, 3, KC>;
     }
   } else if (wmax <= 6) {
     switch (lpg) {
-      case 4: return k_chain_aug<4, 6>;
-      case 8: return k_chain_aug<8, 6>;
-      case 16: return k_chain_aug<16, 6>;
-      case 32: return k_chain_aug<32, 6>;
+      case 8: return k_chain_aug<8, 6, KC>;
+      case 16: return k_chain_aug<16, 6, KC>;
+      case 32: return k_chain_aug<32, 6, KC>;
     }
   }
   return nullptr;
 }
+static aug_fn pick_aug(int lpg, int wmax, int kc) {
+  return kc == 1 ? pick_aug_kc<1>(lpg, wmax) : (kc == 2 ? pick_aug_kc<2>(lpg, wmax) : nullptr);
+}
 
 static size_t aug_smem_bytes(const qocvl_plan* p, int ngroups) {
-  const int J = p->d.n_gen, C = p->d.n_chan, L = p->aug_lpg;
-  const int nwarps = std::max(1, ngroups * L / 32);
-  const size_t tab = (size_t)(p->la.n_row_slots + p->la.n_col_slots) * p->la.kc * L;
-  const size_t cplx_count = tab + (size_t)ngroups * J + (size_t)nwarps * J * C + (size_t)ngroups * 2 * L;
-  return cplx_count * sizeof(cplx) + (size_t)ngroups * J * sizeof(double) + tab * sizeof(int);
+  const int L = p->aug_lpg, nsl = 1 + (p->aug_wmax <= 3 ? 3 : 6);
+  return ((size_t)ngroups * 2 * L + (p->la.KA > 0 ? (size_t)ngroups * 2 * nsl * L : 0)) * sizeof(cplx);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -439,7 +470,7 @@ int qocvl_aug_configure(qocvl_plan* p) {
   off[nv + 1] = off[nv] + (int)sec[nv].rows.size();
   const int N = off[nv + 1];
   if (N < 1 || N > 32) return QOCVL_ERR_UNSUPPORTED;
-  const int L = N <= 4 ? 4 : (N <= 8 ? 8 : (N <= 16 ? 16 : 32));
+  const int L = N <= 8 ? 8 : (N <= 16 ? 16 : 32);
   // ---- stacked generators [J][N][N]
   std::vector<zc> aug((size_t)J * N * N, zc(0, 0));
   auto fill_block = [&](const Sector& rs, int roff, const Sector& cs, int coff, bool wfam) {
@@ -478,23 +509,151 @@ int qocvl_aug_configure(qocvl_plan* p) {
     wq[rq] = (double)sec[va].orbit[a];
     wq[L + rq] = wq[L + rp] = (double)sec[va].orbit[a];
   }
-  int rc = qocvl_build_lane_layout(p, aug, N, L, true, &p->la);
-  if (rc) return rc;
-  const int wmax = std::max(p->la.n_row_slots, p->la.n_col_slots) - 1;
-  if (wmax > 6 || J * d.n_chan > 96) return QOCVL_ERR_UNSUPPORTED;
-  p->aug_n = N; p->aug_lpg = L; p->aug_nnz = p->la.nnz; p->aug_wmax = wmax;
-  aug_fn fn = pick_aug(L, wmax);
-  if (!fn) return QOCVL_ERR_UNSUPPORTED;
+  // ---- generator classes: generators whose per-sample multiplier columns are identical share a class
+  //      (class 0: multiplier 1 for every sample), so their contributions to an entry merge into one table value
+  const int S = p->n_samples;
+  if ((int)p->h_mul.size() != S * J || (int)p->h_add.size() != S * J) return QOCVL_ERR_STATE;
+  std::vector<int> cls(J, 0);
+  std::vector<char> has_add(J, 0);
+  int ncls = 1;
+  {
+    std::map<std::vector<double>, int> seen;
+    for (int g = 0; g < J; ++g) {
+      std::vector<double> col(S);
+      bool ones = true;
+      for (int s = 0; s < S; ++s) {
+        col[s] = p->h_mul[(size_t)s * J + g];
+        ones = ones && col[s] == 1.0;
+        const cplx ad = p->h_add[(size_t)s * J + g];
+        if (ad.x != 0.0 || ad.y != 0.0) has_add[g] = 1;
+      }
+      if (ones) continue;
+      auto it = seen.find(col);
+      if (it == seen.end()) { seen[col] = ncls; cls[g] = ncls++; } else cls[g] = it->second;
+    }
+  }
+  std::vector<double> mcls((size_t)S * ncls, 1.0);
+  for (int g = 0; g < J; ++g)
+    if (cls[g] > 0)
+      for (int s = 0; s < S; ++s) mcls[(size_t)s * ncls + cls[g]] = p->h_mul[(size_t)s * J + g];
+  // ---- sparsity pattern of the stacked system: per-row and per-column off-diagonal lists
+  auto AG = [&](int j, int a, int b) { return aug[((size_t)j * N + a) * N + b]; };
+  std::vector<std::vector<int>> rows(N), cols(N);
+  int nnz = 0;
+  for (int a = 0; a < N; ++a)
+    for (int b = 0; b < N; ++b) {
+      bool any = false;
+      for (int j = 0; j < J; ++j) any = any || std::abs(AG(j, a, b)) > 0.0;
+      if (!any) continue;
+      ++nnz;
+      if (a != b) { rows[a].push_back(b); cols[b].push_back(a); }
+    }
+  int w = 0, wc = 0;
+  for (int r = 0; r < N; ++r) { w = std::max(w, (int)rows[r].size()); wc = std::max(wc, (int)cols[r].size()); }
+  const int wmax = std::max(w, wc);
+  if (wmax > 6) return QOCVL_ERR_UNSUPPORTED;
+  // contributions of entry (a, b) grouped by class, and its generators that carry an additive per-sample term
+  typedef std::vector<std::pair<int, zc>> GenList;
+  auto contribs = [&](int a, int b) {
+    std::map<int, GenList> by_cls;
+    for (int j = 0; j < J; ++j)
+      if (std::abs(AG(j, a, b)) > 0.0) by_cls[cls[j]].push_back({j, AG(j, a, b)});
+    return by_cls;
+  };
+  auto addgens = [&](int a, int b) {
+    GenList l;
+    for (int j = 0; j < J; ++j)
+      if (has_add[j] && std::abs(AG(j, a, b)) > 0.0) l.push_back({j, AG(j, a, b)});
+    return l;
+  };
+  int KC = 1, KG = 1, KA = 0;
+  for (int a = 0; a < N; ++a)
+    for (int b = 0; b < N; ++b) {
+      const auto cb = contribs(a, b);
+      KC = std::max(KC, (int)cb.size());
+      for (const auto& kv : cb) KG = std::max(KG, (int)kv.second.size());
+      KA = std::max(KA, (int)addgens(a, b).size());
+    }
+  if (KC > 2) return QOCVL_ERR_UNSUPPORTED;
+  aug_fn fn = pick_aug(L, wmax, KC);
+  if (!fn || L < 8) {
+    if (L < 8) fn = pick_aug(8, wmax, KC);
+    if (!fn) return QOCVL_ERR_UNSUPPORTED;
+  }
+  const int Lk = std::max(L, 8);                       // lanes per sample of the kernel instance
+  const int nr = 1 + w, nc = 1 + wc;
+  std::vector<int> row_col((size_t)nr * Lk), col_row((size_t)nc * Lk);
+  std::vector<int> r_cls((size_t)nr * KC * Lk, -1), c_cls((size_t)nc * KC * Lk, -1);
+  std::vector<int> r_gen((size_t)nr * KC * KG * Lk, -1), c_gen((size_t)nc * KC * KG * Lk, -1);
+  std::vector<cplx> r_val((size_t)nr * KC * KG * Lk, cmake(0, 0)), c_val((size_t)nc * KC * KG * Lk, cmake(0, 0));
+  const int KAa = std::max(KA, 1);
+  std::vector<int> ra_gen((size_t)nr * KAa * Lk, -1), ca_gen((size_t)nc * KAa * Lk, -1);
+  std::vector<cplx> ra_val((size_t)nr * KAa * Lk, cmake(0, 0)), ca_val((size_t)nc * KAa * Lk, cmake(0, 0));
+  for (int s = 0; s < nr; ++s) for (int r = 0; r < Lk; ++r) row_col[(size_t)s * Lk + r] = r;
+  for (int s = 0; s < nc; ++s) for (int r = 0; r < Lk; ++r) col_row[(size_t)s * Lk + r] = r;
+  unsigned add_row_mask = 0, add_col_mask = 0;
+  auto fill = [&](std::vector<int>& tcls, std::vector<int>& tgen, std::vector<cplx>& tval, std::vector<int>& agen,
+                  std::vector<cplx>& aval, unsigned* mask, int slot, int lane, int a, int b) {
+    int i = 0;
+    for (const auto& kv : contribs(a, b)) {
+      tcls[((size_t)slot * KC + i) * Lk + lane] = kv.first;
+      for (size_t x = 0; x < kv.second.size(); ++x) {
+        const size_t idx = (((size_t)slot * KC + i) * KG + x) * Lk + lane;
+        tgen[idx] = kv.second[x].first;
+        tval[idx] = cmake(kv.second[x].second.real(), kv.second[x].second.imag());
+      }
+      ++i;
+    }
+    const GenList ag = addgens(a, b);
+    for (size_t x = 0; x < ag.size(); ++x) {
+      const size_t idx = ((size_t)slot * KAa + x) * Lk + lane;
+      agen[idx] = ag[x].first;
+      aval[idx] = cmake(ag[x].second.real(), ag[x].second.imag());
+      *mask |= 1u << slot;
+    }
+  };
+  for (int r = 0; r < N; ++r) {
+    fill(r_cls, r_gen, r_val, ra_gen, ra_val, &add_row_mask, 0, r, r, r);
+    fill(c_cls, c_gen, c_val, ca_gen, ca_val, &add_col_mask, 0, r, r, r);
+    for (size_t s = 0; s < rows[r].size(); ++s) {
+      row_col[(1 + s) * Lk + r] = rows[r][s];
+      fill(r_cls, r_gen, r_val, ra_gen, ra_val, &add_row_mask, 1 + (int)s, r, r, rows[r][s]);
+    }
+    for (size_t s = 0; s < cols[r].size(); ++s) {
+      col_row[(1 + s) * Lk + r] = cols[r][s];
+      fill(c_cls, c_gen, c_val, ca_gen, ca_val, &add_col_mask, 1 + (int)s, r, cols[r][s], r);
+    }
+  }
+  st.resize(Lk, cmake(0, 0)); tg.resize(Lk, cmake(0, 0)); pair.resize(Lk, -1);
+  {
+    std::vector<double> wq2(2 * (size_t)Lk, 0.0);
+    for (int r = 0; r < L; ++r) { wq2[r] = wq[r]; wq2[Lk + r] = wq[L + r]; }
+    wq = wq2;
+  }
+  // ---- upload
+  AugLayout& la = p->la;
+  la.release();
+  la.N = N; la.L = Lk; la.w = w; la.wc = wc; la.KC = KC; la.KG = KG; la.KA = KA; la.ncls = ncls; la.nnz = nnz;
+  la.add_row_mask = add_row_mask; la.add_col_mask = add_col_mask;
+  const int M = d.n_slices;
+#define AUG_UP(ptr, vec)                                                                              \
+  do {                                                                                                \
+    QCUDA(cudaMalloc((void**)&(ptr), std::max<size_t>(1, (vec).size()) * sizeof((vec)[0])));           \
+    if (!(vec).empty())                                                                               \
+      QCUDA(cudaMemcpy((ptr), (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice)); \
+  } while (0)
+  AUG_UP(la.row_col, row_col); AUG_UP(la.col_row, col_row);
+  AUG_UP(la.r_cls, r_cls); AUG_UP(la.c_cls, c_cls);
+  AUG_UP(la.r_gen, r_gen); AUG_UP(la.c_gen, c_gen); AUG_UP(la.r_val, r_val); AUG_UP(la.c_val, c_val);
+  AUG_UP(la.ra_gen, ra_gen); AUG_UP(la.ca_gen, ca_gen); AUG_UP(la.ra_val, ra_val); AUG_UP(la.ca_val, ca_val);
+  AUG_UP(la.mcls, mcls);
+  QCUDA(cudaMalloc((void**)&la.p_row, (size_t)M * nr * KC * Lk * sizeof(cplx)));
+  QCUDA(cudaMalloc((void**)&la.p_col, (size_t)M * nc * KC * Lk * sizeof(cplx)));
   for (void** q : {(void**)&p->d_aug_starts, (void**)&p->d_aug_targets, (void**)&p->d_aug_pair, (void**)&p->d_aug_wq})
     if (*q) { cudaFree(*q); *q = nullptr; }
-  QCUDA(cudaMalloc((void**)&p->d_aug_starts, L * sizeof(cplx)));
-  QCUDA(cudaMalloc((void**)&p->d_aug_targets, L * sizeof(cplx)));
-  QCUDA(cudaMalloc((void**)&p->d_aug_pair, L * sizeof(int)));
-  QCUDA(cudaMalloc((void**)&p->d_aug_wq, 2 * L * sizeof(double)));
-  QCUDA(cudaMemcpy(p->d_aug_starts, st.data(), L * sizeof(cplx), cudaMemcpyHostToDevice));
-  QCUDA(cudaMemcpy(p->d_aug_targets, tg.data(), L * sizeof(cplx), cudaMemcpyHostToDevice));
-  QCUDA(cudaMemcpy(p->d_aug_pair, pair.data(), L * sizeof(int), cudaMemcpyHostToDevice));
-  QCUDA(cudaMemcpy(p->d_aug_wq, wq.data(), 2 * L * sizeof(double), cudaMemcpyHostToDevice));
+  AUG_UP(p->d_aug_starts, st); AUG_UP(p->d_aug_targets, tg); AUG_UP(p->d_aug_pair, pair); AUG_UP(p->d_aug_wq, wq);
+#undef AUG_UP
+  p->aug_n = N; p->aug_lpg = Lk; p->aug_nnz = nnz; p->aug_wmax = wmax;
   {
     double inv[QOCVL_QMAX + 2];
     inv[0] = 0.0;
@@ -503,58 +662,74 @@ int qocvl_aug_configure(qocvl_plan* p) {
   }
   // ---- launch geometry: a CTA is only a container of independent groups; pick the number of samples per CTA
   //      that minimises the load of the busiest SM (wave quantisation), as in chain_small.cu
-  const int S = p->n_samples, gpw = 32 / L;
+  const int gpw = 32 / Lk;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
-  const int gmax = 512 / L / gpw * gpw;
+  const int gmax = 512 / Lk / gpw * gpw;
   int ngroups = gpw;
   {
     long best_load = -1;
     for (int g = gpw; g <= gmax; g += gpw) {
       const long n_ctas = (S + g - 1) / g;
       const long load = (n_ctas + sms - 1) / sms * g;
-      if (best_load < 0 || load < best_load || (load == best_load && g * L <= 256 && g > ngroups)) {
+      if (best_load < 0 || load < best_load || (load == best_load && g * Lk <= 256 && g > ngroups)) {
         best_load = load; ngroups = g;
       }
     }
   }
   if (const char* e = getenv("QOCVL_SPB")) ngroups = std::max(gpw, std::min(gmax, (atoi(e) + gpw - 1) / gpw * gpw));
   ngroups = std::min(ngroups, (S + gpw - 1) / gpw * gpw);
-  while (ngroups > gpw && aug_smem_bytes(p, ngroups) > 200 * 1024) ngroups -= gpw;
-  p->spb = ngroups; p->groups = ngroups; p->threads = ngroups * L;
+  p->spb = ngroups; p->groups = ngroups; p->threads = ngroups * Lk;
   p->chain_smem = aug_smem_bytes(p, ngroups);
-  if (p->chain_smem > 227 * 1024) return QOCVL_ERR_UNSUPPORTED;
+  if (p->chain_smem > 200 * 1024) return QOCVL_ERR_UNSUPPORTED;
   p->blocks = (S + ngroups - 1) / ngroups;
   QCUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->chain_smem));
   const size_t total_threads = (size_t)p->blocks * p->threads;
-  p->n_parts = (total_threads + 31) / 32;
-  const size_t ck = (size_t)d.n_slices * total_threads;
+  p->aug_parts = (int)((total_threads + 31) / 32);
+  p->n_parts = 0;                                     // no [warps][M][C] partial-gradient buffer on this path
+  const size_t ck = (size_t)M * total_threads;
   if (p->d_ckpt) { cudaFree(p->d_ckpt); p->d_ckpt = nullptr; p->bytes -= p->ckpt_bytes; }
   QCUDA(cudaMalloc((void**)&p->d_ckpt, ck * sizeof(cplx)));
   p->ckpt_bytes = ck * sizeof(cplx);
-  p->bytes += p->ckpt_bytes;
+  if (p->d_ypart) { cudaFree(p->d_ypart); p->d_ypart = nullptr; p->bytes -= p->ypart_bytes; }
+  p->ypart_bytes = (size_t)p->aug_parts * M * nc * KC * Lk * sizeof(cplx);
+  QCUDA(cudaMalloc((void**)&p->d_ypart, p->ypart_bytes));
+  p->bytes += p->ckpt_bytes + p->ypart_bytes;
   p->qcap_apriori = p->qcap;
   p->qcap = QOCVL_QMAX;
   p->use_aug = true;
   return QOCVL_OK;
 }
 
-int qocvl_aug_launch(qocvl_plan* p, bool want_grad, cudaStream_t st) {
+int qocvl_aug_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t st) {
   const qocvl_desc& d = p->d;
+  const AugLayout& la = p->la;
   AugArgs a;
-  a.N = p->aug_n; a.J = d.n_gen; a.M = d.n_slices; a.C = d.n_chan; a.S = p->n_samples;
-  a.w = p->la.n_row_slots - 1; a.wc = p->la.n_col_slots - 1; a.kc = p->la.kc;
+  a.N = la.N; a.J = d.n_gen; a.M = d.n_slices; a.C = d.n_chan; a.S = p->n_samples;
+  a.w = la.w; a.wc = la.wc; a.ncr = (1 + la.w) * la.KC; a.ncc = (1 + la.wc) * la.KC;
+  a.KA = la.KA; a.KG = la.KG; a.ncls = la.ncls; a.nparts = p->aug_parts;
+  a.add_row_mask = la.add_row_mask; a.add_col_mask = la.add_col_mask;
   a.want_grad = want_grad ? 1 : 0;
   a.dt = d.dt; a.inv_duration = 1.0 / d.duration; a.w_infid = d.w_infid; a.w_adiab = d.w_adiab;
   a.inv_fid_norm = 1.0 / d.fid_norm; a.inv_samples = 1.0 / (double)p->global_samples;
   a.d_const = p->d_const;
-  a.row_col = p->la.row_col; a.col_row = p->la.col_row;
-  a.rc_gen = p->la.rc_gen; a.cc_gen = p->la.cc_gen; a.rc_val = p->la.rc_val; a.cc_val = p->la.cc_val;
-  a.coef = p->d_coef; a.dcoef = p->d_dcoef; a.qdeg = p->d_qdeg; a.mul = p->d_mul; a.add = p->d_add;
+  a.row_col = la.row_col; a.col_row = la.col_row; a.r_cls = la.r_cls; a.c_cls = la.c_cls;
+  a.r_gen = la.r_gen; a.c_gen = la.c_gen; a.r_val = la.r_val; a.c_val = la.c_val;
+  a.ra_gen = la.ra_gen; a.ca_gen = la.ca_gen; a.ra_val = la.ra_val; a.ca_val = la.ca_val;
+  a.p_row = la.p_row; a.p_col = la.p_col;
+  a.coef = p->d_coef; a.dcoef = p->d_dcoef; a.qdeg = p->d_qdeg; a.mcls = la.mcls; a.add = p->d_add;
   a.starts = p->d_aug_starts; a.targets = p->d_aug_targets; a.pair = p->d_aug_pair; a.wq = p->d_aug_wq;
-  a.ckpt = p->d_ckpt; a.sample_out = p->d_sample_out; a.gw_partial = p->d_gw_partial;
-  pick_aug(p->aug_lpg, p->aug_wmax)<<<p->blocks, p->threads, p->chain_smem, st>>>(a);
-  p->launches++;
+  a.ckpt = p->d_ckpt; a.sample_out = p->d_sample_out; a.y_partial = p->d_ypart; a.gwave = gwave;
+  k_aug_tables<<<d.n_slices, 256, 0, st>>>(a, la.L);
+  pick_aug(la.L, p->aug_wmax, la.KC)<<<p->blocks, p->threads, p->chain_smem, st>>>(a);
+  p->launches += 2;
+  if (want_grad) {
+    if (!gwave) return QOCVL_ERR_ARG;
+    int nt = 32;
+    while (nt < a.ncc * la.L) nt <<= 1;
+    k_aug_reduce<<<d.n_slices, nt, 0, st>>>(a, la.L);
+    p->launches++;
+  }
   QCUDA(cudaGetLastError());
   return QOCVL_OK;
 }

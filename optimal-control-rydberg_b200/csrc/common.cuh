@@ -100,6 +100,29 @@ struct CsrLayout {
   std::vector<cplx> h_eval;
 };
 
+// Device tables of the reduced stacked system (chain_aug.cu).  Generators are grouped into "classes" by their
+// per-sample multiplier column (class 0: multiplier 1 for every sample), so that a matrix entry of sample s is
+//   X_e(k, s) = A_e(s) + sum_i m_s[cls_i] * P_i(k),   P_i(k) = dt * sum_{g in class i of e} coef_kg * val_eg
+// with P sample-independent (one small table per slice, k_aug_tables) and A the additive-noise part.
+struct AugLayout {
+  int N = 0, L = 0, w = 0, wc = 0, KC = 1, KG = 1, KA = 0, ncls = 1, nnz = 0;
+  unsigned add_row_mask = 0, add_col_mask = 0;   // slots that carry an additive per-sample term
+  int *row_col = nullptr, *col_row = nullptr;    // [1+w][L], [1+wc][L]  (slot 0 = diagonal)
+  int *r_cls = nullptr, *c_cls = nullptr;        // [(1+w)*KC][L], [(1+wc)*KC][L]  class id or -1
+  int *r_gen = nullptr, *c_gen = nullptr;        // [(1+w)*KC][KG][L] generator ids of the contribution (-1 = none)
+  cplx *r_val = nullptr, *c_val = nullptr;
+  int *ra_gen = nullptr, *ca_gen = nullptr;      // [1+w][KA][L] generators with an additive per-sample coefficient
+  cplx *ra_val = nullptr, *ca_val = nullptr;
+  double* mcls = nullptr;                        // [S][ncls]
+  cplx *p_row = nullptr, *p_col = nullptr;       // [M][(1+w)*KC][L], [M][(1+wc)*KC][L]
+  void release() {
+    void* ptrs[] = {row_col, col_row, r_cls, c_cls, r_gen, c_gen, r_val, c_val, ra_gen, ca_gen, ra_val, ca_val,
+                    mcls, p_row, p_col};
+    for (void* q : ptrs) if (q) cudaFree(q);
+    *this = AugLayout();
+  }
+};
+
 struct qocvl_plan {
   qocvl_desc d;
   int device = 0;
@@ -172,8 +195,12 @@ struct qocvl_plan {
   // reduced ensemble path (chain_aug.cu): every propagated vector restricted to the basis states it can reach,
   // symmetric sectors folded onto orbit representatives, all of it stacked into ONE sparse system of aug_n rows
   bool use_aug = false;
-  int aug_n = 0, aug_lpg = 0, aug_nnz = 0, aug_wmax = 0;
-  BlockLayout la;          // lane-per-row tables of the stacked system (u-family conventions, diagonal in slot 0)
+  int aug_n = 0, aug_lpg = 0, aug_nnz = 0, aug_wmax = 0, aug_parts = 0;
+  cplx* d_ypart = nullptr;        // [warps][M][column contributions][aug_lpg] per-warp sums of m * Xbar
+  size_t ypart_bytes = 0;
+  AugLayout la;            // lane-per-row tables of the stacked system
+  std::vector<double> h_mul;              // [S][J] host copy of the noise tables (generator classes)
+  std::vector<cplx> h_add;
   std::vector<cplx> h_live_s, h_live_t;   // [n_live][n] live start / (weighted) target kets, unpadded
   cplx *d_aug_starts = nullptr, *d_aug_targets = nullptr;   // [aug_lpg]
   int* d_aug_pair = nullptr;      // [aug_lpg] row of the partner (q row <-> p row) in the adiabaticity term, or -1
@@ -196,7 +223,7 @@ int qocvl_tp_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t s
 int qocvl_big_configure(qocvl_plan* p);
 int qocvl_big_launch(qocvl_plan* p, bool want_grad, cudaStream_t st);
 int qocvl_aug_configure(qocvl_plan* p);
-int qocvl_aug_launch(qocvl_plan* p, bool want_grad, cudaStream_t st);
+int qocvl_aug_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t st);
 int qocvl_build_lane_layout(qocvl_plan* p, const std::vector<std::complex<double>>& blocks, int n, int npad,
                             bool diag_slot, BlockLayout* out);
 int qocvl_build_csr(qocvl_plan* p, const std::vector<std::complex<double>>& blocks, CsrLayout* out);

@@ -162,7 +162,7 @@ extern "C" int qocvl_plan_create(qocvl_plan** out, const qocvl_desc* desc, int d
 extern "C" int qocvl_plan_destroy(qocvl_plan* p) {
   if (!p) return QOCVL_OK;
   cudaSetDevice(p->device);
-  free_layout(p->lu); free_layout(p->lw); free_layout(p->la);
+  free_layout(p->lu); free_layout(p->lw); p->la.release();
   for (CsrLayout* c : {&p->cu, &p->cw}) {
     cudaFree(c->rowptr); cudaFree(c->col); cudaFree(c->erow); cudaFree(c->colptr);
     cudaFree(c->crow); cudaFree(c->ceid); cudaFree(c->egen); cudaFree(c->eval);
@@ -172,7 +172,7 @@ extern "C" int qocvl_plan_destroy(qocvl_plan* p) {
                   p->d_mulmax, p->d_addmax, p->d_taps, p->d_raw, p->d_reg, p->d_wave, p->d_coef, p->d_dcoef,
                   p->d_qdeg, p->d_flag, p->d_ckpt, p->d_sample_out, p->d_gw_partial, p->d_gwave, p->d_greg,
                   p->d_graw, p->d_out3, p->d_dense_a, p->d_dense_b, p->d_aug_starts, p->d_aug_targets,
-                  p->d_aug_pair, p->d_aug_wq};
+                  p->d_aug_pair, p->d_aug_wq, p->d_ypart};
   for (void* q : ptrs) if (q) cudaFree(q);
   delete p;
   return QOCVL_OK;
@@ -280,6 +280,7 @@ extern "C" int qocvl_set_noise(qocvl_plan* p, int n_samples, const double* mul, 
     addmax[j] = std::max(addmax[j], std::hypot(ha[i].x, ha[i].y));
   }
   int rc;
+  p->h_mul = hm; p->h_add = ha;
   if ((rc = dev_upload(p, &p->d_mul, hm))) return rc;
   if ((rc = dev_upload(p, &p->d_add, ha))) return rc;
   if ((rc = dev_upload(p, &p->d_mulmax, mulmax))) return rc;
