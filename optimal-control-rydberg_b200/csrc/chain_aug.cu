@@ -142,23 +142,29 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
   // exchange layout: re[LPG] then im[LPG]; 8-byte accesses of the LPG lanes of a sample hit distinct banks
   auto xput = [&](double* xs, cplx val) { xs[r] = val.x; xs[LPG + r] = val.y; };
   auto xget = [&](const double* xs, int idx) -> cplx { return cmake(xs[idx], xs[LPG + idx]); };
-  // entry of slot s: A + sum_i m_i * P_i(k)   (row-owner tables: col = 0, column-owner tables: col = 1)
-  auto slot_value = [&](const cplx* tab, const double* m, unsigned mask, int col, int s) -> cplx {
+  // entry of slot s: A + sum_i m_i * P_i(k).  The table values P_i(k) are fetched one phase ahead into `raw`
+  // (global -> registers, L2-resident tables shared by every sample) so the load latency hides behind the sweeps.
+  auto load_raw = [&](const cplx* tab, int nslots, cplx* raw) {
+#pragma unroll
+    for (int s = 0; s < NSL; ++s)
+#pragma unroll
+      for (int i = 0; i < KC; ++i) raw[s * KC + i] = (s <= nslots) ? __ldg(tab + (size_t)(s * KC + i) * LPG) : czero;
+  };
+  auto slot_value = [&](const cplx* raw, const double* m, unsigned mask, int col, int s) -> cplx {
     cplx acc = czero;
 #pragma unroll
     for (int i = 0; i < KC; ++i) {
-      const cplx pv = __ldg(tab + (size_t)(s * KC + i) * LPG);
-      acc.x = fma(m[s * KC + i], pv.x, acc.x);
-      acc.y = fma(m[s * KC + i], pv.y, acc.y);
+      acc.x = fma(m[s * KC + i], raw[s * KC + i].x, acc.x);
+      acc.y = fma(m[s * KC + i], raw[s * KC + i].y, acc.y);
     }
     if ((mask >> s) & 1u) acc = cadd(acc, s_A[(col * NSL + s) * LPG + r]);
     return acc;
   };
-  auto assemble_rows = [&](int k) {
-    const cplx* tab = P.p_row + (size_t)k * P.ncr * LPG + r;
-    a_d = slot_value(tab, m_row, P.add_row_mask, 0, 0);
+  cplx raw_r[NSL * KC];                              // row-owner table values of the NEXT slice to be visited
+  auto finish_rows = [&]() {
+    a_d = slot_value(raw_r, m_row, P.add_row_mask, 0, 0);
 #pragma unroll
-    for (int s = 0; s < WMAX; ++s) a_row[s] = (s < P.w) ? slot_value(tab, m_row, P.add_row_mask, 0, 1 + s) : czero;
+    for (int s = 0; s < WMAX; ++s) a_row[s] = (s < P.w) ? slot_value(raw_r, m_row, P.add_row_mask, 0, 1 + s) : czero;
   };
   // one forward Taylor step: t <- Xaug t / j
   auto step_fwd = [&](cplx t, double invj) -> cplx {
@@ -176,9 +182,15 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
   };
 
   // =================================== forward sweep ===================================
+  load_raw(P.p_row + r, P.w, raw_r);
+  int q_next = P.qdeg[0];
   for (int k = 0; k < P.M; ++k) {
-    const int q = P.qdeg[k];
-    assemble_rows(k);
+    const int q = q_next;
+    finish_rows();
+    if (k + 1 < P.M) {
+      load_raw(P.p_row + (size_t)(k + 1) * P.ncr * LPG + r, P.w, raw_r);
+      q_next = P.qdeg[k + 1];
+    }
     if (P.want_grad && live) P.ckpt[(size_t)k * gthreads + gtid] = z;
     cplx t = z;
     for (int j = 1; j <= q; ++j) {
@@ -225,21 +237,28 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
 
   // =================================== reverse sweep ===================================
   const size_t gwarp = (size_t)blockIdx.x * nwarps + warp;
+  load_raw(P.p_row + (size_t)(P.M - 1) * P.ncr * LPG + r, P.w, raw_r);
+  q_next = P.qdeg[P.M - 1];
+  cplx t_next = live ? P.ckpt[(size_t)(P.M - 1) * gthreads + gtid] : czero;
   for (int k = P.M - 1; k >= 0; --k) {
-    const int q = P.qdeg[k];
-    assemble_rows(k);
-    cplx a_col[WMAX];                               // column-owner values Xaug[a][r] for the rows a of my column
-    {
-      const cplx* tab = P.p_col + (size_t)k * P.ncc * LPG + r;
-#pragma unroll
-      for (int s = 0; s < WMAX; ++s) a_col[s] = (s < P.wc) ? slot_value(tab, m_col, P.add_col_mask, 1, 1 + s) : czero;
-    }
+    const int q = q_next;
+    finish_rows();
+    cplx raw_c[NSL * KC];                           // column-owner table values: in flight during the recompute
+    load_raw(P.p_col + (size_t)k * P.ncc * LPG + r, P.wc, raw_c);
     // ---- recompute the forward Taylor terms t_0 .. t_{q-1}
-    cplx t = live ? P.ckpt[(size_t)k * gthreads + gtid] : czero;
+    cplx t = t_next;
     t_loc[0] = t;
     for (int j = 1; j < q; ++j) {
       t = step_fwd(t, c_ainv[j]);
       t_loc[j] = t;
+    }
+    cplx a_col[WMAX];                               // column-owner values Xaug[a][r] for the rows a of my column
+#pragma unroll
+    for (int s = 0; s < WMAX; ++s) a_col[s] = (s < P.wc) ? slot_value(raw_c, m_col, P.add_col_mask, 1, 1 + s) : czero;
+    if (k > 0) {                                    // next slice's rows, checkpoint and degree: in flight during the adjoint
+      load_raw(P.p_row + (size_t)(k - 1) * P.ncr * LPG + r, P.w, raw_r);
+      t_next = live ? P.ckpt[(size_t)(k - 1) * gthreads + gtid] : czero;
+      q_next = P.qdeg[k - 1];
     }
     // ---- descending adjoint recurrence, Xbar accumulated on my column's entries
     cplx tb = lam;
