@@ -99,22 +99,17 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
     rcol[s] = (s < P.w) ? P.row_col[(1 + s) * LPG + r] : r;
     crow[s] = (s < P.wc) ? P.col_row[(1 + s) * LPG + r] : r;
   }
-  // per-sample multiplier of each of my contributions (0 = no contribution); real entries form a slot prefix
+  // per-sample multiplier of each of my contributions (0 = no contribution)
   double m_row[NSL * KC], m_col[NSL * KC];
-  int rcnt = 0, ccnt = 0;
 #pragma unroll
   for (int s = 0; s < NSL; ++s) {
-    bool any_r = false, any_c = false;
 #pragma unroll
     for (int i = 0; i < KC; ++i) {
       const int cr = (s <= P.w) ? P.r_cls[(s * KC + i) * LPG + r] : -1;
       const int cc = (s <= P.wc) ? P.c_cls[(s * KC + i) * LPG + r] : -1;
       m_row[s * KC + i] = (cr >= 0 && live) ? P.mcls[(size_t)sm * P.ncls + cr] : 0.0;
       m_col[s * KC + i] = (cc >= 0 && live) ? P.mcls[(size_t)sm * P.ncls + cc] : 0.0;
-      any_r = any_r || cr >= 0;
-      any_c = any_c || cc >= 0;
     }
-    if (s > 0) { rcnt += any_r; ccnt += any_c; }
   }
   const cplx czero = cmake(0.0, 0.0);
   if (P.KA > 0) {   // A_e = dt * sum_g add_sg * val_eg for my row-owner and column-owner slots
@@ -134,14 +129,24 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
   const cplx ytgt = live ? P.targets[r] : czero;
   const int pr = live ? P.pair[r] : -1;
   const double w_qp = live ? P.wq[r] : 0.0, w_lam = live ? P.wq[LPG + r] : 0.0;
-  int ph = 0;                                                       // exchange buffer offset: 0 or LPG
   cplx t_loc[QOCVL_QMAX];
   cplx a_d, a_row[WMAX];
   __syncwarp();
 
-  // exchange layout: re[LPG] then im[LPG]; 8-byte accesses of the LPG lanes of a sample hit distinct banks
-  auto xput = [&](double* xs, cplx val) { xs[r] = val.x; xs[LPG + r] = val.y; };
-  auto xget = [&](const double* xs, int idx) -> cplx { return cmake(xs[idx], xs[LPG + idx]); };
+  // exchange: two buffers per sample, each re[LPG] then im[LPG]; the 8-byte accesses of the LPG lanes of a sample
+  // hit distinct banks whatever the gather pattern.  Every Taylor loop starts on buffer 0 (after a __syncwarp) and
+  // is unrolled by two, so the buffer offsets are immediates; empty slots gather the lane's own element (their
+  // matrix value is zero), which costs no extra shared-memory wavefront and needs no predicate.
+  double* const x_own = (double*)s_x + r;
+  const double* x_row[WMAX];
+  const double* x_col[WMAX];
+#pragma unroll
+  for (int s = 0; s < WMAX; ++s) {
+    x_row[s] = (const double*)s_x + rcol[s];
+    x_col[s] = (const double*)s_x + crow[s];
+  }
+  auto xput = [&](int buf, cplx val) { x_own[buf * 2 * LPG] = val.x; x_own[buf * 2 * LPG + LPG] = val.y; };
+  auto xget = [&](const double* src, int buf) -> cplx { return cmake(src[buf * 2 * LPG], src[buf * 2 * LPG + LPG]); };
   // entry of slot s: A + sum_i m_i * P_i(k).  The table values P_i(k) are fetched one phase ahead into `raw`
   // (global -> registers, L2-resident tables shared by every sample) so the load latency hides behind the sweeps.
   auto load_raw = [&](const cplx* tab, int nslots, cplx* raw) {
@@ -167,17 +172,12 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
     for (int s = 0; s < WMAX; ++s) a_row[s] = (s < P.w) ? slot_value(raw_r, m_row, P.add_row_mask, 0, 1 + s) : czero;
   };
   // one forward Taylor step: t <- Xaug t / j
-  auto step_fwd = [&](cplx t, double invj) -> cplx {
-    double* xs = (double*)(s_x + ph);
-    xput(xs, t);
+  auto step_fwd = [&](cplx t, double invj, int buf) -> cplx {
+    xput(buf, t);
     __syncwarp();
     cplx acc = cmul(a_d, t);
 #pragma unroll
-    for (int s = 0; s < WMAX; ++s) {
-      const cplx xv = (s < rcnt) ? xget(xs, rcol[s]) : czero;
-      acc = cfma(a_row[s], xv, acc);
-    }
-    ph = LPG - ph;
+    for (int s = 0; s < WMAX; ++s) acc = cfma(a_row[s], xget(x_row[s], buf), acc);
     return cscale(acc, invj);
   };
 
@@ -193,8 +193,16 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
     }
     if (P.want_grad && live) P.ckpt[(size_t)k * gthreads + gtid] = z;
     cplx t = z;
-    for (int j = 1; j <= q; ++j) {
-      t = step_fwd(t, c_ainv[j]);
+    __syncwarp();                                   // the previous loop's readers are done with buffer 0
+    int j = 1;
+    for (; j + 1 <= q; j += 2) {
+      t = step_fwd(t, c_ainv[j], 0);
+      z = cadd(z, t);
+      t = step_fwd(t, c_ainv[j + 1], 1);
+      z = cadd(z, t);
+    }
+    if (j <= q) {
+      t = step_fwd(t, c_ainv[j], 0);
       z = cadd(z, t);
     }
   }
@@ -202,11 +210,10 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
   // =================================== cost ============================================
   cplx zp;
   {
-    double* xs = (double*)(s_x + ph);
-    xput(xs, z);
     __syncwarp();
-    zp = (pr >= 0) ? xget(xs, pr) : czero;
-    ph = LPG - ph;
+    xput(0, z);
+    __syncwarp();
+    zp = (pr >= 0) ? xget((const double*)s_x + pr, 0) : czero;
   }
   cplx dsum = cfma_conj(ytgt, z, czero);                            // sum_r conj(y_r) z_r
   cplx qp = cscale(cfma_conj(z, zp, czero), w_qp);                  // q^dag p
@@ -248,9 +255,19 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
     // ---- recompute the forward Taylor terms t_0 .. t_{q-1}
     cplx t = t_next;
     t_loc[0] = t;
-    for (int j = 1; j < q; ++j) {
-      t = step_fwd(t, c_ainv[j]);
-      t_loc[j] = t;
+    __syncwarp();
+    {
+      int j = 1;
+      for (; j + 1 < q; j += 2) {
+        t = step_fwd(t, c_ainv[j], 0);
+        t_loc[j] = t;
+        t = step_fwd(t, c_ainv[j + 1], 1);
+        t_loc[j + 1] = t;
+      }
+      if (j < q) {
+        t = step_fwd(t, c_ainv[j], 0);
+        t_loc[j] = t;
+      }
     }
     cplx a_col[WMAX];                               // column-owner values Xaug[a][r] for the rows a of my column
 #pragma unroll
@@ -265,22 +282,29 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
     cplx xc_d = czero, xc[WMAX];
 #pragma unroll
     for (int s = 0; s < WMAX; ++s) xc[s] = czero;
-    for (int j = q; j >= 1; --j) {
+    auto step_adj = [&](int j, int buf) {
       const double invj = c_ainv[j];
-      double* xs = (double*)(s_x + ph);
-      xput(xs, tb);
+      xput(buf, tb);
       __syncwarp();
       const cplx tprev = cscale(t_loc[j - 1], invj);
       cplx acc = cfma_conj(a_d, tb, czero);
       xc_d = cfma_conj(tb, tprev, xc_d);
 #pragma unroll
       for (int s = 0; s < WMAX; ++s) {
-        const cplx ta = (s < ccnt) ? xget(xs, crow[s]) : czero;
+        const cplx ta = xget(x_col[s], buf);
         acc = cfma_conj(a_col[s], ta, acc);
         xc[s] = cfma_conj(ta, tprev, xc[s]);
       }
       tb = cadd(lam, cscale(acc, invj));
-      ph = LPG - ph;
+    };
+    __syncwarp();
+    {
+      int j = q;
+      for (; j >= 2; j -= 2) {
+        step_adj(j, 0);
+        step_adj(j - 1, 1);
+      }
+      if (j >= 1) step_adj(j, 0);
     }
     lam = tb;
     // ---- Ybar_e = sum over the warp's samples of m_s * Xbar_e: the generators' d coef / d wave is the same for
