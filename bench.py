@@ -36,8 +36,8 @@ def workload_config(samples_per_gpu, n_gpus):
                         "two-atom 16-level Van Loan cost + 3N-gradient, complex128",
             "samples_per_gpu": samples_per_gpu, "samples_total": samples_per_gpu * n_gpus, "slices": 2000,
             "n_gauss": N_GAUSS, "channels": 5, "hilbert_dim": 16,
-            "l2": "per-step working set (state checkpoints, 6.3 GB at 4096 samples, written then read once) "
-                  "exceeds the 126 MB L2; no flush needed",
+            "l2": "per-step working set (state checkpoints + per-warp gradient partials, ~6 GB at 4096 samples, "
+                  "written then read once) exceeds the 126 MB L2; no flush needed",
             "parallelism": f"samples sharded, {n_gpus} rank(s), one 243-double all-reduce per step"}
 
 
@@ -239,9 +239,23 @@ def run_gpu(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    nvec = plan.vectors_propagated                        # 3 for CZ: U|10>, U|11>, W|10>
-    ckpt_bytes = 2.0 * M * S_local * nvec * 16 * 16       # checkpoint write + read: nvec vectors x 16 rows x c128
-    roofline = {"bound": "fp64", "kernel": f"k_chain<16,{nvec - 1},4,2,1>", "achieved": achieved_tf, "peak": peak_tf,
+    info = plan.chain_info()
+    hbm_bytes = plan.hbm_bytes_per_call(True)             # checkpoints + per-warp gradient partials, write + read
+    if info["path"] == "reduced_stacked":
+        kname = f"k_chain_aug<{info['lanes']},{info['slots']},{info['classes']}>"
+        # shared-memory exchange of the Taylor mat-vecs: per step and warp 2 STS.64 + 2*slots LDS.64, 2 wavefronts
+        # each (32 lanes x 8 B); steps per slice = q (forward) + q-1 (recompute) + q (adjoint)
+        steps_total = flops / (8.0 * info["nnz"] * S_local)
+        wavefronts = steps_total * S_local / (32 // info["lanes"]) * 4.0 * (1 + info["slots"])
+        sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+        sm_clock_hz = 1e6 * (peaks.get("sm_max_mhz") or 1965.0)
+        smem = {"wavefronts_per_launch": wavefronts, "peak_wavefronts_per_s": sm_count * sm_clock_hz,
+                "frac": wavefronts / (k_ms * 1e-3) / (sm_count * sm_clock_hz) if k_ms > 0 else None,
+                "note": "modelled exchange traffic (matches ncu l1tex__data_pipe_lsu_wavefronts_mem_shared within 6 %); "
+                        "peak = 1 wavefront (128 B) per clock per SM"}
+    else:
+        kname, smem = f"k_chain<{info['lanes']},{plan.vectors_propagated - 1},4,2,1>", None
+    roofline = {"bound": "fp64", "kernel": kname, "achieved": achieved_tf, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": (achieved_tf / peak_tf) if achieved_tf and peak_tf > 0 else None,
                 "traffic": None,
                 "peak_source": "live DFMA microbenchmark in this run (qocvl_measure_fp64_peak); "
@@ -252,9 +266,14 @@ def run_gpu(args):
                              "peak_register_operands = a=fma(a,b,c) with three register operands, the form every "
                              "real kernel issues: the SM register file sustains only ~2/3 of the issue peak",
                 "flops_per_launch": flops, "flops_per_unit": flops / (M * S_local),
+                "flops_note": "useful complex multiply-adds only (8 flops each) on the non-zeros of the propagated "
+                              "system; since the reduced stacked system that count no longer includes products with "
+                              "structurally-zero vector elements (CZ: 36 non-zeros per Taylor step instead of 145)",
+                "system": info,
                 "kernel_ms": k_ms, "kernel_share_of_step": k_ms * args.steps / elapsed_ms if k_ms > 0 else None,
                 "m1_equivalent_tflops": 840.0 * 16 ** 3 * M * S_local / (k_ms * 1e-3) * 1e-12 if k_ms > 0 else None,
-                "hbm": {"algorithmic_bytes": ckpt_bytes, "achieved_gbs": ckpt_bytes / (k_ms * 1e-3) * 1e-9 if k_ms > 0 else None,
+                "shared_memory": smem,
+                "hbm": {"algorithmic_bytes": hbm_bytes, "achieved_gbs": hbm_bytes / (k_ms * 1e-3) * 1e-9 if k_ms > 0 else None,
                         "peak_gbs": peaks.get("hbm_gbs"), "peak_source": "MEASURED_PEAKS.json"}}
 
     if rank == 0:

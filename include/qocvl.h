@@ -147,6 +147,13 @@ int qocvl_vectors_propagated(const qocvl_plan* plan);
 int qocvl_reduced_rows(const qocvl_plan* plan);
 long long qocvl_launch_count(const qocvl_plan* plan); /* kernels launched so far by this plan */
 double qocvl_flops_per_call(const qocvl_plan* plan, int with_grad); /* executed FP64 flop model */
+/* Algorithmic HBM bytes of one chain evaluation: checkpoints written then read once, plus the per-warp partial
+ * gradient data written by the reverse sweep and read once by the reduction (0 before the first evaluation). */
+double qocvl_hbm_bytes_per_call(const qocvl_plan* plan, int with_grad);
+/* Launch geometry after configuration, out[8] = {path: 0 lane-per-row / 1 reduced stacked system / 2 time-parallel
+ * single sample / 3 rows-strided big-n; rows per sample; lanes per sample; off-diagonal slots per row; multiplier
+ * classes per entry; non-zeros of the propagated system; threads per CTA; CTAs}. */
+int qocvl_chain_info(const qocvl_plan* plan, int* out8);
 /* Kernel timing for the roofline report: when enabled, CUDA events bracket the chain kernel on
  * the launch stream; qocvl_last_chain_ms synchronises on the end event and returns the duration
  * of the most recent chain-kernel launch in milliseconds (< 0 if none was timed). */

@@ -129,6 +129,35 @@ extern "C" double qocvl_flops_per_call(const qocvl_plan* p, int with_grad) {
   return total * 8.0 * (double)p->n_samples;
 }
 
+// Algorithmic HBM bytes of one chain evaluation (what has to cross HBM once by design): state checkpoints written
+// by the forward sweep and read back by the reverse sweep, plus the per-warp partial gradient data written by the
+// reverse sweep and read once by the reduction kernel.
+extern "C" double qocvl_hbm_bytes_per_call(const qocvl_plan* p, int with_grad) {
+  if (!p || p->groups <= 0 || !with_grad) return 0.0;
+  const double M = p->d.n_slices, S = p->n_samples;
+  if (p->use_aug) return 2.0 * M * S * p->aug_n * sizeof(cplx) + 2.0 * (double)p->ypart_bytes;
+  if (p->use_tp || p->use_big) return 2.0 * (double)p->ckpt_bytes;
+  return 2.0 * M * S * (p->n_live + 1) * p->npad * sizeof(cplx) + 2.0 * (double)p->gw_partial_elems * sizeof(double);
+}
+
+// Launch geometry of the chain kernel after configuration: out[8] = {path (0 lane-per-row, 1 reduced stacked
+// system, 2 time-parallel single sample, 3 rows-strided big-n), rows per sample, lanes per sample, off-diagonal
+// slots per row, multiplier classes per entry, non-zeros of the propagated system, threads per CTA, CTAs}.
+extern "C" int qocvl_chain_info(const qocvl_plan* p, int* out) {
+  if (!p || !out) return QOCVL_ERR_ARG;
+  if (p->groups <= 0) return QOCVL_ERR_STATE;
+  const int path = p->use_tp ? 2 : (p->use_aug ? 1 : (p->use_big ? 3 : 0));
+  out[0] = path;
+  out[1] = p->use_aug ? p->aug_n : p->d.n;
+  out[2] = p->use_aug ? p->aug_lpg : p->npad;
+  out[3] = p->use_aug ? (p->aug_wmax <= 3 ? 3 : 6) : 4;
+  out[4] = p->use_aug ? p->la.KC : p->lu.kc;
+  out[5] = p->use_aug ? p->aug_nnz : (p->n_live + 1) * p->cu.nnz + p->cw.nnz;
+  out[6] = p->threads;
+  out[7] = p->blocks;
+  return QOCVL_OK;
+}
+
 extern "C" int qocvl_set_timing(qocvl_plan* p, int enabled) {
   if (!p) return QOCVL_ERR_ARG;
   QCUDA(cudaSetDevice(p->device));

@@ -254,18 +254,19 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
     load_raw(P.p_col + (size_t)k * P.ncc * LPG + r, P.wc, raw_c);
     // ---- recompute the forward Taylor terms t_0 .. t_{q-1}
     cplx t = t_next;
+    // (stored pre-scaled, s_j = t_{j-1} / j, which is what the adjoint pairs with tb_j:  s_{j+1} = X s_j / (j+1))
     t_loc[0] = t;
     __syncwarp();
     {
       int j = 1;
       for (; j + 1 < q; j += 2) {
-        t = step_fwd(t, c_ainv[j], 0);
+        t = step_fwd(t, c_ainv[j + 1], 0);
         t_loc[j] = t;
-        t = step_fwd(t, c_ainv[j + 1], 1);
+        t = step_fwd(t, c_ainv[j + 2], 1);
         t_loc[j + 1] = t;
       }
       if (j < q) {
-        t = step_fwd(t, c_ainv[j], 0);
+        t = step_fwd(t, c_ainv[j + 1], 0);
         t_loc[j] = t;
       }
     }
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
       const double invj = c_ainv[j];
       xput(buf, tb);
       __syncwarp();
-      const cplx tprev = cscale(t_loc[j - 1], invj);
+      const cplx tprev = t_loc[j - 1];
       cplx acc = cfma_conj(a_d, tb, czero);
       xc_d = cfma_conj(tb, tprev, xc_d);
 #pragma unroll

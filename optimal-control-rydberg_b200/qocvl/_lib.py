@@ -45,6 +45,8 @@ SIGNATURES = {
     "qocvl_last_taylor_degree": (C.c_int, [_P]),
     "qocvl_vectors_propagated": (C.c_int, [_P]),
     "qocvl_reduced_rows": (C.c_int, [_P]),
+    "qocvl_hbm_bytes_per_call": (C.c_double, [_P, C.c_int]),
+    "qocvl_chain_info": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "qocvl_launch_count": (C.c_longlong, [_P]),
     "qocvl_flops_per_call": (C.c_double, [_P, C.c_int]),
     "qocvl_set_timing": (C.c_int, [_P, C.c_int]),

@@ -200,6 +200,19 @@ class Plan:
         """Rows per sample of the reduced stacked system (chain_aug.cu), 0 if the last configuration does not use it."""
         return int(self._lib.qocvl_reduced_rows(self._h))
 
+    def hbm_bytes_per_call(self, with_grad=True):
+        return float(self._lib.qocvl_hbm_bytes_per_call(self._h, 1 if with_grad else 0))
+
+    def chain_info(self):
+        """Launch geometry of the chain kernel (after the first evaluation)."""
+        import ctypes
+        buf = (ctypes.c_int * 8)()
+        _lib.check(self._lib.qocvl_chain_info(self._h, buf), "chain_info")
+        keys = ("path", "rows", "lanes", "slots", "classes", "nnz", "threads", "ctas")
+        info = dict(zip(keys, (int(x) for x in buf)))
+        info["path"] = ("lane_per_row", "reduced_stacked", "time_parallel", "rows_strided")[info["path"]]
+        return info
+
     @property
     def vectors_propagated(self):
         return int(self._lib.qocvl_vectors_propagated(self._h))
