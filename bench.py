@@ -241,10 +241,11 @@ def run_gpu(args):
         pass
     info = plan.chain_info()
     hbm_bytes = plan.hbm_bytes_per_call(True)             # checkpoints + per-warp gradient partials, write + read
-    if info["path"] == "reduced_stacked":
-        kname = f"k_chain_aug<{info['lanes']},{info['slots']},{info['classes']}>"
+    if info["path"].startswith("reduced_stacked"):
+        streamed = int(info["path"].endswith("streamed"))
+        kname = f"k_chain_aug<{info['lanes']},{info['slots']},{info['classes']},{streamed}>"
         # shared-memory exchange of the Taylor mat-vecs: per step and warp 2 STS.64 + 2*slots LDS.64, 2 wavefronts
-        # each (32 lanes x 8 B); steps per slice = q (forward) + q-1 (recompute) + q (adjoint)
+        # each (32 lanes x 8 B); steps per slice = q (forward) + q-1 (recompute, unless streamed) + q (adjoint)
         steps_total = flops / (8.0 * info["nnz"] * S_local)
         wavefronts = steps_total * S_local / (32 // info["lanes"]) * 4.0 * (1 + info["slots"])
         sm_count = torch.cuda.get_device_properties(local).multi_processor_count

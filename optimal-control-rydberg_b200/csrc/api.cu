@@ -111,6 +111,7 @@ extern "C" int qocvl_check(qocvl_plan* p) {
 // Counts only the useful complex multiply-adds (8 flops each) of the chain kernel:
 //   forward  : q_k * (R_u*nnz_u + nnz_w)                      R_u = n_vec + 1 vectors
 //   reverse  : (q_k - 1) * (same)  recompute  +  2 * q_k * (same)  adjoint mat-vec and contraction
+//              (no recompute when the reduced kernel streams the Taylor terms through HBM)
 extern "C" double qocvl_flops_per_call(const qocvl_plan* p, int with_grad) {
   if (!p || !p->have_gens) return 0.0;
   const int M = p->d.n_slices;
@@ -124,7 +125,7 @@ extern "C" double qocvl_flops_per_call(const qocvl_plan* p, int with_grad) {
   double total = 0.0;
   for (int k = 0; k < M; ++k) {
     total += q[k] * macs;
-    if (with_grad) total += ((q[k] - 1) + 2.0 * q[k]) * macs;
+    if (with_grad) total += ((p->use_aug && p->aug_store ? 0 : q[k] - 1) + 2.0 * q[k]) * macs;
   }
   return total * 8.0 * (double)p->n_samples;
 }
@@ -135,13 +136,24 @@ extern "C" double qocvl_flops_per_call(const qocvl_plan* p, int with_grad) {
 extern "C" double qocvl_hbm_bytes_per_call(const qocvl_plan* p, int with_grad) {
   if (!p || p->groups <= 0 || !with_grad) return 0.0;
   const double M = p->d.n_slices, S = p->n_samples;
-  if (p->use_aug) return 2.0 * M * S * p->aug_n * sizeof(cplx) + 2.0 * (double)p->ypart_bytes;
+  if (p->use_aug) {
+    double slots = M;                                 // checkpoints only
+    if (p->aug_store) {                               // every Taylor term t_0 .. t_{q_k - 1}
+      std::vector<int> q(p->d.n_slices);
+      cudaSetDevice(p->device);
+      cudaDeviceSynchronize();
+      if (cudaMemcpy(q.data(), p->d_qdeg, q.size() * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 0.0;
+      slots = 0;
+      for (int v : q) slots += v;
+    }
+    return 2.0 * slots * S * p->aug_n * sizeof(cplx) + 2.0 * (double)p->ypart_bytes;
+  }
   if (p->use_tp || p->use_big) return 2.0 * (double)p->ckpt_bytes;
   return 2.0 * M * S * (p->n_live + 1) * p->npad * sizeof(cplx) + 2.0 * (double)p->gw_partial_elems * sizeof(double);
 }
 
 // Launch geometry of the chain kernel after configuration: out[8] = {path (0 lane-per-row, 1 reduced stacked
-// system, 2 time-parallel single sample, 3 rows-strided big-n), rows per sample, lanes per sample, off-diagonal
+// system, 2 time-parallel single sample, 3 rows-strided big-n, 4 reduced stacked system with streamed Taylor terms), rows per sample, lanes per sample, off-diagonal
 // slots per row, multiplier classes per entry, non-zeros of the propagated system, threads per CTA, CTAs}.
 extern "C" int qocvl_chain_info(const qocvl_plan* p, int* out) {
   if (!p || !out) return QOCVL_ERR_ARG;
@@ -152,6 +164,7 @@ extern "C" int qocvl_chain_info(const qocvl_plan* p, int* out) {
   out[2] = p->use_aug ? p->aug_lpg : p->npad;
   out[3] = p->use_aug ? (p->aug_wmax <= 3 ? 3 : 6) : 4;
   out[4] = p->use_aug ? p->la.KC : p->lu.kc;
+  if (p->use_aug && p->aug_store) out[0] = 4;
   out[5] = p->use_aug ? p->aug_nnz : (p->n_live + 1) * p->cu.nnz + p->cw.nnz;
   out[6] = p->threads;
   out[7] = p->blocks;

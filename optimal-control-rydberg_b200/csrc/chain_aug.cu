@@ -50,6 +50,8 @@ struct AugArgs {
   const double* wq;          // [2][LPG]: weight of the row's term in q^dag p (q rows only) / in the cotangent
   cplx* ckpt;                // [M][total threads]
   double* sample_out;        // [S][3]
+  cplx* terms;               // [M][qs][total threads]  Taylor terms t_0 .. t_{q-1} of every slice (STORE = 1)
+  int qs;                    // slots per slice in `terms` (the a-priori Taylor cap)
   cplx* y_partial;           // [warps][M][ncc][LPG]  per-warp sums of m * Xbar
   double* gwave;             // [M][C]
 };
@@ -75,7 +77,11 @@ __global__ void k_aug_tables(const AugArgs P, int L) {
   }
 }
 
-template <int LPG, int WMAX, int KC>
+// STORE = 1: the forward sweep streams every Taylor term t_0 .. t_{q-1} of every slice to HBM and the reverse sweep
+// streams them back (cp.async, eight steps ahead of their use) instead of recomputing them:
+// a third of the mat-vecs and of the shared-memory exchange traffic are traded for HBM bandwidth that the kernel
+// otherwise leaves idle.  STORE = 0 keeps only the checkpoints z_k and recomputes (12x less HBM capacity).
+template <int LPG, int WMAX, int KC, int STORE>
 __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NSL = 1 + WMAX;                  // slots per lane (diagonal + off-diagonals)
@@ -92,6 +98,8 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
   cplx* carve = (cplx*)smem_raw;
   cplx* s_x = carve + (size_t)grp * 2 * LPG; carve += (size_t)ngroups * 2 * LPG;   // [ngroups][2 buffers][LPG]
   cplx* s_A = carve + (size_t)grp * 2 * NSL * LPG;                                 // [ngroups][2][NSL][LPG]
+  carve += P.KA > 0 ? (size_t)ngroups * 2 * NSL * LPG : 0;
+  cplx* s_ring = carve + tid;                                                      // [RING][nthreads] (STORE)
 
   int rcol[WMAX], crow[WMAX];
 #pragma unroll
@@ -129,7 +137,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
   const cplx ytgt = live ? P.targets[r] : czero;
   const int pr = live ? P.pair[r] : -1;
   const double w_qp = live ? P.wq[r] : 0.0, w_lam = live ? P.wq[LPG + r] : 0.0;
-  cplx t_loc[QOCVL_QMAX];
+  cplx t_loc[STORE ? 1 : QOCVL_QMAX];
   cplx a_d, a_row[WMAX];
   __syncwarp();
 
@@ -184,6 +192,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
   // =================================== forward sweep ===================================
   load_raw(P.p_row + r, P.w, raw_r);
   int q_next = P.qdeg[0];
+  size_t n_stream = 0;                               // STORE: Taylor terms written so far (the stream is dense)
   for (int k = 0; k < P.M; ++k) {
     const int q = q_next;
     finish_rows();
@@ -191,15 +200,20 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
       load_raw(P.p_row + (size_t)(k + 1) * P.ncr * LPG + r, P.w, raw_r);
       q_next = P.qdeg[k + 1];
     }
-    if (P.want_grad && live) P.ckpt[(size_t)k * gthreads + gtid] = z;
+    const bool keep = P.want_grad && live;
+    cplx* tout = STORE ? P.terms + n_stream * gthreads + gtid : P.ckpt + (size_t)k * gthreads + gtid;
+    n_stream += q;
+    if (keep) tout[0] = z;
     cplx t = z;
     __syncwarp();                                   // the previous loop's readers are done with buffer 0
     int j = 1;
     for (; j + 1 <= q; j += 2) {
       t = step_fwd(t, c_ainv[j], 0);
       z = cadd(z, t);
+      if (STORE && keep) tout[(size_t)j * gthreads] = t;
       t = step_fwd(t, c_ainv[j + 1], 1);
       z = cadd(z, t);
+      if (STORE && keep && j + 1 < q) tout[(size_t)(j + 1) * gthreads] = t;
     }
     if (j <= q) {
       t = step_fwd(t, c_ainv[j], 0);
@@ -244,86 +258,161 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
 
   // =================================== reverse sweep ===================================
   const size_t gwarp = (size_t)blockIdx.x * nwarps + warp;
-  load_raw(P.p_row + (size_t)(P.M - 1) * P.ncr * LPG + r, P.w, raw_r);
-  q_next = P.qdeg[P.M - 1];
-  cplx t_next = live ? P.ckpt[(size_t)(P.M - 1) * gthreads + gtid] : czero;
-  for (int k = P.M - 1; k >= 0; --k) {
-    const int q = q_next;
-    finish_rows();
-    cplx raw_c[NSL * KC];                           // column-owner table values: in flight during the recompute
-    load_raw(P.p_col + (size_t)k * P.ncc * LPG + r, P.wc, raw_c);
-    // ---- recompute the forward Taylor terms t_0 .. t_{q-1}
-    cplx t = t_next;
-    // (stored pre-scaled, s_j = t_{j-1} / j, which is what the adjoint pairs with tb_j:  s_{j+1} = X s_j / (j+1))
-    t_loc[0] = t;
+  cplx lam_tb = lam, xc_d, xc[WMAX], a_col[WMAX];
+  // one descending step of the adjoint recurrence; Xbar accumulated on my column's entries
+  auto step_adj = [&](cplx tprev, double invj, int buf) {
+    xput(buf, lam_tb);
     __syncwarp();
-    {
-      int j = 1;
-      for (; j + 1 < q; j += 2) {
-        t = step_fwd(t, c_ainv[j + 1], 0);
-        t_loc[j] = t;
-        t = step_fwd(t, c_ainv[j + 2], 1);
-        t_loc[j + 1] = t;
-      }
-      if (j < q) {
-        t = step_fwd(t, c_ainv[j + 1], 0);
-        t_loc[j] = t;
-      }
-    }
-    cplx a_col[WMAX];                               // column-owner values Xaug[a][r] for the rows a of my column
+    cplx acc = cfma_conj(a_d, lam_tb, czero);
+    xc_d = cfma_conj(lam_tb, tprev, xc_d);
 #pragma unroll
-    for (int s = 0; s < WMAX; ++s) a_col[s] = (s < P.wc) ? slot_value(raw_c, m_col, P.add_col_mask, 1, 1 + s) : czero;
-    if (k > 0) {                                    // next slice's rows, checkpoint and degree: in flight during the adjoint
-      load_raw(P.p_row + (size_t)(k - 1) * P.ncr * LPG + r, P.w, raw_r);
-      t_next = live ? P.ckpt[(size_t)(k - 1) * gthreads + gtid] : czero;
-      q_next = P.qdeg[k - 1];
+    for (int s = 0; s < WMAX; ++s) {
+      const cplx ta = xget(x_col[s], buf);
+      acc = cfma_conj(a_col[s], ta, acc);
+      xc[s] = cfma_conj(ta, tprev, xc[s]);
     }
-    // ---- descending adjoint recurrence, Xbar accumulated on my column's entries
-    cplx tb = lam;
-    cplx xc_d = czero, xc[WMAX];
+    lam_tb = cadd(lam, cscale(acc, invj));
+  };
+  auto clear_xbar = [&]() {
+    xc_d = czero;
 #pragma unroll
     for (int s = 0; s < WMAX; ++s) xc[s] = czero;
-    auto step_adj = [&](int j, int buf) {
-      const double invj = c_ainv[j];
-      xput(buf, tb);
-      __syncwarp();
-      const cplx tprev = t_loc[j - 1];
-      cplx acc = cfma_conj(a_d, tb, czero);
-      xc_d = cfma_conj(tb, tprev, xc_d);
+  };
+  if constexpr (STORE != 0) {
+    // The terms were written as one dense stream t_0 .. t_{q_0 - 1} | t_0 .. t_{q_1 - 1} | ... ; the reverse sweep
+    // consumes it strictly backwards, across slice boundaries, so it is fetched RING steps ahead of its use with
+    // cp.async into a small thread-private shared-memory ring (HBM latency under load is ~6 adjoint steps).
+    constexpr int RING = 8;
+    const cplx* const base = P.terms + gtid;
+    const cplx* sp = base + (n_stream - 1) * gthreads;
+    const unsigned ring0 = (unsigned)__cvta_generic_to_shared(s_ring);
+    const unsigned ring_stride = (unsigned)(nthreads * sizeof(cplx));
 #pragma unroll
-      for (int s = 0; s < WMAX; ++s) {
-        const cplx ta = xget(x_col[s], buf);
-        acc = cfma_conj(a_col[s], ta, acc);
-        xc[s] = cfma_conj(ta, tprev, xc[s]);
-      }
-      tb = cadd(lam, cscale(acc, invj));
+    for (int i = 0; i < RING; ++i) s_ring[(size_t)i * nthreads] = czero;   // dead lanes read zeros for ever
+    int head = 0, tail = 0;
+    auto issue = [&]() {
+      if (live && sp >= base)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring0 + head * ring_stride), "l"(sp) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      sp -= gthreads;
+      head = (head + 1) & (RING - 1);
     };
-    __syncwarp();
-    {
-      int j = q;
-      for (; j >= 2; j -= 2) {
-        step_adj(j, 0);
-        step_adj(j - 1, 1);
+    auto fetch = [&]() -> cplx {
+      asm volatile("cp.async.wait_group %0;" ::"n"(RING - 1) : "memory");
+      const cplx v = s_ring[(size_t)tail * nthreads];
+      tail = (tail + 1) & (RING - 1);
+      issue();
+      return v;
+    };
+#pragma unroll
+    for (int i = 0; i < RING; ++i) issue();
+    cplx raw_c[NSL * KC];
+    int q_cur = P.qdeg[P.M - 1];
+    q_next = P.M > 1 ? P.qdeg[P.M - 2] : 0;
+    load_raw(P.p_col + (size_t)(P.M - 1) * P.ncc * LPG + r, P.wc, raw_c);
+    for (int k = P.M - 1; k >= 0; --k) {
+      const int q = q_cur;
+      a_d = slot_value(raw_c, m_col, P.add_col_mask, 1, 0);
+#pragma unroll
+      for (int s = 0; s < WMAX; ++s) a_col[s] = (s < P.wc) ? slot_value(raw_c, m_col, P.add_col_mask, 1, 1 + s) : czero;
+      if (k > 0) {                                  // next slice's tables and degree in flight during this one
+        load_raw(P.p_col + (size_t)(k - 1) * P.ncc * LPG + r, P.wc, raw_c);
+        q_cur = q_next;
+        q_next = k > 1 ? P.qdeg[k - 2] : 0;
       }
-      if (j >= 1) step_adj(j, 0);
-    }
-    lam = tb;
-    // ---- Ybar_e = sum over the warp's samples of m_s * Xbar_e: the generators' d coef / d wave is the same for
-    //      every sample, so the contraction with it happens once per slice in k_aug_reduce, not here
-    cplx* yout = P.y_partial + ((gwarp * P.M + k) * P.ncc) * LPG + r;
-#pragma unroll
-    for (int s = 0; s < NSL; ++s) {
-      if (s <= P.wc) {
-        const cplx xval = (s == 0) ? xc_d : xc[s > 0 ? s - 1 : 0];
-#pragma unroll
-        for (int i = 0; i < KC; ++i) {
-          cplx y = cscale(xval, m_col[s * KC + i]);
-#pragma unroll
-          for (int off = LPG; off < 32; off <<= 1) {
-            y.x += __shfl_xor_sync(0xffffffffu, y.x, off);
-            y.y += __shfl_xor_sync(0xffffffffu, y.y, off);
+      lam = lam_tb;
+      clear_xbar();
+      __syncwarp();
+      {
+        int j = q;
+        for (; j >= 2; j -= 2) {
+          step_adj(cscale(fetch(), c_ainv[j]), c_ainv[j], 0);
+          step_adj(cscale(fetch(), c_ainv[j - 1]), c_ainv[j - 1], 1);
+        }
+        if (j >= 1) step_adj(cscale(fetch(), c_ainv[j]), c_ainv[j], 0);
+      }
+      // ---- Ybar_e = sum over the warp's samples of m_s * Xbar_e: the generators' d coef / d wave is the same for
+      //      every sample, so the contraction with it happens once per slice in k_aug_reduce, not here
+      cplx* yout = P.y_partial + ((gwarp * P.M + k) * P.ncc) * LPG + r;
+  #pragma unroll
+      for (int s = 0; s < NSL; ++s) {
+        if (s <= P.wc) {
+          const cplx xval = (s == 0) ? xc_d : xc[s > 0 ? s - 1 : 0];
+  #pragma unroll
+          for (int i = 0; i < KC; ++i) {
+            cplx y = cscale(xval, m_col[s * KC + i]);
+  #pragma unroll
+            for (int off = LPG; off < 32; off <<= 1) {
+              y.x += __shfl_xor_sync(0xffffffffu, y.x, off);
+              y.y += __shfl_xor_sync(0xffffffffu, y.y, off);
+            }
+            if (lane < LPG) yout[(size_t)(s * KC + i) * LPG] = y;
           }
-          if (lane < LPG) yout[(size_t)(s * KC + i) * LPG] = y;
+        }
+      }
+    }
+  } else {
+    load_raw(P.p_row + (size_t)(P.M - 1) * P.ncr * LPG + r, P.w, raw_r);
+    q_next = P.qdeg[P.M - 1];
+    cplx t_next = live ? P.ckpt[(size_t)(P.M - 1) * gthreads + gtid] : czero;
+    for (int k = P.M - 1; k >= 0; --k) {
+      const int q = q_next;
+      finish_rows();
+      cplx raw_c[NSL * KC];                         // column-owner table values: in flight during the recompute
+      load_raw(P.p_col + (size_t)k * P.ncc * LPG + r, P.wc, raw_c);
+      // ---- recompute the forward Taylor terms, stored pre-scaled: s_j = t_{j-1} / j is what the adjoint pairs
+      //      with tb_j, and s_{j+1} = X s_j / (j+1)
+      cplx t = t_next;
+      t_loc[0] = t;
+      __syncwarp();
+      {
+        int j = 1;
+        for (; j + 1 < q; j += 2) {
+          t = step_fwd(t, c_ainv[j + 1], 0);
+          t_loc[j] = t;
+          t = step_fwd(t, c_ainv[j + 2], 1);
+          t_loc[j + 1] = t;
+        }
+        if (j < q) {
+          t = step_fwd(t, c_ainv[j + 1], 0);
+          t_loc[j] = t;
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < WMAX; ++s) a_col[s] = (s < P.wc) ? slot_value(raw_c, m_col, P.add_col_mask, 1, 1 + s) : czero;
+      if (k > 0) {                                  // next slice's rows, checkpoint and degree: in flight during the adjoint
+        load_raw(P.p_row + (size_t)(k - 1) * P.ncr * LPG + r, P.w, raw_r);
+        t_next = live ? P.ckpt[(size_t)(k - 1) * gthreads + gtid] : czero;
+        q_next = P.qdeg[k - 1];
+      }
+      lam = lam_tb;
+      clear_xbar();
+      __syncwarp();
+      {
+        int j = q;
+        for (; j >= 2; j -= 2) {
+          step_adj(t_loc[j - 1], c_ainv[j], 0);
+          step_adj(t_loc[j - 2], c_ainv[j - 1], 1);
+        }
+        if (j >= 1) step_adj(t_loc[j - 1], c_ainv[j], 0);
+      }
+      // ---- Ybar_e = sum over the warp's samples of m_s * Xbar_e: the generators' d coef / d wave is the same for
+      //      every sample, so the contraction with it happens once per slice in k_aug_reduce, not here
+      cplx* yout = P.y_partial + ((gwarp * P.M + k) * P.ncc) * LPG + r;
+  #pragma unroll
+      for (int s = 0; s < NSL; ++s) {
+        if (s <= P.wc) {
+          const cplx xval = (s == 0) ? xc_d : xc[s > 0 ? s - 1 : 0];
+  #pragma unroll
+          for (int i = 0; i < KC; ++i) {
+            cplx y = cscale(xval, m_col[s * KC + i]);
+  #pragma unroll
+            for (int off = LPG; off < 32; off <<= 1) {
+              y.x += __shfl_xor_sync(0xffffffffu, y.x, off);
+              y.y += __shfl_xor_sync(0xffffffffu, y.y, off);
+            }
+            if (lane < LPG) yout[(size_t)(s * KC + i) * LPG] = y;
+          }
         }
       }
     }
@@ -378,30 +467,33 @@ __global__ void __launch_bounds__(1024) k_aug_reduce(const AugArgs P, int L) {
 }
 
 typedef void (*aug_fn)(const AugArgs);
-template <int KC>
+template <int KC, int STORE>
 static aug_fn pick_aug_kc(int lpg, int wmax) {
   if (wmax <= 3) {
     switch (lpg) {
-      case 8: return k_chain_aug<8, 3, KC>;
-      case 16: return k_chain_aug<16, 3, KC>;
-      case 32: return k_chain_aug<32, 3, KC>;
+      case 8: return k_chain_aug<8, 3, KC, STORE>;
+      case 16: return k_chain_aug<16, 3, KC, STORE>;
+      case 32: return k_chain_aug<32, 3, KC, STORE>;
     }
   } else if (wmax <= 6) {
     switch (lpg) {
-      case 8: return k_chain_aug<8, 6, KC>;
-      case 16: return k_chain_aug<16, 6, KC>;
-      case 32: return k_chain_aug<32, 6, KC>;
+      case 8: return k_chain_aug<8, 6, KC, STORE>;
+      case 16: return k_chain_aug<16, 6, KC, STORE>;
+      case 32: return k_chain_aug<32, 6, KC, STORE>;
     }
   }
   return nullptr;
 }
-static aug_fn pick_aug(int lpg, int wmax, int kc) {
-  return kc == 1 ? pick_aug_kc<1>(lpg, wmax) : (kc == 2 ? pick_aug_kc<2>(lpg, wmax) : nullptr);
+static aug_fn pick_aug(int lpg, int wmax, int kc, bool store) {
+  if (kc == 1) return store ? pick_aug_kc<1, 1>(lpg, wmax) : pick_aug_kc<1, 0>(lpg, wmax);
+  if (kc == 2) return store ? pick_aug_kc<2, 1>(lpg, wmax) : pick_aug_kc<2, 0>(lpg, wmax);
+  return nullptr;
 }
 
 static size_t aug_smem_bytes(const qocvl_plan* p, int ngroups) {
   const int L = p->aug_lpg, nsl = 1 + (p->aug_wmax <= 3 ? 3 : 6);
-  return ((size_t)ngroups * 2 * L + (p->la.KA > 0 ? (size_t)ngroups * 2 * nsl * L : 0)) * sizeof(cplx);
+  return ((size_t)ngroups * 2 * L + (p->la.KA > 0 ? (size_t)ngroups * 2 * nsl * L : 0) +
+          (p->aug_store ? (size_t)8 * ngroups * L : 0)) * sizeof(cplx);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -619,12 +711,8 @@ int qocvl_aug_configure(qocvl_plan* p) {
       KA = std::max(KA, (int)addgens(a, b).size());
     }
   if (KC > 2) return QOCVL_ERR_UNSUPPORTED;
-  aug_fn fn = pick_aug(L, wmax, KC);
-  if (!fn || L < 8) {
-    if (L < 8) fn = pick_aug(8, wmax, KC);
-    if (!fn) return QOCVL_ERR_UNSUPPORTED;
-  }
-  const int Lk = std::max(L, 8);                       // lanes per sample of the kernel instance
+  if (!pick_aug(L, wmax, KC, false)) return QOCVL_ERR_UNSUPPORTED;
+  const int Lk = L;                                    // lanes per sample of the kernel instance
   const int nr = 1 + w, nc = 1 + wc;
   std::vector<int> row_col((size_t)nr * Lk), col_row((size_t)nc * Lk);
   std::vector<int> r_cls((size_t)nr * KC * Lk, -1), c_cls((size_t)nc * KC * Lk, -1);
@@ -704,43 +792,55 @@ int qocvl_aug_configure(qocvl_plan* p) {
     for (int j = 1; j < QOCVL_QMAX + 2; ++j) inv[j] = 1.0 / (double)j;
     QCUDA(cudaMemcpyToSymbol(c_ainv, inv, sizeof(inv)));
   }
-  // ---- launch geometry: a CTA is only a container of independent groups; pick the number of samples per CTA
-  //      that minimises the load of the busiest SM (wave quantisation), as in chain_small.cu
+  // ---- Taylor terms: streamed through HBM (STORE) when the a-priori degree cap and the device memory allow it
   const int gpw = 32 / Lk;
+  p->aug_qs = p->qcap;                                // a-priori cap (qocvl_chain_configure); k_coefficients flags excess
+  p->aug_store = p->aug_qs <= 16;
+  if (const char* e = getenv("QOCVL_STORE")) p->aug_store = p->aug_store && atoi(e) != 0;
+  if (p->d_ckpt) { cudaFree(p->d_ckpt); p->d_ckpt = nullptr; p->bytes -= p->ckpt_bytes; p->ckpt_bytes = 0; }
+  if (p->d_ypart) { cudaFree(p->d_ypart); p->d_ypart = nullptr; p->bytes -= p->ypart_bytes; p->ypart_bytes = 0; }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
-  const int gmax = 512 / Lk / gpw * gpw;
-  int ngroups = gpw;
-  {
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    // launch geometry: a CTA is only a container of independent groups (<= 256 threads, 128 registers per thread,
+    // so two CTAs fit an SM).  Pick the number of samples per CTA that minimises the number of samples the busiest
+    // SM has to process (wave quantisation), preferring larger CTAs on ties.
+    const int gmax = 256 / Lk / gpw * gpw;
+    int ngroups = gpw;
     long best_load = -1;
     for (int g = gpw; g <= gmax; g += gpw) {
       const long n_ctas = (S + g - 1) / g;
-      const long load = (n_ctas + sms - 1) / sms * g;
-      if (best_load < 0 || load < best_load || (load == best_load && g * Lk <= 256 && g > ngroups)) {
-        best_load = load; ngroups = g;
-      }
+      const long per_sm = std::max(1, std::min(32, 512 / (g * Lk)));     // resident CTAs per SM (register-limited)
+      const long waves = (n_ctas + per_sm * sms - 1) / (per_sm * sms);
+      const long load = waves * per_sm * g;
+      if (best_load < 0 || load <= best_load) { best_load = load; ngroups = g; }
     }
+    if (const char* e = getenv("QOCVL_SPB")) ngroups = std::max(gpw, std::min(gmax, (atoi(e) + gpw - 1) / gpw * gpw));
+    ngroups = std::min(ngroups, (S + gpw - 1) / gpw * gpw);
+    p->spb = ngroups; p->groups = ngroups; p->threads = ngroups * Lk;
+    p->chain_smem = aug_smem_bytes(p, ngroups);
+    if (p->chain_smem > 200 * 1024) return QOCVL_ERR_UNSUPPORTED;
+    p->blocks = (S + ngroups - 1) / ngroups;
+    const size_t total_threads = (size_t)p->blocks * p->threads;
+    p->aug_parts = (int)((total_threads + 31) / 32);
+    p->ckpt_bytes = (size_t)M * (p->aug_store ? p->aug_qs : 1) * total_threads * sizeof(cplx);
+    p->ypart_bytes = (size_t)p->aug_parts * M * nc * KC * Lk * sizeof(cplx);
+    if (p->aug_store) {                                // fall back to recomputation when HBM capacity is short
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      if (p->ckpt_bytes + p->ypart_bytes > free_b / 10 * 8) { p->aug_store = false; continue; }
+    }
+    break;
   }
-  if (const char* e = getenv("QOCVL_SPB")) ngroups = std::max(gpw, std::min(gmax, (atoi(e) + gpw - 1) / gpw * gpw));
-  ngroups = std::min(ngroups, (S + gpw - 1) / gpw * gpw);
-  p->spb = ngroups; p->groups = ngroups; p->threads = ngroups * Lk;
-  p->chain_smem = aug_smem_bytes(p, ngroups);
-  if (p->chain_smem > 200 * 1024) return QOCVL_ERR_UNSUPPORTED;
-  p->blocks = (S + ngroups - 1) / ngroups;
+  aug_fn fn = pick_aug(Lk, wmax, KC, p->aug_store);
+  if (!fn) return QOCVL_ERR_UNSUPPORTED;
   QCUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->chain_smem));
-  const size_t total_threads = (size_t)p->blocks * p->threads;
-  p->aug_parts = (int)((total_threads + 31) / 32);
   p->n_parts = 0;                                     // no [warps][M][C] partial-gradient buffer on this path
-  const size_t ck = (size_t)M * total_threads;
-  if (p->d_ckpt) { cudaFree(p->d_ckpt); p->d_ckpt = nullptr; p->bytes -= p->ckpt_bytes; }
-  QCUDA(cudaMalloc((void**)&p->d_ckpt, ck * sizeof(cplx)));
-  p->ckpt_bytes = ck * sizeof(cplx);
-  if (p->d_ypart) { cudaFree(p->d_ypart); p->d_ypart = nullptr; p->bytes -= p->ypart_bytes; }
-  p->ypart_bytes = (size_t)p->aug_parts * M * nc * KC * Lk * sizeof(cplx);
+  QCUDA(cudaMalloc((void**)&p->d_ckpt, p->ckpt_bytes));   // checkpoints z_k, or all Taylor terms in STORE mode
   QCUDA(cudaMalloc((void**)&p->d_ypart, p->ypart_bytes));
   p->bytes += p->ckpt_bytes + p->ypart_bytes;
   p->qcap_apriori = p->qcap;
-  p->qcap = QOCVL_QMAX;
+  if (!p->aug_store) p->qcap = QOCVL_QMAX;            // thread-local ring: no limit on the degree
   p->use_aug = true;
   return QOCVL_OK;
 }
@@ -763,9 +863,10 @@ int qocvl_aug_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t 
   a.p_row = la.p_row; a.p_col = la.p_col;
   a.coef = p->d_coef; a.dcoef = p->d_dcoef; a.qdeg = p->d_qdeg; a.mcls = la.mcls; a.add = p->d_add;
   a.starts = p->d_aug_starts; a.targets = p->d_aug_targets; a.pair = p->d_aug_pair; a.wq = p->d_aug_wq;
-  a.ckpt = p->d_ckpt; a.sample_out = p->d_sample_out; a.y_partial = p->d_ypart; a.gwave = gwave;
+  a.ckpt = p->d_ckpt; a.terms = p->d_ckpt; a.qs = p->aug_qs;
+  a.sample_out = p->d_sample_out; a.y_partial = p->d_ypart; a.gwave = gwave;
   k_aug_tables<<<d.n_slices, 256, 0, st>>>(a, la.L);
-  pick_aug(la.L, p->aug_wmax, la.KC)<<<p->blocks, p->threads, p->chain_smem, st>>>(a);
+  pick_aug(la.L, p->aug_wmax, la.KC, p->aug_store)<<<p->blocks, p->threads, p->chain_smem, st>>>(a);
   p->launches += 2;
   if (want_grad) {
     if (!gwave) return QOCVL_ERR_ARG;

@@ -195,7 +195,8 @@ struct qocvl_plan {
   // reduced ensemble path (chain_aug.cu): every propagated vector restricted to the basis states it can reach,
   // symmetric sectors folded onto orbit representatives, all of it stacked into ONE sparse system of aug_n rows
   bool use_aug = false;
-  int aug_n = 0, aug_lpg = 0, aug_nnz = 0, aug_wmax = 0, aug_parts = 0;
+  int aug_n = 0, aug_lpg = 0, aug_nnz = 0, aug_wmax = 0, aug_parts = 0, aug_qs = 0;
+  bool aug_store = false;         // Taylor terms streamed through HBM instead of recomputed in the reverse sweep
   cplx* d_ypart = nullptr;        // [warps][M][column contributions][aug_lpg] per-warp sums of m * Xbar
   size_t ypart_bytes = 0;
   AugLayout la;            // lane-per-row tables of the stacked system

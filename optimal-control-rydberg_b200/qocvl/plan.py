@@ -210,7 +210,8 @@ class Plan:
         _lib.check(self._lib.qocvl_chain_info(self._h, buf), "chain_info")
         keys = ("path", "rows", "lanes", "slots", "classes", "nnz", "threads", "ctas")
         info = dict(zip(keys, (int(x) for x in buf)))
-        info["path"] = ("lane_per_row", "reduced_stacked", "time_parallel", "rows_strided")[info["path"]]
+        info["path"] = ("lane_per_row", "reduced_stacked", "time_parallel", "rows_strided",
+                        "reduced_stacked_streamed")[info["path"]]
         return info
 
     @property
