@@ -25,6 +25,9 @@
 
 typedef std::complex<double> zc;
 
+#ifndef QOCVL_RING
+#define QOCVL_RING 8   // depth (Taylor terms) of the cp.async ring that streams the terms back in STORE mode
+#endif
 __constant__ double c_ainv[QOCVL_QMAX + 2];   // 1/j
 
 struct AugArgs {
@@ -133,6 +136,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
       s_A[(NSL + s) * LPG + r] = cscale(ac, P.dt);
     }
   }
+  const cplx A_diag = P.KA > 0 ? s_A[r] : czero;
   cplx z = live ? P.starts[r] : czero;
   const cplx ytgt = live ? P.targets[r] : czero;
   const int pr = live ? P.pair[r] : -1;
@@ -170,7 +174,8 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
       acc.x = fma(m[s * KC + i], raw[s * KC + i].x, acc.x);
       acc.y = fma(m[s * KC + i], raw[s * KC + i].y, acc.y);
     }
-    if ((mask >> s) & 1u) acc = cadd(acc, s_A[(col * NSL + s) * LPG + r]);
+    if (s == 0) acc = cadd(acc, A_diag);             // the diagonal's additive term lives in registers
+    else if ((mask >> s) & 1u) acc = cadd(acc, s_A[(col * NSL + s) * LPG + r]);
     return acc;
   };
   cplx raw_r[NSL * KC];                              // row-owner table values of the NEXT slice to be visited
@@ -282,7 +287,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
     // The terms were written as one dense stream t_0 .. t_{q_0 - 1} | t_0 .. t_{q_1 - 1} | ... ; the reverse sweep
     // consumes it strictly backwards, across slice boundaries, so it is fetched RING steps ahead of its use with
     // cp.async into a small thread-private shared-memory ring (HBM latency under load is ~6 adjoint steps).
-    constexpr int RING = 8;
+    constexpr int RING = QOCVL_RING;
     const cplx* const base = P.terms + gtid;
     const cplx* sp = base + (n_stream - 1) * gthreads;
     const unsigned ring0 = (unsigned)__cvta_generic_to_shared(s_ring);
@@ -493,7 +498,7 @@ static aug_fn pick_aug(int lpg, int wmax, int kc, bool store) {
 static size_t aug_smem_bytes(const qocvl_plan* p, int ngroups) {
   const int L = p->aug_lpg, nsl = 1 + (p->aug_wmax <= 3 ? 3 : 6);
   return ((size_t)ngroups * 2 * L + (p->la.KA > 0 ? (size_t)ngroups * 2 * nsl * L : 0) +
-          (p->aug_store ? (size_t)8 * ngroups * L : 0)) * sizeof(cplx);
+          (p->aug_store ? (size_t)QOCVL_RING * ngroups * L : 0)) * sizeof(cplx);
 }
 
 // ---------------------------------------------------------------------------------------------------
