@@ -23,6 +23,7 @@ for _p in (ROOT, PKG):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
+os.environ["NCCL_DEBUG"] = os.environ.get("QOCVL_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -246,8 +247,12 @@ def run_gpu(args):
         kname = f"k_chain_aug<{info['lanes']},{info['slots']},{info['classes']},{streamed}>"
         # shared-memory exchange of the Taylor mat-vecs: per step and warp 2 STS.64 + 2*slots LDS.64, 2 wavefronts
         # each (32 lanes x 8 B); steps per slice = q (forward) + q-1 (recompute, unless streamed) + q (adjoint)
-        steps_total = flops / (8.0 * info["nnz"] * S_local)
-        wavefronts = steps_total * S_local / (32 // info["lanes"]) * 4.0 * (1 + info["slots"])
+        steps_total = flops / (8.0 * info["nnz"] * S_local)       # Taylor-step equivalents per sample (3q or 4q-1 per slice)
+        per_step = 4.0 * (1 + info["slots"]) / (32 // info["lanes"])   # exchange wavefronts per sample and step
+        if streamed:   # forward q + adjoint q exchanges; plus cp.async write + LDS.128 read of one term per adjoint step
+            wavefronts = steps_total / 3.0 * S_local * (2.0 * per_step + 8.0 / (32 // info["lanes"]))
+        else:
+            wavefronts = steps_total * S_local * per_step
         sm_count = torch.cuda.get_device_properties(local).multi_processor_count
         sm_clock_hz = 1e6 * (peaks.get("sm_max_mhz") or 1965.0)
         smem = {"wavefronts_per_launch": wavefronts, "peak_wavefronts_per_s": sm_count * sm_clock_hz,
@@ -310,7 +315,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--samples", type=int, default=4096, help="noise samples per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
