@@ -800,7 +800,7 @@ int qocvl_aug_configure(qocvl_plan* p) {
   // ---- Taylor terms: streamed through HBM (STORE) when the a-priori degree cap and the device memory allow it
   const int gpw = 32 / Lk;
   p->aug_qs = p->qcap;                                // a-priori cap (qocvl_chain_configure); k_coefficients flags excess
-  p->aug_store = p->aug_qs <= 16;
+  p->aug_store = true;
   if (const char* e = getenv("QOCVL_STORE")) p->aug_store = p->aug_store && atoi(e) != 0;
   if (p->d_ckpt) { cudaFree(p->d_ckpt); p->d_ckpt = nullptr; p->bytes -= p->ckpt_bytes; p->ckpt_bytes = 0; }
   if (p->d_ypart) { cudaFree(p->d_ypart); p->d_ypart = nullptr; p->bytes -= p->ypart_bytes; p->ypart_bytes = 0; }

@@ -242,6 +242,58 @@ class EngineBase:
         return hist[:num_iters], abc[0], abc[1], abc[2]
 
 
+    # -- adiabatic seeding (notebook 05 cells 8-12): fit the pulses THROUGH the pulse map, on the device ----------
+    def match_amplitudes(self, targets, ctrl_a, ctrl_b, ctrl_c, num_iters=1000, lr=0.03, use_graph=True):
+        """Gradient-descent fit of selected physical-amplitude channels to target shapes, the notebook's
+        ``cost_match_rabi`` / ``single_match_step``:  cost = mean over the chosen channels of
+        mean_k (wave[k, ch] - target_ch[k])**2  (NB05 cell 10 uses channels 1 and 3, the two Rabi magnitudes),
+        ``ctrl -= lr * grad`` with the cost recorded BEFORE each update.  ``targets``: {channel: array [M]}.
+        The pulse map and its reverse pass are the CUDA kernels of the hot path's first stage
+        (``qocvl_physical_amplitudes`` / ``qocvl_physical_amplitudes_vjp``); one step is captured in a CUDA
+        graph and replayed, with no host synchronisation per step.
+
+        Returns (cost_history [num_iters] CUDA tensor, a, b, c) with a, b, c CUDA tensors [input_dim, C]."""
+        dev = self.device
+        abc = self._pack(ctrl_a, ctrl_b, ctrl_c).clone()
+        M = self._plan.desc.n_slices
+        if not targets:
+            raise ValueError("targets must name at least one channel")
+        tgt = torch.zeros((M, self.num_ctrls), dtype=torch.float64, device=dev)
+        wsel = torch.zeros((1, self.num_ctrls), dtype=torch.float64, device=dev)
+        for ch, arr in targets.items():
+            if not 0 <= int(ch) < self.num_ctrls:
+                raise ValueError(f"channel {ch} out of range")
+            t = torch.as_tensor(np.asarray(arr, dtype=np.float64))
+            if tuple(t.shape) != (M,):
+                raise ValueError(f"target of channel {ch} must have shape ({M},), got {tuple(t.shape)}")
+            tgt[:, int(ch)] = t.to(dev)
+            wsel[0, int(ch)] = 1.0 / (len(targets) * M)
+        hist = torch.zeros(max(1, num_iters), dtype=torch.float64, device=dev)
+        step_idx = torch.zeros(1, dtype=torch.long, device=dev)
+
+        def one_step():
+            diff = (self._plan.physical_amplitudes(abc) - tgt) * wsel          # (wave - target) / (n_ch * M)
+            hist.index_copy_(0, step_idx, ((diff * diff).sum() / wsel.max()).view(1))
+            abc.sub_(float(lr) * self._plan.physical_amplitudes_vjp(abc, 2.0 * diff).view_as(abc))
+            step_idx.add_(1)
+
+        if use_graph and num_iters > 2:
+            self._plan.physical_amplitudes(abc)               # configure the plan outside of the capture
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    one_step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            for _ in range(num_iters):
+                graph.replay()
+        else:
+            for _ in range(num_iters):
+                one_step()
+        return hist[:num_iters], abc[0], abc[1], abc[2]
+
+
 def shard_bounds(n_items, world, rank):
     """Contiguous block partition of n_items over world ranks (first ranks get the remainder)."""
     base, rem = divmod(n_items, world)

@@ -203,3 +203,58 @@ def test_reduced_system_state_transfer_ensemble():
             assert bool(prop._plan.reduced_rows) == bool(flag)
     assert np.abs(outs[1][:3] - outs[0][:3]).max() < 1e-13
     assert rel(outs[1][3:], outs[0][3:]) < 1e-10
+
+
+@pytest.mark.parametrize("kind", ["two_classes", "offdiag_additive", "too_many_classes"])
+def test_reduced_system_with_general_noise_tables(kind):
+    """The reduced kernel groups generators into multiplier classes and keeps additive per-sample terms per entry.
+    Noise tables the reference-style ensembles never produce: (i) a multiplier on the Delta_i generator, which gives
+    the diagonal two classes; (ii) additive complex terms on the Rabi generators (off-diagonal entries);
+    (iii) an independent multiplier on every generator (> 2 classes per entry: the engine must fall back to the full
+    lane-per-row kernel).  Reference = the same plan API with QOCVL_AUG=0."""
+    from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL
+    po, a, b, c = otq.notebook02_setup(seed=3, n_gauss=6, nt=77)
+    args = (6, 77, po.padding, 50e6, po.delta_t, 0.0, po.Vint, po.Delta_i_val, po.Rabi_i_val, po.Rabi_r_val, otq.GAMMAS_CZ)
+    rng = np.random.default_rng(21)
+    S, J = 11, 11
+    mul, add = np.ones((S, J)), np.zeros((S, J), complex)
+    if kind == "two_classes":
+        mul[:, 2] = 1 + 0.05 * rng.standard_normal(S)
+        mul[:, 3:7] = (1 + 0.02 * rng.standard_normal(S))[:, None]
+        add[:, 1] = -1j * rng.normal(0, 2 * np.pi * 1e5, S)
+    elif kind == "offdiag_additive":
+        mul[:, 3:5] = (1 + 0.02 * rng.standard_normal(S))[:, None]
+        mul[:, 5:7] = (1 + 0.02 * rng.standard_normal(S))[:, None]
+        add[:, 3] = 1e-2 * (rng.standard_normal(S) + 1j * rng.standard_normal(S))
+        add[:, 6] = 1e-2 * (rng.standard_normal(S) + 1j * rng.standard_normal(S))
+    else:
+        mul = 1 + 0.02 * rng.standard_normal((S, J))
+    outs, rows = [], []
+    for flag in (0, 1):
+        with env(QOCVL_AUG=flag):
+            prop = PropagatorVL(*args)
+            prop._plan.set_noise(mul, add)
+            outs.append(np_(prop.cost_and_grad_packed(prop._pack(a, b, c))).copy())
+            prop._plan.check()
+            rows.append(prop._plan.reduced_rows)
+    assert rows[0] == 0 and rows[1] == (0 if kind == "too_many_classes" else 12)
+    assert np.abs(outs[1][:3] - outs[0][:3]).max() < 1e-13
+    assert rel(outs[1][3:], outs[0][3:]) < 1e-10
+
+
+def test_reduced_system_streamed_terms_equal_recomputed_terms():
+    """STORE mode (Taylor terms streamed through HBM) against the checkpoint + recompute mode of the same kernel."""
+    from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL
+    po, a, b, c = otq.notebook02_setup(seed=4, n_gauss=6, nt=77)
+    args = (6, 77, po.padding, 50e6, po.delta_t, 0.0, po.Vint, po.Delta_i_val, po.Rabi_i_val, po.Rabi_r_val, otq.GAMMAS_CZ)
+    dl, rs = ensemble.robust_cz_noise(70)
+    outs = []
+    for flag in (0, 1):
+        with env(QOCVL_STORE=flag):
+            prop = PropagatorVL(*args)
+            prop.set_ensemble(del_total=dl, rabi_scale=rs)
+            outs.append(np_(prop.cost_and_grad_packed(prop._pack(a, b, c))).copy())
+            prop._plan.check()
+            assert prop._plan.chain_info()["path"] == ("reduced_stacked_streamed" if flag else "reduced_stacked")
+    assert np.abs(outs[1][:3] - outs[0][:3]).max() < 1e-14
+    assert rel(outs[1][3:], outs[0][3:]) < 1e-11

@@ -324,3 +324,41 @@ def test_device_side_optimiser_loop_matches_manual_steps():
     cost0, a1, b1, c1 = single_optimization_step(prop, a, b, c, lr=lr)
     hist, a3, b3, c3 = prop.optimize(a, b, c, 3, lr)
     assert abs(float(hist[0]) - float(cost0)) < 1e-14
+
+
+def test_match_amplitudes_equals_notebook05_seeding_loop():
+    """Notebook 05 cells 8-12 (cost_match_rabi / single_match_step): fit the two Rabi magnitudes to the analytic
+    counter-intuitive pulse pair through the pulse map.  Device-side loop (CUDA graph) vs a NumPy loop over the
+    oracle's pulse map and its hand-written reverse pass: same cost history, same parameters."""
+    from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL
+    po, a, b, c = otq.notebook02_setup(seed=5, n_gauss=6, nt=77)
+    prop = PropagatorVL(6, 77, po.padding, 50e6, po.delta_t, 0.0, po.Vint, po.Delta_i_val, po.Rabi_i_val,
+                        po.Rabi_r_val, otq.GAMMAS_CZ)
+    M = 77 + 2 * po.padding
+    tl = np.linspace(0.0, 2.0, M)
+    targets = {1: np.sin(0.5 * np.pi * tl / 2.0), 3: np.abs(np.cos(0.5 * np.pi * tl / 2.0))}   # NB05 cell 8
+    rng = np.random.default_rng(11)
+    a0, b0, c0 = (0.3 * rng.standard_normal((6, 5)) for _ in range(3))
+    iters, lr = 40, 0.03
+    hist, ga, gb, gc = prop.match_amplitudes(targets, a0, b0, c0, num_iters=iters, lr=lr)
+    hist_loop, la, lb, lc = prop.match_amplitudes(targets, a0, b0, c0, num_iters=iters, lr=lr, use_graph=False)
+    ra, rb, rc, ref_hist = a0.copy(), b0.copy(), c0.copy(), []
+    for _ in range(iters):
+        wave, cache = vector_model.pulse_map(po, ra, rb, rc, "tq")
+        gwave = np.zeros_like(wave)
+        cost = 0.0
+        for ch, tgt in targets.items():
+            diff = wave[:, ch] - tgt
+            cost += np.mean(diff ** 2) / len(targets)
+            gwave[:, ch] = 2.0 * diff / (len(targets) * M)
+        ref_hist.append(cost)
+        da, db, dc = vector_model.pulse_map_vjp(cache, gwave)
+        ra, rb, rc = ra - lr * da, rb - lr * db, rc - lr * dc
+    assert rel(np_(hist), ref_hist) < 1e-11 and rel(np_(hist_loop), ref_hist) < 1e-11
+    assert ref_hist[-1] < ref_hist[0]
+    for mine, ref in ((ga, ra), (gb, rb), (gc, rc), (la, ra)):
+        assert rel(np_(mine), ref) < 1e-10
+    with pytest.raises(ValueError):
+        prop.match_amplitudes({7: np.zeros(M)}, a0, b0, c0)
+    with pytest.raises(ValueError):
+        prop.match_amplitudes({1: np.zeros(M + 1)}, a0, b0, c0)
