@@ -167,6 +167,18 @@ double qocvl_measure_fp64_peak(int device, int repeats);
 /* Same loop with three REGISTER operands per FMA (a = fma(a, b, c)), which is what real kernels issue:
  * the register file of the B200 SM sustains ~25 TFLOP/s of these, 2/3 of the issue peak above. */
 double qocvl_measure_fp64_peak_reg(int device, int repeats);
+/* ---- master-equation validation (the step after the hot path) -------------------------------------------
+ * Replaces QuTiP's mesolve as the reference uses it in two_qubit/qutip_simulation.py:57-103 and
+ * two_qubit/qutip_five_level.py:88-142: propagates vectorised density matrices under
+ *   d rho/dt = (sum_j coef[traj][step][j] * L_j) rho,  L_j given as complex values vals[J][nnz] on one union
+ * CSR pattern (rowptr[n+1], col[nnz]), with the exponential midpoint rule rho <- exp(L dt) rho per step (Taylor
+ * series with remainder < 2^-55, as the chain kernels).  One CTA per trajectory.  expect_out receives
+ * sum_i obs[o][i] * rho[i] at every step boundary, [n_traj][n_steps+1][n_obs] complex; rho_out the final vectors.
+ * ALL pointers are HOST pointers; the call allocates, runs and synchronises (one-shot validation, not stream-ordered).
+ * QOCVL_ERR_NORM: a step has |L dt|_1 > 4, sub-step finer.  QOCVL_ERR_UNSUPPORTED: pattern does not fit shared memory. */
+int qocvl_lindblad_propagate(int device, int n, int nnz, int n_gen, int n_steps, int n_traj, int n_obs,
+                             const int* rowptr, const int* col, const double* vals, const double* coef,
+                             const double* rho0, const double* obs, double dt, double* expect_out, double* rho_out);
 const char* qocvl_strerror(int status);
 const char* qocvl_last_cuda_error(void);
 int qocvl_version(void);

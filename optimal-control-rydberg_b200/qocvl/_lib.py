@@ -53,6 +53,7 @@ SIGNATURES = {
     "qocvl_last_chain_ms": (C.c_double, [_P]),
     "qocvl_measure_fp64_peak": (C.c_double, [C.c_int, C.c_int]),
     "qocvl_measure_fp64_peak_reg": (C.c_double, [C.c_int, C.c_int]),
+    "qocvl_lindblad_propagate": (C.c_int, [C.c_int] * 7 + [_D] * 6 + [C.c_double, _D, _D]),
     "qocvl_strerror": (C.c_char_p, [C.c_int]),
     "qocvl_last_cuda_error": (C.c_char_p, []),
     "qocvl_version": (C.c_int, []),
