@@ -15,9 +15,13 @@
 // system of N rows (CZ: 3 + 6 + 3 = 12 instead of 3 x 16 = 48 vector elements per sample):
 //     Z = [q_0 | q_1 | ... | p],   Xaug = blockdiag(A'_0, A'_1, ..., A'_p) + (p <- q_va block B').
 // Kernel mapping: one noise sample per group of LPG >= N lanes, lane r owns row r of Xaug (diagonal + <= WMAX
-// off-diagonals, assembled per slice from the per-sample coefficients) and element r of Z.  Off-row elements
-// are gathered through a double-buffered shared-memory exchange guarded by __syncwarp only; Taylor terms of
-// the reverse sweep sit in thread-local memory (L1); checkpoints Z_k go to HBM once per slice, coalesced.
+// off-diagonals) and element r of Z.  A matrix entry of sample s is A_e(s) + sum_i m_s[class_i] * P_i(k): generators
+// are grouped into classes by their per-sample multiplier column, P_i(k) comes from per-slice tables that
+// k_aug_tables fills once per evaluation, A_e is the additive-noise constant.  Off-row elements are gathered through
+// a double-buffered shared-memory exchange guarded by __syncwarp only (no CTA barrier in the sweeps).  The forward
+// sweep streams every Taylor term to HBM as one dense stream; the reverse sweep reads the stream backwards through
+// a cp.async ring and emits per-warp sums of m_s * Xbar_e, which k_aug_reduce adds up in a fixed order and contracts
+// with d coef / d wave once per slice.  (STORE = 0: only checkpoints go to HBM and the terms are recomputed.)
 #include "common.cuh"
 #include <algorithm>
 #include <cmath>
