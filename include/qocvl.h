@@ -151,9 +151,11 @@ double qocvl_flops_per_call(const qocvl_plan* plan, int with_grad); /* executed 
  * gradient data written by the reverse sweep and read once by the reduction (0 before the first evaluation). */
 double qocvl_hbm_bytes_per_call(const qocvl_plan* plan, int with_grad);
 /* Launch geometry after configuration, out[8] = {path: 0 lane-per-row / 1 reduced stacked system / 2 time-parallel
- * single sample / 3 rows-strided big-n / 4 reduced stacked system with the Taylor terms streamed through HBM;
- * rows per sample; lanes per sample; off-diagonal slots per row; multiplier
- * classes per entry; non-zeros of the propagated system; threads per CTA; CTAs}. */
+ * single sample / 3 rows-strided big-n / 4 reduced stacked system with the Taylor terms streamed through HBM /
+ * 5 samples-minor big-n ensemble kernel with streamed Taylor terms / 6 the same with recomputed terms;
+ * rows per sample; lanes per sample (paths 5-6: samples per CTA); off-diagonal slots per row (5-6: generator blocks
+ * with off-diagonal entries); multiplier classes per entry (5-6: generator blocks with diagonal entries);
+ * non-zeros of the propagated system; threads per CTA; CTAs}. */
 int qocvl_chain_info(const qocvl_plan* plan, int* out8);
 /* Kernel timing for the roofline report: when enabled, CUDA events bracket the chain kernel on
  * the launch stream; qocvl_last_chain_ms synchronises on the end event and returns the duration

@@ -121,11 +121,13 @@ extern "C" double qocvl_flops_per_call(const qocvl_plan* p, int with_grad) {
   if (cudaMemcpy(q.data(), p->d_qdeg, M * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 0.0;
   // vectors that are actually propagated: the moving start kets plus p = W psi
   // (reduced stacked system of chain_aug.cu: only the entries that meet a populated vector element)
-  const double macs = p->use_aug ? (double)p->aug_nnz : (double)(p->n_live + 1) * p->cu.nnz + p->cw.nnz;
+  const double macs = p->use_aug ? (double)p->aug_nnz
+                      : (p->use_wide ? p->lwide.macs : (double)(p->n_live + 1) * p->cu.nnz + p->cw.nnz);
+  const bool stored = (p->use_aug && p->aug_store) || (p->use_wide && p->lwide.store);
   double total = 0.0;
   for (int k = 0; k < M; ++k) {
     total += q[k] * macs;
-    if (with_grad) total += ((p->use_aug && p->aug_store ? 0 : q[k] - 1) + 2.0 * q[k]) * macs;
+    if (with_grad) total += ((stored ? 0 : q[k] - 1) + 2.0 * q[k]) * macs;
   }
   return total * 8.0 * (double)p->n_samples;
 }
@@ -148,6 +150,16 @@ extern "C" double qocvl_hbm_bytes_per_call(const qocvl_plan* p, int with_grad) {
     }
     return 2.0 * slots * S * p->aug_n * sizeof(cplx) + 2.0 * (double)p->ypart_bytes;
   }
+  if (p->use_wide) {   // streamed Taylor terms (or checkpoints + the recompute ring) written once, read once
+    const double vs = 2.0 * p->d.n * p->lwide.spc * sizeof(cplx) * p->blocks;
+    std::vector<int> q(p->d.n_slices);
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    if (cudaMemcpy(q.data(), p->d_qdeg, q.size() * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 0.0;
+    double slots = 0;
+    for (int v : q) slots += v;
+    return 2.0 * (slots + (p->lwide.store ? 0.0 : M)) * vs;
+  }
   if (p->use_tp || p->use_big) return 2.0 * (double)p->ckpt_bytes;
   return 2.0 * M * S * (p->n_live + 1) * p->npad * sizeof(cplx) + 2.0 * (double)p->gw_partial_elems * sizeof(double);
 }
@@ -158,7 +170,7 @@ extern "C" double qocvl_hbm_bytes_per_call(const qocvl_plan* p, int with_grad) {
 extern "C" int qocvl_chain_info(const qocvl_plan* p, int* out) {
   if (!p || !out) return QOCVL_ERR_ARG;
   if (p->groups <= 0) return QOCVL_ERR_STATE;
-  const int path = p->use_tp ? 2 : (p->use_aug ? 1 : (p->use_big ? 3 : 0));
+  const int path = p->use_tp ? 2 : (p->use_aug ? 1 : (p->use_wide ? (p->lwide.store ? 5 : 6) : (p->use_big ? 3 : 0)));
   out[0] = path;
   out[1] = p->use_aug ? p->aug_n : p->d.n;
   out[2] = p->use_aug ? p->aug_lpg : p->npad;
@@ -166,6 +178,11 @@ extern "C" int qocvl_chain_info(const qocvl_plan* p, int* out) {
   out[4] = p->use_aug ? p->la.KC : p->lu.kc;
   if (p->use_aug && p->aug_store) out[0] = 4;
   out[5] = p->use_aug ? p->aug_nnz : (p->n_live + 1) * p->cu.nnz + p->cw.nnz;
+  if (p->use_wide) {
+    out[2] = p->lwide.spc;                       // samples per CTA
+    out[3] = p->lwide.nb; out[4] = p->lwide.nd;  // generator blocks with off-diagonal / diagonal entries
+    out[5] = (int)p->lwide.macs;
+  }
   out[6] = p->threads;
   out[7] = p->blocks;
   return QOCVL_OK;

@@ -201,7 +201,16 @@ int qocvl_chain_configure(qocvl_plan* p) {
     rc = qocvl_aug_configure(p);
     if (rc != QOCVL_OK && rc != QOCVL_ERR_UNSUPPORTED) { p->groups = 0; return rc; }
   }
-  if (!p->use_aug) {
+  p->use_wide = false;
+  if (!p->use_aug && p->use_big) {          // large Hilbert spaces: the samples-minor kernel when it takes the problem
+    bool try_wide = true;
+    if (const char* e = getenv("QOCVL_WIDE")) try_wide = atoi(e) != 0;
+    if (try_wide) {
+      rc = qocvl_wide_configure(p);
+      if (rc != QOCVL_OK && rc != QOCVL_ERR_UNSUPPORTED) { p->groups = 0; return rc; }
+    }
+  }
+  if (!p->use_aug && !p->use_wide) {
     rc = p->use_big ? qocvl_big_configure(p) : qocvl_small_configure(p);
     if (rc) { p->groups = 0; return rc; }
   }
@@ -220,6 +229,7 @@ int qocvl_launch_chain(qocvl_plan* p, bool want_grad, double* out3, double* gwav
   if (p->timing) QCUDA(cudaEventRecord(p->ev0, st));
   if (p->use_tp) rc = qocvl_tp_launch(p, want_grad, gwave, st);
   else if (p->use_aug) rc = qocvl_aug_launch(p, want_grad, gwave, st);
+  else if (p->use_wide) rc = qocvl_wide_launch(p, want_grad, st);
   else rc = p->use_big ? qocvl_big_launch(p, want_grad, st) : qocvl_small_launch(p, want_grad, st);
   if (rc) return rc;
   if (p->timing) { QCUDA(cudaEventRecord(p->ev1, st)); p->timed_once = true; }

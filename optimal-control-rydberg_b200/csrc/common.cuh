@@ -123,6 +123,22 @@ struct AugLayout {
   }
 };
 
+// Device tables of the wide ensemble kernel (chain_wide.cu): rows sorted by off-diagonal work and dealt to the warps
+// in groups; per (generator block, group) an interleaved, padded entry block for the row lists (forward sweep) and
+// the column lists (reverse sweep); the diagonal of every generator block as a dense vector.
+struct WideLayout {
+  int spc = 0, items = 0, max_threads = 0, ngroups = 0, nb = 0, nd = 0;
+  int bgen[8] = {0}, bfam[8] = {0}, dgen[8] = {0}, dfam[8] = {0};
+  bool store = false;
+  double macs = 0.0;                         // useful complex multiply-adds of one Taylor step of one sample
+  long long padded_entries = 0, true_entries = 0;
+  int* grow = nullptr;
+  int2 *fwd_co = nullptr, *rev_co = nullptr;
+  cplx *fwd_val = nullptr, *rev_val = nullptr, *dval = nullptr;
+  int *fwd_col = nullptr, *rev_col = nullptr;
+  void release();
+};
+
 struct qocvl_plan {
   qocvl_desc d;
   int device = 0;
@@ -194,6 +210,8 @@ struct qocvl_plan {
   size_t chain_smem = 0;
   // reduced ensemble path (chain_aug.cu): every propagated vector restricted to the basis states it can reach,
   // symmetric sectors folded onto orbit representatives, all of it stacked into ONE sparse system of aug_n rows
+  bool use_wide = false;   // big-n ensembles: samples-minor CTA kernel (chain_wide.cu)
+  WideLayout lwide;
   bool use_aug = false;
   int aug_n = 0, aug_lpg = 0, aug_nnz = 0, aug_wmax = 0, aug_parts = 0, aug_qs = 0;
   bool aug_store = false;         // Taylor terms streamed through HBM instead of recomputed in the reverse sweep
@@ -223,6 +241,8 @@ int qocvl_tp_configure(qocvl_plan* p);
 int qocvl_tp_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t st);
 int qocvl_big_configure(qocvl_plan* p);
 int qocvl_big_launch(qocvl_plan* p, bool want_grad, cudaStream_t st);
+int qocvl_wide_configure(qocvl_plan* p);
+int qocvl_wide_launch(qocvl_plan* p, bool want_grad, cudaStream_t st);
 int qocvl_aug_configure(qocvl_plan* p);
 int qocvl_aug_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t st);
 int qocvl_build_lane_layout(qocvl_plan* p, const std::vector<std::complex<double>>& blocks, int n, int npad,

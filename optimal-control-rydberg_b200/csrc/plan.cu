@@ -162,7 +162,7 @@ extern "C" int qocvl_plan_create(qocvl_plan** out, const qocvl_desc* desc, int d
 extern "C" int qocvl_plan_destroy(qocvl_plan* p) {
   if (!p) return QOCVL_OK;
   cudaSetDevice(p->device);
-  free_layout(p->lu); free_layout(p->lw); p->la.release();
+  free_layout(p->lu); free_layout(p->lw); p->la.release(); p->lwide.release();
   for (CsrLayout* c : {&p->cu, &p->cw}) {
     cudaFree(c->rowptr); cudaFree(c->col); cudaFree(c->erow); cudaFree(c->colptr);
     cudaFree(c->crow); cudaFree(c->ceid); cudaFree(c->egen); cudaFree(c->eval);

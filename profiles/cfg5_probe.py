@@ -11,12 +11,14 @@ import torch  # noqa: E402
 from quantum_optimal_control.blockade_chain.propagator_vl import PropagatorVL as Chain  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else "cfg5"
+n_samples = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 if which == "cfg5":
     rng = np.random.default_rng(100)
     prop = Chain(16, 256, 2e-6 / 256, 12, 2 * np.pi * 2e6, 2 * np.pi * 4e6)
     nrng = np.random.default_rng(1234)
-    prop.set_ensemble(del_total=nrng.normal(0, 2 * np.pi * 0.1e6, 512), rabi_scale=1 + nrng.normal(0, 0.01, 512))
-    units = 256 * 512
+    prop.set_ensemble(del_total=nrng.normal(0, 2 * np.pi * 0.1e6, n_samples),
+                      rabi_scale=1 + nrng.normal(0, 0.01, n_samples))
+    units = 256 * n_samples
 else:
     rng = np.random.default_rng(7)
     prop = Chain(16, 4000, 1e-9, 10, 2 * np.pi * 2e6, 2 * np.pi * 4e6)

@@ -258,3 +258,67 @@ def test_reduced_system_streamed_terms_equal_recomputed_terms():
             assert prop._plan.chain_info()["path"] == ("reduced_stacked_streamed" if flag else "reduced_stacked")
     assert np.abs(outs[1][:3] - outs[0][:3]).max() < 1e-14
     assert rel(outs[1][3:], outs[0][3:]) < 1e-11
+
+
+def _chain_ensemble(n_atoms, nt, n_samples, seed=11, n_gauss=6):
+    po, a, b, c = obc.chain_setup(n_atoms=n_atoms, n_gauss=n_gauss, nt=nt, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    dl, rs = rng.normal(0, 2 * np.pi * 0.1e6, n_samples), 1 + rng.normal(0, 0.01, n_samples)
+    return po, a, b, c, dl, rs
+
+
+def _run_chain(po, a, b, c, dl, rs, **kv):
+    with env(**kv):
+        prop = make_chain(po)
+        if dl is not None:
+            prop.set_ensemble(del_total=dl, rabi_scale=rs)
+        out = np_(prop.cost_and_grad_packed(prop._pack(a, b, c))).copy()
+        cost_only = float(prop.target(a, b, c))
+        prop._plan.check()
+        info = prop._plan.chain_info()
+    return out, cost_only, info
+
+
+@pytest.mark.parametrize("n_atoms,n_samples", [(6, 11), (7, 19), (10, 9), (10, 1)])
+def test_samples_minor_kernel_equals_one_cta_per_sample_kernel(n_atoms, n_samples):
+    """chain_wide.cu (8 samples per CTA, samples-minor vectors, generator-by-generator products, streamed Taylor
+    terms) against chain_big.cu (one CTA per sample, assembled CSR values, per-entry Xbar) on blockade-chain
+    ensembles with a ragged last CTA; a single sample runs the one-sample-per-CTA variant of the same kernel."""
+    po, a, b, c, dl, rs = _chain_ensemble(n_atoms, 40, n_samples)
+    if n_samples == 1:
+        dl = rs = None
+    out_old, cost_old, info_old = _run_chain(po, a, b, c, dl, rs, QOCVL_WIDE=0)
+    out_new, cost_new, info_new = _run_chain(po, a, b, c, dl, rs)
+    assert info_old["path"] == "rows_strided" and info_new["path"] == "samples_minor_streamed"
+    assert info_new["lanes"] == (8 if n_samples >= 5 else 1)
+    assert np.abs(out_new[:3] - out_old[:3]).max() < 1e-13 and abs(cost_new - out_old[0]) < 1e-13
+    assert rel(out_new[3:], out_old[3:]) < 1e-10
+
+
+@pytest.mark.parametrize("threads", [256, 384, 512])
+def test_samples_minor_kernel_streamed_equals_recomputed_and_any_geometry(threads):
+    """STORE mode against checkpoint + recompute mode, for every CTA size the kernel is compiled for (different rows
+    per thread and warps per CTA): identical sums up to the order of the per-warp reductions."""
+    po, a, b, c, dl, rs = _chain_ensemble(8, 33, 13, seed=5)          # n = 55
+    ref, cost_ref, _ = _run_chain(po, a, b, c, dl, rs, QOCVL_WIDE=0)
+    for store in (1, 0):
+        out, cost, info = _run_chain(po, a, b, c, dl, rs, QOCVL_WIDE_STORE=store, QOCVL_WIDE_THREADS=threads)
+        assert info["path"] == ("samples_minor_streamed" if store else "samples_minor_recomputed")
+        assert np.abs(out[:3] - ref[:3]).max() < 1e-13 and abs(cost - ref[0]) < 1e-13
+        assert rel(out[3:], ref[3:]) < 1e-10
+
+
+def test_samples_minor_kernel_dim377_against_dense_oracle_sample():
+    """cfg 5 Hilbert space (12 atoms, n = 377) on a short grid: ensemble of 8 = one full CTA; the ensemble mean must
+    equal the mean of the dense torch oracle evaluated member by member for the cost, and the one-CTA-per-sample
+    kernel for the gradient."""
+    po, a, b, c, dl, rs = _chain_ensemble(12, 12, 8, seed=2, n_gauss=4)
+    out_new, _, info = _run_chain(po, a, b, c, dl, rs)
+    assert info["rows"] == 377 and info["path"] == "samples_minor_streamed"
+    out_old, _, _ = _run_chain(po, a, b, c, dl, rs, QOCVL_WIDE=0)
+    acc = 0.0
+    for d, s in zip(dl, rs):
+        member, *_ = obc.chain_setup(n_atoms=12, n_gauss=4, nt=12, seed=2, del_offset=float(d), rabi_scale=float(s))
+        acc += float(member.cost_torch(*(torch.tensor(x) for x in (a, b, c)))[0])
+    assert abs(out_new[0] - acc / 8) < 1e-10
+    assert np.abs(out_new[:3] - out_old[:3]).max() < 1e-13 and rel(out_new[3:], out_old[3:]) < 1e-10
