@@ -128,14 +128,17 @@ struct AugLayout {
 // the column lists (reverse sweep); the diagonal of every generator block as a dense vector.
 struct WideLayout {
   int spc = 0, items = 0, max_threads = 0, ngroups = 0, nb = 0, nd = 0;
-  int bgen[8] = {0}, bfam[8] = {0}, dgen[8] = {0}, dfam[8] = {0};
-  bool store = false;
+  int bgen[8] = {0}, bfam[8] = {0}, dgen[8] = {0}, dfam[8] = {0}, buni[8] = {0};
+  cplx bval[8] = {};
+  int ent_fwd = 0, ent_rev = 0;
+  bool store = false, dreal = false;
   double macs = 0.0;                         // useful complex multiply-adds of one Taylor step of one sample
   long long padded_entries = 0, true_entries = 0;
   int* grow = nullptr;
   int2 *fwd_co = nullptr, *rev_co = nullptr;
   cplx *fwd_val = nullptr, *rev_val = nullptr, *dval = nullptr;
-  int *fwd_col = nullptr, *rev_col = nullptr;
+  double* dval_re = nullptr;
+  unsigned short *fwd_col = nullptr, *rev_col = nullptr;
   void release();
 };
 
