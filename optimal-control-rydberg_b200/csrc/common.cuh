@@ -131,13 +131,14 @@ struct WideLayout {
   int bgen[8] = {0}, bfam[8] = {0}, dgen[8] = {0}, dfam[8] = {0}, buni[8] = {0};
   cplx bval[8] = {};
   int ent_fwd = 0, ent_rev = 0;
-  bool store = false, dreal = false;
+  bool store = false, dreal = false, simple = false;
   double macs = 0.0;                         // useful complex multiply-adds of one Taylor step of one sample
   long long padded_entries = 0, true_entries = 0;
   int* grow = nullptr;
   int2 *fwd_co = nullptr, *rev_co = nullptr;
   cplx *fwd_val = nullptr, *rev_val = nullptr, *dval = nullptr;
   double* dval_re = nullptr;
+  unsigned char* dmask = nullptr;
   unsigned short *fwd_col = nullptr, *rev_col = nullptr;
   void release();
 };

@@ -322,3 +322,34 @@ def test_samples_minor_kernel_dim377_against_dense_oracle_sample():
         acc += float(member.cost_torch(*(torch.tensor(x) for x in (a, b, c)))[0])
     assert abs(out_new[0] - acc / 8) < 1e-10
     assert np.abs(out_new[:3] - out_old[:3]).max() < 1e-13 and rel(out_new[3:], out_old[3:]) < 1e-10
+
+
+def test_samples_minor_kernel_general_blocks(monkeypatch):
+    """The general instantiation of chain_wide.cu: off-diagonal entries with DIFFERENT values (site-dependent Rabi
+    frequencies, complex phases) and an off-diagonal pair in a top-right (penalty) block, which the blockade-chain
+    model never produces.  Reference: the one-CTA-per-sample kernel on the same generators."""
+    import quantum_optimal_control.blockade_chain.propagator_vl as mod
+    plain = mod.chain_generators
+
+    def perturbed(n_atoms, Rabi_max, Delta_max):
+        states, gu, gw, i_g, i_z = plain(n_atoms, Rabi_max, Delta_max)
+        n = len(states)
+        rng = np.random.default_rng(0)
+        phase = np.exp(1j * rng.uniform(-0.3, 0.3, (n, n)))
+        scale = 1 + 0.2 * rng.uniform(-1, 1, (n, n))
+        factor = np.triu(scale * phase, 1)
+        gu[0] = gu[0] * (factor + factor.conj().T)            # Hermitian, entries all different
+        gw[2][1, 3] = 0.3 + 0.1j; gw[2][3, 1] = 0.3 - 0.1j    # off-diagonal pair in a penalty block
+        return states, gu, gw, i_g, i_z
+
+    monkeypatch.setattr(mod, "chain_generators", perturbed)
+    po, a, b, c, dl, rs = _chain_ensemble(7, 36, 10, seed=9)
+    out_old, cost_old, info_old = _run_chain(po, a, b, c, dl, rs, QOCVL_WIDE=0)
+    out_new, cost_new, info_new = _run_chain(po, a, b, c, dl, rs)
+    assert info_old["path"] == "rows_strided" and info_new["path"] == "samples_minor_streamed"
+    assert info_new["slots"] == 2 and info_new["classes"] == 3     # generator blocks: 2 off-diagonal, 3 diagonal
+    assert np.abs(out_new[:3] - out_old[:3]).max() < 1e-13 and abs(cost_new - out_old[0]) < 1e-13
+    assert rel(out_new[3:], out_old[3:]) < 1e-10
+    out_rec, _, info_rec = _run_chain(po, a, b, c, dl, rs, QOCVL_WIDE_STORE=0)
+    assert info_rec["path"] == "samples_minor_recomputed"
+    assert np.abs(out_rec[:3] - out_old[:3]).max() < 1e-13 and rel(out_rec[3:], out_old[3:]) < 1e-10
