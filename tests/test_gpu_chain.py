@@ -353,3 +353,37 @@ def test_samples_minor_kernel_general_blocks(monkeypatch):
     out_rec, _, info_rec = _run_chain(po, a, b, c, dl, rs, QOCVL_WIDE_STORE=0)
     assert info_rec["path"] == "samples_minor_recomputed"
     assert np.abs(out_rec[:3] - out_old[:3]).max() < 1e-13 and rel(out_rec[3:], out_old[3:]) < 1e-10
+
+
+def test_multi_start_concurrent_seeds_equal_sequential_evaluation():
+    """MultiStart (several replicas of the propagator evaluating different pulse seeds concurrently on separate
+    streams) must return, per seed, exactly what one propagator returns evaluating the seeds one after the other;
+    its device-side descent must lower every seed's cost."""
+    from quantum_optimal_control.multi_start import MultiStart
+    po, a, b, c, dl, rs = _chain_ensemble(7, 30, 9, seed=4)
+
+    def make():
+        prop = make_chain(po)
+        prop.set_ensemble(del_total=dl, rabi_scale=rs)
+        return prop
+
+    single = make()
+    seeds = []
+    for k in range(5):
+        rng = np.random.default_rng(50 + k)
+        seeds.append(single._pack(rng.uniform(-1, 1, (6, 2)), rng.uniform(-1, 1, (6, 2)), rng.uniform(0, 0.5, (6, 2))))
+    seeds = torch.stack(seeds)
+    ref = torch.stack([single.cost_and_grad_packed(x).clone() for x in seeds])
+    ms = MultiStart(make, n_concurrent=3)
+    out = ms.cost_and_grad(seeds)
+    torch.cuda.synchronize()
+    ms.check()
+    assert ms.n_concurrent == 3 and len(ms.replicas) == 3
+    assert torch.equal(out, ref)
+    hist, final = ms.optimize(seeds, num_iters=6, lr=0.05)
+    assert bool((hist[-1] < hist[0]).all())
+    i, best = ms.best(hist[-1], 5)
+    assert best == float(hist[-1].min()) and i == int(hist[-1].argmin())
+    auto = MultiStart(make, sm_count=4)       # 2 CTAs per evaluation on a pretend 4-SM device -> 2 replicas
+    auto.cost_and_grad(seeds[:2])
+    assert auto.n_concurrent == 2
