@@ -170,7 +170,7 @@ extern "C" double qocvl_hbm_bytes_per_call(const qocvl_plan* p, int with_grad) {
 extern "C" int qocvl_chain_info(const qocvl_plan* p, int* out) {
   if (!p || !out) return QOCVL_ERR_ARG;
   if (p->groups <= 0) return QOCVL_ERR_STATE;
-  const int path = p->use_tp ? 2 : (p->use_aug ? 1 : (p->use_wide ? (p->lwide.store ? 5 : 6) : (p->use_big ? 3 : 0)));
+  const int path = p->use_tp ? 2 : (p->use_aug ? 1 : (p->use_wide ? (p->use_wide_tp ? 7 : (p->lwide.store ? 5 : 6)) : (p->use_big ? 3 : 0)));
   out[0] = path;
   out[1] = p->use_aug ? p->aug_n : p->d.n;
   out[2] = p->use_aug ? p->aug_lpg : p->npad;

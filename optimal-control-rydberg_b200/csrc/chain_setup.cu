@@ -229,13 +229,13 @@ int qocvl_launch_chain(qocvl_plan* p, bool want_grad, double* out3, double* gwav
   if (p->timing) QCUDA(cudaEventRecord(p->ev0, st));
   if (p->use_tp) rc = qocvl_tp_launch(p, want_grad, gwave, st);
   else if (p->use_aug) rc = qocvl_aug_launch(p, want_grad, gwave, st);
-  else if (p->use_wide) rc = qocvl_wide_launch(p, want_grad, st);
+  else if (p->use_wide) rc = qocvl_wide_launch(p, want_grad, gwave, st);
   else rc = p->use_big ? qocvl_big_launch(p, want_grad, st) : qocvl_small_launch(p, want_grad, st);
   if (rc) return rc;
   if (p->timing) { QCUDA(cudaEventRecord(p->ev1, st)); p->timed_once = true; }
   k_reduce_samples<<<1, 256, 0, st>>>(p->n_samples, 1.0 / (double)p->global_samples, p->d_sample_out, out3);
   p->launches++;
-  if (want_grad && !p->use_tp && !p->use_aug) {
+  if (want_grad && !p->use_tp && !p->use_aug && !p->use_wide_tp) {
     const int MC = d.n_slices * d.n_chan;
     k_reduce_gwave<<<(MC + 255) / 256, 256, 0, st>>>((int)p->n_parts, MC, p->d_gw_partial, gwave);
     p->launches++;

@@ -75,14 +75,11 @@ void WideLayout::release() {
   *this = WideLayout();
 }
 
-// Build the tables of the wide kernel.  QOCVL_ERR_UNSUPPORTED when the problem does not fit it (the caller then
-// falls back to the one-CTA-per-sample kernel).
-int qocvl_wide_configure(qocvl_plan* p) {
+// Tables and launch geometry of the wide kernel for (up to) spc_request samples per CTA.  QOCVL_ERR_UNSUPPORTED when
+// the problem does not fit the kernel.
+static int wide_build(qocvl_plan* p, int spc_request, WideLayout& L) {
   const qocvl_desc& d = p->d;
-  const int n = d.n, J = d.n_gen, S = p->n_samples, M = d.n_slices;
-  p->use_wide = false;
-  if (p->n_live != 1 || p->adiab_live != 0) return QOCVL_ERR_UNSUPPORTED;
-  WideLayout& L = p->lwide;
+  const int n = d.n, J = d.n_gen;
   L.release();
   // ---- generator blocks: off-diagonal part and diagonal part of every (generator, family)
   struct Blk { int g, fam; };
@@ -195,8 +192,7 @@ int qocvl_wide_configure(qocvl_plan* p) {
   };
   // ---- samples per CTA (8 when the CTA's vectors and tables fit shared memory), warps, rows per thread
   if ((n + 1) * WIDE_NVP * 8 > 65535) return QOCVL_ERR_UNSUPPORTED;   // pre-scaled 16-bit element offsets
-  int spc = (S >= 5) ? 8 : 1;
-  if (const char* e = getenv("QOCVL_WIDE_SPC")) spc = (atoi(e) == 8) ? 8 : 1;
+  int spc = spc_request;
   Tables T;
   int max_threads = 0, nwarps = 0, items = 0;
   wide_kernel_t kern = nullptr;
@@ -235,16 +231,180 @@ int qocvl_wide_configure(qocvl_plan* p) {
   L.spc = spc; L.items = items; L.max_threads = max_threads; L.ngroups = ngroups; L.nb = nb; L.nd = nd;
   for (int i = 0; i < nb; ++i) { L.bgen[i] = off_blk[i].g; L.bfam[i] = off_blk[i].fam; }
   for (int i = 0; i < nd; ++i) { L.dgen[i] = diag_blk[i].g; L.dfam[i] = diag_blk[i].fam; }
-  // ---- geometry and buffers
-  const int ctas = (S + spc - 1) / spc;
   QCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  p->chain_smem = smem;
-  p->threads = nwarps * 32;
+  L.smem = smem;
+  L.threads = nwarps * 32;
+  return QOCVL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// time-parallel single-sample path: stitch the chunk propagators together (one CTA).
+//   forward : z_{c+1} = (U_c q_c , U_c p_c + W_c q_c), boundary states zc[c]
+//   cost, terminal cotangents lc[n_chunks]
+//   backward: lam_c = (U_c^dag lq + W_c^dag lp , U_c^dag lp), boundary cotangents lc[c]
+// U_c, W_c are stored column by column ([column][row]: each column was written by one lane of the column sweep).
+// ---------------------------------------------------------------------------------------------------
+struct WideCombineArgs {
+  int n, n_chunks, want_grad;
+  double inv_duration, w_infid, w_adiab, inv_fid_norm, inv_samples;
+  cplx d_const;
+  const cplx *uc, *wc, *starts, *targets;
+  cplx *zc, *lc;
+  double* sample_out;
+};
+
+__global__ void __launch_bounds__(1024) k_wide_combine(const WideCombineArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = A.n, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  cplx* s_q = (cplx*)smem_raw;          // [n]
+  cplx* s_p = s_q + n;                  // [n]
+  cplx* s_part = s_p + n;               // [parts][2][n] partial sums of the forward products
+  const int parts = max(1, nt / n);     // thread (part, r): rows r, columns b = part, part + parts, ...
+  double* s_red = (double*)(s_part + (size_t)parts * 2 * n);   // [3][32]
+  const cplx czero = cmake(0, 0);
+  for (int r = tid; r < n; r += nt) {
+    s_q[r] = A.starts[r]; s_p[r] = czero;
+    A.zc[r] = A.starts[r]; A.zc[n + r] = czero;
+  }
+  __syncthreads();
+  const int part = tid / n, r = tid % n;
+  for (int c = 0; c < A.n_chunks; ++c) {
+    const cplx* U = A.uc + (size_t)c * n * n;
+    const cplx* W = A.wc + (size_t)c * n * n;
+    if (part < parts) {
+      cplx aq = czero, ap = czero;
+      for (int b = part; b < n; b += parts) {
+        const cplx u = U[(size_t)b * n + r], w = W[(size_t)b * n + r], qb = s_q[b], pb = s_p[b];
+        aq = cfma(u, qb, aq);
+        ap = cfma(w, qb, cfma(u, pb, ap));
+      }
+      s_part[((size_t)part * 2 + 0) * n + r] = aq;
+      s_part[((size_t)part * 2 + 1) * n + r] = ap;
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * n; i += nt) {
+      cplx a = czero;
+      for (int pp = 0; pp < parts; ++pp) a = cadd(a, s_part[(size_t)pp * 2 * n + i]);
+      (i < n ? s_q[i] : s_p[i - n]) = a;
+      A.zc[(size_t)(c + 1) * 2 * n + i] = a;
+    }
+    __syncthreads();
+  }
+  // ---- cost
+  double red[3] = {0, 0, 0};
+  for (int i = tid; i < n; i += nt) {
+    const cplx y = A.targets[i], zq = s_q[i], zp = s_p[i];
+    red[0] += y.x * zq.x + y.y * zq.y;
+    red[1] += y.x * zq.y - y.y * zq.x;
+    red[2] += zq.x * zp.x + zq.y * zp.y;
+  }
+  for (int k = 0; k < 3; ++k) {
+    for (int off = 16; off > 0; off >>= 1) red[k] += __shfl_xor_sync(0xffffffffu, red[k], off);
+    if (lane == 0) s_red[k * 32 + warp] = red[k];
+  }
+  __syncthreads();
+  double tot[3] = {0, 0, 0};
+  for (int k = 0; k < 3; ++k)
+    for (int w = 0; w < nwarps; ++w) tot[k] += s_red[k * 32 + w];
+  const cplx dsum = cmake(tot[0] + A.d_const.x, tot[1] + A.d_const.y);
+  if (tid == 0) {
+    const double infid = 1.0 - (dsum.x * dsum.x + dsum.y * dsum.y) * A.inv_fid_norm;
+    const double adiab = 1.0 - tot[2] * A.inv_duration;
+    A.sample_out[0] = A.w_infid * infid + A.w_adiab * adiab;
+    A.sample_out[1] = infid;
+    A.sample_out[2] = adiab;
+  }
+  if (!A.want_grad) return;
+  // ---- terminal cotangents
+  __syncthreads();
+  const double ca = -0.5 * A.w_adiab * A.inv_duration * A.inv_samples;
+  const double cf = -A.w_infid * A.inv_fid_norm * A.inv_samples;
+  cplx* s_lq = s_part;                  // reuse: [n], [n]
+  cplx* s_lp = s_part + n;
+  for (int i = tid; i < n; i += nt) {
+    const cplx lq = cadd(cscale(cmul(dsum, A.targets[i]), cf), cscale(s_p[i], ca));
+    const cplx lp = cscale(s_q[i], ca);
+    s_lq[i] = lq; s_lp[i] = lp;
+    A.lc[(size_t)A.n_chunks * 2 * n + i] = lq;
+    A.lc[(size_t)A.n_chunks * 2 * n + n + i] = lp;
+  }
+  __syncthreads();
+  // ---- backward walk: one warp per output element b, lanes over the rows of column b
+  for (int c = A.n_chunks - 1; c >= 0; --c) {
+    const cplx* U = A.uc + (size_t)c * n * n;
+    const cplx* W = A.wc + (size_t)c * n * n;
+    for (int b = warp; b < n; b += nwarps) {
+      cplx aq = czero, ap = czero;
+      for (int rr = lane; rr < n; rr += 32) {
+        const cplx u = U[(size_t)b * n + rr], w = W[(size_t)b * n + rr], lq = s_lq[rr], lp = s_lp[rr];
+        aq = cfma_conj(w, lp, cfma_conj(u, lq, aq));
+        ap = cfma_conj(u, lp, ap);
+      }
+      for (int off = 16; off > 0; off >>= 1) {
+        aq.x += __shfl_xor_sync(0xffffffffu, aq.x, off); aq.y += __shfl_xor_sync(0xffffffffu, aq.y, off);
+        ap.x += __shfl_xor_sync(0xffffffffu, ap.x, off); ap.y += __shfl_xor_sync(0xffffffffu, ap.y, off);
+      }
+      if (lane == 0) { s_q[b] = aq; s_p[b] = ap; }     // s_q / s_p are free after the cost
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+      s_lq[i] = s_q[i]; s_lp[i] = s_p[i];
+      A.lc[(size_t)c * 2 * n + i] = s_q[i];
+      A.lc[(size_t)c * 2 * n + n + i] = s_p[i];
+    }
+    __syncthreads();
+  }
+}
+
+// Build the tables of the wide kernel.  QOCVL_ERR_UNSUPPORTED when the problem does not fit it (the caller then
+// falls back to the one-CTA-per-sample kernel).
+int qocvl_wide_configure(qocvl_plan* p) {
+  const qocvl_desc& d = p->d;
+  const int n = d.n, S = p->n_samples, M = d.n_slices;
+  p->use_wide = false; p->use_wide_tp = false;
+  if (p->n_live != 1 || p->adiab_live != 0) return QOCVL_ERR_UNSUPPORTED;
+  int spc = (S >= 5) ? 8 : 1;
+  if (const char* e = getenv("QOCVL_WIDE_SPC")) spc = (atoi(e) == 8) ? 8 : 1;
+  WideLayout& L = p->lwide;
+  int rc = wide_build(p, spc, L);
+  if (rc) return rc;
+  spc = L.spc;
+  // ---- a single sample has no ensemble parallelism: cut the slice axis into chunks (column sweeps of every chunk
+  //      with 8 basis columns per CTA -> combine -> per-chunk forward + reverse sweeps)
+  bool tp = (S == 1 && M >= 64);
+  if (const char* e = getenv("QOCVL_TP")) tp = tp && atoi(e) != 0;
+  if (tp) {
+    rc = wide_build(p, 8, p->lwide_a);
+    if (rc == QOCVL_ERR_UNSUPPORTED || (rc == QOCVL_OK && p->lwide_a.spc != 8)) tp = false;
+    else if (rc) return rc;
+  }
+  int lc = 0, nchunks = 0;
+  if (tp) {
+    lc = (M + 63) / 64;                                // ~64 chunks: 64 * ceil(n/8) column CTAs fill the machine
+    lc = std::max(lc, 8);
+    if (const char* e = getenv("QOCVL_TP_CHUNK")) lc = std::max(1, std::min(M, atoi(e)));
+    nchunks = (M + lc - 1) / lc;
+    const size_t blk = (size_t)nchunks * n * n, bnd = (size_t)(nchunks + 1) * WIDE_NVP * n;
+    for (cplx** q : {&p->d_tp_uc, &p->d_tp_wc, &p->d_tp_zc, &p->d_tp_lc}) if (*q) { cudaFree(*q); *q = nullptr; }
+    QCUDA(cudaMalloc((void**)&p->d_tp_uc, blk * sizeof(cplx)));
+    QCUDA(cudaMalloc((void**)&p->d_tp_wc, blk * sizeof(cplx)));
+    QCUDA(cudaMalloc((void**)&p->d_tp_zc, bnd * sizeof(cplx)));
+    QCUDA(cudaMalloc((void**)&p->d_tp_lc, bnd * sizeof(cplx)));
+    p->bytes += (2 * blk + 2 * bnd) * sizeof(cplx);
+    p->tp_chunk = lc; p->tp_nchunks = nchunks;
+    p->tp_blocks_a = nchunks * ((n + 7) / 8);
+    p->use_wide_tp = true;
+  }
+  // ---- geometry and buffers
+  const int ctas = tp ? nchunks : (S + spc - 1) / spc;
+  const int cta_slices = tp ? lc : M;
+  p->chain_smem = L.smem;
+  p->threads = L.threads;
   p->blocks = ctas;
   p->spb = spc; p->groups = 1;
   p->n_parts = (size_t)ctas;
   const size_t vs = (size_t)WIDE_NVP * (n + 1) * spc * sizeof(cplx);
-  const size_t stream_bytes = (size_t)ctas * M * p->qcap * vs;
+  const size_t stream_bytes = (size_t)ctas * cta_slices * p->qcap * vs;
   size_t free_b = 0, total_b = 0;
   QCUDA(cudaMemGetInfo(&free_b, &total_b));
   bool store = stream_bytes <= (size_t)(0.6 * (double)free_b);
@@ -254,7 +414,7 @@ int qocvl_wide_configure(qocvl_plan* p) {
   p->tring_bytes = store ? stream_bytes : (size_t)ctas * p->qcap * vs;
   QCUDA(cudaMalloc((void**)&p->d_tring, p->tring_bytes));
   if (!store) {
-    p->ckpt_bytes = (size_t)ctas * M * vs;
+    p->ckpt_bytes = (size_t)ctas * cta_slices * vs;
     QCUDA(cudaMalloc((void**)&p->d_ckpt, p->ckpt_bytes));
   }
   p->bytes += p->ckpt_bytes + p->tring_bytes;
@@ -263,13 +423,11 @@ int qocvl_wide_configure(qocvl_plan* p) {
   return QOCVL_OK;
 }
 
-int qocvl_wide_launch(qocvl_plan* p, bool want_grad, cudaStream_t st) {
+static void wide_fill_args(const qocvl_plan* p, const WideLayout& L, WideArgs& a) {
   const qocvl_desc& d = p->d;
-  const WideLayout& L = p->lwide;
-  WideArgs a;
   memset(&a, 0, sizeof(a));
   a.n = d.n; a.J = d.n_gen; a.M = d.n_slices; a.C = d.n_chan; a.S = p->n_samples;
-  a.qcap = p->qcap; a.want_grad = want_grad ? 1 : 0; a.store = L.store ? 1 : 0;
+  a.qcap = p->qcap;
   a.ngroups = L.ngroups; a.nb = L.nb; a.nd = L.nd;
   a.ent_fwd = L.ent_fwd; a.ent_rev = L.ent_rev; a.dreal = L.dreal ? 1 : 0;
   a.dt = d.dt; a.inv_duration = 1.0 / d.duration; a.w_infid = d.w_infid; a.w_adiab = d.w_adiab;
@@ -278,14 +436,51 @@ int qocvl_wide_launch(qocvl_plan* p, bool want_grad, cudaStream_t st) {
   for (int i = 0; i < WIDE_MAXB; ++i) { a.bgen[i] = L.bgen[i]; a.bfam[i] = L.bfam[i]; a.buni[i] = L.buni[i]; a.bval[i] = L.bval[i]; }
   for (int i = 0; i < WIDE_MAXD; ++i) { a.dgen[i] = L.dgen[i]; a.dfam[i] = L.dfam[i]; }
   a.grow = L.grow; a.fwd_co = L.fwd_co; a.rev_co = L.rev_co;
-  a.fwd_val = L.fwd_val; a.fwd_col = L.fwd_col; a.rev_val = L.rev_val; a.rev_col = L.rev_col; a.dval = L.dval; a.dval_re = L.dval_re; a.dmask = L.dmask;
+  a.fwd_val = L.fwd_val; a.fwd_col = L.fwd_col; a.rev_val = L.rev_val; a.rev_col = L.rev_col;
+  a.dval = L.dval; a.dval_re = L.dval_re; a.dmask = L.dmask;
   a.coef = p->d_coef; a.dcoef = p->d_dcoef; a.qdeg = p->d_qdeg; a.mul = p->d_mul; a.add = p->d_add;
   a.starts = p->d_starts; a.targets = p->d_targets;
   a.ring = p->d_tring; a.ckpt = p->d_ckpt;
   a.sample_out = p->d_sample_out; a.gw_partial = p->d_gw_partial;
+  a.chunk_len = p->tp_chunk; a.n_chunks = p->tp_nchunks; a.ctas_per_chunk = (d.n + 7) / 8;
+  a.tp_uc = p->d_tp_uc; a.tp_wc = p->d_tp_wc; a.tp_zc = p->d_tp_zc; a.tp_lc = p->d_tp_lc;
+}
+
+// gwave: [M][C] device buffer; the time-parallel path writes d cost / d wave into it directly
+int qocvl_wide_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t st) {
+  const WideLayout& L = p->lwide;
+  WideArgs a;
+  wide_fill_args(p, L, a);
+  a.want_grad = want_grad ? 1 : 0; a.store = L.store ? 1 : 0;
   wide_kernel_t kern = wide_pick(L.spc, L.items, L.max_threads, L.nb, L.nd, L.simple);
-  kern<<<p->blocks, p->threads, p->chain_smem, st>>>(a);
-  p->launches++;
+  if (!p->use_wide_tp) {
+    kern<<<p->blocks, p->threads, p->chain_smem, st>>>(a);
+    p->launches++;
+    QCUDA(cudaGetLastError());
+    return QOCVL_OK;
+  }
+  // ---- time-parallel: column sweeps -> combine -> chunk sweeps
+  const WideLayout& LA = p->lwide_a;
+  WideArgs pa;
+  wide_fill_args(p, LA, pa);
+  pa.mode = 1; pa.want_grad = 0; pa.store = 0;
+  wide_pick(LA.spc, LA.items, LA.max_threads, LA.nb, LA.nd, LA.simple)<<<p->tp_blocks_a, LA.threads, LA.smem, st>>>(pa);
+  WideCombineArgs c;
+  c.n = p->d.n; c.n_chunks = p->tp_nchunks; c.want_grad = want_grad ? 1 : 0;
+  c.inv_duration = a.inv_duration; c.w_infid = a.w_infid; c.w_adiab = a.w_adiab; c.inv_fid_norm = a.inv_fid_norm;
+  c.inv_samples = a.inv_samples; c.d_const = a.d_const;
+  c.uc = p->d_tp_uc; c.wc = p->d_tp_wc; c.starts = p->d_starts; c.targets = p->d_targets;
+  c.zc = p->d_tp_zc; c.lc = p->d_tp_lc; c.sample_out = p->d_sample_out;
+  const int cthreads = 1024, parts = std::max(1, cthreads / p->d.n);
+  const size_t csmem = (size_t)(2 + 2 * parts) * p->d.n * sizeof(cplx) + 3 * 32 * sizeof(double);
+  if (csmem > 48 * 1024) QCUDA(cudaFuncSetAttribute(k_wide_combine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+  k_wide_combine<<<1, cthreads, csmem, st>>>(c);
+  p->launches += 2;
+  if (want_grad) {
+    a.mode = 2; a.tp_gwave = gwave;
+    kern<<<p->tp_nchunks, p->threads, p->chain_smem, st>>>(a);
+    p->launches++;
+  }
   QCUDA(cudaGetLastError());
   return QOCVL_OK;
 }

@@ -35,7 +35,14 @@ struct WideArgs {
   const cplx* add;        // [S][J]
   const cplx* starts;     // [1][n]
   const cplx* targets;    // [1][n]
-  cplx* ring;             // [cta][(store ? M : 1) * qcap][NVP][n][SPC]
+  // time-parallel single-sample path: mode 1 = CTA propagates 8 basis columns through one chunk of slices (forward
+  // only) and writes the columns of the chunk's Van Loan blocks U_c, W_c; mode 2 = CTA runs the forward + reverse
+  // sweep of one chunk between the boundary states / cotangents k_wide_combine stitched together; mode 0 = ensemble.
+  int mode, chunk_len, n_chunks, ctas_per_chunk;
+  cplx *tp_uc, *tp_wc;    // [chunk][column][n]
+  const cplx *tp_zc, *tp_lc;   // [chunk + 1][NVP][n]
+  double* tp_gwave;       // [M][C], written directly (every slice belongs to one chunk)
+  cplx* ring;             // [cta][(store ? slices of the CTA : 1) * qcap][NVP][n][SPC]
   cplx* ckpt;             // recompute mode: [cta][M][NVP][n][SPC]
   double* sample_out;     // [S][3]
   double* gw_partial;     // [cta][M][C]
@@ -56,8 +63,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_wide(const WideArgs P) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int s = lane % SPC, rw = lane / SPC;
   const int n = P.n, J = P.J, C = P.C, M = P.M;
-  const int cta = blockIdx.x;
-  const int nact = min(SPC, P.S - cta * SPC);            // live samples of this CTA (padding lanes repeat the last)
+  const int cta = blockIdx.x, mode = P.mode;
+  int chunk = 0, colbase = 0, k_begin = 0, k_end = P.M;
+  if (mode == 1) { chunk = cta / P.ctas_per_chunk; colbase = (cta % P.ctas_per_chunk) * SPC; }
+  if (mode == 2) chunk = cta;
+  if (mode) { k_begin = chunk * P.chunk_len; k_end = min(P.M, k_begin + P.chunk_len); }
+  const int nslices = mode ? P.chunk_len : P.M;          // slices a CTA owns (ring / checkpoint stride)
+  // live lanes of this CTA (padding lanes repeat the last): noise samples, or basis columns in mode 1
+  const int nact = mode == 0 ? min(SPC, P.S - cta * SPC) : (mode == 1 ? min(SPC, n - colbase) : 1);
   const int nr = n + 1;                                  // row n of every vector stays zero (read by padding entries)
   const int VS = NVP * nr * SPC;                         // elements of one "all vectors" buffer
   const cplx czero = cmake(0, 0);
@@ -104,7 +117,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_wide(const WideArgs P) {
     s_buf[(i / (NVP * SPC)) * VS + n * NVP * SPC + (i % (NVP * SPC))] = czero;
 
   for (int i = tid; i < J * SPC; i += blockDim.x) {
-    const int g = i / SPC, ss = i % SPC, sm = cta * SPC + min(ss, nact - 1);
+    const int g = i / SPC, ss = i % SPC, sm = mode ? 0 : cta * SPC + min(ss, nact - 1);
     s_mul[i] = P.mul[(size_t)sm * J + g];
     s_add[i] = P.add[(size_t)sm * J + g];
   }
@@ -129,6 +142,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_wide(const WideArgs P) {
   for (int i = 0; i < ITEMS; ++i) {
     z[i][0] = (row[i] >= 0) ? P.starts[row[i]] : czero;
     z[i][NV] = czero;
+    if (mode == 1) z[i][0] = (row[i] == colbase + min(s, nact - 1)) ? cmake(1.0, 0.0) : czero;   // basis column
+    if (mode == 2 && row[i] >= 0) {
+      z[i][0] = P.tp_zc[((size_t)chunk * NVP + 0) * n + row[i]];
+      z[i][NV] = P.tp_zc[((size_t)chunk * NVP + NV) * n + row[i]];
+    }
   }
   // sum of the gathered elements of one list (4 pre-scaled 16-bit indices per 8-byte load): q and p, or q only
   auto gather_sum = [&](const cplx* ts, const unsigned short* list, int chunks, bool both, cplx& sq, cplx& sp) {
@@ -202,18 +220,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_wide(const WideArgs P) {
     y[NV] = cscale(accp, invj);
   };
 
-  const size_t ring_slices = P.store ? (size_t)M : 1;
+  const size_t ring_slices = P.store ? (size_t)nslices : 1;
   cplx* ring = P.ring + (size_t)cta * ring_slices * P.qcap * VS;
-  cplx* ckpt = P.store ? nullptr : P.ckpt + (size_t)cta * M * VS;
+  cplx* ckpt = P.store ? nullptr : P.ckpt + (size_t)cta * nslices * VS;
 
   // =================================== forward sweep ===================================
-  load_cs(0, 0);
+  load_cs(k_begin, k_begin & 1);
   __syncthreads();
-  for (int k = 0; k < M; ++k) {
+  for (int k = k_begin; k < k_end; ++k) {
     const int q = P.qdeg[k], b = k & 1;
-    if (k + 1 < M) load_cs(k + 1, b ^ 1);
+    if (k + 1 < k_end) load_cs(k + 1, b ^ 1);
     coefficients(b);
-    cplx* t0 = (P.store ? ring + (size_t)k * P.qcap * VS : ckpt + (size_t)k * VS);
+    const int kl = k - k_begin;
+    cplx* t0 = (P.store ? ring + (size_t)kl * P.qcap * VS : ckpt + (size_t)kl * VS);
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
       if (row[i] < 0) continue;
@@ -229,7 +248,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_wide(const WideArgs P) {
       const cplx* t = s_buf + cur * VS;
       cplx* y = s_buf + (cur ^ 1) * VS;
       const double invj = 1.0 / (double)j;
-      cplx* rj = ring + ((size_t)k * P.qcap + j) * VS;
+      cplx* rj = ring + ((size_t)kl * P.qcap + j) * VS;
       const bool keep = (j < q);
 #pragma unroll
       for (int i = 0; i < ITEMS; ++i) {
@@ -250,8 +269,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_wide(const WideArgs P) {
     }
   }
 
+  if (mode == 1) {       // columns colbase .. of the chunk's blocks: U_c e_b = q, W_c e_b = p
+    if (s < nact) {
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        if (row[i] < 0) continue;
+        const size_t o = ((size_t)chunk * n + colbase + s) * n + row[i];
+        P.tp_uc[o] = z[i][0];
+        P.tp_wc[o] = z[i][NV];
+      }
+    }
+    return;
+  }
   // =================================== cost ============================================
-  {
+  if (mode == 0) {
     double red[3] = {0, 0, 0};   // Re d, Im d, Re q^dag p
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
@@ -287,7 +318,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_wide(const WideArgs P) {
   if (!P.want_grad) return;
 
   // terminal cotangents (scaled by 1 / global sample count):  lam_q = cf * d * y + ca * p,  lam_p = ca * q
-  {
+  if (mode == 2) {
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      if (row[i] < 0) continue;
+      z[i][0] = P.tp_lc[((size_t)(chunk + 1) * NVP + 0) * n + row[i]];
+      z[i][NV] = P.tp_lc[((size_t)(chunk + 1) * NVP + NV) * n + row[i]];
+    }
+  } else {
     const double ca = -0.5 * P.w_adiab * P.inv_duration * P.inv_samples;
     const double cf = -P.w_infid * P.inv_fid_norm * P.inv_samples;
     const cplx dsum = cmake(s_dsum[s], s_dsum[SPC + s]);
@@ -301,17 +339,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_wide(const WideArgs P) {
   }
 
   // =================================== reverse sweep ===================================
-  load_cs(M - 1, (M - 1) & 1);
+  load_cs(k_end - 1, (k_end - 1) & 1);
   __syncthreads();
-  for (int k = M - 1; k >= 0; --k) {
-    const int q = P.qdeg[k], b = k & 1, qprev = k > 0 ? P.qdeg[k - 1] : 0;
-    if (k > 0) load_cs(k - 1, b ^ 1);
+  for (int k = k_end - 1; k >= k_begin; --k) {
+    const int q = P.qdeg[k], b = k & 1, qprev = k > k_begin ? P.qdeg[k - 1] : 0, kl = k - k_begin;
+    if (k > k_begin) load_cs(k - 1, b ^ 1);
     coefficients(b);
-    cplx* rk = ring + (P.store ? (size_t)k * P.qcap * VS : 0);
+    cplx* rk = ring + (P.store ? (size_t)kl * P.qcap * VS : 0);
     int cur = 0;
     if (!P.store) {
       // ---- recompute the forward terms t_0 .. t_{q-1} of this slice into the ring (own elements)
-      const cplx* ck = ckpt + (size_t)k * VS;
+      const cplx* ck = ckpt + (size_t)kl * VS;
 #pragma unroll
       for (int i = 0; i < ITEMS; ++i) {
         if (row[i] < 0) continue;
@@ -368,7 +406,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_wide(const WideArgs P) {
         if (j > 2) {                                                // pull the terms of step j-2 from HBM into L2
           prefetch_l2(&rj[at(VA, c) - 2 * VS]);
           prefetch_l2(&rj[at(NV, c) - 2 * VS]);
-        } else if (P.store && k > 0 && qprev - 3 + j >= 0) {       // ... or the top terms of the next slice to process
+        } else if (P.store && k > k_begin && qprev - 3 + j >= 0) {       // ... or the top terms of the next slice to process
           const cplx* nx = rk - (size_t)P.qcap * VS + (size_t)(qprev - 3 + j) * VS;
           prefetch_l2(&nx[at(VA, c)]);
           prefetch_l2(&nx[at(NV, c)]);
@@ -482,7 +520,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_wide(const WideArgs P) {
           gw += yv.x * dc.x - yv.y * dc.y;
         }
       }
-      P.gw_partial[((size_t)cta * M + k) * C + tid] = gw;
+      if (mode == 2) P.tp_gwave[(size_t)k * C + tid] = gw;
+      else P.gw_partial[((size_t)cta * M + k) * C + tid] = gw;
     }
     // s_dco / s_scr / s_ysum are rewritten only after a barrier of the next slice
   }

@@ -132,6 +132,8 @@ struct WideLayout {
   cplx bval[8] = {};
   int ent_fwd = 0, ent_rev = 0;
   bool store = false, dreal = false, simple = false;
+  size_t smem = 0;
+  int threads = 0;
   double macs = 0.0;                         // useful complex multiply-adds of one Taylor step of one sample
   long long padded_entries = 0, true_entries = 0;
   int* grow = nullptr;
@@ -216,6 +218,8 @@ struct qocvl_plan {
   // symmetric sectors folded onto orbit representatives, all of it stacked into ONE sparse system of aug_n rows
   bool use_wide = false;   // big-n ensembles: samples-minor CTA kernel (chain_wide.cu)
   WideLayout lwide;
+  WideLayout lwide_a;      // 8 basis columns per CTA: column sweeps of the time-parallel single-sample path
+  bool use_wide_tp = false;
   bool use_aug = false;
   int aug_n = 0, aug_lpg = 0, aug_nnz = 0, aug_wmax = 0, aug_parts = 0, aug_qs = 0;
   bool aug_store = false;         // Taylor terms streamed through HBM instead of recomputed in the reverse sweep
@@ -246,7 +250,7 @@ int qocvl_tp_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t s
 int qocvl_big_configure(qocvl_plan* p);
 int qocvl_big_launch(qocvl_plan* p, bool want_grad, cudaStream_t st);
 int qocvl_wide_configure(qocvl_plan* p);
-int qocvl_wide_launch(qocvl_plan* p, bool want_grad, cudaStream_t st);
+int qocvl_wide_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t st);
 int qocvl_aug_configure(qocvl_plan* p);
 int qocvl_aug_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t st);
 int qocvl_build_lane_layout(qocvl_plan* p, const std::vector<std::complex<double>>& blocks, int n, int npad,

@@ -162,7 +162,7 @@ extern "C" int qocvl_plan_create(qocvl_plan** out, const qocvl_desc* desc, int d
 extern "C" int qocvl_plan_destroy(qocvl_plan* p) {
   if (!p) return QOCVL_OK;
   cudaSetDevice(p->device);
-  free_layout(p->lu); free_layout(p->lw); p->la.release(); p->lwide.release();
+  free_layout(p->lu); free_layout(p->lw); p->la.release(); p->lwide.release(); p->lwide_a.release();
   for (CsrLayout* c : {&p->cu, &p->cw}) {
     cudaFree(c->rowptr); cudaFree(c->col); cudaFree(c->erow); cudaFree(c->colptr);
     cudaFree(c->crow); cudaFree(c->ceid); cudaFree(c->egen); cudaFree(c->eval);
@@ -172,7 +172,7 @@ extern "C" int qocvl_plan_destroy(qocvl_plan* p) {
                   p->d_mulmax, p->d_addmax, p->d_taps, p->d_raw, p->d_reg, p->d_wave, p->d_coef, p->d_dcoef,
                   p->d_qdeg, p->d_flag, p->d_ckpt, p->d_sample_out, p->d_gw_partial, p->d_gwave, p->d_greg,
                   p->d_graw, p->d_out3, p->d_dense_a, p->d_dense_b, p->d_aug_starts, p->d_aug_targets,
-                  p->d_aug_pair, p->d_aug_wq, p->d_ypart};
+                  p->d_aug_pair, p->d_aug_wq, p->d_ypart, p->d_tp_uc, p->d_tp_wc, p->d_tp_zc, p->d_tp_lc};
   for (void* q : ptrs) if (q) cudaFree(q);
   delete p;
   return QOCVL_OK;

@@ -211,7 +211,8 @@ class Plan:
         keys = ("path", "rows", "lanes", "slots", "classes", "nnz", "threads", "ctas")
         info = dict(zip(keys, (int(x) for x in buf)))
         info["path"] = ("lane_per_row", "reduced_stacked", "time_parallel", "rows_strided",
-                        "reduced_stacked_streamed", "samples_minor_streamed", "samples_minor_recomputed")[info["path"]]
+                        "reduced_stacked_streamed", "samples_minor_streamed", "samples_minor_recomputed",
+                        "samples_minor_time_parallel")[info["path"]]
         return info
 
     @property

@@ -387,3 +387,20 @@ def test_multi_start_concurrent_seeds_equal_sequential_evaluation():
     auto = MultiStart(make, sm_count=4)       # 2 CTAs per evaluation on a pretend 4-SM device -> 2 replicas
     auto.cost_and_grad(seeds[:2])
     assert auto.n_concurrent == 2
+
+
+@pytest.mark.parametrize("chunk", [None, 7, 33, 90])
+def test_samples_minor_time_parallel_single_sample(chunk):
+    """A single sample on a large Hilbert space: column sweeps of every chunk (8 basis columns per CTA) -> combine ->
+    per-chunk forward + reverse sweeps must equal the plain sequential sweep of the same kernel (QOCVL_TP=0) and the
+    one-CTA-per-sample kernel, for chunk lengths that do not divide M = 100 and for a single short tail chunk."""
+    po, a, b, c, _, _ = _chain_ensemble(8, 100, 1, seed=6)          # n = 55
+    out_old, cost_old, _ = _run_chain(po, a, b, c, None, None, QOCVL_WIDE=0)
+    out_seq, cost_seq, info_seq = _run_chain(po, a, b, c, None, None, QOCVL_TP=0)
+    kv = {} if chunk is None else {"QOCVL_TP_CHUNK": chunk}
+    out_tp, cost_tp, info_tp = _run_chain(po, a, b, c, None, None, **kv)
+    assert info_seq["path"] == "samples_minor_streamed" and info_tp["path"] == "samples_minor_time_parallel"
+    assert info_tp["ctas"] == -(-100 // (chunk or 8))
+    for out, cost in ((out_seq, cost_seq), (out_tp, cost_tp)):
+        assert np.abs(out[:3] - out_old[:3]).max() < 1e-13 and abs(cost - out_old[0]) < 1e-13
+        assert rel(out[3:], out_old[3:]) < 1e-10
