@@ -43,6 +43,9 @@ class MultiStart:
     def _ensure_replicas(self, abc0):
         if self.streams:
             return
+        if self.device.type != "cuda":                         # host-logic tests: one replica, no streams
+            self.streams = [None]
+            return
         first = self.replicas[0]
         first.cost_and_grad_packed(abc0)                       # configures the launch: CTAs and workspace are known now
         torch.cuda.synchronize(self.device)
@@ -77,6 +80,10 @@ class MultiStart:
         if n_local == 0:
             return out
         self._ensure_replicas(abc_seeds[0])
+        if self.streams[0] is None:
+            for i in range(n_local):
+                self.replicas[0].cost_and_grad_packed(abc_seeds[i], out[i])
+            return out
         main = torch.cuda.current_stream(self.device)
         ready = torch.cuda.Event()
         ready.record(main)
@@ -106,10 +113,12 @@ class MultiStart:
 
     def best(self, costs, n_seeds):
         """Global (seed index, cost) of the lowest final cost; one all_gather when sharded."""
-        local = list(self.local_seeds(n_seeds))
+        local = self.local_seeds(n_seeds)
         vals = costs.detach().to("cpu", torch.float64).numpy() if isinstance(costs, torch.Tensor) else np.asarray(costs)
+        if len(vals) != len(local):
+            raise ValueError(f"rank {self.rank} owns {len(local)} of {n_seeds} seeds, got {len(vals)} costs")
         table = np.full(n_seeds, np.inf)
-        table[local[0]:local[0] + len(vals)] = vals
+        table[local.start:local.stop] = vals
         if self.shard and self.world > 1:
             import torch.distributed as dist
             t = torch.from_numpy(table).to(self.device if dist.get_backend() == "nccl" else "cpu")

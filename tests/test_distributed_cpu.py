@@ -115,6 +115,54 @@ def test_two_rank_sharded_mean_equals_single_process_mean():
         assert np.allclose(ga.ravel(), full[3:3 + N_GAUSS * N_CHAN], rtol=1e-14)
 
 
+def _multistart_worker(rank, world, port, queue):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from quantum_optimal_control.multi_start import MultiStart
+    n_seeds = 5                                             # ragged: 3 + 2
+
+    def make():
+        eng = StubEngine()
+        eng.set_ensemble(del_total=np.linspace(-1e5, 1e5, 4), rabi_scale=np.linspace(0.99, 1.01, 4))   # not sharded
+        return eng
+
+    ms = MultiStart(make, shard=True)
+    mine = ms.local_seeds(n_seeds)
+    seeds = torch.stack([torch.from_numpy(np.random.default_rng(40 + k).uniform(-1, 1, (3, N_GAUSS, N_CHAN)))
+                         for k in mine])
+    out = ms.cost_and_grad(seeds)
+    hist, final = ms.optimize(seeds, num_iters=3, lr=0.1)
+    best = ms.best(hist[-1], n_seeds)
+    queue.put((rank, list(mine), out.numpy().copy(), hist.numpy().copy(), best))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_multi_start_shards_seeds_without_collective_in_the_loop():
+    """MultiStart(shard=True): the ranks split the SEEDS (3 + 2 of 5), every seed sees the whole ensemble, per-seed
+    results equal a single-process evaluation, and `best` agrees on both ranks (one MIN all-reduce at the end)."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    procs = [ctx.Process(target=_multistart_worker, args=(r, world, port, queue)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted((queue.get(timeout=120) for _ in range(world)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results[0][1] == [0, 1, 2] and results[1][1] == [3, 4]
+    eng = StubEngine()
+    eng.set_ensemble(del_total=np.linspace(-1e5, 1e5, 4), rabi_scale=np.linspace(0.99, 1.01, 4))
+    finals = []
+    for rank, mine, out, hist, best in results:
+        for row, k in zip(out, mine):
+            abc = torch.from_numpy(np.random.default_rng(40 + k).uniform(-1, 1, (3, N_GAUSS, N_CHAN)))
+            assert np.allclose(row, eng.cost_and_grad_packed(abc).numpy(), rtol=1e-14, atol=1e-15)
+        finals.extend(hist[-1].tolist())
+    assert results[0][4] == results[1][4] == (int(np.argmin(finals)), float(np.min(finals)))
+
+
 def test_shard_bounds_cover_ragged_and_tiny_cases():
     for n, w in ((7, 2), (4096, 8), (3, 8), (0, 2)):
         spans = [_engine.shard_bounds(n, w, r) for r in range(w)]
