@@ -63,7 +63,11 @@ static int wide_threads_for(int spc, int ngroups) {
   if (ngroups <= 8 * 12) return 384;
   return 256;
 }
-static wide_kernel_t wide_pick(int spc, int items, int threads, int nb, int nd, bool simple) {
+static wide_kernel_t wide_pick(int spc, int items, int threads, int nb, int nd, bool simple, bool fwd = false) {
+  if (fwd) {
+    if (spc != 8 || threads != 384) return nullptr;
+    return simple ? qocvl_wide_pick_b13_fwd(items) : qocvl_wide_pick_b24_fwd(items);
+  }
   if (simple) return qocvl_wide_pick_b13(spc, items, threads);
   if (nb <= WIDE_MAXB && nd <= WIDE_MAXD) return qocvl_wide_pick_b24(spc, items, threads);
   return nullptr;
@@ -77,7 +81,7 @@ void WideLayout::release() {
 
 // Tables and launch geometry of the wide kernel for (up to) spc_request samples per CTA.  QOCVL_ERR_UNSUPPORTED when
 // the problem does not fit the kernel.
-static int wide_build(qocvl_plan* p, int spc_request, WideLayout& L) {
+static int wide_build(qocvl_plan* p, int spc_request, WideLayout& L, bool fwd = false) {
   const qocvl_desc& d = p->d;
   const int n = d.n, J = d.n_gen;
   L.release();
@@ -199,11 +203,11 @@ static int wide_build(qocvl_plan* p, int spc_request, WideLayout& L) {
   size_t smem = 0;
   for (;;) {
     T = build(spc);
-    max_threads = wide_threads_for(spc, T.ngroups);
+    max_threads = fwd ? 384 : wide_threads_for(spc, T.ngroups);
     nwarps = std::min(max_threads / 32, T.ngroups);
     items = (T.ngroups + nwarps - 1) / nwarps;
     nwarps = (T.ngroups + items - 1) / items;              // fewest warps that still need `items` passes
-    kern = wide_pick(spc, items, max_threads, nb, nd, simple);
+    kern = wide_pick(spc, items, max_threads, nb, nd, simple, fwd);
     // (n + 1 rows per vector: row n is the zero row the padding entries of uniform-valued blocks read)
     smem = wide_smem_bytes(n + 1, J, d.n_chan, spc, max_threads, nb_c, nd_c, T.ngroups, T.col[0].size(),
                            T.col[1].size(), dreal);
@@ -223,7 +227,7 @@ static int wide_build(qocvl_plan* p, int spc_request, WideLayout& L) {
   if ((rc = wide_upload(&L.dval, T.dval))) return rc;
   if ((rc = wide_upload(&L.dval_re, T.dval_re))) return rc;
   if ((rc = wide_upload(&L.dmask, T.dmask))) return rc;
-  L.simple = simple;
+  L.simple = simple; L.fwd = fwd;
   L.ent_fwd = (int)T.col[0].size(); L.ent_rev = (int)T.col[1].size(); L.dreal = dreal;
   for (int i = 0; i < nb; ++i) { L.buni[i] = buni[i]; L.bval[i] = cmake(bval[i].real(), bval[i].imag()); }
   L.macs = offdiag_macs + 3.0 * n;   // useful complex multiply-adds of one Taylor step (+ du*tq, du*tp, dw*tq)
@@ -374,7 +378,7 @@ int qocvl_wide_configure(qocvl_plan* p) {
   bool tp = (S == 1 && M >= 64);
   if (const char* e = getenv("QOCVL_TP")) tp = tp && atoi(e) != 0;
   if (tp) {
-    rc = wide_build(p, 8, p->lwide_a);
+    rc = wide_build(p, 8, p->lwide_a, true);
     if (rc == QOCVL_ERR_UNSUPPORTED || (rc == QOCVL_OK && p->lwide_a.spc != 8)) tp = false;
     else if (rc) return rc;
   }
@@ -464,7 +468,7 @@ int qocvl_wide_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t
   WideArgs pa;
   wide_fill_args(p, LA, pa);
   pa.mode = 1; pa.want_grad = 0; pa.store = 0;
-  wide_pick(LA.spc, LA.items, LA.max_threads, LA.nb, LA.nd, LA.simple)<<<p->tp_blocks_a, LA.threads, LA.smem, st>>>(pa);
+  wide_pick(LA.spc, LA.items, LA.max_threads, LA.nb, LA.nd, LA.simple, LA.fwd)<<<p->tp_blocks_a, LA.threads, LA.smem, st>>>(pa);
   WideCombineArgs c;
   c.n = p->d.n; c.n_chunks = p->tp_nchunks; c.want_grad = want_grad ? 1 : 0;
   c.inv_duration = a.inv_duration; c.w_infid = a.w_infid; c.w_adiab = a.w_adiab; c.inv_fid_norm = a.inv_fid_norm;

@@ -55,8 +55,10 @@ __device__ __forceinline__ cplx ld_stream(const cplx* p) {
 __device__ __forceinline__ void st_stream(cplx* p, cplx v) { __stcs(reinterpret_cast<double2*>(p), v); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-template <int SPC, int ITEMS, int THREADS, int NB, int ND, bool SIMPLE>
-__global__ void __launch_bounds__(THREADS, 1) k_chain_wide(const WideArgs P) {
+// FWD = true compiles the forward sweep only (mode 1, the column sweeps of the time-parallel path): without the
+// cotangent / gradient state it needs few enough registers for two CTAs per SM when a thread owns <= 4 rows.
+template <int SPC, int ITEMS, int THREADS, int NB, int ND, bool SIMPLE, bool FWD = false>
+__global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_wide(const WideArgs P) {
   constexpr int NVP = WIDE_NVP, NV = NVP - 1, VA = 0;   // vectors: q (index 0, also psi of the adiabaticity term), p
   constexpr int RW = 32 / SPC, NSLOT = NB + ND;   // compiled generator-block counts (off-diagonal, diagonal)
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_wide(const WideArgs P) {
 #pragma unroll
       for (int v = 0; v < NVP; ++v) {
         s_buf[at(v, row[i])] = z[i][v];
-        if (P.want_grad) st_stream(&t0[at(v, row[i])], z[i][v]);
+        if (!FWD && P.want_grad) st_stream(&t0[at(v, row[i])], z[i][v]);
       }
     }
     __syncthreads();
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_wide(const WideArgs P) {
           z[i][v] = cadd(z[i][v], yy[v]);
           if (keep) {
             y[at(v, row[i])] = yy[v];
-            if (P.want_grad && P.store) st_stream(&rj[at(v, row[i])], yy[v]);
+            if (!FWD && P.want_grad && P.store) st_stream(&rj[at(v, row[i])], yy[v]);
           }
         }
       }
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_wide(const WideArgs P) {
     }
   }
 
-  if (mode == 1) {       // columns colbase .. of the chunk's blocks: U_c e_b = q, W_c e_b = p
+  if (FWD || mode == 1) {       // columns colbase .. of the chunk's blocks: U_c e_b = q, W_c e_b = p
     if (s < nact) {
 #pragma unroll
       for (int i = 0; i < ITEMS; ++i) {
@@ -549,6 +551,15 @@ static inline wide_kernel_t wide_pick_blocks(int spc, int items, int threads) {
   }
   return nullptr;
 }
+// forward-only column sweeps (8 basis columns per CTA, 384 threads)
+template <int NB, int ND, bool SIMPLE>
+static inline wide_kernel_t wide_pick_blocks_fwd(int items) {
+  if (items <= 4) return k_chain_wide<8, 4, 384, NB, ND, SIMPLE, true>;
+  if (items <= 8) return k_chain_wide<8, 8, 384, NB, ND, SIMPLE, true>;
+  return nullptr;
+}
 
+wide_kernel_t qocvl_wide_pick_b13_fwd(int items);
+wide_kernel_t qocvl_wide_pick_b24_fwd(int items);
 wide_kernel_t qocvl_wide_pick_b13(int spc, int items, int threads);   // one uniform-valued off-diagonal u block, <= 3 diagonal blocks
 wide_kernel_t qocvl_wide_pick_b24(int spc, int items, int threads);   // <= 2 off-diagonal, <= 4 diagonal blocks

@@ -131,7 +131,7 @@ struct WideLayout {
   int bgen[8] = {0}, bfam[8] = {0}, dgen[8] = {0}, dfam[8] = {0}, buni[8] = {0};
   cplx bval[8] = {};
   int ent_fwd = 0, ent_rev = 0;
-  bool store = false, dreal = false, simple = false;
+  bool store = false, dreal = false, simple = false, fwd = false;
   size_t smem = 0;
   int threads = 0;
   double macs = 0.0;                         // useful complex multiply-adds of one Taylor step of one sample
