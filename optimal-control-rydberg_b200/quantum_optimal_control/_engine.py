@@ -198,14 +198,19 @@ class EngineBase:
         return out
 
     # -- the optimiser loop of the notebooks, kept on the device ------------------------------------------
-    def optimize(self, ctrl_a, ctrl_b, ctrl_c, num_iters, lr, masks=None, use_graph=True):
+    def optimize(self, ctrl_a, ctrl_b, ctrl_c, num_iters, lr, masks=None, use_graph=True, method="gd",
+                 betas=(0.9, 0.999), eps=1e-8):
         """``num_iters`` plain gradient-descent steps (notebook 01 cell 9, notebook 02 cell 13:
         ``ctrl -= lr * grad`` with the cost recorded BEFORE each update, TQ:580-600) without a host
         synchronisation per step.  ``masks`` = optional (mask_a, mask_b, mask_c) multiplied into the
         gradients (notebook 04 cells 5, 12: frozen columns).  One step is captured in a CUDA graph and
-        replayed; the cost history stays on the device.
+        replayed; the cost history stays on the device.  ``method="adam"`` replaces the update by Adam (Kingma & Ba;
+        bias-corrected moments, the masks multiply the final step so frozen entries stay frozen) -- the reference only
+        has plain descent; same loop, same graph capture.
 
         Returns (cost_history [num_iters] CUDA tensor, a, b, c) with a, b, c CUDA tensors [input_dim, C]."""
+        if method not in ("gd", "adam"):
+            raise ValueError("method must be 'gd' or 'adam'")
         dev = self.device
         abc = self._pack(ctrl_a, ctrl_b, ctrl_c).clone()
         n = 3 * self.input_dim * self.num_ctrls
@@ -218,10 +223,21 @@ class EngineBase:
             scale = float(lr) * torch.stack([torch.as_tensor(np.asarray(m, dtype=np.float64)) for m in masks]).to(dev)
             scale = scale.expand(3, self.input_dim, self.num_ctrls).contiguous()
 
+        m1, m2 = torch.zeros_like(abc), torch.zeros_like(abc)
+        pow1 = torch.ones(1, dtype=torch.float64, device=dev)      # beta1^t, beta2^t kept on the device (graph replay)
+        pow2 = torch.ones(1, dtype=torch.float64, device=dev)
+
         def one_step():
             self.cost_and_grad_packed(abc, out)
             hist.index_copy_(0, step_idx, out[0:1])
-            abc.sub_(scale * out[3:].view_as(abc))
+            g = out[3:].view_as(abc)
+            if method == "gd":
+                abc.sub_(scale * g)
+            else:
+                m1.mul_(betas[0]).add_(g, alpha=1.0 - betas[0])
+                m2.mul_(betas[1]).addcmul_(g, g, value=1.0 - betas[1])
+                pow1.mul_(betas[0]); pow2.mul_(betas[1])
+                abc.sub_(scale * (m1 / (1.0 - pow1)) / ((m2 / (1.0 - pow2)).sqrt() + eps))
             step_idx.add_(1)
 
         graph_ok = use_graph and self._world is None and num_iters > 2

@@ -379,3 +379,29 @@ def test_device_side_optimiser_loop_on_an_ensemble():
     assert prop._plan.chain_info()["path"] == "reduced_stacked_streamed"
     assert torch.equal(hist_g, hist_e) and torch.equal(ag, ae) and torch.equal(cg, ce)      # deterministic kernels
     assert float(hist_g[-1]) < float(hist_g[0])
+
+
+def test_device_side_adam_matches_a_host_adam_loop():
+    """optimize(method="adam"): the graph-replayed device loop equals a NumPy Adam driven by the engine's own
+    gradients (same moments, bias correction and masks), and frozen entries stay frozen."""
+    from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL
+    po, a, b, c = otq.notebook02_setup(seed=12, n_gauss=5, nt=60)
+    prop = PropagatorVL(5, 60, po.padding, 50e6, po.delta_t, 0.0, po.Vint, po.Delta_i_val, po.Rabi_i_val,
+                        po.Rabi_r_val, otq.GAMMAS_CZ)
+    masks = (np.ones((5, 5)), np.ones((5, 5)), np.zeros((5, 5)))          # widths frozen
+    hist, fa, fb, fc = prop.optimize(a, b, c, num_iters=8, lr=0.01, masks=masks, method="adam")
+    x = np.stack([a, b, c]).astype(float)
+    m1, m2, costs = np.zeros_like(x), np.zeros_like(x), []
+    for t in range(1, 9):
+        cost, (ga, gb, gc) = prop.target_and_grad(x[0], x[1], x[2])
+        g = np.stack([ga.cpu().numpy(), gb.cpu().numpy(), gc.cpu().numpy()])
+        costs.append(float(cost))
+        m1 = 0.9 * m1 + 0.1 * g
+        m2 = 0.999 * m2 + 0.001 * g * g
+        x = x - 0.01 * np.stack(masks) * (m1 / (1 - 0.9 ** t)) / (np.sqrt(m2 / (1 - 0.999 ** t)) + 1e-8)
+    assert np.abs(hist.cpu().numpy() - np.array(costs)).max() < 1e-10
+    assert np.abs(fa.cpu().numpy() - x[0]).max() < 1e-9 and np.abs(fb.cpu().numpy() - x[1]).max() < 1e-9
+    assert np.array_equal(fc.cpu().numpy(), np.asarray(c, float))
+    assert float(hist[-1]) < float(hist[0])
+    with pytest.raises(ValueError):
+        prop.optimize(a, b, c, num_iters=2, lr=0.01, method="lbfgs")
