@@ -279,7 +279,7 @@ def _run_chain(po, a, b, c, dl, rs, **kv):
     return out, cost_only, info
 
 
-@pytest.mark.parametrize("n_atoms,n_samples", [(6, 11), (7, 19), (10, 9), (10, 1)])
+@pytest.mark.parametrize("n_atoms,n_samples", [(6, 11), (7, 19), (7, 3), (10, 9), (10, 1)])
 def test_samples_minor_kernel_equals_one_cta_per_sample_kernel(n_atoms, n_samples):
     """chain_wide.cu (8 samples per CTA, samples-minor vectors, generator-by-generator products, streamed Taylor
     terms) against chain_big.cu (one CTA per sample, assembled CSR values, per-entry Xbar) on blockade-chain
