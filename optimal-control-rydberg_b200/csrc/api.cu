@@ -129,6 +129,10 @@ extern "C" double qocvl_flops_per_call(const qocvl_plan* p, int with_grad) {
     total += q[k] * macs;
     if (with_grad) total += ((stored ? 0 : q[k] - 1) + 2.0 * q[k]) * macs;
   }
+  // time-parallel path of the wide kernel: the column sweeps (n basis columns pushed forward through every slice) are
+  // executed work on top of the per-chunk forward + reverse sweeps
+  if (p->use_wide_tp)
+    for (int k = 0; k < M; ++k) total += (double)p->d.n * q[k] * macs;
   return total * 8.0 * (double)p->n_samples;
 }
 
@@ -151,7 +155,7 @@ extern "C" double qocvl_hbm_bytes_per_call(const qocvl_plan* p, int with_grad) {
     return 2.0 * slots * S * p->aug_n * sizeof(cplx) + 2.0 * (double)p->ypart_bytes;
   }
   if (p->use_wide) {   // streamed Taylor terms (or checkpoints + the recompute ring) written once, read once
-    const double vs = 2.0 * (p->d.n + 1) * p->lwide.spc * sizeof(cplx) * p->blocks;
+    const double vs = 2.0 * (p->d.n + 1) * p->lwide.spc * sizeof(cplx) * (p->use_wide_tp ? 1 : p->blocks);   // every slice once
     std::vector<int> q(p->d.n_slices);
     cudaSetDevice(p->device);
     cudaDeviceSynchronize();
