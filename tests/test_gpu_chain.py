@@ -404,3 +404,18 @@ def test_samples_minor_time_parallel_single_sample(chunk):
     for out, cost in ((out_seq, cost_seq), (out_tp, cost_tp)):
         assert np.abs(out[:3] - out_old[:3]).max() < 1e-13 and abs(cost - out_old[0]) < 1e-13
         assert rel(out[3:], out_old[3:]) < 1e-10
+
+
+def test_chain_ensemble_golden_fixture(golden_dir):
+    """The committed blockade-chain fixture (n = 55, 3 noise samples, dense-oracle mean): cost to 1e-10, gradients to
+    1e-8 relative, through every kernel that can run it."""
+    gold = np.load(os.path.join(golden_dir, "chain8_ensemble.npz"))
+    po, *_ = obc.chain_setup(n_atoms=8, n_gauss=5, nt=48, seed=21)
+    a, b, c = gold["a"], gold["b"], gold["c"]
+    for kv in ({}, {"QOCVL_WIDE_SPC": 8}, {"QOCVL_WIDE_STORE": 0}, {"QOCVL_WIDE": 0}):
+        out, cost_only, info = _run_chain(po, a, b, c, gold["del_total"], gold["rabi_scale"], **kv)
+        assert abs(out[0] - float(gold["cost"])) < 1e-10 and abs(cost_only - float(gold["cost"])) < 1e-10, info
+        assert abs(out[1] - float(gold["infid"])) < 1e-10 and abs(out[2] - float(gold["adiab"])) < 1e-10
+        g = out[3:].reshape(3, 5, 2)
+        for mine, key in ((g[0], "ga"), (g[1], "gb"), (g[2], "gc")):
+            assert rel(mine, gold[key]) < 1e-8, (kv, key)

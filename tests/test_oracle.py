@@ -108,3 +108,19 @@ def test_finite_difference_gradient():
                 fd += sgn * wt * prop.target(*arrs)
         fd /= h
         assert abs(fd - g[idx]) < 1e-6 * max(1.0, abs(g[idx]))
+
+
+def test_chain_golden_fixture_reproduces(golden_dir):
+    """Blockade-chain ensemble fixture (tests/golden/make_golden.py::chain_ensemble_case): the dense oracle evaluated
+    member by member reproduces the committed mean cost and gradient."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(golden_dir, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    gold = np.load(os.path.join(golden_dir, "chain8_ensemble.npz"))
+    po, a, b, c, dl, rs, mean = mg.chain_ensemble_case()
+    assert po.dim == 55
+    assert np.array_equal(a, gold["a"]) and np.array_equal(dl, gold["del_total"]) and np.array_equal(rs, gold["rabi_scale"])
+    assert abs(mean[0] - float(gold["cost"])) < 1e-12 and abs(mean[1] - float(gold["infid"])) < 1e-12
+    for mine, key in ((mean[3], "ga"), (mean[4], "gb"), (mean[5], "gc")):
+        assert np.abs(mine - gold[key]).max() < 1e-10 * max(1.0, np.abs(gold[key]).max())
