@@ -224,16 +224,23 @@ __global__ void __launch_bounds__(512, QOCVL_MINB) k_chain(const ChainArgs P) {
     for (int v = 0; v < NVP; ++v) {
       // one accumulator per vector: with >= 3 resident warps per scheduler the dependent chain is hidden,
       // and the FP64 pipe (not latency) is what the sweep is bound by -- fewer instructions win
-      cplx acc0 = cmul(a_d, t[v]);
+      // (the single-sample time-parallel sweeps, TP != 0, run ONE warp per SM sub-core: there the dependent FP64
+      // chain is the step time, so they split it over two accumulators)
+      cplx acc0 = cmul(a_d, t[v]), acc1 = czero;
 #pragma unroll
       for (int s = 0; s < WMAX; ++s) {
         const cplx xv = (s < rcnt) ? xget(xs, v, rcol[s]) : czero;
-        acc0 = cfma(a_row[s], xv, acc0);
+        if (TP && (s & 1)) acc1 = cfma(a_row[s], xv, acc1);
+        else acc0 = cfma(a_row[s], xv, acc0);
       }
       if (v == NV) {
 #pragma unroll
-        for (int s = 0; s < WBMAX; ++s) acc0 = cfma(b_row[s], tq_b[s], acc0);
+        for (int s = 0; s < WBMAX; ++s) {
+          if (TP) acc1 = cfma(b_row[s], tq_b[s], acc1);
+          else acc0 = cfma(b_row[s], tq_b[s], acc0);
+        }
       }
+      if (TP) acc0 = cadd(acc0, acc1);
       t[v] = cscale(acc0, invj);
     }
     ph = NVP * LPG - ph;
@@ -409,22 +416,25 @@ __global__ void __launch_bounds__(512, QOCVL_MINB) k_chain(const ChainArgs P) {
 #pragma unroll
       for (int v = 0; v < NVP; ++v) {
         const cplx tprev = cscale(TLOCAL ? t_loc[(j - 1) * NVP + v] : s_T[((size_t)(j - 1) * NVP + v) * LPG + r], invj);
-        cplx acc0 = cfma_conj(a_d, tb[v], czero);
+        cplx acc0 = cfma_conj(a_d, tb[v], czero), acc1 = czero;
         xc_d = cfma_conj(tb[v], tprev, xc_d);
 #pragma unroll
         for (int s = 0; s < WMAX; ++s) {
           const cplx ta = (s < ccnt) ? xget(xs, v, crow[s]) : czero;
-          acc0 = cfma_conj(a_col[s], ta, acc0);
+          if (TP && (s & 1)) acc1 = cfma_conj(a_col[s], ta, acc1);
+          else acc0 = cfma_conj(a_col[s], ta, acc0);
           xc[s] = cfma_conj(ta, tprev, xc[s]);
         }
         if (v == va) {                              // q receives B^dag tb_p; Bbar pairs tb_p with t_q
 #pragma unroll
           for (int s = 0; s < WBMAX; ++s) {
             const cplx ta = (s < bccnt) ? xget(xs, NV, bcrow[s]) : czero;
-            acc0 = cfma_conj(b_col[s], ta, acc0);
+            if (TP) acc1 = cfma_conj(b_col[s], ta, acc1);
+            else acc0 = cfma_conj(b_col[s], ta, acc0);
             xcb[s] = cfma_conj(ta, tprev, xcb[s]);
           }
         }
+        if (TP) acc0 = cadd(acc0, acc1);
         tb[v] = cadd(lam[v], cscale(acc0, invj));
       }
       ph = NVP * LPG - ph;
@@ -620,10 +630,11 @@ __global__ void __launch_bounds__(128) k_tp_combine(const CombineArgs A) {
   // Sequential over the chunks, so latency is everything: the propagator blocks of the NEXT chunk are
   // staged global -> registers -> shared memory while the current chunk (already in shared memory) is applied.
   __shared__ cplx z[5][16], y[5][16];
-  __shared__ cplx s_u[2][256], s_w[2][256];       // [buffer][column i][row r] of U_c / W_c  (n, L <= 16)
+  __shared__ cplx s_u[2][16 * 17], s_w[2][16 * 17];   // [buffer][column i][row r] of U_c / W_c (n, L <= 16); row stride L + 1:
+                                                  // the backward walk reads columns (r * LS + a) without bank conflicts
   __shared__ cplx s_d;
   const int tid = threadIdx.x, L = A.lpg, n = A.n, NV = A.nv, NVP = A.nv + 1, va = A.va;
-  const int v = tid / L, r = tid % L, nL = n * L;
+  const int v = tid / L, r = tid % L, nL = n * L, LS = L + 1;
   const bool mine = v < NVP;
   const cplx czero = cmake(0, 0);
   cplx stage[4];                                   // 2 * nL <= 512 elements over 128 threads
@@ -638,8 +649,8 @@ __global__ void __launch_bounds__(128) k_tp_combine(const CombineArgs A) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int e = tid + 128 * i;
-      if (e < nL) s_u[buf][e] = stage[i];
-      else if (e - nL < nL) s_w[buf][e - nL] = stage[i];
+      if (e < nL) s_u[buf][(e / L) * LS + e % L] = stage[i];
+      else if (e - nL < nL) s_w[buf][((e - nL) / L) * LS + (e - nL) % L] = stage[i];
     }
   };
   if (mine) {
@@ -652,22 +663,26 @@ __global__ void __launch_bounds__(128) k_tp_combine(const CombineArgs A) {
   for (int c = 0; c < A.n_chunks; ++c) {
     const int buf = c & 1;
     if (c + 1 < A.n_chunks) fetch(c + 1);
-    cplx acc0 = czero, acc1 = czero;
+    // the walk is one dependent chain of mat-vecs: four independent accumulators per matrix keep the FP64
+    // dependency depth of a step at n/4 complex multiply-adds instead of n
+    cplx au[4] = {czero, czero, czero, czero}, aw[4] = {czero, czero, czero, czero};
     if (mine && r < n) {
-      for (int i = 0; i + 1 < n; i += 2) {
-        acc0 = cfma(s_u[buf][i * L + r], z[v][i], acc0);
-        acc1 = cfma(s_u[buf][(i + 1) * L + r], z[v][i + 1], acc1);
+      int i = 0;
+      for (; i + 3 < n; i += 4) {
+#pragma unroll
+        for (int x = 0; x < 4; ++x) au[x] = cfma(s_u[buf][(i + x) * LS + r], z[v][i + x], au[x]);
       }
-      if (n & 1) acc0 = cfma(s_u[buf][(n - 1) * L + r], z[v][n - 1], acc0);
+      for (; i < n; ++i) au[0] = cfma(s_u[buf][i * LS + r], z[v][i], au[0]);
       if (v == NV) {
-        for (int i = 0; i + 1 < n; i += 2) {
-          acc0 = cfma(s_w[buf][i * L + r], z[va][i], acc0);
-          acc1 = cfma(s_w[buf][(i + 1) * L + r], z[va][i + 1], acc1);
+        i = 0;
+        for (; i + 3 < n; i += 4) {
+#pragma unroll
+          for (int x = 0; x < 4; ++x) aw[x] = cfma(s_w[buf][(i + x) * LS + r], z[va][i + x], aw[x]);
         }
-        if (n & 1) acc0 = cfma(s_w[buf][(n - 1) * L + r], z[va][n - 1], acc0);
+        for (; i < n; ++i) aw[0] = cfma(s_w[buf][i * LS + r], z[va][i], aw[0]);
       }
     }
-    const cplx acc = cadd(acc0, acc1);
+    const cplx acc = cadd(cadd(cadd(au[0], au[1]), cadd(au[2], au[3])), cadd(cadd(aw[0], aw[1]), cadd(aw[2], aw[3])));
     __syncthreads();                               // everyone has read z and buffer `buf`
     if (mine) {
       z[v][r] = acc;
@@ -710,22 +725,24 @@ __global__ void __launch_bounds__(128) k_tp_combine(const CombineArgs A) {
   for (int c = A.n_chunks - 1; c >= 0; --c) {
     const int buf = c & 1;
     if (c > 0) fetch(c - 1);
-    cplx acc0 = czero, acc1 = czero;
+    cplx au[4] = {czero, czero, czero, czero}, aw[4] = {czero, czero, czero, czero};
     if (mine && r < n) {
-      for (int a = 0; a + 1 < n; a += 2) {
-        acc0 = cfma_conj(s_u[buf][r * L + a], y[v][a], acc0);
-        acc1 = cfma_conj(s_u[buf][r * L + a + 1], y[v][a + 1], acc1);
+      int a = 0;
+      for (; a + 3 < n; a += 4) {
+#pragma unroll
+        for (int x = 0; x < 4; ++x) au[x] = cfma_conj(s_u[buf][r * LS + a + x], y[v][a + x], au[x]);
       }
-      if (n & 1) acc0 = cfma_conj(s_u[buf][r * L + n - 1], y[v][n - 1], acc0);
+      for (; a < n; ++a) au[0] = cfma_conj(s_u[buf][r * LS + a], y[v][a], au[0]);
       if (v == va) {
-        for (int a = 0; a + 1 < n; a += 2) {
-          acc0 = cfma_conj(s_w[buf][r * L + a], y[NV][a], acc0);
-          acc1 = cfma_conj(s_w[buf][r * L + a + 1], y[NV][a + 1], acc1);
+        a = 0;
+        for (; a + 3 < n; a += 4) {
+#pragma unroll
+          for (int x = 0; x < 4; ++x) aw[x] = cfma_conj(s_w[buf][r * LS + a + x], y[NV][a + x], aw[x]);
         }
-        if (n & 1) acc0 = cfma_conj(s_w[buf][r * L + n - 1], y[NV][n - 1], acc0);
+        for (; a < n; ++a) aw[0] = cfma_conj(s_w[buf][r * LS + a], y[NV][a], aw[0]);
       }
     }
-    const cplx acc = cadd(acc0, acc1);
+    const cplx acc = cadd(cadd(cadd(au[0], au[1]), cadd(au[2], au[3])), cadd(cadd(aw[0], aw[1]), cadd(aw[2], aw[3])));
     __syncthreads();
     if (mine) {
       y[v][r] = acc;

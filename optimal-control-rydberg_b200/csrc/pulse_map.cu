@@ -12,25 +12,32 @@ __device__ __forceinline__ double basis_time(int t, int nt) {
 
 // raw[t][c] = sum_n a[n][c] exp(-(tau_t - tanh b)^2 / tanh(c)^2)   (ST:173-202, TQ:319-353)
 // reg = model regularisation (ST:204-227, TQ:355-373)
-__global__ void k_raw_reg(int model, int nt, int N, int C, const double* __restrict__ abc,
-                          double* __restrict__ raw, double* __restrict__ reg) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nt) return;
-  const double* a = abc;
-  const double* b = abc + (size_t)N * C;
-  const double* c = abc + (size_t)2 * N * C;
-  const double tau = basis_time(t, nt);
-  double r[QOCVL_MAX_CHAN];
-  for (int ch = 0; ch < C; ++ch) {
-    double acc = 0.0;
+// Eight lanes per basis point, one channel per lane (C <= 5): the N-term sums of the channels run side by side, then
+// lane 0 of the group applies the regularisation to the gathered channel values.  tanh(b), tanh(c) once per CTA.
+__global__ void __launch_bounds__(128) k_raw_reg(int model, int nt, int N, int C, const double* __restrict__ abc,
+                                                 double* __restrict__ raw, double* __restrict__ reg) {
+  extern __shared__ double s_bc[];                 // [2][N][C]: tanh(b), tanh(c)
+  for (int i = threadIdx.x; i < N * C; i += blockDim.x) {
+    s_bc[i] = tanh(abc[(size_t)N * C + i]);
+    s_bc[N * C + i] = tanh(abc[(size_t)2 * N * C + i]);
+  }
+  __syncthreads();
+  const int t = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3), ch = threadIdx.x & 7;
+  const bool ok = t < nt;
+  const double tau = basis_time(ok ? t : 0, nt);
+  double acc = 0.0;
+  if (ok && ch < C) {
     for (int n = 0; n < N; ++n) {
-      const double bt = tanh(b[n * C + ch]), ct = tanh(c[n * C + ch]);
+      const double bt = s_bc[n * C + ch], ct = s_bc[N * C + n * C + ch];
       const double dev = tau - bt;
-      acc += exp(-(dev * dev) / (ct * ct)) * a[n * C + ch];
+      acc += exp(-(dev * dev) / (ct * ct)) * abc[n * C + ch];
     }
-    r[ch] = acc;
     raw[(size_t)t * C + ch] = acc;
   }
+  double r[QOCVL_MAX_CHAN];
+#pragma unroll
+  for (int c = 0; c < QOCVL_MAX_CHAN; ++c) r[c] = __shfl_sync(0xffffffffu, acc, (threadIdx.x & 24) + c);
+  if (!ok || ch != 0) return;
   double* o = reg + (size_t)t * C;
   if (model == QOCVL_MODEL_CHAIN) {                // Omega: 1 - exp(-x^2) in [0,1);  Delta: tanh(x) in (-1,1)
     o[0] = 1.0 - exp(-(r[0] * r[0]));
@@ -196,7 +203,7 @@ int qocvl_launch_pulse_forward(qocvl_plan* p, const double* abc, cudaStream_t st
   const int nt = d.n_basis_pts, M = d.n_slices, C = d.n_chan;
   if (d.pad > 0 && !p->have_filter) return QOCVL_ERR_STATE;
   double* reg_out = p->have_filter ? p->d_reg : p->d_wave;   // no filter: wave == reg (ST)
-  k_raw_reg<<<(nt + 127) / 128, 128, 0, st>>>(d.model, nt, d.n_gauss, C, abc, p->d_raw, reg_out);
+  k_raw_reg<<<(nt + 15) / 16, 128, 2 * d.n_gauss * C * sizeof(double), st>>>(d.model, nt, d.n_gauss, C, abc, p->d_raw, reg_out);
   p->launches++;
   if (p->have_filter) {
     k_filter<<<(M * 32 + 255) / 256, 256, 0, st>>>(M, nt, d.pad, C, 0, p->d_taps, p->d_reg, p->d_wave);
