@@ -637,21 +637,28 @@ __global__ void __launch_bounds__(128) k_tp_combine(const CombineArgs A) {
   const int v = tid / L, r = tid % L, nL = n * L, LS = L + 1;
   const bool mine = v < NVP;
   const cplx czero = cmake(0, 0);
+  // each thread moves up to 4 elements of [U_c | W_c] per chunk; source and destination are fixed, so they are
+  // worked out once (the walk executes one warp per scheduler: every instruction of the loop body counts)
   cplx stage[4];                                   // 2 * nL <= 512 elements over 128 threads
+  const cplx* src[4];
+  cplx* dst[4];                                    // position in buffer 0; buffer 1 is 16 * 17 elements further
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int e = tid + 128 * i;                   // element of [U_c | W_c]
+    const bool is_w = e >= nL;
+    const int f = is_w ? e - nL : e;
+    src[i] = f < nL ? (is_w ? A.wc : A.uc) + f : nullptr;
+    dst[i] = (is_w ? &s_w[0][0] : &s_u[0][0]) + (f / L) * LS + f % L;
+  }
   auto fetch = [&](int c) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int e = tid + 128 * i;                 // element of [U_c | W_c]
-      stage[i] = e < nL ? A.uc[(size_t)c * nL + e] : (e - nL < nL && e >= nL ? A.wc[(size_t)c * nL + e - nL] : czero);
-    }
+    for (int i = 0; i < 4; ++i)
+      if (src[i]) stage[i] = src[i][(size_t)c * nL];
   };
   auto commit = [&](int buf) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int e = tid + 128 * i;
-      if (e < nL) s_u[buf][(e / L) * LS + e % L] = stage[i];
-      else if (e - nL < nL) s_w[buf][((e - nL) / L) * LS + (e - nL) % L] = stage[i];
-    }
+    for (int i = 0; i < 4; ++i)
+      if (src[i]) dst[i][buf * 16 * 17] = stage[i];
   };
   if (mine) {
     z[v][r] = (v < NV && r < n) ? A.starts[v * L + r] : czero;
