@@ -132,6 +132,16 @@ int qocvl_cost_grad_from_wave(qocvl_plan* plan, const double* wave, double* out3
  * are normalised by global_samples. */
 int qocvl_set_shard(qocvl_plan* plan, int global_samples);
 
+/* Arithmetic type of the ensemble kernel (north_star: "batched complex128 (optional complex64)"; the reference
+ * itself runs complex128 only, jax_enable_x64 at TQ:1-12).  QOCVL_C64 runs the reduced stacked system
+ * (qocvl_reduced_rows) with complex64 state, Taylor terms and matrix entries, Taylor remainder 2^-26; the pulse
+ * map, the coefficients, the per-sample cost and the reduction of the gradient stay in fp64.  Stated bounds
+ * against the complex128 result: cost 5e-5 absolute, gradient 1e-2 of its largest entry.  An evaluation whose
+ * problem does not fit the reduced kernel returns QOCVL_ERR_UNSUPPORTED in this mode (no silent fp64 run). */
+enum { QOCVL_C128 = 0, QOCVL_C64 = 1 };
+int qocvl_set_precision(qocvl_plan* plan, int dtype);
+int qocvl_precision(const qocvl_plan* plan);
+
 /* Diagnostics */
 /* Synchronises; returns QOCVL_ERR_NORM if any evaluation since the last check saw a slice whose
  * norm bound exceeded the Taylor propagator's range (or NaN pulses), QOCVL_OK otherwise. */

@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cmath>
 #include <map>
+#include <type_traits>
 
 typedef std::complex<double> zc;
 
@@ -33,6 +34,24 @@ typedef std::complex<double> zc;
 #define QOCVL_RING 8   // depth (Taylor terms) of the cp.async ring that streams the terms back in STORE mode
 #endif
 __constant__ double c_ainv[QOCVL_QMAX + 2];   // 1/j
+__constant__ float c_ainvf[QOCVL_QMAX + 2];   // 1/j for the complex64 instantiation
+
+// Arithmetic type of the sweeps: R = double (complex128, the parity path) or float (qocvl_set_precision(QOCVL_C64)).
+// The state, the Taylor terms (registers, exchange buffers and the HBM stream), the assembled matrix entries and the
+// per-warp Xbar partials are R; tables, per-sample cost, terminal cotangent and k_aug_reduce's sums stay double.
+template <typename R> struct AugT;
+template <> struct AugT<double> {
+  typedef cplx C;
+  static __device__ __forceinline__ C mk(double re, double im) { return cmake(re, im); }
+  static __device__ __forceinline__ double ainv(int j) { return c_ainv[j]; }
+};
+template <> struct AugT<float> {
+  typedef cplxf C;
+  static __device__ __forceinline__ C mk(double re, double im) { return cmakef((float)re, (float)im); }
+  static __device__ __forceinline__ float ainv(int j) { return c_ainvf[j]; }
+};
+__device__ __forceinline__ cplx aug_to_d(cplx v) { return v; }
+__device__ __forceinline__ cplx aug_to_d(cplxf v) { return cmake((double)v.x, (double)v.y); }
 
 struct AugArgs {
   int N, J, M, C, S;
@@ -55,11 +74,11 @@ struct AugArgs {
   const cplx* targets;       // [LPG] (symmetry / orbit weights folded in)
   const int* pair;           // [LPG] partner row in q^dag p, or -1
   const double* wq;          // [2][LPG]: weight of the row's term in q^dag p (q rows only) / in the cotangent
-  cplx* ckpt;                // [M][total threads]
+  void* ckpt;                // [M][total threads]  (complex of the kernel's arithmetic type, like terms / y_partial)
   double* sample_out;        // [S][3]
-  cplx* terms;               // [M][qs][total threads]  Taylor terms t_0 .. t_{q-1} of every slice (STORE = 1)
+  void* terms;               // [M][qs][total threads]  Taylor terms t_0 .. t_{q-1} of every slice (STORE = 1)
   int qs;                    // slots per slice in `terms` (the a-priori Taylor cap)
-  cplx* y_partial;           // [warps][M][ncc][LPG]  per-warp sums of m * Xbar
+  void* y_partial;           // [warps][M][ncc][LPG]  per-warp sums of m * Xbar
   double* gwave;             // [M][C]
 };
 
@@ -88,9 +107,12 @@ __global__ void k_aug_tables(const AugArgs P, int L) {
 // streams them back (cp.async, eight steps ahead of their use) instead of recomputing them:
 // a third of the mat-vecs and of the shared-memory exchange traffic are traded for HBM bandwidth that the kernel
 // otherwise leaves idle.  STORE = 0 keeps only the checkpoints z_k and recomputes (12x less HBM capacity).
-template <int LPG, int WMAX, int KC, int STORE>
+template <typename R, int LPG, int WMAX, int KC, int STORE>
 __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  typedef AugT<R> T;
+  typedef typename T::C CT;                      // complex of the sweep's arithmetic type
+  constexpr bool F64 = sizeof(R) == 8;
   constexpr int NSL = 1 + WMAX;                  // slots per lane (diagonal + off-diagonals)
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int grp = tid / LPG, r = tid % LPG, ngroups = nthreads / LPG;
@@ -102,11 +124,11 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
   const int sm = item_ok ? sample : P.S - 1;
 
   // ---- shared memory: exchange buffers and (only with additive noise) the per-sample constant terms
-  cplx* carve = (cplx*)smem_raw;
-  cplx* s_x = carve + (size_t)grp * 2 * LPG; carve += (size_t)ngroups * 2 * LPG;   // [ngroups][2 buffers][LPG]
-  cplx* s_A = carve + (size_t)grp * 2 * NSL * LPG;                                 // [ngroups][2][NSL][LPG]
+  CT* carve = (CT*)smem_raw;
+  CT* s_x = carve + (size_t)grp * 2 * LPG; carve += (size_t)ngroups * 2 * LPG;     // [ngroups][2 buffers][LPG]
+  CT* s_A = carve + (size_t)grp * 2 * NSL * LPG;                                   // [ngroups][2][NSL][LPG]
   carve += P.KA > 0 ? (size_t)ngroups * 2 * NSL * LPG : 0;
-  cplx* s_ring = carve + tid;                                                      // [RING][nthreads] (STORE)
+  CT* s_ring = carve + tid;                                                      // [RING][nthreads] (STORE)
 
   int rcol[WMAX], crow[WMAX];
 #pragma unroll
@@ -115,64 +137,76 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
     crow[s] = (s < P.wc) ? P.col_row[(1 + s) * LPG + r] : r;
   }
   // per-sample multiplier of each of my contributions (0 = no contribution)
-  double m_row[NSL * KC], m_col[NSL * KC];
+  R m_row[NSL * KC], m_col[NSL * KC];
 #pragma unroll
   for (int s = 0; s < NSL; ++s) {
 #pragma unroll
     for (int i = 0; i < KC; ++i) {
       const int cr = (s <= P.w) ? P.r_cls[(s * KC + i) * LPG + r] : -1;
       const int cc = (s <= P.wc) ? P.c_cls[(s * KC + i) * LPG + r] : -1;
-      m_row[s * KC + i] = (cr >= 0 && live) ? P.mcls[(size_t)sm * P.ncls + cr] : 0.0;
-      m_col[s * KC + i] = (cc >= 0 && live) ? P.mcls[(size_t)sm * P.ncls + cc] : 0.0;
+      m_row[s * KC + i] = (R)((cr >= 0 && live) ? P.mcls[(size_t)sm * P.ncls + cr] : 0.0);
+      m_col[s * KC + i] = (R)((cc >= 0 && live) ? P.mcls[(size_t)sm * P.ncls + cc] : 0.0);
     }
   }
-  const cplx czero = cmake(0.0, 0.0);
+  const cplx dzero = cmake(0.0, 0.0);
+  const CT czero = T::mk(0.0, 0.0);
   if (P.KA > 0) {   // A_e = dt * sum_g add_sg * val_eg for my row-owner and column-owner slots
     for (int s = 0; s < NSL; ++s) {
-      cplx ar = czero, ac = czero;
+      cplx ar = dzero, ac = dzero;
       for (int i = 0; i < P.KA; ++i) {
         const int gr = (s <= P.w) ? P.ra_gen[(s * P.KA + i) * LPG + r] : -1;
         const int gc = (s <= P.wc) ? P.ca_gen[(s * P.KA + i) * LPG + r] : -1;
         if (gr >= 0 && live) ar = cfma(P.add[(size_t)sm * P.J + gr], P.ra_val[(s * P.KA + i) * LPG + r], ar);
         if (gc >= 0 && live) ac = cfma(P.add[(size_t)sm * P.J + gc], P.ca_val[(s * P.KA + i) * LPG + r], ac);
       }
-      s_A[s * LPG + r] = cscale(ar, P.dt);
-      s_A[(NSL + s) * LPG + r] = cscale(ac, P.dt);
+      s_A[s * LPG + r] = T::mk(ar.x * P.dt, ar.y * P.dt);
+      s_A[(NSL + s) * LPG + r] = T::mk(ac.x * P.dt, ac.y * P.dt);
     }
   }
-  const cplx A_diag = P.KA > 0 ? s_A[r] : czero;
-  cplx z = live ? P.starts[r] : czero;
-  const cplx ytgt = live ? P.targets[r] : czero;
+  const CT A_diag = P.KA > 0 ? s_A[r] : czero;
+  CT z = live ? T::mk(P.starts[r].x, P.starts[r].y) : czero;
+  const cplx ytgt = live ? P.targets[r] : dzero;
   const int pr = live ? P.pair[r] : -1;
   const double w_qp = live ? P.wq[r] : 0.0, w_lam = live ? P.wq[LPG + r] : 0.0;
-  cplx t_loc[STORE ? 1 : QOCVL_QMAX];
-  cplx a_d, a_row[WMAX];
+  CT t_loc[STORE ? 1 : QOCVL_QMAX];
+  CT a_d, a_row[WMAX];
   __syncwarp();
 
   // exchange: two buffers per sample, each re[LPG] then im[LPG]; the 8-byte accesses of the LPG lanes of a sample
   // hit distinct banks whatever the gather pattern.  Every Taylor loop starts on buffer 0 (after a __syncwarp) and
   // is unrolled by two, so the buffer offsets are immediates; empty slots gather the lane's own element (their
   // matrix value is zero), which costs no extra shared-memory wavefront and needs no predicate.
-  double* const x_own = (double*)s_x + r;
-  const double* x_row[WMAX];
-  const double* x_col[WMAX];
+  // complex64: one 8-byte element per row ([2 buffers][LPG] float2), a single load per gather.
+  typedef typename std::conditional<F64, double, CT>::type XE;
+  XE* const x_own = (XE*)s_x + r;
+  const XE* x_row[WMAX];
+  const XE* x_col[WMAX];
 #pragma unroll
   for (int s = 0; s < WMAX; ++s) {
-    x_row[s] = (const double*)s_x + rcol[s];
-    x_col[s] = (const double*)s_x + crow[s];
+    x_row[s] = (const XE*)s_x + rcol[s];
+    x_col[s] = (const XE*)s_x + crow[s];
   }
-  auto xput = [&](int buf, cplx val) { x_own[buf * 2 * LPG] = val.x; x_own[buf * 2 * LPG + LPG] = val.y; };
-  auto xget = [&](const double* src, int buf) -> cplx { return cmake(src[buf * 2 * LPG], src[buf * 2 * LPG + LPG]); };
+  auto xput = [&](int buf, CT val) {
+    if constexpr (F64) { x_own[buf * 2 * LPG] = val.x; x_own[buf * 2 * LPG + LPG] = val.y; }
+    else x_own[buf * LPG] = val;
+  };
+  auto xget = [&](const XE* src, int buf) -> CT {
+    if constexpr (F64) return T::mk(src[buf * 2 * LPG], src[buf * 2 * LPG + LPG]);
+    else return src[buf * LPG];
+  };
   // entry of slot s: A + sum_i m_i * P_i(k).  The table values P_i(k) are fetched one phase ahead into `raw`
   // (global -> registers, L2-resident tables shared by every sample) so the load latency hides behind the sweeps.
-  auto load_raw = [&](const cplx* tab, int nslots, cplx* raw) {
+  auto load_raw = [&](const cplx* tab, int nslots, CT* raw) {
 #pragma unroll
     for (int s = 0; s < NSL; ++s)
 #pragma unroll
-      for (int i = 0; i < KC; ++i) raw[s * KC + i] = (s <= nslots) ? __ldg(tab + (size_t)(s * KC + i) * LPG) : czero;
+      for (int i = 0; i < KC; ++i) {
+        const cplx v = (s <= nslots) ? __ldg(tab + (size_t)(s * KC + i) * LPG) : dzero;
+        raw[s * KC + i] = T::mk(v.x, v.y);
+      }
   };
-  auto slot_value = [&](const cplx* raw, const double* m, unsigned mask, int col, int s) -> cplx {
-    cplx acc = czero;
+  auto slot_value = [&](const CT* raw, const R* m, unsigned mask, int col, int s) -> CT {
+    CT acc = czero;
 #pragma unroll
     for (int i = 0; i < KC; ++i) {
       acc.x = fma(m[s * KC + i], raw[s * KC + i].x, acc.x);
@@ -182,17 +216,17 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
     else if ((mask >> s) & 1u) acc = cadd(acc, s_A[(col * NSL + s) * LPG + r]);
     return acc;
   };
-  cplx raw_r[NSL * KC];                              // row-owner table values of the NEXT slice to be visited
+  CT raw_r[NSL * KC];                                // row-owner table values of the NEXT slice to be visited
   auto finish_rows = [&]() {
     a_d = slot_value(raw_r, m_row, P.add_row_mask, 0, 0);
 #pragma unroll
     for (int s = 0; s < WMAX; ++s) a_row[s] = (s < P.w) ? slot_value(raw_r, m_row, P.add_row_mask, 0, 1 + s) : czero;
   };
   // one forward Taylor step: t <- Xaug t / j
-  auto step_fwd = [&](cplx t, double invj, int buf) -> cplx {
+  auto step_fwd = [&](CT t, R invj, int buf) -> CT {
     xput(buf, t);
     __syncwarp();
-    cplx acc = cmul(a_d, t);
+    CT acc = cmul(a_d, t);
 #pragma unroll
     for (int s = 0; s < WMAX; ++s) acc = cfma(a_row[s], xget(x_row[s], buf), acc);
     return cscale(acc, invj);
@@ -210,36 +244,37 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
       q_next = P.qdeg[k + 1];
     }
     const bool keep = P.want_grad && live;
-    cplx* tout = STORE ? P.terms + n_stream * gthreads + gtid : P.ckpt + (size_t)k * gthreads + gtid;
+    CT* tout = STORE ? (CT*)P.terms + n_stream * gthreads + gtid : (CT*)P.ckpt + (size_t)k * gthreads + gtid;
     n_stream += q;
     if (keep) tout[0] = z;
-    cplx t = z;
+    CT t = z;
     __syncwarp();                                   // the previous loop's readers are done with buffer 0
     int j = 1;
     for (; j + 1 <= q; j += 2) {
-      t = step_fwd(t, c_ainv[j], 0);
+      t = step_fwd(t, T::ainv(j), 0);
       z = cadd(z, t);
       if (STORE && keep) tout[(size_t)j * gthreads] = t;
-      t = step_fwd(t, c_ainv[j + 1], 1);
+      t = step_fwd(t, T::ainv(j + 1), 1);
       z = cadd(z, t);
       if (STORE && keep && j + 1 < q) tout[(size_t)(j + 1) * gthreads] = t;
     }
     if (j <= q) {
-      t = step_fwd(t, c_ainv[j], 0);
+      t = step_fwd(t, T::ainv(j), 0);
       z = cadd(z, t);
     }
   }
 
   // =================================== cost ============================================
-  cplx zp;
+  cplx zp;                                                          // the cost itself is always evaluated in fp64
   {
     __syncwarp();
     xput(0, z);
     __syncwarp();
-    zp = (pr >= 0) ? xget((const double*)s_x + pr, 0) : czero;
+    zp = (pr >= 0) ? aug_to_d(xget((const XE*)s_x + pr, 0)) : dzero;
   }
-  cplx dsum = cfma_conj(ytgt, z, czero);                            // sum_r conj(y_r) z_r
-  cplx qp = cscale(cfma_conj(z, zp, czero), w_qp);                  // q^dag p
+  const cplx zd = aug_to_d(z);
+  cplx dsum = cfma_conj(ytgt, zd, dzero);                           // sum_r conj(y_r) z_r
+  cplx qp = cscale(cfma_conj(zd, zp, dzero), w_qp);                 // q^dag p
 #pragma unroll
   for (int off = LPG / 2; off > 0; off >>= 1) {
     dsum.x += __shfl_xor_sync(0xffffffffu, dsum.x, off);
@@ -257,26 +292,27 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
   if (!P.want_grad) return;
 
   // terminal cotangent lam = d cost / d conj(Z), scaled by 1/S_global (ensemble mean)
-  cplx lam;
+  CT lam;
   {
     const double ws = live ? P.inv_samples : 0.0;
     const double ca = -0.5 * P.w_adiab * P.inv_duration * ws;
-    lam = cscale(cmul(dsum, ytgt), -P.w_infid * P.inv_fid_norm * ws);
-    lam = cadd(lam, cscale(zp, ca * w_lam));        // q rows receive -(wa/2T) p, p rows -(wa/2T) q
+    cplx l = cscale(cmul(dsum, ytgt), -P.w_infid * P.inv_fid_norm * ws);
+    l = cadd(l, cscale(zp, ca * w_lam));            // q rows receive -(wa/2T) p, p rows -(wa/2T) q
+    lam = T::mk(l.x, l.y);
   }
 
   // =================================== reverse sweep ===================================
   const size_t gwarp = (size_t)blockIdx.x * nwarps + warp;
-  cplx lam_tb = lam, xc_d, xc[WMAX], a_col[WMAX];
+  CT lam_tb = lam, xc_d, xc[WMAX], a_col[WMAX];
   // one descending step of the adjoint recurrence; Xbar accumulated on my column's entries
-  auto step_adj = [&](cplx tprev, double invj, int buf) {
+  auto step_adj = [&](CT tprev, R invj, int buf) {
     xput(buf, lam_tb);
     __syncwarp();
-    cplx acc = cfma_conj(a_d, lam_tb, czero);
+    CT acc = cfma_conj(a_d, lam_tb, czero);
     xc_d = cfma_conj(lam_tb, tprev, xc_d);
 #pragma unroll
     for (int s = 0; s < WMAX; ++s) {
-      const cplx ta = xget(x_col[s], buf);
+      const CT ta = xget(x_col[s], buf);
       acc = cfma_conj(a_col[s], ta, acc);
       xc[s] = cfma_conj(ta, tprev, xc[s]);
     }
@@ -292,30 +328,34 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
     // consumes it strictly backwards, across slice boundaries, so it is fetched RING steps ahead of its use with
     // cp.async into a small thread-private shared-memory ring (HBM latency under load is ~6 adjoint steps).
     constexpr int RING = QOCVL_RING;
-    const cplx* const base = P.terms + gtid;
-    const cplx* sp = base + (n_stream - 1) * gthreads;
+    const CT* const base = (const CT*)P.terms + gtid;
+    const CT* sp = base + (n_stream - 1) * gthreads;
     const unsigned ring0 = (unsigned)__cvta_generic_to_shared(s_ring);
-    const unsigned ring_stride = (unsigned)(nthreads * sizeof(cplx));
+    const unsigned ring_stride = (unsigned)(nthreads * sizeof(CT));
 #pragma unroll
     for (int i = 0; i < RING; ++i) s_ring[(size_t)i * nthreads] = czero;   // dead lanes read zeros for ever
     int head = 0, tail = 0;
     auto issue = [&]() {
-      if (live && sp >= base)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring0 + head * ring_stride), "l"(sp) : "memory");
+      if (live && sp >= base) {
+        if constexpr (F64)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring0 + head * ring_stride), "l"(sp) : "memory");
+        else   // 8-byte copies exist only in the .ca flavour
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ring0 + head * ring_stride), "l"(sp) : "memory");
+      }
       asm volatile("cp.async.commit_group;" ::: "memory");
       sp -= gthreads;
       head = (head + 1) & (RING - 1);
     };
-    auto fetch = [&]() -> cplx {
+    auto fetch = [&]() -> CT {
       asm volatile("cp.async.wait_group %0;" ::"n"(RING - 1) : "memory");
-      const cplx v = s_ring[(size_t)tail * nthreads];
+      const CT v = s_ring[(size_t)tail * nthreads];
       tail = (tail + 1) & (RING - 1);
       issue();
       return v;
     };
 #pragma unroll
     for (int i = 0; i < RING; ++i) issue();
-    cplx raw_c[NSL * KC];
+    CT raw_c[NSL * KC];
     int q_cur = P.qdeg[P.M - 1];
     q_next = P.M > 1 ? P.qdeg[P.M - 2] : 0;
     load_raw(P.p_col + (size_t)(P.M - 1) * P.ncc * LPG + r, P.wc, raw_c);
@@ -335,21 +375,21 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
       {
         int j = q;
         for (; j >= 2; j -= 2) {
-          step_adj(cscale(fetch(), c_ainv[j]), c_ainv[j], 0);
-          step_adj(cscale(fetch(), c_ainv[j - 1]), c_ainv[j - 1], 1);
+          step_adj(cscale(fetch(), T::ainv(j)), T::ainv(j), 0);
+          step_adj(cscale(fetch(), T::ainv(j - 1)), T::ainv(j - 1), 1);
         }
-        if (j >= 1) step_adj(cscale(fetch(), c_ainv[j]), c_ainv[j], 0);
+        if (j >= 1) step_adj(cscale(fetch(), T::ainv(j)), T::ainv(j), 0);
       }
       // ---- Ybar_e = sum over the warp's samples of m_s * Xbar_e: the generators' d coef / d wave is the same for
       //      every sample, so the contraction with it happens once per slice in k_aug_reduce, not here
-      cplx* yout = P.y_partial + ((gwarp * P.M + k) * P.ncc) * LPG + r;
+      CT* yout = (CT*)P.y_partial + ((gwarp * P.M + k) * P.ncc) * LPG + r;
   #pragma unroll
       for (int s = 0; s < NSL; ++s) {
         if (s <= P.wc) {
-          const cplx xval = (s == 0) ? xc_d : xc[s > 0 ? s - 1 : 0];
+          const CT xval = (s == 0) ? xc_d : xc[s > 0 ? s - 1 : 0];
   #pragma unroll
           for (int i = 0; i < KC; ++i) {
-            cplx y = cscale(xval, m_col[s * KC + i]);
+            CT y = cscale(xval, m_col[s * KC + i]);
   #pragma unroll
             for (int off = LPG; off < 32; off <<= 1) {
               y.x += __shfl_xor_sync(0xffffffffu, y.x, off);
@@ -363,27 +403,27 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
   } else {
     load_raw(P.p_row + (size_t)(P.M - 1) * P.ncr * LPG + r, P.w, raw_r);
     q_next = P.qdeg[P.M - 1];
-    cplx t_next = live ? P.ckpt[(size_t)(P.M - 1) * gthreads + gtid] : czero;
+    CT t_next = live ? ((const CT*)P.ckpt)[(size_t)(P.M - 1) * gthreads + gtid] : czero;
     for (int k = P.M - 1; k >= 0; --k) {
       const int q = q_next;
       finish_rows();
-      cplx raw_c[NSL * KC];                         // column-owner table values: in flight during the recompute
+      CT raw_c[NSL * KC];                           // column-owner table values: in flight during the recompute
       load_raw(P.p_col + (size_t)k * P.ncc * LPG + r, P.wc, raw_c);
       // ---- recompute the forward Taylor terms, stored pre-scaled: s_j = t_{j-1} / j is what the adjoint pairs
       //      with tb_j, and s_{j+1} = X s_j / (j+1)
-      cplx t = t_next;
+      CT t = t_next;
       t_loc[0] = t;
       __syncwarp();
       {
         int j = 1;
         for (; j + 1 < q; j += 2) {
-          t = step_fwd(t, c_ainv[j + 1], 0);
+          t = step_fwd(t, T::ainv(j + 1), 0);
           t_loc[j] = t;
-          t = step_fwd(t, c_ainv[j + 2], 1);
+          t = step_fwd(t, T::ainv(j + 2), 1);
           t_loc[j + 1] = t;
         }
         if (j < q) {
-          t = step_fwd(t, c_ainv[j + 1], 0);
+          t = step_fwd(t, T::ainv(j + 1), 0);
           t_loc[j] = t;
         }
       }
@@ -391,7 +431,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
       for (int s = 0; s < WMAX; ++s) a_col[s] = (s < P.wc) ? slot_value(raw_c, m_col, P.add_col_mask, 1, 1 + s) : czero;
       if (k > 0) {                                  // next slice's rows, checkpoint and degree: in flight during the adjoint
         load_raw(P.p_row + (size_t)(k - 1) * P.ncr * LPG + r, P.w, raw_r);
-        t_next = live ? P.ckpt[(size_t)(k - 1) * gthreads + gtid] : czero;
+        t_next = live ? ((const CT*)P.ckpt)[(size_t)(k - 1) * gthreads + gtid] : czero;
         q_next = P.qdeg[k - 1];
       }
       lam = lam_tb;
@@ -400,21 +440,21 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
       {
         int j = q;
         for (; j >= 2; j -= 2) {
-          step_adj(t_loc[j - 1], c_ainv[j], 0);
-          step_adj(t_loc[j - 2], c_ainv[j - 1], 1);
+          step_adj(t_loc[j - 1], T::ainv(j), 0);
+          step_adj(t_loc[j - 2], T::ainv(j - 1), 1);
         }
-        if (j >= 1) step_adj(t_loc[j - 1], c_ainv[j], 0);
+        if (j >= 1) step_adj(t_loc[j - 1], T::ainv(j), 0);
       }
       // ---- Ybar_e = sum over the warp's samples of m_s * Xbar_e: the generators' d coef / d wave is the same for
       //      every sample, so the contraction with it happens once per slice in k_aug_reduce, not here
-      cplx* yout = P.y_partial + ((gwarp * P.M + k) * P.ncc) * LPG + r;
+      CT* yout = (CT*)P.y_partial + ((gwarp * P.M + k) * P.ncc) * LPG + r;
   #pragma unroll
       for (int s = 0; s < NSL; ++s) {
         if (s <= P.wc) {
-          const cplx xval = (s == 0) ? xc_d : xc[s > 0 ? s - 1 : 0];
+          const CT xval = (s == 0) ? xc_d : xc[s > 0 ? s - 1 : 0];
   #pragma unroll
           for (int i = 0; i < KC; ++i) {
-            cplx y = cscale(xval, m_col[s * KC + i]);
+            CT y = cscale(xval, m_col[s * KC + i]);
   #pragma unroll
             for (int off = LPG; off < 32; off <<= 1) {
               y.x += __shfl_xor_sync(0xffffffffu, y.x, off);
@@ -430,6 +470,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
 
 // gwave[k][c] = 2 dt Re sum_{e,i} Ybar_{e,i}(k) * sum_{g in (e,i)} val_eg * dcoef_kgc, with Ybar summed over the
 // per-warp partials in a fixed order (deterministic).  One block per slice, one thread per (contribution, lane).
+template <typename CT>
 __global__ void __launch_bounds__(1024) k_aug_reduce(const AugArgs P, int L) {
   __shared__ double red[QOCVL_MAX_CHAN][1024];
   const int k = blockIdx.x, t = threadIdx.x, nt = P.ncc * L;
@@ -438,16 +479,16 @@ __global__ void __launch_bounds__(1024) k_aug_reduce(const AugArgs P, int L) {
   for (int c = 0; c < QOCVL_MAX_CHAN; ++c) term[c] = 0.0;
   if (t < nt) {
     cplx y0 = cmake(0, 0), y1 = cmake(0, 0), y2 = cmake(0, 0), y3 = cmake(0, 0);
-    const cplx* src = P.y_partial + (size_t)k * nt + t;
+    const CT* src = (const CT*)P.y_partial + (size_t)k * nt + t;
     const size_t stride = (size_t)P.M * nt;
     int wv = 0;
     for (; wv + 4 <= P.nparts; wv += 4) {          // 4 independent chains (fixed association: still deterministic)
-      y0 = cadd(y0, src[(size_t)wv * stride]);
-      y1 = cadd(y1, src[(size_t)(wv + 1) * stride]);
-      y2 = cadd(y2, src[(size_t)(wv + 2) * stride]);
-      y3 = cadd(y3, src[(size_t)(wv + 3) * stride]);
+      y0 = cadd(y0, aug_to_d(src[(size_t)wv * stride]));
+      y1 = cadd(y1, aug_to_d(src[(size_t)(wv + 1) * stride]));
+      y2 = cadd(y2, aug_to_d(src[(size_t)(wv + 2) * stride]));
+      y3 = cadd(y3, aug_to_d(src[(size_t)(wv + 3) * stride]));
     }
-    for (; wv < P.nparts; ++wv) y0 = cadd(y0, src[(size_t)wv * stride]);
+    for (; wv < P.nparts; ++wv) y0 = cadd(y0, aug_to_d(src[(size_t)wv * stride]));
     const cplx y = cadd(cadd(y0, y1), cadd(y2, y3));
     const int c = t / L, lane = t % L;
     for (int i = 0; i < P.KG; ++i) {
@@ -476,33 +517,38 @@ __global__ void __launch_bounds__(1024) k_aug_reduce(const AugArgs P, int L) {
 }
 
 typedef void (*aug_fn)(const AugArgs);
-template <int KC, int STORE>
+template <typename R, int KC, int STORE>
 static aug_fn pick_aug_kc(int lpg, int wmax) {
   if (wmax <= 3) {
     switch (lpg) {
-      case 8: return k_chain_aug<8, 3, KC, STORE>;
-      case 16: return k_chain_aug<16, 3, KC, STORE>;
-      case 32: return k_chain_aug<32, 3, KC, STORE>;
+      case 8: return k_chain_aug<R, 8, 3, KC, STORE>;
+      case 16: return k_chain_aug<R, 16, 3, KC, STORE>;
+      case 32: return k_chain_aug<R, 32, 3, KC, STORE>;
     }
   } else if (wmax <= 6) {
     switch (lpg) {
-      case 8: return k_chain_aug<8, 6, KC, STORE>;
-      case 16: return k_chain_aug<16, 6, KC, STORE>;
-      case 32: return k_chain_aug<32, 6, KC, STORE>;
+      case 8: return k_chain_aug<R, 8, 6, KC, STORE>;
+      case 16: return k_chain_aug<R, 16, 6, KC, STORE>;
+      case 32: return k_chain_aug<R, 32, 6, KC, STORE>;
     }
   }
   return nullptr;
 }
-static aug_fn pick_aug(int lpg, int wmax, int kc, bool store) {
-  if (kc == 1) return store ? pick_aug_kc<1, 1>(lpg, wmax) : pick_aug_kc<1, 0>(lpg, wmax);
-  if (kc == 2) return store ? pick_aug_kc<2, 1>(lpg, wmax) : pick_aug_kc<2, 0>(lpg, wmax);
+template <typename R>
+static aug_fn pick_aug_r(int lpg, int wmax, int kc, bool store) {
+  if (kc == 1) return store ? pick_aug_kc<R, 1, 1>(lpg, wmax) : pick_aug_kc<R, 1, 0>(lpg, wmax);
+  if (kc == 2) return store ? pick_aug_kc<R, 2, 1>(lpg, wmax) : pick_aug_kc<R, 2, 0>(lpg, wmax);
   return nullptr;
 }
+static aug_fn pick_aug(int lpg, int wmax, int kc, bool store, bool c64) {
+  return c64 ? pick_aug_r<float>(lpg, wmax, kc, store) : pick_aug_r<double>(lpg, wmax, kc, store);
+}
+static size_t aug_elem_bytes(const qocvl_plan* p) { return p->c64 ? sizeof(cplxf) : sizeof(cplx); }
 
 static size_t aug_smem_bytes(const qocvl_plan* p, int ngroups) {
   const int L = p->aug_lpg, nsl = 1 + (p->aug_wmax <= 3 ? 3 : 6);
   return ((size_t)ngroups * 2 * L + (p->la.KA > 0 ? (size_t)ngroups * 2 * nsl * L : 0) +
-          (p->aug_store ? (size_t)QOCVL_RING * ngroups * L : 0)) * sizeof(cplx);
+          (p->aug_store ? (size_t)QOCVL_RING * ngroups * L : 0)) * aug_elem_bytes(p);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -720,7 +766,7 @@ int qocvl_aug_configure(qocvl_plan* p) {
       KA = std::max(KA, (int)addgens(a, b).size());
     }
   if (KC > 2) return QOCVL_ERR_UNSUPPORTED;
-  if (!pick_aug(L, wmax, KC, false)) return QOCVL_ERR_UNSUPPORTED;
+  if (!pick_aug(L, wmax, KC, false, p->c64 != 0)) return QOCVL_ERR_UNSUPPORTED;
   const int Lk = L;                                    // lanes per sample of the kernel instance
   const int nr = 1 + w, nc = 1 + wc;
   std::vector<int> row_col((size_t)nr * Lk), col_row((size_t)nc * Lk);
@@ -800,6 +846,9 @@ int qocvl_aug_configure(qocvl_plan* p) {
     inv[0] = 0.0;
     for (int j = 1; j < QOCVL_QMAX + 2; ++j) inv[j] = 1.0 / (double)j;
     QCUDA(cudaMemcpyToSymbol(c_ainv, inv, sizeof(inv)));
+    float invf[QOCVL_QMAX + 2];
+    for (int j = 0; j < QOCVL_QMAX + 2; ++j) invf[j] = (float)inv[j];
+    QCUDA(cudaMemcpyToSymbol(c_ainvf, invf, sizeof(invf)));
   }
   // ---- Taylor terms: streamed through HBM (STORE) when the a-priori degree cap and the device memory allow it
   const int gpw = 32 / Lk;
@@ -819,7 +868,8 @@ int qocvl_aug_configure(qocvl_plan* p) {
     long best_load = -1;
     for (int g = gpw; g <= gmax; g += gpw) {
       const long n_ctas = (S + g - 1) / g;
-      const long per_sm = std::max(1, std::min(32, 512 / (g * Lk)));     // resident CTAs per SM (register-limited)
+      // resident CTAs per SM (register-limited: 128 registers per thread in complex128, 96 in complex64)
+      const long per_sm = std::max(1, std::min(32, (p->c64 ? 640 : 512) / (g * Lk)));
       const long waves = (n_ctas + per_sm * sms - 1) / (per_sm * sms);
       const long load = waves * per_sm * g;
       if (best_load < 0 || load <= best_load) { best_load = load; ngroups = g; }
@@ -832,8 +882,8 @@ int qocvl_aug_configure(qocvl_plan* p) {
     p->blocks = (S + ngroups - 1) / ngroups;
     const size_t total_threads = (size_t)p->blocks * p->threads;
     p->aug_parts = (int)((total_threads + 31) / 32);
-    p->ckpt_bytes = (size_t)M * (p->aug_store ? p->aug_qs : 1) * total_threads * sizeof(cplx);
-    p->ypart_bytes = (size_t)p->aug_parts * M * nc * KC * Lk * sizeof(cplx);
+    p->ckpt_bytes = (size_t)M * (p->aug_store ? p->aug_qs : 1) * total_threads * aug_elem_bytes(p);
+    p->ypart_bytes = (size_t)p->aug_parts * M * nc * KC * Lk * aug_elem_bytes(p);
     if (p->aug_store) {                                // fall back to recomputation when HBM capacity is short
       size_t free_b = 0, total_b = 0;
       cudaMemGetInfo(&free_b, &total_b);
@@ -841,7 +891,7 @@ int qocvl_aug_configure(qocvl_plan* p) {
     }
     break;
   }
-  aug_fn fn = pick_aug(Lk, wmax, KC, p->aug_store);
+  aug_fn fn = pick_aug(Lk, wmax, KC, p->aug_store, p->c64 != 0);
   if (!fn) return QOCVL_ERR_UNSUPPORTED;
   QCUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->chain_smem));
   p->n_parts = 0;                                     // no [warps][M][C] partial-gradient buffer on this path
@@ -875,13 +925,14 @@ int qocvl_aug_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t 
   a.ckpt = p->d_ckpt; a.terms = p->d_ckpt; a.qs = p->aug_qs;
   a.sample_out = p->d_sample_out; a.y_partial = p->d_ypart; a.gwave = gwave;
   k_aug_tables<<<d.n_slices, 256, 0, st>>>(a, la.L);
-  pick_aug(la.L, p->aug_wmax, la.KC, p->aug_store)<<<p->blocks, p->threads, p->chain_smem, st>>>(a);
+  pick_aug(la.L, p->aug_wmax, la.KC, p->aug_store, p->c64 != 0)<<<p->blocks, p->threads, p->chain_smem, st>>>(a);
   p->launches += 2;
   if (want_grad) {
     if (!gwave) return QOCVL_ERR_ARG;
     int nt = 32;
     while (nt < a.ncc * la.L) nt <<= 1;
-    k_aug_reduce<<<d.n_slices, nt, 0, st>>>(a, la.L);
+    if (p->c64) k_aug_reduce<cplxf><<<d.n_slices, nt, 0, st>>>(a, la.L);
+    else k_aug_reduce<cplx><<<d.n_slices, nt, 0, st>>>(a, la.L);
     p->launches++;
   }
   QCUDA(cudaGetLastError());

@@ -186,11 +186,11 @@ int qocvl_chain_configure(qocvl_plan* p) {
   QCUDA(cudaMemcpy(addmax.data(), p->d_addmax, J * sizeof(double), cudaMemcpyDeviceToHost));
   const double bound = apriori_norm_bound(p, mulmax, addmax);
   if (!(bound == bound)) return QOCVL_ERR_ARG;
-  p->qcap = qocvl_taylor_degree(bound);
+  p->qcap = qocvl_taylor_degree(bound, p->taylor_tol());
   if (const char* e = getenv("QOCVL_QCAP")) p->qcap = std::max(2, std::min(QOCVL_QMAX, atoi(e)));
   // ---- kernel-specific geometry and buffers
   // a single sample has no ensemble parallelism: cut the slice axis into concurrent chunks instead
-  p->use_tp = !p->use_big && p->n_samples == 1 && d.n_slices >= 32;
+  p->use_tp = !p->use_big && p->n_samples == 1 && d.n_slices >= 32 && !p->c64;
   if (const char* e = getenv("QOCVL_TP")) p->use_tp = p->use_tp && atoi(e) != 0;
   // ensembles: the reduced stacked system (chain_aug.cu) whenever it fits its kernel
   p->use_aug = false;
@@ -201,6 +201,8 @@ int qocvl_chain_configure(qocvl_plan* p) {
     rc = qocvl_aug_configure(p);
     if (rc != QOCVL_OK && rc != QOCVL_ERR_UNSUPPORTED) { p->groups = 0; return rc; }
   }
+  // complex64 exists only on the reduced stacked system: anything else fails loudly instead of running in fp64
+  if (p->c64 && !p->use_aug) { p->groups = 0; return QOCVL_ERR_UNSUPPORTED; }
   p->use_wide = false;
   if (!p->use_aug && p->use_big) {          // large Hilbert spaces: the samples-minor kernel when it takes the problem
     bool try_wide = true;

@@ -38,11 +38,31 @@ __device__ __forceinline__ cplx cfma_conj(cplx a, cplx b, cplx acc) {
   return acc;
 }
 
-// Smallest q with  nrm^(q+1)/(q+1)! <= 2^-55 = u/4 (u = fp64 unit round-off: a smaller remainder is not
-// representable next to the O(1) state; the oracle's twin rule, oracle/vector_model.py::taylor_degree,
-// uses the stricter 2^-60)
-__host__ __device__ inline int qocvl_taylor_degree(double nrm) {
-  const double tol = 2.7755575615628914e-17;  // 2^-55
+// complex64 twins of the helpers above (the optional single-precision mode of chain_aug.cu)
+typedef float2 cplxf;
+__host__ __device__ __forceinline__ cplxf cmakef(float re, float im) { cplxf r; r.x = re; r.y = im; return r; }
+__host__ __device__ __forceinline__ cplxf cadd(cplxf a, cplxf b) { return cmakef(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ cplxf cmul(cplxf a, cplxf b) {
+  return cmakef(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ __forceinline__ cplxf cscale(cplxf a, float s) { return cmakef(a.x * s, a.y * s); }
+__device__ __forceinline__ cplxf cfma(cplxf a, cplxf b, cplxf acc) {
+  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x);
+  acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(a.y, b.x, acc.y);
+  return acc;
+}
+__device__ __forceinline__ cplxf cfma_conj(cplxf a, cplxf b, cplxf acc) {
+  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(a.y, b.y, acc.x);
+  acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(-a.y, b.x, acc.y);
+  return acc;
+}
+
+// Smallest q with  nrm^(q+1)/(q+1)! <= tol.  complex128: tol = 2^-55 = u/4 (u = fp64 unit round-off: a smaller
+// remainder is not representable next to the O(1) state; the oracle's twin rule,
+// oracle/vector_model.py::taylor_degree, uses the stricter 2^-60).  complex64: 2^-26 = u_fp32/4.
+#define QOCVL_TAYLOR_TOL_C128 2.7755575615628914e-17  // 2^-55
+#define QOCVL_TAYLOR_TOL_C64 1.4901161193847656e-08   // 2^-26
+__host__ __device__ inline int qocvl_taylor_degree(double nrm, double tol = QOCVL_TAYLOR_TOL_C128) {
   double term = 1.0;
   int q = 0;
   while (q < QOCVL_QMAX) {
@@ -221,9 +241,11 @@ struct qocvl_plan {
   WideLayout lwide_a;      // 8 basis columns per CTA: column sweeps of the time-parallel single-sample path
   bool use_wide_tp = false;
   bool use_aug = false;
+  int c64 = 0;             // qocvl_set_precision: 1 = the ensemble kernel runs in complex64 (reduced stacked system only)
+  double taylor_tol() const { return c64 ? QOCVL_TAYLOR_TOL_C64 : QOCVL_TAYLOR_TOL_C128; }
   int aug_n = 0, aug_lpg = 0, aug_nnz = 0, aug_wmax = 0, aug_parts = 0, aug_qs = 0;
   bool aug_store = false;         // Taylor terms streamed through HBM instead of recomputed in the reverse sweep
-  cplx* d_ypart = nullptr;        // [warps][M][column contributions][aug_lpg] per-warp sums of m * Xbar
+  cplx* d_ypart = nullptr;        // [warps][M][column contributions][aug_lpg] per-warp sums of m * Xbar (c64: float2)
   size_t ypart_bytes = 0;
   AugLayout la;            // lane-per-row tables of the stacked system
   std::vector<double> h_mul;              // [S][J] host copy of the noise tables (generator classes)

@@ -311,6 +311,13 @@ extern "C" int qocvl_set_shard(qocvl_plan* p, int global_samples) {
   return QOCVL_OK;
 }
 
+extern "C" int qocvl_set_precision(qocvl_plan* p, int dtype) {
+  if (!p || (dtype != QOCVL_C128 && dtype != QOCVL_C64)) return QOCVL_ERR_ARG;
+  if (p->c64 != dtype) { p->c64 = dtype; p->groups = 0; }
+  return QOCVL_OK;
+}
+extern "C" int qocvl_precision(const qocvl_plan* p) { return p ? p->c64 : 0; }
+
 extern "C" size_t qocvl_workspace_bytes(const qocvl_plan* p) { return p ? p->bytes : 0; }
 extern "C" long long qocvl_launch_count(const qocvl_plan* p) { return p ? p->launches : 0; }
 extern "C" int qocvl_last_taylor_degree(const qocvl_plan* p) { return p ? p->qcap : 0; }

@@ -97,7 +97,7 @@ struct NormTables {   // CSC views of the two block families (plan.cu / chain_bi
 __global__ void k_coefficients(ModelParams mp, int M, const double* __restrict__ wave,
                                const cplx* __restrict__ coef_const, NormTables nt,
                                const double* __restrict__ mulmax, const double* __restrict__ addmax, int qcap,
-                               cplx* __restrict__ coef, cplx* __restrict__ dcoef, int* __restrict__ qdeg,
+                               double taylor_tol, cplx* __restrict__ coef, cplx* __restrict__ dcoef, int* __restrict__ qdeg,
                                int* __restrict__ flag) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= M) return;
@@ -112,7 +112,7 @@ __global__ void k_coefficients(ModelParams mp, int M, const double* __restrict__
   const double nrm = qocvl_slice_norm_csr(mp, co, nt.u_colptr, nt.u_ceid, nt.u_egen, nt.u_eval, nt.u_kc,
                                           nt.w_colptr, nt.w_ceid, nt.w_egen, nt.w_eval, nt.w_kc, nt.gcol,
                                           mulmax, addmax);
-  int q = qocvl_taylor_degree(nrm);
+  int q = qocvl_taylor_degree(nrm, taylor_tol);
   if (!(nrm <= QOCVL_NORM_MAX) || q > qcap) {   // also catches NaN pulses
     atomicOr(flag, 1);
     q = 2;
@@ -219,7 +219,7 @@ int qocvl_launch_coefficients(qocvl_plan* p, const double* wave, cudaStream_t st
   NormTables nt = {p->cu.colptr, p->cu.ceid, p->cu.egen, p->cu.eval, p->cu.kc,
                    p->cw.colptr, p->cw.ceid, p->cw.egen, p->cw.eval, p->cw.kc, p->d_gnorm};
   k_coefficients<<<(d.n_slices + 63) / 64, 64, 0, st>>>(mp, d.n_slices, wave, p->d_coef_const, nt, p->d_mulmax,
-                                                       p->d_addmax, p->qcap, p->d_coef, p->d_dcoef, p->d_qdeg,
+                                                       p->d_addmax, p->qcap, p->taylor_tol(), p->d_coef, p->d_dcoef, p->d_qdeg,
                                                        p->d_flag);
   p->launches++;
   QCUDA(cudaGetLastError());

@@ -108,6 +108,17 @@ class Plan:
         if global_samples is not None:
             _lib.check(self._lib.qocvl_set_shard(self._h, int(global_samples)), "set_shard")
 
+    def set_precision(self, dtype):
+        """'complex128' (default) or 'complex64': arithmetic type of the ensemble kernel (qocvl_set_precision)."""
+        code = {"complex128": 0, "c128": 0, "complex64": 1, "c64": 1}.get(str(dtype).replace("torch.", ""))
+        if code is None:
+            raise ValueError("dtype must be 'complex128' or 'complex64'")
+        _lib.check(self._lib.qocvl_set_precision(self._h, code), "set_precision")
+
+    @property
+    def precision(self):
+        return ("complex128", "complex64")[int(self._lib.qocvl_precision(self._h))]
+
     # ---- hot path -------------------------------------------------------------------------
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

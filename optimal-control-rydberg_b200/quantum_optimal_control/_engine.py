@@ -191,6 +191,13 @@ class EngineBase:
             self._world = None
         self._plan.set_noise(mul, add, global_samples=S)
 
+    def set_precision(self, dtype="complex128"):
+        """north_star's optional complex64 mode: the ensemble kernel (reduced stacked system) carries state, Taylor
+        terms and matrix entries in complex64; pulse map, coefficients and reductions stay float64.  Stated bounds
+        against complex128: cost 5e-5 absolute, gradient 1e-2 of its largest entry.  The
+        reference itself is complex128 only (TQ:1-12 enables x64)."""
+        self._plan.set_precision(dtype)
+
     def _allreduce(self, out):
         if self._world is not None and self._world > 1:
             import torch.distributed as dist

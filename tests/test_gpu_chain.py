@@ -419,3 +419,84 @@ def test_chain_ensemble_golden_fixture(golden_dir):
         g = out[3:].reshape(3, 5, 2)
         for mine, key in ((g[0], "ga"), (g[1], "gb"), (g[2], "gc")):
             assert rel(mine, gold[key]) < 1e-8, (kv, key)
+
+
+# ---- optional complex64 mode of the ensemble kernel (north_star: "batched complex128 (optional complex64)") ------------
+# Stated bounds against the complex128 result (include/qocvl.h): cost, infidelity and adiabaticity
+# 5e-5 absolute, every gradient array 1e-2 of its largest entry.
+TOL_C64_COST = 5e-5
+TOL_C64_GRAD_REL = 1e-2
+
+
+def test_complex64_ensemble_within_stated_bounds_of_oracle_and_of_complex128():
+    from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL
+    S = 6
+    dl, rs = ensemble.robust_cz_noise(S)
+    members, (a, b, c) = ensemble.robust_cz_members(dl, rs, seed=5, n_gauss=8, nt=120)
+    ref = ensemble.ensemble_value_and_grad(members, a, b, c)
+    po, *_ = otq.notebook02_setup(seed=5, n_gauss=8, nt=120)
+    args = (8, 120, po.padding, 50e6, po.delta_t, 0.0, po.Vint, po.Delta_i_val, po.Rabi_i_val, po.Rabi_r_val, otq.GAMMAS_CZ)
+    prop = PropagatorVL(*args)
+    prop.set_ensemble(del_total=dl, rabi_scale=rs)
+    full = np_(prop.cost_and_grad_packed(prop._pack(a, b, c))).copy()
+    outs = {}
+    for flag in (1, 0):                                    # streamed terms / checkpoints + recomputation
+        with env(QOCVL_STORE=flag):
+            p64 = PropagatorVL(*args)
+            p64.set_precision("complex64")
+            assert p64._plan.precision == "complex64"
+            p64.set_ensemble(del_total=dl, rabi_scale=rs)
+            outs[flag] = np_(p64.cost_and_grad_packed(p64._pack(a, b, c))).copy()
+            p64._plan.check()
+            assert p64._plan.chain_info()["path"] == ("reduced_stacked_streamed" if flag else "reduced_stacked")
+    n = 8 * 5
+    for out in outs.values():
+        assert np.abs(out[:3] - np.array(ref[:3])).max() < TOL_C64_COST          # vs the CPU oracle
+        assert np.abs(out[:3] - full[:3]).max() < TOL_C64_COST                   # vs the complex128 kernel
+        for i, r in enumerate(ref[3:6]):
+            assert rel(out[3 + i * n:3 + (i + 1) * n], np.asarray(r).ravel()) < TOL_C64_GRAD_REL
+        assert np.abs(out - full).max() > 0.0                                    # it really is another arithmetic
+    # both modes of the complex64 kernel see the same terms up to fp32 rounding
+    assert np.abs(outs[1][:3] - outs[0][:3]).max() < TOL_C64_COST
+    # switching back gives the complex128 numbers bit for bit
+    p64.set_precision("complex128")
+    with env(QOCVL_STORE=0):
+        back = np_(p64.cost_and_grad_packed(p64._pack(a, b, c))).copy()
+    assert np.abs(back[:3] - full[:3]).max() < 1e-13 and rel(back[3:], full[3:]) < 1e-10
+
+
+def test_complex64_single_sample_and_state_transfer():
+    """One sample (no time-parallel path in complex64: the reduced kernel takes it) and the 5-level model."""
+    from oracle import autograd_ref, state_transfer as ost
+    from quantum_optimal_control.state_transfer.propagator_vl import PropagatorVL as StVL
+    from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL as TqVL
+    po, a, b, c = otq.notebook02_setup(seed=3, n_gauss=6, nt=77)
+    prop = TqVL(6, 77, po.padding, 50e6, po.delta_t, 0.0, po.Vint, po.Delta_i_val, po.Rabi_i_val, po.Rabi_r_val,
+                otq.GAMMAS_CZ)
+    so, sa, sb, sc = ost.notebook01_setup()
+    pst = StVL(so.input_dim, so.no_of_steps, so.delta_t, so.del_total, so.Delta_1, so.Rabi_1, so.Rabi_2, so.Gamma_r,
+               so.Gamma_i)
+    for engine, model, ctrl in ((prop, po, (a, b, c)), (pst, so, (sa, sb, sc))):
+        engine.set_precision("complex64")
+        cost, grads = engine.target_and_grad(*ctrl)
+        engine._plan.check()
+        assert engine._plan.chain_info()["path"].startswith("reduced_stacked")
+        ref = autograd_ref.value_and_grad(model, *ctrl)
+        assert abs(float(cost) - ref[0]) < TOL_C64_COST
+        for mine, r in zip(grads, ref[3:]):
+            assert rel(np_(mine), r) < TOL_C64_GRAD_REL
+
+
+def test_complex64_fails_loudly_where_the_reduced_kernel_does_not_apply():
+    """Large Hilbert spaces have no complex64 kernel: the evaluation raises instead of running in fp64."""
+    from qocvl import QocvlError
+    po, a, b, c = obc.chain_setup(n_atoms=7, n_gauss=6, nt=64)      # dim 34: q and p together exceed 32 rows
+    prop = make_chain(po)
+    prop.set_precision("complex64")
+    with pytest.raises(QocvlError):
+        prop.target_and_grad(a, b, c)
+    with pytest.raises(ValueError):
+        prop.set_precision("complex32")
+    prop.set_precision("complex128")                                # and the plan is still usable afterwards
+    cost, _ = prop.target_and_grad(a, b, c)
+    assert abs(float(cost) - po.value_and_grad(a, b, c)[0]) < 1e-10
