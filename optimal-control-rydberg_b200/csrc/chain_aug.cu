@@ -64,7 +64,7 @@ struct AugArgs {
   cplx d_const;              // overlap contribution of the start kets that never move
   const int *row_col, *col_row, *r_cls, *c_cls, *r_gen, *c_gen, *ra_gen, *ca_gen;
   const cplx *r_val, *c_val, *ra_val, *ca_val;
-  cplx *p_row, *p_col;       // per-slice entry tables (written by k_aug_tables, read by k_chain_aug)
+  void *p_row, *p_col;       // per-slice entry tables (written by k_aug_tables, read by k_chain_aug) in the sweep's type
   const cplx* coef;          // [M][J]
   const cplx* dcoef;         // [M][J][C]
   const int* qdeg;           // [M]
@@ -84,6 +84,7 @@ struct AugArgs {
 
 // P_i(k) = dt * sum_{g in contribution i} coef_kg * val_ig for every row-owner and column-owner contribution:
 // the sample-independent part of the slice generators, computed once per evaluation (M * (ncr+ncc) * L values).
+template <typename CT>
 __global__ void k_aug_tables(const AugArgs P, int L) {
   const int k = blockIdx.x;
   for (int t = threadIdx.x; t < (P.ncr + P.ncc) * L; t += blockDim.x) {
@@ -98,8 +99,10 @@ __global__ void k_aug_tables(const AugArgs P, int L) {
       if (g >= 0) acc = cfma(P.coef[(size_t)k * P.J + g], val[((size_t)c * P.KG + i) * L + lane], acc);
     }
     acc = cscale(acc, P.dt);
-    if (rowtab) P.p_row[((size_t)k * P.ncr + c) * L + lane] = acc;
-    else P.p_col[((size_t)k * P.ncc + c) * L + lane] = acc;
+    CT v;   // stored in the sweep's own type: a conversion in k_chain_aug would wait on the load it sits behind
+    v.x = acc.x; v.y = acc.y;
+    if (rowtab) ((CT*)P.p_row)[((size_t)k * P.ncr + c) * L + lane] = v;
+    else ((CT*)P.p_col)[((size_t)k * P.ncc + c) * L + lane] = v;
   }
 }
 
@@ -196,14 +199,13 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
   };
   // entry of slot s: A + sum_i m_i * P_i(k).  The table values P_i(k) are fetched one phase ahead into `raw`
   // (global -> registers, L2-resident tables shared by every sample) so the load latency hides behind the sweeps.
-  auto load_raw = [&](const cplx* tab, int nslots, CT* raw) {
+  const CT* const p_row = (const CT*)P.p_row;
+  const CT* const p_col = (const CT*)P.p_col;
+  auto load_raw = [&](const CT* tab, int nslots, CT* raw) {
 #pragma unroll
     for (int s = 0; s < NSL; ++s)
 #pragma unroll
-      for (int i = 0; i < KC; ++i) {
-        const cplx v = (s <= nslots) ? __ldg(tab + (size_t)(s * KC + i) * LPG) : dzero;
-        raw[s * KC + i] = T::mk(v.x, v.y);
-      }
+      for (int i = 0; i < KC; ++i) raw[s * KC + i] = (s <= nslots) ? __ldg(tab + (size_t)(s * KC + i) * LPG) : czero;
   };
   auto slot_value = [&](const CT* raw, const R* m, unsigned mask, int col, int s) -> CT {
     CT acc = czero;
@@ -233,14 +235,14 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
   };
 
   // =================================== forward sweep ===================================
-  load_raw(P.p_row + r, P.w, raw_r);
+  load_raw(p_row + r, P.w, raw_r);
   int q_next = P.qdeg[0];
   size_t n_stream = 0;                               // STORE: Taylor terms written so far (the stream is dense)
   for (int k = 0; k < P.M; ++k) {
     const int q = q_next;
     finish_rows();
     if (k + 1 < P.M) {
-      load_raw(P.p_row + (size_t)(k + 1) * P.ncr * LPG + r, P.w, raw_r);
+      load_raw(p_row + (size_t)(k + 1) * P.ncr * LPG + r, P.w, raw_r);
       q_next = P.qdeg[k + 1];
     }
     const bool keep = P.want_grad && live;
@@ -358,14 +360,14 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
     CT raw_c[NSL * KC];
     int q_cur = P.qdeg[P.M - 1];
     q_next = P.M > 1 ? P.qdeg[P.M - 2] : 0;
-    load_raw(P.p_col + (size_t)(P.M - 1) * P.ncc * LPG + r, P.wc, raw_c);
+    load_raw(p_col + (size_t)(P.M - 1) * P.ncc * LPG + r, P.wc, raw_c);
     for (int k = P.M - 1; k >= 0; --k) {
       const int q = q_cur;
       a_d = slot_value(raw_c, m_col, P.add_col_mask, 1, 0);
 #pragma unroll
       for (int s = 0; s < WMAX; ++s) a_col[s] = (s < P.wc) ? slot_value(raw_c, m_col, P.add_col_mask, 1, 1 + s) : czero;
       if (k > 0) {                                  // next slice's tables and degree in flight during this one
-        load_raw(P.p_col + (size_t)(k - 1) * P.ncc * LPG + r, P.wc, raw_c);
+        load_raw(p_col + (size_t)(k - 1) * P.ncc * LPG + r, P.wc, raw_c);
         q_cur = q_next;
         q_next = k > 1 ? P.qdeg[k - 2] : 0;
       }
@@ -401,14 +403,14 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
       }
     }
   } else {
-    load_raw(P.p_row + (size_t)(P.M - 1) * P.ncr * LPG + r, P.w, raw_r);
+    load_raw(p_row + (size_t)(P.M - 1) * P.ncr * LPG + r, P.w, raw_r);
     q_next = P.qdeg[P.M - 1];
     CT t_next = live ? ((const CT*)P.ckpt)[(size_t)(P.M - 1) * gthreads + gtid] : czero;
     for (int k = P.M - 1; k >= 0; --k) {
       const int q = q_next;
       finish_rows();
       CT raw_c[NSL * KC];                           // column-owner table values: in flight during the recompute
-      load_raw(P.p_col + (size_t)k * P.ncc * LPG + r, P.wc, raw_c);
+      load_raw(p_col + (size_t)k * P.ncc * LPG + r, P.wc, raw_c);
       // ---- recompute the forward Taylor terms, stored pre-scaled: s_j = t_{j-1} / j is what the adjoint pairs
       //      with tb_j, and s_{j+1} = X s_j / (j+1)
       CT t = t_next;
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
 #pragma unroll
       for (int s = 0; s < WMAX; ++s) a_col[s] = (s < P.wc) ? slot_value(raw_c, m_col, P.add_col_mask, 1, 1 + s) : czero;
       if (k > 0) {                                  // next slice's rows, checkpoint and degree: in flight during the adjoint
-        load_raw(P.p_row + (size_t)(k - 1) * P.ncr * LPG + r, P.w, raw_r);
+        load_raw(p_row + (size_t)(k - 1) * P.ncr * LPG + r, P.w, raw_r);
         t_next = live ? ((const CT*)P.ckpt)[(size_t)(k - 1) * gthreads + gtid] : czero;
         q_next = P.qdeg[k - 1];
       }
@@ -924,7 +926,8 @@ int qocvl_aug_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t 
   a.starts = p->d_aug_starts; a.targets = p->d_aug_targets; a.pair = p->d_aug_pair; a.wq = p->d_aug_wq;
   a.ckpt = p->d_ckpt; a.terms = p->d_ckpt; a.qs = p->aug_qs;
   a.sample_out = p->d_sample_out; a.y_partial = p->d_ypart; a.gwave = gwave;
-  k_aug_tables<<<d.n_slices, 256, 0, st>>>(a, la.L);
+  if (p->c64) k_aug_tables<cplxf><<<d.n_slices, 256, 0, st>>>(a, la.L);
+  else k_aug_tables<cplx><<<d.n_slices, 256, 0, st>>>(a, la.L);
   pick_aug(la.L, p->aug_wmax, la.KC, p->aug_store, p->c64 != 0)<<<p->blocks, p->threads, p->chain_smem, st>>>(a);
   p->launches += 2;
   if (want_grad) {
