@@ -32,9 +32,10 @@ UNIT = "slice-samples/s"
 N_GAUSS, NT, SEED = 16, 1888, 0          # cfg 3: nt=1888, pad=int(0.03*nt)=56 -> M=2000
 
 
-def workload_config(samples_per_gpu, n_gpus):
+def workload_config(samples_per_gpu, n_gpus, dtype="c128"):
     return {"workload": "robust CZ (BASELINE.json configs[2]): 4096 noise samples x 2000 slices x N=16 Gaussians, "
-                        "two-atom 16-level Van Loan cost + 3N-gradient, complex128",
+                        "two-atom 16-level Van Loan cost + 3N-gradient, "
+                        + ("complex64 (optional mode)" if dtype == "c64" else "complex128"),
             "samples_per_gpu": samples_per_gpu, "samples_total": samples_per_gpu * n_gpus, "slices": 2000,
             "n_gauss": N_GAUSS, "channels": 5, "hilbert_dim": 16,
             "l2": "per-step working set (state checkpoints + per-warp gradient partials, ~6 GB at 4096 samples, "
@@ -181,6 +182,8 @@ def run_gpu(args):
     if world == 1:
         assert prop._plan.n_samples == S_total
 
+    if args.dtype == "c64":       # the whole bench in the optional complex64 mode (the default line stays complex128)
+        prop.set_precision("complex64")
     abc = prop._pack(a, b, c)
     out = torch.empty(3 + 3 * N_GAUSS * 5, dtype=torch.float64, device=abc.device)
     plan = prop._plan
@@ -244,7 +247,8 @@ def run_gpu(args):
     hbm_bytes = plan.hbm_bytes_per_call(True)             # checkpoints + per-warp gradient partials, write + read
     if info["path"].startswith("reduced_stacked"):
         streamed = int(info["path"].endswith("streamed"))
-        kname = f"k_chain_aug<{info['lanes']},{info['slots']},{info['classes']},{streamed}>"
+        kname = (f"k_chain_aug<{'float' if args.dtype == 'c64' else 'double'},{info['lanes']},{info['slots']},"
+                 f"{info['classes']},{streamed}>")
         # shared-memory exchange of the Taylor mat-vecs: per step and warp 2 STS.64 + 2*slots LDS.64, 2 wavefronts
         # each (32 lanes x 8 B); steps per slice = q (forward) + q-1 (recompute, unless streamed) + q (adjoint)
         steps_total = flops / (8.0 * info["nnz"] * S_local)       # Taylor-step equivalents per sample (3q or 4q-1 per slice)
@@ -280,13 +284,17 @@ def run_gpu(args):
     streamed_kernel = info["path"] == "reduced_stacked_streamed"
     # ncu --set full of this kernel at 4144 samples (profiles/r1_aug_key_metrics.txt): dram read 25.28 GB + write 23.20 GB
     traffic = (25.278179e9 + 23.202109e9) / 4144.0 * S_local if streamed_kernel else None
+    if streamed_kernel and args.dtype == "c64":   # profiles/r1_c64_key_metrics.txt, capture 2
+        traffic = (6.856972e9 + 7.261934e9) / 4144.0 * S_local
     if streamed_kernel:
         # the streamed kernel trades a third of its mat-vecs (FP64 + shared-memory exchange) for HBM traffic: HBM is the
         # most utilised of the peaks the contract names, and its algorithmic bytes are what ncu measures (no re-reads)
         roofline = {"bound": "hbm", "kernel": kname, "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
                     "frac": hbm_gbs / hbm_peak if hbm_gbs else None, "traffic": traffic,
-                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of profiles/r1_aug_full_raw.csv "
-                                      "(4144 samples), scaled to this launch's sample count",
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of "
+                                      + ("profiles/r1_c64_key_metrics.txt (capture 2)" if args.dtype == "c64"
+                                         else "profiles/r1_aug_full_raw.csv")
+                                      + " (4144 samples), scaled to this launch's sample count",
                     "algorithmic_bytes_per_launch": hbm_bytes, "algorithmic_bytes_per_unit": hbm_bytes / (M * S_local),
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth)" if peaks.get("hbm_gbs")
                                    else "B200_PROFILING.md fallback",
@@ -295,6 +303,8 @@ def run_gpu(args):
     else:
         roofline = {"bound": "fp64", "kernel": kname, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": fp64["frac"], "traffic": traffic}
+    if args.dtype == "c64":
+        fp64["flops_note"] += "; complex64 run: these are fp32 flops, the FP64 peaks do not apply"
     roofline.update({"system": info, "kernel_ms": k_ms,
                      "kernel_share_of_step": k_ms * args.steps / elapsed_ms if k_ms > 0 else None,
                      "fp64": fp64, "shared_memory": smem,
@@ -302,7 +312,7 @@ def run_gpu(args):
 
     # ---- the optional complex64 mode of the same kernel (N = 1 only; reported beside the complex128 headline) ----
     c64 = None
-    if world == 1 and not args.no_c64:
+    if world == 1 and not args.no_c64 and args.dtype == "c128":
         ref_out = out.detach().cpu().numpy().copy()
         prop.set_precision("complex64")
         out64 = torch.empty_like(out)
@@ -346,8 +356,8 @@ def run_gpu(args):
                             "seconds": cpu_s}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-                "config": workload_config(S_local, world),
+                "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                "config": workload_config(S_local, world, args.dtype),
                 "clocks": clocks.summary(),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * N_GAUSS * 5 * 8,
                         "d2h_bytes_per_step": (3 + 3 * N_GAUSS * 5) * 8,
@@ -370,6 +380,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--samples", type=int, default=4096, help="noise samples per GPU")
+    ap.add_argument("--dtype", default="c128", choices=["c128", "c64"],
+                    help="arithmetic of the ensemble kernel; c128 is the parity path and the headline")
     ap.add_argument("--no-c64", dest="no_c64", action="store_true", help="skip the extra complex64 measurement")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
