@@ -312,6 +312,7 @@ def run_gpu(args):
 
     # ---- the optional complex64 mode of the same kernel (N = 1 only; reported beside the complex128 headline) ----
     c64 = None
+    taylor_cap_main = plan.taylor_cap
     if world == 1 and not args.no_c64 and args.dtype == "c128":
         ref_out = out.detach().cpu().numpy().copy()
         prop.set_precision("complex64")
@@ -367,7 +368,7 @@ def run_gpu(args):
                 "cpu_baseline": cpu_baseline,
                 "complex64": c64,
                 "result": {"cost": float(cost_e2e), "infidelity": float(out[1]), "adiabaticity": float(out[2]),
-                           "taylor_degree_cap": plan.taylor_cap}}
+                           "taylor_degree_cap": taylor_cap_main}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
