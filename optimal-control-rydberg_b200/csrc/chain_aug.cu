@@ -252,13 +252,15 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
     CT t = z;
     __syncwarp();                                   // the previous loop's readers are done with buffer 0
     int j = 1;
-    for (; j + 1 <= q; j += 2) {
+    for (; j + 1 <= q; j += 2) {                    // running store pointer: two adds per term instead of a 64-bit multiply
       t = step_fwd(t, T::ainv(j), 0);
       z = cadd(z, t);
-      if (STORE && keep) tout[(size_t)j * gthreads] = t;
+      tout += gthreads;
+      if (STORE && keep) *tout = t;
       t = step_fwd(t, T::ainv(j + 1), 1);
       z = cadd(z, t);
-      if (STORE && keep && j + 1 < q) tout[(size_t)(j + 1) * gthreads] = t;
+      tout += gthreads;
+      if (STORE && keep && j + 1 < q) *tout = t;
     }
     if (j <= q) {
       t = step_fwd(t, T::ainv(j), 0);
@@ -337,14 +339,16 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
 #pragma unroll
     for (int i = 0; i < RING; ++i) s_ring[(size_t)i * nthreads] = czero;   // dead lanes read zeros for ever
     int head = 0, tail = 0;
+    int left = live ? (int)n_stream : 0;            // terms this lane still has to request (dead lanes: none)
     auto issue = [&]() {
-      if (live && sp >= base) {
+      if (left > 0) {
         if constexpr (F64)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring0 + head * ring_stride), "l"(sp) : "memory");
         else   // 8-byte copies exist only in the .ca flavour
           asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ring0 + head * ring_stride), "l"(sp) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
+      --left;
       sp -= gthreads;
       head = (head + 1) & (RING - 1);
     };
@@ -855,7 +859,7 @@ int qocvl_aug_configure(qocvl_plan* p) {
   // ---- Taylor terms: streamed through HBM (STORE) when the a-priori degree cap and the device memory allow it
   const int gpw = 32 / Lk;
   p->aug_qs = p->qcap;                                // a-priori cap (qocvl_chain_configure); k_coefficients flags excess
-  p->aug_store = true;
+  p->aug_store = (size_t)M * p->aug_qs < ((size_t)1 << 31);   // the kernel counts the stream's terms in 32 bits
   if (const char* e = getenv("QOCVL_STORE")) p->aug_store = p->aug_store && atoi(e) != 0;
   if (p->d_ckpt) { cudaFree(p->d_ckpt); p->d_ckpt = nullptr; p->bytes -= p->ckpt_bytes; p->ckpt_bytes = 0; }
   if (p->d_ypart) { cudaFree(p->d_ypart); p->d_ypart = nullptr; p->bytes -= p->ypart_bytes; p->ypart_bytes = 0; }
