@@ -332,30 +332,28 @@ __global__ void __launch_bounds__(512, 1) k_chain_aug(const AugArgs P) {
     // consumes it strictly backwards, across slice boundaries, so it is fetched RING steps ahead of its use with
     // cp.async into a small thread-private shared-memory ring (HBM latency under load is ~6 adjoint steps).
     constexpr int RING = QOCVL_RING;
-    const CT* const base = (const CT*)P.terms + gtid;
-    const CT* sp = base + (n_stream - 1) * gthreads;
+    const CT* sp = (const CT*)P.terms + gtid + (n_stream - 1) * gthreads;
     const unsigned ring0 = (unsigned)__cvta_generic_to_shared(s_ring);
     const unsigned ring_stride = (unsigned)(nthreads * sizeof(CT));
 #pragma unroll
     for (int i = 0; i < RING; ++i) s_ring[(size_t)i * nthreads] = czero;   // dead lanes read zeros for ever
-    int head = 0, tail = 0;
-    int left = live ? (int)n_stream : 0;            // terms this lane still has to request (dead lanes: none)
+    int slot = 0;                                   // the slot just consumed is the one the next request refills:
+    int left = live ? (int)n_stream : 0;            // one ring index; `left` = terms this lane still has to request
     auto issue = [&]() {
       if (left > 0) {
         if constexpr (F64)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring0 + head * ring_stride), "l"(sp) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring0 + slot * ring_stride), "l"(sp) : "memory");
         else   // 8-byte copies exist only in the .ca flavour
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ring0 + head * ring_stride), "l"(sp) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ring0 + slot * ring_stride), "l"(sp) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
       --left;
       sp -= gthreads;
-      head = (head + 1) & (RING - 1);
+      slot = (slot + 1) & (RING - 1);
     };
     auto fetch = [&]() -> CT {
       asm volatile("cp.async.wait_group %0;" ::"n"(RING - 1) : "memory");
-      const CT v = s_ring[(size_t)tail * nthreads];
-      tail = (tail + 1) & (RING - 1);
+      const CT v = s_ring[(size_t)slot * nthreads];
       issue();
       return v;
     };
