@@ -282,18 +282,18 @@ def run_gpu(args):
     hbm_gbs = hbm_bytes / (k_ms * 1e-3) * 1e-9 if k_ms > 0 else None
     hbm_peak = peaks.get("hbm_gbs") or 6554.6
     streamed_kernel = info["path"] == "reduced_stacked_streamed"
-    # ncu --set full of this kernel at 4144 samples (profiles/r1_aug_key_metrics.txt): dram read 25.28 GB + write 23.20 GB
-    traffic = (25.278179e9 + 23.202109e9) / 4144.0 * S_local if streamed_kernel else None
-    if streamed_kernel and args.dtype == "c64":   # profiles/r1_c64_key_metrics.txt, capture 2
-        traffic = (6.856972e9 + 7.261934e9) / 4144.0 * S_local
+    # ncu --set full of this kernel at 4144 samples (profiles/r1_aug_final_key_metrics.txt): dram read 25.28 GB + write 23.20 GB
+    traffic = (25.276345e9 + 23.200028e9) / 4144.0 * S_local if streamed_kernel else None
+    if streamed_kernel and args.dtype == "c64":   # profiles/r1_aug_final_key_metrics.txt
+        traffic = (6.846358e9 + 7.262013e9) / 4144.0 * S_local
     if streamed_kernel:
         # the streamed kernel trades a third of its mat-vecs (FP64 + shared-memory exchange) for HBM traffic: HBM is the
         # most utilised of the peaks the contract names, and its algorithmic bytes are what ncu measures (no re-reads)
         roofline = {"bound": "hbm", "kernel": kname, "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
                     "frac": hbm_gbs / hbm_peak if hbm_gbs else None, "traffic": traffic,
                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of "
-                                      + ("profiles/r1_c64_key_metrics.txt (capture 2)" if args.dtype == "c64"
-                                         else "profiles/r1_aug_full_raw.csv")
+                                      + ("profiles/r1_aug_final_key_metrics.txt (float)" if args.dtype == "c64"
+                                         else "profiles/r1_aug_final_key_metrics.txt (double)")
                                       + " (4144 samples), scaled to this launch's sample count",
                     "algorithmic_bytes_per_launch": hbm_bytes, "algorithmic_bytes_per_unit": hbm_bytes / (M * S_local),
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth)" if peaks.get("hbm_gbs")
