@@ -500,3 +500,24 @@ def test_complex64_fails_loudly_where_the_reduced_kernel_does_not_apply():
     prop.set_precision("complex128")                                # and the plan is still usable afterwards
     cost, _ = prop.target_and_grad(a, b, c)
     assert abs(float(cost) - po.value_and_grad(a, b, c)[0]) < 1e-10
+
+
+def test_complex64_optimiser_loop_replays_from_a_graph_and_tracks_complex128():
+    """The device-side optimiser loop in complex64: graph replay equals eager launches bit for bit (the kernel is
+    deterministic in either arithmetic), the cost descends, and the 12-step history stays within the stated bound of the
+    complex128 history."""
+    from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL
+    po, a, b, c = otq.notebook02_setup(seed=8, n_gauss=6, nt=77)
+    prop = PropagatorVL(6, 77, po.padding, 50e6, po.delta_t, 0.0, po.Vint, po.Delta_i_val, po.Rabi_i_val,
+                        po.Rabi_r_val, otq.GAMMAS_CZ)
+    dl, rs = ensemble.robust_cz_noise(9)
+    prop.set_ensemble(del_total=dl, rabi_scale=rs)
+    hist_128, *_ = prop.optimize(a, b, c, num_iters=12, lr=0.02)
+    prop.set_precision("complex64")
+    hist_g, ag, bg, cg = prop.optimize(a, b, c, num_iters=12, lr=0.02)
+    hist_e, ae, be, ce = prop.optimize(a, b, c, num_iters=12, lr=0.02, use_graph=False)
+    prop._plan.check()
+    assert prop._plan.precision == "complex64" and prop._plan.chain_info()["path"] == "reduced_stacked_streamed"
+    assert torch.equal(hist_g, hist_e) and torch.equal(ag, ae) and torch.equal(cg, ce)
+    assert float(hist_g[-1]) < float(hist_g[0])
+    assert float((hist_g - hist_128).abs().max()) < TOL_C64_COST
