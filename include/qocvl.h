@@ -132,6 +132,17 @@ int qocvl_cost_grad_from_wave(qocvl_plan* plan, const double* wave, double* out3
  * are normalised by global_samples. */
 int qocvl_set_shard(qocvl_plan* plan, int global_samples);
 
+/* Explicit per-plan switches; the library reads NO environment variables.  value < 0 restores the automatic choice.
+ * Names: "aug" (0 = do not use the reduced stacked system), "rows" (0 = lane-per-row-group kernel of chain_aug.cu instead
+ * of the sector-per-warp kernel of chain_rows.cu), "rows_tma" (0 = plain loads instead of bulk-TMA for the Taylor stream),
+ * "store" (0 = recompute the Taylor terms instead of streaming them through HBM), "spb" (samples per CTA), "nofold"
+ * (1 = no orbit folding), "force_big" (1 = rows-strided kernel for any n), "qcap" (Taylor-degree cap), "tp" (0 = no
+ * time-parallel single-sample path), "tp_chunk" (slices per chunk), "tlocal", "wide" (0 = no samples-minor kernel),
+ * "wide_store", "wide_spc", "wide_threads", "strong_chunks" (slice-axis chunks per sample of the ensemble path).
+ * They exist so that every kernel path can be cross-checked against the others on the same plan API.
+ * QOCVL_ERR_ARG for an unknown name. */
+int qocvl_set_option(qocvl_plan* plan, const char* name, int value);
+
 /* Arithmetic type of the ensemble kernel (north_star: "batched complex128 (optional complex64)"; the reference
  * itself runs complex128 only, jax_enable_x64 at TQ:1-12).  QOCVL_C64 runs the reduced stacked system
  * (qocvl_reduced_rows) with complex64 state, Taylor terms and matrix entries, Taylor remainder 2^-26; the pulse

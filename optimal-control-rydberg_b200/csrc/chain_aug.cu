@@ -643,7 +643,7 @@ int qocvl_aug_configure(qocvl_plan* p) {
     }
     const std::vector<char> sup = closure(PU, n, seed);
     bool fold = have_perm && invariant(p->h_live_s, v) && (v != va || !any_w || w_invariant);
-    if (getenv("QOCVL_NOFOLD")) fold = false;
+    if (p->opt("nofold")) fold = false;
     if (!make_sector(sup, n, pm, fold, &sec[v])) {
       if (!make_sector(sup, n, pm, false, &sec[v])) return QOCVL_ERR_UNSUPPORTED;
       fold = false;
@@ -858,7 +858,7 @@ int qocvl_aug_configure(qocvl_plan* p) {
   const int gpw = 32 / Lk;
   p->aug_qs = p->qcap;                                // a-priori cap (qocvl_chain_configure); k_coefficients flags excess
   p->aug_store = (size_t)M * p->aug_qs < ((size_t)1 << 31);   // the kernel counts the stream's terms in 32 bits
-  if (const char* e = getenv("QOCVL_STORE")) p->aug_store = p->aug_store && atoi(e) != 0;
+  if (p->has_opt("store")) p->aug_store = p->aug_store && p->opt("store") != 0;
   if (p->d_ckpt) { cudaFree(p->d_ckpt); p->d_ckpt = nullptr; p->bytes -= p->ckpt_bytes; p->ckpt_bytes = 0; }
   if (p->d_ypart) { cudaFree(p->d_ypart); p->d_ypart = nullptr; p->bytes -= p->ypart_bytes; p->ypart_bytes = 0; }
   int sms = 148;
@@ -878,7 +878,7 @@ int qocvl_aug_configure(qocvl_plan* p) {
       const long load = waves * per_sm * g;
       if (best_load < 0 || load <= best_load) { best_load = load; ngroups = g; }
     }
-    if (const char* e = getenv("QOCVL_SPB")) ngroups = std::max(gpw, std::min(gmax, (atoi(e) + gpw - 1) / gpw * gpw));
+    if (p->has_opt("spb")) ngroups = std::max(gpw, std::min(gmax, (p->opt("spb") + gpw - 1) / gpw * gpw));
     ngroups = std::min(ngroups, (S + gpw - 1) / gpw * gpw);
     p->spb = ngroups; p->groups = ngroups; p->threads = ngroups * Lk;
     p->chain_smem = aug_smem_bytes(p, ngroups);

@@ -94,7 +94,7 @@ int qocvl_chain_configure(qocvl_plan* p) {
   const qocvl_desc& d = p->d;
   const int J = d.n_gen, n = d.n;
   p->use_big = (p->npad == 0);
-  if (const char* e = getenv("QOCVL_FORCE_BIG")) p->use_big = p->use_big || atoi(e) != 0;
+  if (p->opt("force_big")) p->use_big = true;
   // the lane-per-row kernel holds <= 4 off-diagonals per row/column (<= 2 for the top-right block)
   if (!p->use_big && (p->lu.n_row_slots - 1 > 4 || p->lu.n_col_slots - 1 > 4 || p->lw.n_row_slots > 2 ||
                       p->lw.n_col_slots > 2 || d.n_vec > 4))
@@ -187,16 +187,16 @@ int qocvl_chain_configure(qocvl_plan* p) {
   const double bound = apriori_norm_bound(p, mulmax, addmax);
   if (!(bound == bound)) return QOCVL_ERR_ARG;
   p->qcap = qocvl_taylor_degree(bound, p->taylor_tol());
-  if (const char* e = getenv("QOCVL_QCAP")) p->qcap = std::max(2, std::min(QOCVL_QMAX, atoi(e)));
+  if (p->has_opt("qcap")) p->qcap = std::max(2, std::min(QOCVL_QMAX, p->opt("qcap")));
   // ---- kernel-specific geometry and buffers
   // a single sample has no ensemble parallelism: cut the slice axis into concurrent chunks instead
   p->use_tp = !p->use_big && p->n_samples == 1 && d.n_slices >= 32 && !p->c64;
-  if (const char* e = getenv("QOCVL_TP")) p->use_tp = p->use_tp && atoi(e) != 0;
+  if (p->has_opt("tp")) p->use_tp = p->use_tp && p->opt("tp") != 0;
   // ensembles: the reduced stacked system (chain_aug.cu) whenever it fits its kernel
   p->use_aug = false;
   int rc = QOCVL_ERR_UNSUPPORTED;
-  bool try_aug = !p->use_tp && !getenv("QOCVL_FORCE_BIG");
-  if (const char* e = getenv("QOCVL_AUG")) try_aug = try_aug && atoi(e) != 0;
+  bool try_aug = !p->use_tp && !p->opt("force_big");
+  if (p->has_opt("aug")) try_aug = try_aug && p->opt("aug") != 0;
   if (try_aug) {
     rc = qocvl_aug_configure(p);
     if (rc != QOCVL_OK && rc != QOCVL_ERR_UNSUPPORTED) { p->groups = 0; return rc; }
@@ -206,7 +206,7 @@ int qocvl_chain_configure(qocvl_plan* p) {
   p->use_wide = false;
   if (!p->use_aug && p->use_big) {          // large Hilbert spaces: the samples-minor kernel when it takes the problem
     bool try_wide = true;
-    if (const char* e = getenv("QOCVL_WIDE")) try_wide = atoi(e) != 0;
+    if (p->has_opt("wide")) try_wide = p->opt("wide") != 0;
     if (try_wide) {
       rc = qocvl_wide_configure(p);
       if (rc != QOCVL_OK && rc != QOCVL_ERR_UNSUPPORTED) { p->groups = 0; return rc; }
@@ -228,13 +228,20 @@ int qocvl_launch_chain(qocvl_plan* p, bool want_grad, double* out3, double* gwav
   int rc = qocvl_chain_configure(p);
   if (rc) return rc;
   const qocvl_desc& d = p->d;
-  if (p->timing) QCUDA(cudaEventRecord(p->ev0, st));
+  // event timing is skipped while the stream is being captured into a CUDA graph (the recorded events would not be
+  // valid for cudaEventElapsedTime)
+  bool timing = p->timing;
+  if (timing) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) timing = false;
+  }
+  if (timing) QCUDA(cudaEventRecord(p->ev0, st));
   if (p->use_tp) rc = qocvl_tp_launch(p, want_grad, gwave, st);
   else if (p->use_aug) rc = qocvl_aug_launch(p, want_grad, gwave, st);
   else if (p->use_wide) rc = qocvl_wide_launch(p, want_grad, gwave, st);
   else rc = p->use_big ? qocvl_big_launch(p, want_grad, st) : qocvl_small_launch(p, want_grad, st);
   if (rc) return rc;
-  if (p->timing) { QCUDA(cudaEventRecord(p->ev1, st)); p->timed_once = true; }
+  if (timing) { QCUDA(cudaEventRecord(p->ev1, st)); p->timed_once = true; }
   k_reduce_samples<<<1, 256, 0, st>>>(p->n_samples, 1.0 / (double)p->global_samples, p->d_sample_out, out3);
   p->launches++;
   if (want_grad && !p->use_tp && !p->use_aug && !p->use_wide_tp) {

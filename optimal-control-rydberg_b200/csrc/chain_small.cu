@@ -551,7 +551,7 @@ int qocvl_small_configure(qocvl_plan* p) {
   // a CTA is only a container of independent groups (no barrier inside the sweeps)
   const int gpw = 32 / L;
   p->tlocal = true;                                        // Taylor terms in thread-local memory (L1)
-  if (const char* e = getenv("QOCVL_TLOCAL")) p->tlocal = atoi(e) != 0;
+  if (p->has_opt("tlocal")) p->tlocal = p->opt("tlocal") != 0;
   // Samples per CTA.  The kernel is compiled for <= 128 registers (512 threads / SM); beyond ~8 resident
   // warps an SM's throughput is flat, so the makespan is the number of samples the busiest SM has to process.
   // Pick the CTA size that minimises it (wave quantisation was worth 20 % on cfg 3: 4096 samples / 148 SMs ->
@@ -571,7 +571,7 @@ int qocvl_small_configure(qocvl_plan* p) {
     }
   }
   if (!p->tlocal) ngroups = std::min(ngroups, 2 * gpw);
-  if (const char* e = getenv("QOCVL_SPB")) ngroups = std::max(gpw, (atoi(e) + gpw - 1) / gpw * gpw);
+  if (p->has_opt("spb")) ngroups = std::max(gpw, (p->opt("spb") + gpw - 1) / gpw * gpw);
   ngroups = std::min(ngroups, (S + gpw - 1) / gpw * gpw);  // small ensembles: do not launch idle warps
   const int q_smem = p->tlocal ? 0 : p->qcap;
   while (ngroups > gpw && chain_smem_bytes(p, ngroups, q_smem) > 100 * 1024) ngroups -= gpw;
@@ -765,7 +765,7 @@ int qocvl_tp_configure(qocvl_plan* p) {
   const int L = p->npad, n = d.n, M = d.n_slices, nvp = p->n_live + 1;
   // depth ~ chunk_len * 4 q Taylor steps (A + C) + 2 * n_chunks combine steps: balance the two
   int lc = (int)lround(sqrt(2.0 * (double)M / (double)std::max(4, p->qcap_apriori)));   // measured optimum on cfg 2
-  if (const char* e = getenv("QOCVL_TP_CHUNK")) lc = atoi(e);
+  if (p->has_opt("tp_chunk")) lc = p->opt("tp_chunk");
   lc = std::max(2, std::min(lc, M));
   p->tp_chunk = lc;
   p->tp_nchunks = (M + lc - 1) / lc;

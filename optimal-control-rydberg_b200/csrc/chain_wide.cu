@@ -53,9 +53,9 @@ static size_t wide_smem_bytes(int n, int J, int C, int spc, int threads, int nb_
 
 // The register file bounds rows per thread (state, diagonal and cotangent of every owned row live in registers):
 // 512 threads x 128 registers up to 4 rows, 384 x 168 up to 8, 256 x 255 up to 14.
-static int wide_threads_for(int spc, int ngroups) {
-  if (const char* e = getenv("QOCVL_WIDE_THREADS")) {
-    const int t = atoi(e);
+static int wide_threads_for(const qocvl_plan* p, int spc, int ngroups) {
+  if (p->has_opt("wide_threads")) {
+    const int t = p->opt("wide_threads");
     if (t == 256 || t == 384 || t == 512) return t;
   }
   if (spc != 8) return 512;
@@ -203,7 +203,7 @@ static int wide_build(qocvl_plan* p, int spc_request, WideLayout& L, bool fwd = 
   size_t smem = 0;
   for (;;) {
     T = build(spc);
-    max_threads = fwd ? 384 : wide_threads_for(spc, T.ngroups);
+    max_threads = fwd ? 384 : wide_threads_for(p, spc, T.ngroups);
     nwarps = std::min(max_threads / 32, T.ngroups);
     items = (T.ngroups + nwarps - 1) / nwarps;
     nwarps = (T.ngroups + items - 1) / items;              // fewest warps that still need `items` passes
@@ -368,7 +368,7 @@ int qocvl_wide_configure(qocvl_plan* p) {
   p->use_wide = false; p->use_wide_tp = false;
   if (p->n_live != 1 || p->adiab_live != 0) return QOCVL_ERR_UNSUPPORTED;
   int spc = (S >= 5) ? 8 : 1;
-  if (const char* e = getenv("QOCVL_WIDE_SPC")) spc = (atoi(e) == 8) ? 8 : 1;
+  if (p->has_opt("wide_spc")) spc = (p->opt("wide_spc") == 8) ? 8 : 1;
   WideLayout& L = p->lwide;
   int rc = wide_build(p, spc, L);
   if (rc) return rc;
@@ -376,7 +376,7 @@ int qocvl_wide_configure(qocvl_plan* p) {
   // ---- a single sample has no ensemble parallelism: cut the slice axis into chunks (column sweeps of every chunk
   //      with 8 basis columns per CTA -> combine -> per-chunk forward + reverse sweeps)
   bool tp = (S == 1 && M >= 64);
-  if (const char* e = getenv("QOCVL_TP")) tp = tp && atoi(e) != 0;
+  if (p->has_opt("tp")) tp = tp && p->opt("tp") != 0;
   if (tp) {
     rc = wide_build(p, 8, p->lwide_a, true);
     if (rc == QOCVL_ERR_UNSUPPORTED || (rc == QOCVL_OK && p->lwide_a.spc != 8)) tp = false;
@@ -386,7 +386,7 @@ int qocvl_wide_configure(qocvl_plan* p) {
   if (tp) {
     lc = (M + 63) / 64;                                // ~64 chunks: 64 * ceil(n/8) column CTAs fill the machine
     lc = std::max(lc, 8);
-    if (const char* e = getenv("QOCVL_TP_CHUNK")) lc = std::max(1, std::min(M, atoi(e)));
+    if (p->has_opt("tp_chunk")) lc = std::max(1, std::min(M, p->opt("tp_chunk")));
     nchunks = (M + lc - 1) / lc;
     const size_t blk = (size_t)nchunks * n * n, bnd = (size_t)(nchunks + 1) * WIDE_NVP * n;
     for (cplx** q : {&p->d_tp_uc, &p->d_tp_wc, &p->d_tp_zc, &p->d_tp_lc}) if (*q) { cudaFree(*q); *q = nullptr; }
@@ -412,7 +412,7 @@ int qocvl_wide_configure(qocvl_plan* p) {
   size_t free_b = 0, total_b = 0;
   QCUDA(cudaMemGetInfo(&free_b, &total_b));
   bool store = stream_bytes <= (size_t)(0.6 * (double)free_b);
-  if (const char* e = getenv("QOCVL_WIDE_STORE")) store = store && atoi(e) != 0;
+  if (p->has_opt("wide_store")) store = store && p->opt("wide_store") != 0;
   if (p->d_ckpt) { cudaFree(p->d_ckpt); p->d_ckpt = nullptr; p->bytes -= p->ckpt_bytes; p->ckpt_bytes = 0; }
   if (p->d_tring) { cudaFree(p->d_tring); p->d_tring = nullptr; p->bytes -= p->tring_bytes; p->tring_bytes = 0; }
   p->tring_bytes = store ? stream_bytes : (size_t)ctas * p->qcap * vs;

@@ -7,6 +7,7 @@
 #include <vector>
 #include <complex>
 #include <string>
+#include <map>
 
 #include "../../include/qocvl.h"
 
@@ -167,6 +168,10 @@ struct WideLayout {
 
 struct qocvl_plan {
   qocvl_desc d;
+  // qocvl_set_option: explicit per-plan tuning / cross-check switches (the library reads no environment variables)
+  std::map<std::string, int> opts;
+  bool has_opt(const char* name) const { return opts.count(name) != 0; }
+  int opt(const char* name, int dflt = 0) const { auto it = opts.find(name); return it == opts.end() ? dflt : it->second; }
   int device = 0;
   int npad = 0;            // lanes per vector (8, 16 or 32)
   int n_samples = 1;

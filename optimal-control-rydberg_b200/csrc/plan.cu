@@ -168,6 +168,8 @@ extern "C" int qocvl_plan_destroy(qocvl_plan* p) {
     cudaFree(c->crow); cudaFree(c->ceid); cudaFree(c->egen); cudaFree(c->eval);
   }
   if (p->d_tring) cudaFree(p->d_tring);
+  if (p->ev0) cudaEventDestroy(p->ev0);
+  if (p->ev1) cudaEventDestroy(p->ev1);
   void* ptrs[] = {p->d_gdense, p->d_coef_const, p->d_gnorm, p->d_starts, p->d_targets, p->d_mul, p->d_add,
                   p->d_mulmax, p->d_addmax, p->d_taps, p->d_raw, p->d_reg, p->d_wave, p->d_coef, p->d_dcoef,
                   p->d_qdeg, p->d_flag, p->d_ckpt, p->d_sample_out, p->d_gw_partial, p->d_gwave, p->d_greg,
@@ -308,6 +310,21 @@ extern "C" int qocvl_set_symmetry(qocvl_plan* p, const int* perm) {
 extern "C" int qocvl_set_shard(qocvl_plan* p, int global_samples) {
   if (!p || global_samples < p->n_samples) return QOCVL_ERR_ARG;
   p->global_samples = global_samples;
+  return QOCVL_OK;
+}
+
+// Explicit per-plan switches (tuning knobs and the cross-check paths the tests compare against each other).
+// The library reads no environment variables: everything that changes a plan's behaviour is set on the plan.
+extern "C" int qocvl_set_option(qocvl_plan* p, const char* name, int value) {
+  static const char* known[] = {"aug", "store", "spb", "nofold", "force_big", "qcap", "tp", "tp_chunk", "tlocal",
+                                "wide", "wide_store", "wide_spc", "wide_threads", "rows", "rows_tma", "strong_chunks"};
+  if (!p || !name) return QOCVL_ERR_ARG;
+  bool ok = false;
+  for (const char* k : known) ok = ok || strcmp(k, name) == 0;
+  if (!ok) return QOCVL_ERR_ARG;
+  if (value < 0) p->opts.erase(name);   // negative = back to automatic
+  else p->opts[name] = value;
+  p->groups = 0;                        // re-configure at the next evaluation
   return QOCVL_OK;
 }
 

@@ -41,6 +41,7 @@ SIGNATURES = {
     "qocvl_cost_grad": (C.c_int, [_P, _D, _D, _V]),
     "qocvl_cost_grad_from_wave": (C.c_int, [_P, _D, _D, _D, _V]),
     "qocvl_set_shard": (C.c_int, [_P, C.c_int]),
+    "qocvl_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "qocvl_set_precision": (C.c_int, [_P, C.c_int]),
     "qocvl_precision": (C.c_int, [_P]),
     "qocvl_check": (C.c_int, [_P]),

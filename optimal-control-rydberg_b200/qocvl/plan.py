@@ -21,6 +21,24 @@ def _host_f64(x):
     return arr, arr.ctypes.data_as(C.c_void_p)
 
 
+class options:
+    """``with qocvl.options(store=0, tp_chunk=7): ...`` -- explicit switches (``qocvl_set_option``) applied to every Plan
+    CREATED inside the block.  They exist so that each kernel path can be cross-checked against the others; the
+    library itself reads no environment variables."""
+    _active: dict = {}
+
+    def __init__(self, **kv):
+        self.kv = {str(k): int(v) for k, v in kv.items()}
+
+    def __enter__(self):
+        self._saved = dict(options._active)
+        options._active = {**options._active, **self.kv}
+        return self
+
+    def __exit__(self, *exc):
+        options._active = self._saved
+
+
 class Plan:
     """Owns the device-side constants (generators, cost kets, filter taps, noise tables) and the
     workspaces of one problem on one GPU.  Not thread-safe; one Plan per device / rank."""
@@ -31,8 +49,8 @@ class Plan:
         self._lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("qocvl.Plan needs a CUDA device (no CPU fallback exists)")
-        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else
-                                   torch.device(device).index or 0)
+        index = None if device is None else torch.device(device).index
+        self.device = torch.device("cuda", torch.cuda.current_device() if index is None else index)
         d = _lib.Desc()
         d.model, d.n, d.n_gen, d.n_slices, d.n_basis_pts, d.pad = model, n, n_gen, n_slices, n_basis_pts, pad
         d.n_gauss, d.n_chan, d.n_vec, d.adiab_index = n_gauss, n_chan, n_vec, adiab_index
@@ -44,6 +62,8 @@ class Plan:
         _lib.check(self._lib.qocvl_plan_create(C.byref(self._h), C.byref(d), self.device.index), "plan_create")
         self.n_samples = 1
         self.n_grad = 3 * n_gauss * n_chan
+        for key, value in options._active.items():
+            self.set_option(key, value)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -107,6 +127,10 @@ class Plan:
             self.n_samples = S
         if global_samples is not None:
             _lib.check(self._lib.qocvl_set_shard(self._h, int(global_samples)), "set_shard")
+
+    def set_option(self, name, value):
+        """Explicit per-plan switch (``qocvl_set_option``; names in include/qocvl.h); a negative value = automatic."""
+        _lib.check(self._lib.qocvl_set_option(self._h, str(name).encode(), int(value)), f"set_option({name})")
 
     def set_precision(self, dtype):
         """'complex128' (default) or 'complex64': arithmetic type of the ensemble kernel (qocvl_set_precision)."""

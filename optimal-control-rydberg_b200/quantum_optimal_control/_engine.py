@@ -33,7 +33,7 @@ class _TargetFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, prop, a, b, c):
-        out = prop._plan.cost_grad(prop._pack(a, b, c))
+        out = prop._allreduce(prop._plan.cost_grad(prop._pack(a, b, c)))    # sharded ensembles: the one all-reduce
         n, ch = prop.input_dim, prop.num_ctrls
         ctx.grads = out[3:].view(3, n, ch)
         ctx.like = (a, b, c)
@@ -127,7 +127,7 @@ class EngineBase:
         return out[1], out[2]
 
     def target(self, ctrl_a, ctrl_b, ctrl_c):
-        if self._wants_grad(ctrl_a, ctrl_b, ctrl_c) and self._world is None:
+        if self._wants_grad(ctrl_a, ctrl_b, ctrl_c):      # also when sharded: the all-reduce sits inside _TargetFn.forward
             return _TargetFn.apply(self, ctrl_a, ctrl_b, ctrl_c)
         return self._allreduce(self._plan.cost(self._pack(ctrl_a, ctrl_b, ctrl_c)))[0]
 
@@ -159,6 +159,8 @@ class EngineBase:
         self._pin_out.copy_(out, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         res = self._pin_out.numpy()
+        if not np.isfinite(res[0]):          # a slice left the Taylor range: the engine poisons the result and flags it
+            self._plan.check()               # -> QocvlError(ERR_NORM); never hand NaNs to a host optimiser silently
         g = res[3:].reshape(3, self.input_dim, self.num_ctrls)
         return float(res[0]), (g[0].copy(), g[1].copy(), g[2].copy())
 
@@ -184,6 +186,8 @@ class EngineBase:
         if shard:
             import torch.distributed as dist
             world, rank = dist.get_world_size(), dist.get_rank()
+            if S < world:        # identical on every rank, so every rank raises (no rank is left waiting in a collective)
+                raise ValueError(f"cannot shard {S} noise samples over {world} ranks: every rank needs at least one")
             lo, hi = shard_bounds(S, world, rank)
             mul, add = mul[lo:hi], add[lo:hi]
             self._world = world
@@ -262,6 +266,7 @@ class EngineBase:
         else:
             for _ in range(num_iters):
                 one_step()
+        self._plan.check()       # one sync after the loop: a slice that left the Taylor range raises instead of returning NaNs
         return hist[:num_iters], abc[0], abc[1], abc[2]
 
 
@@ -314,6 +319,7 @@ class EngineBase:
         else:
             for _ in range(num_iters):
                 one_step()
+        self._plan.check()
         return hist[:num_iters], abc[0], abc[1], abc[2]
 
 

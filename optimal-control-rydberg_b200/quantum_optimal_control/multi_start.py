@@ -109,6 +109,7 @@ class MultiStart:
             out = self.cost_and_grad(abc, out)
             hist[it] = out[:, 0]
             abc -= lr * out[:, 3:].view_as(abc)
+        self.check()             # one sync after the loop: a seed whose pulses left the Taylor range raises (never NaN histories)
         return hist, abc
 
     def best(self, costs, n_seeds):

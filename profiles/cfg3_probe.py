@@ -26,8 +26,8 @@ dl, eps = nrng.normal(0.0, 2 * np.pi * 0.1e6, S), nrng.normal(0.0, 0.01, S)
 abc = prop._pack(a, b, c)
 for spb in spbs:
     if spb:
-        os.environ["QOCVL_SPB"] = str(spb)
-    prop.set_ensemble(del_total=dl, rabi_scale=1.0 + eps)      # re-configures the launch (reads the environment)
+        prop._plan.set_option("spb", spb)
+    prop.set_ensemble(del_total=dl, rabi_scale=1.0 + eps)      # re-configures the launch
     prop._plan.set_timing(True)
     for _ in range(2):
         out = prop.cost_and_grad_packed(abc)

@@ -50,6 +50,9 @@ class StubPlan:
     def cost(self, abc, out=None):
         return self.cost_grad(abc)[:3].clone()
 
+    def check(self):
+        pass
+
 
 class StubEngine(_engine.EngineBase):
     input_dim, num_ctrls, del_total = N_GAUSS, N_CHAN, 0.0
@@ -86,6 +89,16 @@ def _worker(rank, world, port, queue):
     out = eng.cost_and_grad_packed(eng._pack(a, b, c))
     cost, (ga, gb, gc) = eng.target_and_grad(a, b, c)
     infid, adiab = eng.metrics(a, b, c)
+    # torch-autograd callers of a SHARDED engine get a differentiable cost whose gradient is the ensemble mean
+    # (round-1 bug: target() silently fell through to the non-differentiable branch when sharded)
+    ta, tb, tc = (torch.tensor(x, requires_grad=True) for x in (a, b, c))
+    tcost = eng.target(ta, tb, tc)
+    assert tcost.requires_grad
+    tcost.backward()
+    assert abs(float(tcost) - float(cost)) < 1e-15 and np.allclose(ta.grad.numpy(), ga.numpy(), rtol=1e-14)
+    # fewer samples than ranks: the same ValueError on every rank, before any collective (no hang)
+    with pytest.raises(ValueError, match="cannot shard"):
+        StubEngine().set_ensemble(del_total=dl[:1], rabi_scale=rs[:1], shard=True)
     queue.put((rank, out.numpy().copy(), float(cost), float(infid), float(adiab), ga.numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()

@@ -28,14 +28,10 @@ def make_chain(po):
     return PropagatorVL(po.input_dim, po.no_of_steps, po.delta_t, po.n_atoms, po.Rabi_max, po.Delta_max)
 
 
-class force_big:
-    """QOCVL_FORCE_BIG is read when the plan configures its launch (first evaluation)."""
-
-    def __enter__(self):
-        os.environ["QOCVL_FORCE_BIG"] = "1"
-
-    def __exit__(self, *exc):
-        os.environ.pop("QOCVL_FORCE_BIG", None)
+def force_big():
+    """Plans created inside the block run every problem on the rows-strided kernel (qocvl_set_option "force_big")."""
+    import qocvl
+    return qocvl.options(force_big=1)
 
 
 @pytest.mark.parametrize("n_atoms,expect_dim", [(4, 8), (5, 13), (7, 34)])
@@ -112,16 +108,11 @@ def test_dense_api_is_unsupported_for_large_n():
         prop.exponentials(a, b, c)
 
 
-class env:
-    def __init__(self, **kv):
-        self.kv = kv
-
-    def __enter__(self):
-        os.environ.update({k: str(v) for k, v in self.kv.items()})
-
-    def __exit__(self, *exc):
-        for k in self.kv:
-            os.environ.pop(k, None)
+def env(**kv):
+    """env(QOCVL_TP=0) -> qocvl.options(tp=0): explicit plan options for the plans created inside the block (the names
+    keep the historical QOCVL_ prefix in the test bodies; the library reads no environment variables)."""
+    import qocvl
+    return qocvl.options(**{k.replace("QOCVL_", "").lower(): v for k, v in kv.items()})
 
 
 @pytest.mark.parametrize("chunk", [None, 2, 7, 64])
