@@ -173,7 +173,9 @@ double qocvl_flops_per_call(const qocvl_plan* plan, int with_grad); /* executed 
 double qocvl_hbm_bytes_per_call(const qocvl_plan* plan, int with_grad);
 /* Launch geometry after configuration, out[8] = {path: 0 lane-per-row / 1 reduced stacked system / 2 time-parallel
  * single sample / 3 rows-strided big-n / 4 reduced stacked system with the Taylor terms streamed through HBM /
- * 5 samples-minor big-n ensemble kernel with streamed Taylor terms / 6 the same with recomputed terms;
+ * 5 samples-minor big-n ensemble kernel with streamed Taylor terms / 6 the same with recomputed terms / 7 its
+ * time-parallel single-sample form / 8 reduced stacked system on the sector-per-warp kernel (chain_rows.cu) with the
+ * Taylor terms streamed through HBM (bulk TMA) / 9 the same with recomputed terms (8-9: lanes = samples per CTA);
  * rows per sample; lanes per sample (paths 5-6: samples per CTA); off-diagonal slots per row (5-6: generator blocks
  * with off-diagonal entries); multiplier classes per entry (5-6: generator blocks with diagonal entries);
  * non-zeros of the propagated system; threads per CTA; CTAs}. */

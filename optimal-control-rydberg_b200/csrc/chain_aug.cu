@@ -22,7 +22,7 @@
 // sweep streams every Taylor term to HBM as one dense stream; the reverse sweep reads the stream backwards through
 // a cp.async ring and emits per-warp sums of m_s * Xbar_e, which k_aug_reduce adds up in a fixed order and contracts
 // with d coef / d wave once per slice.  (STORE = 0: only checkpoints go to HBM and the terms are recomputed.)
-#include "common.cuh"
+#include "chain_aug.cuh"
 #include <algorithm>
 #include <cmath>
 #include <map>
@@ -50,61 +50,6 @@ template <> struct AugT<float> {
   static __device__ __forceinline__ C mk(double re, double im) { return cmakef((float)re, (float)im); }
   static __device__ __forceinline__ float ainv(int j) { return c_ainvf[j]; }
 };
-__device__ __forceinline__ cplx aug_to_d(cplx v) { return v; }
-__device__ __forceinline__ cplx aug_to_d(cplxf v) { return cmake((double)v.x, (double)v.y); }
-
-struct AugArgs {
-  int N, J, M, C, S;
-  int w, wc;                 // off-diagonal row slots / column slots in use
-  int ncr, ncc;              // contribution slots per lane: (1+w)*KC, (1+wc)*KC
-  int KA, KG, ncls, nparts;
-  unsigned add_row_mask, add_col_mask;
-  int want_grad;
-  double dt, inv_duration, w_infid, w_adiab, inv_fid_norm, inv_samples;
-  cplx d_const;              // overlap contribution of the start kets that never move
-  const int *row_col, *col_row, *r_cls, *c_cls, *r_gen, *c_gen, *ra_gen, *ca_gen;
-  const cplx *r_val, *c_val, *ra_val, *ca_val;
-  void *p_row, *p_col;       // per-slice entry tables (written by k_aug_tables, read by k_chain_aug) in the sweep's type
-  const cplx* coef;          // [M][J]
-  const cplx* dcoef;         // [M][J][C]
-  const int* qdeg;           // [M]
-  const double* mcls;        // [S][ncls]
-  const cplx* add;           // [S][J]
-  const cplx* starts;        // [LPG]
-  const cplx* targets;       // [LPG] (symmetry / orbit weights folded in)
-  const int* pair;           // [LPG] partner row in q^dag p, or -1
-  const double* wq;          // [2][LPG]: weight of the row's term in q^dag p (q rows only) / in the cotangent
-  void* ckpt;                // [M][total threads]  (complex of the kernel's arithmetic type, like terms / y_partial)
-  double* sample_out;        // [S][3]
-  void* terms;               // [M][qs][total threads]  Taylor terms t_0 .. t_{q-1} of every slice (STORE = 1)
-  int qs;                    // slots per slice in `terms` (the a-priori Taylor cap)
-  void* y_partial;           // [warps][M][ncc][LPG]  per-warp sums of m * Xbar
-  double* gwave;             // [M][C]
-};
-
-// P_i(k) = dt * sum_{g in contribution i} coef_kg * val_ig for every row-owner and column-owner contribution:
-// the sample-independent part of the slice generators, computed once per evaluation (M * (ncr+ncc) * L values).
-template <typename CT>
-__global__ void k_aug_tables(const AugArgs P, int L) {
-  const int k = blockIdx.x;
-  for (int t = threadIdx.x; t < (P.ncr + P.ncc) * L; t += blockDim.x) {
-    const bool rowtab = t < P.ncr * L;
-    const int u = rowtab ? t : t - P.ncr * L;
-    const int c = u / L, lane = u % L;
-    const int* gen = rowtab ? P.r_gen : P.c_gen;
-    const cplx* val = rowtab ? P.r_val : P.c_val;
-    cplx acc = cmake(0, 0);
-    for (int i = 0; i < P.KG; ++i) {
-      const int g = gen[((size_t)c * P.KG + i) * L + lane];
-      if (g >= 0) acc = cfma(P.coef[(size_t)k * P.J + g], val[((size_t)c * P.KG + i) * L + lane], acc);
-    }
-    acc = cscale(acc, P.dt);
-    CT v;   // stored in the sweep's own type: a conversion in k_chain_aug would wait on the load it sits behind
-    v.x = acc.x; v.y = acc.y;
-    if (rowtab) ((CT*)P.p_row)[((size_t)k * P.ncr + c) * L + lane] = v;
-    else ((CT*)P.p_col)[((size_t)k * P.ncc + c) * L + lane] = v;
-  }
-}
 
 // STORE = 1: the forward sweep streams every Taylor term t_0 .. t_{q-1} of every slice to HBM and the reverse sweep
 // streams them back (cp.async, eight steps ahead of their use) instead of recomputing them:
@@ -845,6 +790,7 @@ int qocvl_aug_configure(qocvl_plan* p) {
   AUG_UP(p->d_aug_starts, st); AUG_UP(p->d_aug_targets, tg); AUG_UP(p->d_aug_pair, pair); AUG_UP(p->d_aug_wq, wq);
 #undef AUG_UP
   p->aug_n = N; p->aug_lpg = Lk; p->aug_nnz = nnz; p->aug_wmax = wmax;
+  p->h_aug_row_col = row_col; p->h_aug_col_row = col_row; p->h_aug_pair = pair;
   {
     double inv[QOCVL_QMAX + 2];
     inv[0] = 0.0;
@@ -853,6 +799,13 @@ int qocvl_aug_configure(qocvl_plan* p) {
     float invf[QOCVL_QMAX + 2];
     for (int j = 0; j < QOCVL_QMAX + 2; ++j) invf[j] = (float)inv[j];
     QCUDA(cudaMemcpyToSymbol(c_ainvf, invf, sizeof(invf)));
+  }
+  // ---- second-generation kernel (chain_rows.cu: one coupled sector per warp) whenever it takes the system
+  p->use_rows = false;
+  if (p->opt("rows", 1) != 0) {
+    const int rc = qocvl_rows_configure(p);
+    if (rc == QOCVL_OK) { p->use_aug = true; return QOCVL_OK; }
+    if (rc != QOCVL_ERR_UNSUPPORTED) return rc;
   }
   // ---- Taylor terms: streamed through HBM (STORE) when the a-priori degree cap and the device memory allow it
   const int gpw = 32 / Lk;
@@ -928,6 +881,10 @@ int qocvl_aug_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t 
   a.starts = p->d_aug_starts; a.targets = p->d_aug_targets; a.pair = p->d_aug_pair; a.wq = p->d_aug_wq;
   a.ckpt = p->d_ckpt; a.terms = p->d_ckpt; a.qs = p->aug_qs;
   a.sample_out = p->d_sample_out; a.y_partial = p->d_ypart; a.gwave = gwave;
+  if (p->use_rows) {
+    if (want_grad && !gwave) return QOCVL_ERR_ARG;
+    return qocvl_rows_launch(p, a, want_grad, st);
+  }
   if (p->c64) k_aug_tables<cplxf><<<d.n_slices, 256, 0, st>>>(a, la.L);
   else k_aug_tables<cplx><<<d.n_slices, 256, 0, st>>>(a, la.L);
   pick_aug(la.L, p->aug_wmax, la.KC, p->aug_store, p->c64 != 0)<<<p->blocks, p->threads, p->chain_smem, st>>>(a);

@@ -166,6 +166,16 @@ struct WideLayout {
   void release();
 };
 
+// Launch geometry of the sector-per-warp ensemble kernel (chain_rows.cu): roles = connected components of the stacked
+// pattern; a warp holds spw = 32 / rows samples of one role, a CTA holds G samples of every role.
+struct RowsGeom {
+  int nroles = 0, G = 0, wpc = 0, wmax = 0;
+  int rows[8] = {0}, spw[8] = {0}, w[8] = {0}, wc[8] = {0}, warp0[8] = {0}, warps[8] = {0}, parts[8] = {0};
+  size_t yoff[8] = {0}, cap = 0, total_warps = 0;
+  bool tma = true;
+  int *d_grow = nullptr, *d_lrow = nullptr;
+};
+
 struct qocvl_plan {
   qocvl_desc d;
   // qocvl_set_option: explicit per-plan tuning / cross-check switches (the library reads no environment variables)
@@ -246,6 +256,9 @@ struct qocvl_plan {
   WideLayout lwide_a;      // 8 basis columns per CTA: column sweeps of the time-parallel single-sample path
   bool use_wide_tp = false;
   bool use_aug = false;
+  bool use_rows = false;   // ... on the sector-per-warp kernel (chain_rows.cu) instead of the lane-group kernel
+  RowsGeom rg;
+  std::vector<int> h_aug_row_col, h_aug_col_row, h_aug_pair;   // host copies of the stacked pattern ([slot][L]) for chain_rows.cu
   int c64 = 0;             // qocvl_set_precision: 1 = the ensemble kernel runs in complex64 (reduced stacked system only)
   double taylor_tol() const { return c64 ? QOCVL_TAYLOR_TOL_C64 : QOCVL_TAYLOR_TOL_C128; }
   int aug_n = 0, aug_lpg = 0, aug_nnz = 0, aug_wmax = 0, aug_parts = 0, aug_qs = 0;
@@ -280,6 +293,9 @@ int qocvl_wide_configure(qocvl_plan* p);
 int qocvl_wide_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t st);
 int qocvl_aug_configure(qocvl_plan* p);
 int qocvl_aug_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t st);
+int qocvl_rows_configure(qocvl_plan* p);
+struct AugArgs;
+int qocvl_rows_launch(qocvl_plan* p, const AugArgs& a, bool want_grad, cudaStream_t st);
 int qocvl_build_lane_layout(qocvl_plan* p, const std::vector<std::complex<double>>& blocks, int n, int npad,
                             bool diag_slot, BlockLayout* out);
 int qocvl_build_csr(qocvl_plan* p, const std::vector<std::complex<double>>& blocks, CsrLayout* out);

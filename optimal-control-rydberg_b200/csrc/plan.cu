@@ -168,6 +168,8 @@ extern "C" int qocvl_plan_destroy(qocvl_plan* p) {
     cudaFree(c->crow); cudaFree(c->ceid); cudaFree(c->egen); cudaFree(c->eval);
   }
   if (p->d_tring) cudaFree(p->d_tring);
+  if (p->rg.d_grow) cudaFree(p->rg.d_grow);
+  if (p->rg.d_lrow) cudaFree(p->rg.d_lrow);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
   void* ptrs[] = {p->d_gdense, p->d_coef_const, p->d_gnorm, p->d_starts, p->d_targets, p->d_mul, p->d_add,

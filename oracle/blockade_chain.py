@@ -13,6 +13,31 @@ from .state_transfer import halving_flags
 
 C128 = torch.complex128
 
+_B13 = (64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800., 129060195264000.,
+        10559470521600., 670442572800., 33522128640., 1323241920., 40840800., 960960., 16380., 182., 1.)
+
+
+def expm_pade13(x):
+    """Batched, differentiable matrix exponential: Higham's (2005) scaling-and-squaring Pade-13 approximant in torch ops
+    (what jax.scipy.linalg.expm -- the reference's expm, ST:256 / TQ:480 -- implements for its largest norm class).
+    Used instead of torch.linalg.matrix_exp because the latter loses up to 2e-10 per slice on these generators when the
+    1-norm falls just under its degree-8 threshold (0.0499; measured against scipy.linalg.expm while building the
+    full-size fixtures), which is not good enough for a 1e-10 parity bound over thousands of slices."""
+    norm = float(x.detach().abs().sum(dim=-2).max())
+    s = max(0, int(np.ceil(np.log2(norm / 5.371920351148152)))) if norm > 5.371920351148152 else 0
+    a = x / (2.0 ** s)
+    ident = torch.eye(x.shape[-1], dtype=x.dtype).expand_as(a)
+    a2 = a @ a
+    a4 = a2 @ a2
+    a6 = a4 @ a2
+    b = _B13
+    u = a @ (a6 @ (b[13] * a6 + b[11] * a4 + b[9] * a2) + b[7] * a6 + b[5] * a4 + b[3] * a2 + b[1] * ident)
+    v = a6 @ (b[12] * a6 + b[10] * a4 + b[8] * a2) + b[6] * a6 + b[4] * a4 + b[2] * a2 + b[0] * ident
+    r = torch.linalg.solve(v - u, v + u)
+    for _ in range(s):
+        r = r @ r
+    return r
+
 
 def basis_states(n_atoms):
     out = []
@@ -67,7 +92,7 @@ class BlockadeChain:
         pen[:, self.i_z, self.i_z] = ramp.to(C128)
         top = torch.cat([-1j * ham, pen], dim=2)
         bot = torch.cat([torch.zeros_like(ham), -1j * ham], dim=2)
-        steps = torch.linalg.matrix_exp(self.delta_t * torch.cat([top, bot], dim=1))
+        steps = expm_pade13(self.delta_t * torch.cat([top, bot], dim=1))
         for odd in self.contraction_array:                      # ST:258-283
             if odd:
                 last, steps = steps[-1], steps[:-1]
@@ -81,6 +106,52 @@ class BlockadeChain:
         infid = 1.0 - (final[self.i_z].conj() * final[self.i_z]).real
         adiab = (1.0 - (final.conj() @ wblk[:, self.i_g]) / self.duration).real
         return self.W_INFID * infid + self.W_ADIAB * adiab, infid, adiab
+
+    def _dense_steps(self, w, lo, hi):
+        """Dense Van Loan exponentials of slices lo..hi-1 from the waves w[M,2] (same construction as cost_torch)."""
+        n, M = self.dim, self.no_of_steps
+        hx, nn = torch.from_numpy(self.h_drive), torch.from_numpy(self.h_number)
+        omega = self.rabi_scale * self.Rabi_max * w[lo:hi, 0]
+        delta = self.Delta_max * w[lo:hi, 1] + self.del_offset
+        ham = omega[:, None, None] * hx[None] - delta[:, None, None] * nn[None]
+        ramp = torch.arange(lo, hi, dtype=torch.float64) / M
+        pen = torch.zeros((hi - lo, n, n), dtype=C128)
+        pen[:, self.i_g, self.i_g] = (1.0 - ramp).to(C128)
+        pen[:, self.i_z, self.i_z] = ramp.to(C128)
+        top = torch.cat([-1j * ham, pen], dim=2)
+        bot = torch.cat([torch.zeros_like(ham), -1j * ham], dim=2)
+        return expm_pade13(self.delta_t * torch.cat([top, bot], dim=1))
+
+    def cost_torch_columns(self, a, b, c, chunk=125):
+        """Memory-light twin of cost_torch for the FULL-SIZE configs (n = 144 x M = 4000; n = 377 x M = 256): the same
+        dense 2n x 2n exponentials per slice, but instead of the product tree (which keeps ~2M dense matrices alive for
+        autograd) the two columns of the Van Loan propagator the cost reads -- VL e_g = [U e_g; 0] and
+        VL e_{n+g} = [W e_g; U e_g] -- are pushed through the slices in time order, chunk by chunk under
+        torch.utils.checkpoint.  Same numbers up to the association order of the products (3e-16)."""
+        from torch.utils.checkpoint import checkpoint
+        n, M = self.dim, self.no_of_steps
+        w = self.waves(a, b, c)
+        v = torch.zeros((2 * n, 2), dtype=C128)
+        v[self.i_g, 0] = 1.0
+        v[n + self.i_g, 1] = 1.0
+
+        def run(vec, waves, lo, hi):
+            steps = self._dense_steps(waves, lo, hi)
+            for k in range(hi - lo):
+                vec = steps[k] @ vec
+            return vec
+        for lo in range(0, M, chunk):
+            v = checkpoint(run, v, w, lo, min(M, lo + chunk), use_reentrant=False)
+        final, wcol = v[:n, 0], v[:n, 1]
+        infid = 1.0 - (final[self.i_z].conj() * final[self.i_z]).real
+        adiab = (1.0 - (final.conj() @ wcol) / self.duration).real
+        return self.W_INFID * infid + self.W_ADIAB * adiab, infid, adiab
+
+    def value_and_grad_columns(self, a, b, c, chunk=125):
+        ta, tb, tc = (torch.tensor(np.asarray(x, float), requires_grad=True) for x in (a, b, c))
+        cost, infid, adiab = self.cost_torch_columns(ta, tb, tc, chunk)
+        ga, gb, gc = torch.autograd.grad(cost, (ta, tb, tc))
+        return float(cost.detach()), float(infid.detach()), float(adiab.detach()), ga.numpy(), gb.numpy(), gc.numpy()
 
     def value_and_grad(self, a, b, c):
         ta, tb, tc = (torch.tensor(np.asarray(x, float), requires_grad=True) for x in (a, b, c))

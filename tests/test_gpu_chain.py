@@ -233,22 +233,33 @@ def test_reduced_system_with_general_noise_tables(kind):
     assert rel(outs[1][3:], outs[0][3:]) < 1e-10
 
 
-def test_reduced_system_streamed_terms_equal_recomputed_terms():
-    """STORE mode (Taylor terms streamed through HBM) against the checkpoint + recompute mode of the same kernel."""
+@pytest.mark.parametrize("n_samples", [70, 3, 1])
+def test_reduced_system_kernels_and_modes_agree(n_samples):
+    """The two ensemble kernels of the reduced stacked system -- chain_rows.cu (one coupled sector per warp, shuffles,
+    unscaled Taylor powers; Taylor terms streamed back by bulk TMA, by per-thread cp.async, or recomputed) and
+    chain_aug.cu (one sample per lane group; streamed or recomputed) -- on a ragged ensemble: five independent code
+    paths, same numbers."""
     from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL
     po, a, b, c = otq.notebook02_setup(seed=4, n_gauss=6, nt=77)
     args = (6, 77, po.padding, 50e6, po.delta_t, 0.0, po.Vint, po.Delta_i_val, po.Rabi_i_val, po.Rabi_r_val, otq.GAMMAS_CZ)
-    dl, rs = ensemble.robust_cz_noise(70)
+    dl, rs = ensemble.robust_cz_noise(n_samples)
+    variants = [({"tp": 0}, "reduced_rows_streamed"), ({"tp": 0, "rows_tma": 0}, "reduced_rows_streamed"),
+                ({"tp": 0, "store": 0}, "reduced_rows"), ({"tp": 0, "rows": 0}, "reduced_stacked_streamed"),
+                ({"tp": 0, "rows": 0, "store": 0}, "reduced_stacked")]
     outs = []
-    for flag in (0, 1):
-        with env(QOCVL_STORE=flag):
+    for kv, path in variants:
+        with env(**kv):
             prop = PropagatorVL(*args)
             prop.set_ensemble(del_total=dl, rabi_scale=rs)
             outs.append(np_(prop.cost_and_grad_packed(prop._pack(a, b, c))).copy())
+            cost_only = float(prop.target(a, b, c))
             prop._plan.check()
-            assert prop._plan.chain_info()["path"] == ("reduced_stacked_streamed" if flag else "reduced_stacked")
-    assert np.abs(outs[1][:3] - outs[0][:3]).max() < 1e-14
-    assert rel(outs[1][3:], outs[0][3:]) < 1e-11
+            assert prop._plan.chain_info()["path"] == path, kv
+            assert abs(cost_only - outs[-1][0]) < 1e-14
+    for out, (kv, _) in zip(outs[1:], variants[1:]):
+        assert np.abs(out[:3] - outs[0][:3]).max() < 1e-13, kv
+        assert rel(out[3:], outs[0][3:]) < 1e-10, kv
+    assert np.array_equal(outs[0], outs[1])          # bulk TMA vs cp.async: same arithmetic, bit for bit
 
 
 def _chain_ensemble(n_atoms, nt, n_samples, seed=11, n_gauss=6):

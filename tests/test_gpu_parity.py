@@ -376,7 +376,7 @@ def test_device_side_optimiser_loop_on_an_ensemble():
     hist_g, ag, bg, cg = prop.optimize(a, b, c, num_iters=12, lr=0.02)
     hist_e, ae, be, ce = prop.optimize(a, b, c, num_iters=12, lr=0.02, use_graph=False)
     prop._plan.check()
-    assert prop._plan.chain_info()["path"] == "reduced_stacked_streamed"
+    assert prop._plan.chain_info()["path"] == "reduced_rows_streamed"
     assert torch.equal(hist_g, hist_e) and torch.equal(ag, ae) and torch.equal(cg, ce)      # deterministic kernels
     assert float(hist_g[-1]) < float(hist_g[0])
 
