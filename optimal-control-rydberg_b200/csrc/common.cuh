@@ -172,7 +172,7 @@ struct RowsGeom {
   int nroles = 0, G = 0, wpc = 0, wmax = 0;
   int rows[8] = {0}, spw[8] = {0}, w[8] = {0}, wc[8] = {0}, warp0[8] = {0}, warps[8] = {0}, parts[8] = {0};
   size_t yoff[8] = {0}, cap = 0, total_warps = 0;
-  bool tma = true;
+  bool tma = true, split = false;
   int *d_grow = nullptr, *d_lrow = nullptr;
 };
 
