@@ -173,8 +173,8 @@ def max_over_ranks(x, device, world):
 
 def kernel_name(info, dtype):
     streamed = int(info["path"].endswith("streamed"))
-    if info["path"].startswith("reduced_rows"):
-        return f"k_chain_rows<{info['slots']},{info['classes']},{streamed},{int(bool(streamed))}>"
+    if info["path"] == "reduced_duo":
+        return "k_duo_reverse"
     if info["path"].startswith("reduced_stacked"):
         return (f"k_chain_aug<{'float' if dtype == 'c64' else 'double'},{info['lanes']},{info['slots']},"
                 f"{info['classes']},{streamed}>")

@@ -133,9 +133,9 @@ int qocvl_cost_grad_from_wave(qocvl_plan* plan, const double* wave, double* out3
 int qocvl_set_shard(qocvl_plan* plan, int global_samples);
 
 /* Explicit per-plan switches; the library reads NO environment variables.  value < 0 restores the automatic choice.
- * Names: "aug" (0 = do not use the reduced stacked system), "rows" (0 = lane-per-row-group kernel of chain_aug.cu instead
- * of the sector-per-warp kernel of chain_rows.cu), "rows_tma" (0 = plain loads instead of bulk-TMA for the Taylor stream),
- * "store" (0 = recompute the Taylor terms instead of streaming them through HBM), "spb" (samples per CTA), "nofold"
+ * Names: "aug" (0 = do not use the reduced stacked system), "duo" (0 = lane-group kernel of chain_aug.cu instead
+ * of the two-lanes-per-sector kernels of chain_duo.cu), "duo_wpc" (warps per CTA of those kernels), "store" (lane-group
+ * kernel: 0 = recompute the Taylor terms instead of streaming them through HBM), "spb" (samples per CTA), "nofold"
  * (1 = no orbit folding), "force_big" (1 = rows-strided kernel for any n), "qcap" (Taylor-degree cap), "tp" (0 = no
  * time-parallel single-sample path), "tp_chunk" (slices per chunk), "tlocal", "wide" (0 = no samples-minor kernel),
  * "wide_store", "wide_spc", "wide_threads", "strong_chunks" (slice-axis chunks per sample of the ensemble path).
@@ -174,8 +174,8 @@ double qocvl_hbm_bytes_per_call(const qocvl_plan* plan, int with_grad);
 /* Launch geometry after configuration, out[8] = {path: 0 lane-per-row / 1 reduced stacked system / 2 time-parallel
  * single sample / 3 rows-strided big-n / 4 reduced stacked system with the Taylor terms streamed through HBM /
  * 5 samples-minor big-n ensemble kernel with streamed Taylor terms / 6 the same with recomputed terms / 7 its
- * time-parallel single-sample form / 8 reduced stacked system on the sector-per-warp kernel (chain_rows.cu) with the
- * Taylor terms streamed through HBM (bulk TMA) / 9 the same with recomputed terms (8-9: lanes = samples per CTA);
+ * time-parallel single-sample form / 8, 9 retired / 10 reduced stacked system on the two-lanes-per-sector kernels
+ * (chain_duo.cu; lanes = lanes per sample, slots = widest entry list of a lane);
  * rows per sample; lanes per sample (paths 5-6: samples per CTA); off-diagonal slots per row (5-6: generator blocks
  * with off-diagonal entries); multiplier classes per entry (5-6: generator blocks with diagonal entries);
  * non-zeros of the propagated system; threads per CTA; CTAs}. */

@@ -152,8 +152,8 @@ extern "C" double qocvl_hbm_bytes_per_call(const qocvl_plan* p, int with_grad) {
       slots = 0;
       for (int v : q) slots += v;
     }
-    if (p->use_rows)     // one 512-byte slab per warp and term (30 of 32 lanes live on the CZ system)
-      return 2.0 * slots * (double)p->rg.total_warps * 32.0 * sizeof(cplx) + 2.0 * (double)p->ypart_bytes;
+    if (p->use_duo)      // checkpoints only: one 1.5 KB slab (3 rows x 32 lanes) per warp and slice, written once, read once
+      return 2.0 * (double)p->ckpt_bytes + 2.0 * (double)p->ypart_bytes;
     return 2.0 * slots * S * p->aug_n * (p->c64 ? sizeof(cplxf) : sizeof(cplx)) + 2.0 * (double)p->ypart_bytes;
   }
   if (p->use_wide) {   // streamed Taylor terms (or checkpoints + the recompute ring) written once, read once
@@ -183,10 +183,10 @@ extern "C" int qocvl_chain_info(const qocvl_plan* p, int* out) {
   out[3] = p->use_aug ? (p->aug_wmax <= 3 ? 3 : 6) : 4;
   out[4] = p->use_aug ? p->la.KC : p->lu.kc;
   if (p->use_aug && p->aug_store) out[0] = 4;
-  if (p->use_aug && p->use_rows) {       // sector-per-warp kernel: samples per CTA, deepest slot loop of any role
-    out[0] = p->aug_store ? 8 : 9;
-    out[2] = p->rg.G;
-    out[3] = p->rg.wmax <= 3 ? 3 : 6;
+  if (p->use_aug && p->use_duo) {        // two lanes per coupled sector: lanes per sample, widest entry list of a lane
+    out[0] = 10;
+    out[2] = 2 * p->duo.nroles;
+    out[3] = p->duo.numax;
   }
   out[5] = p->use_aug ? p->aug_nnz : (p->n_live + 1) * p->cu.nnz + p->cw.nnz;
   if (p->use_wide) {

@@ -790,7 +790,7 @@ int qocvl_aug_configure(qocvl_plan* p) {
   AUG_UP(p->d_aug_starts, st); AUG_UP(p->d_aug_targets, tg); AUG_UP(p->d_aug_pair, pair); AUG_UP(p->d_aug_wq, wq);
 #undef AUG_UP
   p->aug_n = N; p->aug_lpg = Lk; p->aug_nnz = nnz; p->aug_wmax = wmax;
-  p->h_aug_row_col = row_col; p->h_aug_col_row = col_row; p->h_aug_pair = pair;
+  p->h_aug_pair = pair;
   {
     double inv[QOCVL_QMAX + 2];
     inv[0] = 0.0;
@@ -800,10 +800,12 @@ int qocvl_aug_configure(qocvl_plan* p) {
     for (int j = 0; j < QOCVL_QMAX + 2; ++j) invf[j] = (float)inv[j];
     QCUDA(cudaMemcpyToSymbol(c_ainvf, invf, sizeof(invf)));
   }
-  // ---- second-generation kernel (chain_rows.cu: one coupled sector per warp) whenever it takes the system
-  p->use_rows = false;
-  if (p->opt("rows", 1) != 0) {
-    const int rc = qocvl_rows_configure(p);
+  // ---- third-generation kernels (chain_duo.cu: two lanes per coupled sector) whenever they take the system
+  p->use_duo = false;
+  p->h_aug_gen = aug; p->h_aug_cls = cls; p->h_aug_hasadd = has_add; p->h_aug_mcls = mcls; p->h_aug_wq = wq;
+  p->h_aug_st = st; p->h_aug_tg = tg;
+  if (p->opt("duo", 1) != 0) {
+    const int rc = qocvl_duo_configure(p);
     if (rc == QOCVL_OK) { p->use_aug = true; return QOCVL_OK; }
     if (rc != QOCVL_ERR_UNSUPPORTED) return rc;
   }
@@ -881,10 +883,7 @@ int qocvl_aug_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t 
   a.starts = p->d_aug_starts; a.targets = p->d_aug_targets; a.pair = p->d_aug_pair; a.wq = p->d_aug_wq;
   a.ckpt = p->d_ckpt; a.terms = p->d_ckpt; a.qs = p->aug_qs;
   a.sample_out = p->d_sample_out; a.y_partial = p->d_ypart; a.gwave = gwave;
-  if (p->use_rows) {
-    if (want_grad && !gwave) return QOCVL_ERR_ARG;
-    return qocvl_rows_launch(p, a, want_grad, st);
-  }
+  if (p->use_duo) return qocvl_duo_launch(p, want_grad, gwave, st);
   if (p->c64) k_aug_tables<cplxf><<<d.n_slices, 256, 0, st>>>(a, la.L);
   else k_aug_tables<cplx><<<d.n_slices, 256, 0, st>>>(a, la.L);
   pick_aug(la.L, p->aug_wmax, la.KC, p->aug_store, p->c64 != 0)<<<p->blocks, p->threads, p->chain_smem, st>>>(a);

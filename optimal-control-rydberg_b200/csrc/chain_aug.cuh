@@ -1,5 +1,4 @@
-// chain_aug.cuh -- what the two ensemble kernels of the reduced stacked system share (chain_aug.cu: one sample per
-// lane group; chain_rows.cu: one coupled sector per warp): the argument block and the per-slice entry tables.
+// chain_aug.cuh -- argument block and per-slice entry tables of the lane-group ensemble kernel (chain_aug.cu).
 #pragma once
 #include "common.cuh"
 

@@ -1,0 +1,430 @@
+// chain_duo.cu -- host side of the two-lanes-per-sector ensemble kernels (chain_duo.cuh): the search for the cut of
+// every role, the tables, the launch sequence; and the three small kernels around the sweeps
+// (k_duo_tables, k_duo_terminal, k_duo_reduce).
+#include "chain_duo.cuh"
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+typedef std::complex<double> zc;
+
+// P_u(k) = dt * sum_g coef_kg * val_ug for every (role, lane type, slot): the sample-independent part of the slice
+// generators, once per evaluation.  One block per slice.
+__global__ void k_duo_tables(const DuoArgs Q, const unsigned long long* __restrict__ ent_out,
+                             const int* __restrict__ ent_stride) {
+  const int k = blockIdx.x;
+  for (int d = threadIdx.x; d < Q.ntot; d += blockDim.x) {
+    cplx acc = cmake(0.0, 0.0);
+    for (int i = 0; i < Q.KG; ++i) {
+      const int g = Q.ent_gen[d * Q.KG + i];
+      if (g >= 0) acc = cfma(Q.coef[(size_t)k * Q.J + g], Q.ent_val[d * Q.KG + i], acc);
+    }
+    ((cplx*)Q.tab)[ent_out[d] + (size_t)k * ent_stride[d]] = cscale(acc, Q.dt);
+  }
+}
+
+// Per-sample cost (TQ:549-574 / ST:285-310 on the stacked vector) and terminal cotangent lam = d cost / d conj(Z),
+// scaled by 1 / S_global (ensemble mean).  One thread per sample.
+__global__ void k_duo_terminal(const DuoArgs Q) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= Q.S) return;
+  const cplx* z = Q.zfin + (size_t)s * Q.N;
+  cplx dsum = Q.d_const;
+  double qp = 0.0;
+  for (int r = 0; r < Q.N; ++r) {
+    const cplx zr = z[r];
+    dsum = cfma_conj(Q.targets[r], zr, dsum);
+    const int pr = Q.pair[r];
+    if (pr >= 0) {
+      const cplx zp = z[pr];
+      qp += Q.wq[r] * (zr.x * zp.x + zr.y * zp.y);
+    }
+  }
+  const double infid = 1.0 - (dsum.x * dsum.x + dsum.y * dsum.y) * Q.inv_fid_norm;
+  const double adiab = 1.0 - qp * Q.inv_duration;
+  Q.sample_out[(size_t)s * 3 + 0] = Q.w_infid * infid + Q.w_adiab * adiab;
+  Q.sample_out[(size_t)s * 3 + 1] = infid;
+  Q.sample_out[(size_t)s * 3 + 2] = adiab;
+  if (!Q.want_grad) return;
+  const double ws = Q.inv_samples, ca = -0.5 * Q.w_adiab * Q.inv_duration * ws;
+  for (int r = 0; r < Q.N; ++r) {
+    cplx l = cscale(cmul(dsum, Q.targets[r]), -Q.w_infid * Q.inv_fid_norm * ws);
+    const int pr = Q.pair[r];
+    if (pr >= 0) l = cadd(l, cscale(z[pr], ca * Q.wq[Q.N + r]));   // q rows receive -(wa/2T) p, p rows -(wa/2T) q
+    Q.lam[(size_t)s * Q.N + r] = l;
+  }
+}
+
+// gwave[k][c] = 2 dt Re sum_x Ybar_x(k) * sum_{g in x} val_xg * dcoef_kgc, with Ybar summed over the per-warp partials
+// in a fixed order (deterministic).  One block of 256 threads per slice: 64 descriptor slots x 4 interleaved parts.
+__global__ void __launch_bounds__(256) k_duo_reduce(const DuoArgs Q, const unsigned long long* __restrict__ ent_ysrc,
+                                                     const int* __restrict__ ent_ystride, const int* __restrict__ ent_ywarps) {
+  __shared__ cplx part[4][64];
+  __shared__ double red[QOCVL_MAX_CHAN][64];
+  const int k = blockIdx.x, d = threadIdx.x & 63, pt = threadIdx.x >> 6;
+  const bool on = d < Q.ntot && Q.ent_x[d] >= 0;
+  cplx y0 = cmake(0.0, 0.0), y1 = cmake(0.0, 0.0);
+  if (on) {
+    const int stride = ent_ystride[d], nw = ent_ywarps[d];
+    const cplx* src = Q.ypart + ent_ysrc[d] + (size_t)k * stride;
+    const size_t wstride = (size_t)Q.M * stride;
+    int wv = pt;
+    for (; wv + 4 < nw; wv += 8) {
+      y0 = cadd(y0, src[(size_t)wv * wstride]);
+      y1 = cadd(y1, src[(size_t)(wv + 4) * wstride]);
+    }
+    if (wv < nw) y0 = cadd(y0, src[(size_t)wv * wstride]);
+  }
+  part[pt][d] = cadd(y0, y1);
+  __syncthreads();
+  if (pt == 0) {
+    double term[QOCVL_MAX_CHAN];
+#pragma unroll
+    for (int c = 0; c < QOCVL_MAX_CHAN; ++c) term[c] = 0.0;
+    if (on) {
+      const cplx y = cadd(cadd(part[0][d], part[1][d]), cadd(part[2][d], part[3][d]));
+      for (int i = 0; i < Q.KG; ++i) {
+        const int g = Q.ent_gen[d * Q.KG + i];
+        if (g < 0) continue;
+        const cplx yv = cmul(y, Q.ent_val[d * Q.KG + i]);
+#pragma unroll
+        for (int c = 0; c < QOCVL_MAX_CHAN; ++c)
+          if (c < Q.C) {
+            const cplx dc = Q.dcoef[((size_t)k * Q.J + g) * Q.C + c];
+            term[c] += yv.x * dc.x - yv.y * dc.y;
+          }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < QOCVL_MAX_CHAN; ++c) red[c][d] = term[c];
+  }
+  __syncthreads();
+  if (threadIdx.x < Q.C) {
+    double acc = 0.0;
+    for (int i = 0; i < 64; ++i) acc += red[threadIdx.x][i];
+    Q.gwave[(size_t)k * Q.C + threadIdx.x] = 2.0 * Q.dt * acc;
+  }
+}
+
+__global__ void __launch_bounds__(128, 1) k_duo_forward(const DuoArgs Q) {
+  extern __shared__ __align__(128) unsigned char duo_smem[];
+  const int role = blockIdx.x % Q.nroles;
+  switch (Q.variant[role]) {
+    case 0: duo_forward<DuoPat0>(Q, role, duo_smem); break;
+    case 1: duo_forward<DuoPat1>(Q, role, duo_smem); break;
+    default: duo_forward<DuoPat2>(Q, role, duo_smem); break;
+  }
+}
+
+__global__ void __launch_bounds__(128, 1) k_duo_reverse(const DuoArgs Q) {
+  extern __shared__ __align__(128) unsigned char duo_smem[];
+  const int role = blockIdx.x % Q.nroles;
+  switch (Q.variant[role]) {
+    case 0: duo_reverse<DuoPat0>(Q, role, duo_smem); break;
+    case 1: duo_reverse<DuoPat1>(Q, role, duo_smem); break;
+    default: duo_reverse<DuoPat2>(Q, role, duo_smem); break;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Host
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct PatInfo { unsigned tm, cm; int s0, s1, nt, nc; };
+const PatInfo kPat[DUO_NVAR] = {
+    {(unsigned)DuoPat0::TM, (unsigned)DuoPat0::CM, DuoPat0::S0, DuoPat0::S1, DuoPat0::NT, DuoPat0::NC},
+    {(unsigned)DuoPat1::TM, (unsigned)DuoPat1::CM, DuoPat1::S0, DuoPat1::S1, DuoPat1::NT, DuoPat1::NC},
+    {(unsigned)DuoPat2::TM, (unsigned)DuoPat2::CM, DuoPat2::S0, DuoPat2::S1, DuoPat2::NT, DuoPat2::NC}};
+
+// compact slot index of a bit inside a mask
+int slot_of(unsigned mask, int bit) { return duo_popc(mask & ((1u << bit) - 1u)); }
+}  // namespace
+
+void DuoState::release() {
+  void* ptrs[] = {d_tab, d_con_m, d_con_a, d_srow, d_ent_gen, d_ent_val, d_ent_x, d_ent_out, d_ent_stride, d_ent_ysrc,
+                  d_ent_ystride, d_ent_ywarps, d_starts, d_targets, d_pair, d_wq, d_zfin, d_lam};
+  for (void* q : ptrs) if (q) cudaFree(q);
+  *this = DuoState();
+}
+
+// Called by qocvl_aug_configure once the stacked system exists on the host (p->h_aug_*).  Returns
+// QOCVL_ERR_UNSUPPORTED when some role does not split into two triples coupled through <= 2 rows each (or the system
+// needs two multiplier classes per entry / complex64): the older kernels then run.
+int qocvl_duo_configure(qocvl_plan* p) {
+  DuoState& D = p->duo;
+  D.release();
+  p->use_duo = false;
+  if (p->c64) return QOCVL_ERR_UNSUPPORTED;
+  const int N = p->aug_n, J = p->d.n_gen, M = p->d.n_slices, S = p->n_samples;
+  const std::vector<zc>& aug = p->h_aug_gen;
+  if ((int)aug.size() != J * N * N || N < 1) return QOCVL_ERR_UNSUPPORTED;
+  auto AG = [&](int j, int a, int b) { return aug[((size_t)j * N + a) * N + b]; };
+  std::vector<char> pat((size_t)N * N, 0);
+  for (int j = 0; j < J; ++j)
+    for (int a = 0; a < N; ++a)
+      for (int b = 0; b < N; ++b)
+        if (std::abs(AG(j, a, b)) > 0.0) pat[(size_t)a * N + b] = 1;
+  // ---- roles: connected components of the pattern (undirected)
+  std::vector<int> parent(N);
+  std::iota(parent.begin(), parent.end(), 0);
+  auto find = [&](int x) { while (parent[x] != x) x = parent[x] = parent[parent[x]]; return x; };
+  for (int a = 0; a < N; ++a)
+    for (int b = 0; b < N; ++b)
+      if (pat[(size_t)a * N + b]) {
+        const int ra = find(a), rb = find(b);
+        if (ra != rb) parent[std::max(ra, rb)] = std::min(ra, rb);
+      }
+  std::vector<std::vector<int>> comp;
+  {
+    std::vector<int> comp_of(N, -1);
+    for (int r = 0; r < N; ++r) {
+      const int root = find(r);
+      if (comp_of[root] < 0) { comp_of[root] = (int)comp.size(); comp.emplace_back(); }
+      comp[comp_of[root]].push_back(r);
+    }
+  }
+  // small components may share a role (two of <= 3 rows: one lane each, no coupling)
+  std::sort(comp.begin(), comp.end(), [](const std::vector<int>& a, const std::vector<int>& b) { return a.size() > b.size(); });
+  for (size_t i = 0; i < comp.size(); ++i) {
+    if (comp[i].size() > 6) return QOCVL_ERR_UNSUPPORTED;
+    if (comp[i].size() > 3) continue;
+    for (size_t j2 = i + 1; j2 < comp.size(); ++j2)
+      if (comp[j2].size() <= 3) {
+        // keep them apart with padding rows so that the search below puts one component per lane
+        std::vector<int> merged = comp[i];
+        merged.resize(3, -1);
+        merged.insert(merged.end(), comp[j2].begin(), comp[j2].end());
+        comp[i] = merged;
+        comp.erase(comp.begin() + j2);
+        break;
+      }
+  }
+  const int nroles = (int)comp.size();
+  if (nroles > DUO_MAXR) return QOCVL_ERR_UNSUPPORTED;
+  // ---- cut and order of every role: cheapest compiled pattern that covers some arrangement of its rows
+  std::vector<int> srow((size_t)nroles * 6, -1);
+  int variant[DUO_MAXR] = {0};
+  for (int r = 0; r < nroles; ++r) {
+    std::vector<int> rows = comp[r];
+    rows.resize(6, -1);
+    std::sort(rows.begin(), rows.end());
+    auto nz = [&](int a, int b) { return a >= 0 && b >= 0 && pat[(size_t)a * N + b]; };
+    int best_v = -1, best_cost = 1 << 30;
+    std::vector<int> best_perm;
+    std::vector<int> perm = rows;
+    do {
+      for (int v = 0; v < DUO_NVAR; ++v) {
+        const PatInfo& pi = kPat[v];
+        const int cost = pi.nt + pi.nc;
+        if (cost >= best_cost) continue;
+        const int snd[2] = {pi.s0, pi.s1};
+        bool ok = true;
+        for (int t = 0; t < 2 && ok; ++t) {
+          const int* mine = &perm[t * 3];
+          const int* other = &perm[(1 - t) * 3];
+          for (int i = 0; i < 3 && ok; ++i) {
+            for (int ip = 0; ip < 3 && ok; ++ip)
+              if (nz(mine[i], mine[ip]) && !((pi.tm >> (3 * i + ip)) & 1u)) ok = false;
+            for (int ip = 0; ip < 3 && ok; ++ip) {
+              if (!nz(mine[i], other[ip])) continue;
+              int g = -1, h = -1;
+              for (int x = 0; x < 2; ++x) { if (snd[x] == i) g = x; if (snd[x] == ip) h = x; }
+              if (g < 0 || h < 0 || !((pi.cm >> (2 * g + h)) & 1u)) ok = false;
+            }
+          }
+        }
+        if (ok) { best_cost = cost; best_v = v; best_perm = perm; }
+      }
+    } while (std::next_permutation(perm.begin(), perm.end()));
+    if (best_v < 0) return QOCVL_ERR_UNSUPPORTED;
+    variant[r] = best_v;
+    for (int i = 0; i < 6; ++i) srow[(size_t)r * 6 + i] = best_perm[i];
+  }
+  // ---- generator classes (as in chain_aug.cu): one class per entry is all this kernel takes
+  const std::vector<int>& cls = p->h_aug_cls;
+  const std::vector<char>& has_add = p->h_aug_hasadd;
+  const int ncls = p->la.ncls;
+  if ((int)cls.size() != J || (int)p->h_aug_mcls.size() != S * ncls) return QOCVL_ERR_STATE;
+  // ---- descriptors: (role, lane type, slot) -> stacked (row, col), generators, class, additive generators
+  struct Desc { int role, type, u, a, b, x; };
+  std::vector<Desc> desc;
+  int KG = 1;
+  int nu[DUO_MAXR] = {0}, nx[DUO_MAXR] = {0}, ent0[DUO_MAXR] = {0};
+  for (int r = 0; r < nroles; ++r) {
+    const PatInfo& pi = kPat[variant[r]];
+    nu[r] = pi.nt + 2 * pi.nc;
+    nx[r] = pi.nt + pi.nc;
+    ent0[r] = (int)desc.size();
+    const int snd[2] = {pi.s0, pi.s1};
+    for (int t = 0; t < 2; ++t) {
+      const int* mine = &srow[(size_t)r * 6 + t * 3];
+      const int* other = &srow[(size_t)r * 6 + (1 - t) * 3];
+      std::vector<Desc> lane(nu[r]);
+      for (int i = 0; i < 3; ++i)
+        for (int ip = 0; ip < 3; ++ip)
+          if ((pi.tm >> (3 * i + ip)) & 1u) {
+            const int u = slot_of(pi.tm, 3 * i + ip);
+            lane[u] = {r, t, u, mine[i], mine[ip], u};
+          }
+      for (int g = 0; g < 2; ++g)
+        for (int h = 0; h < 2; ++h)
+          if ((pi.cm >> (2 * g + h)) & 1u) {
+            const int c = slot_of(pi.cm, 2 * g + h);
+            lane[pi.nt + c] = {r, t, pi.nt + c, mine[snd[g]], other[snd[h]], -1};                     // row owner
+            lane[pi.nt + pi.nc + c] = {r, t, pi.nt + pi.nc + c, other[snd[g]], mine[snd[h]], pi.nt + c};   // column owner
+          }
+      desc.insert(desc.end(), lane.begin(), lane.end());
+    }
+  }
+  const int ntot = (int)desc.size();
+  if (ntot > 64) return QOCVL_ERR_UNSUPPORTED;          // k_duo_reduce: 64 descriptor slots
+  for (const Desc& d : desc) {
+    if (d.a < 0 || d.b < 0) continue;
+    int cnt = 0, c0 = -1;
+    for (int j = 0; j < J; ++j)
+      if (std::abs(AG(j, d.a, d.b)) > 0.0) {
+        ++cnt;
+        if (c0 < 0) c0 = cls[j];
+        else if (cls[j] != c0) return QOCVL_ERR_UNSUPPORTED;   // two multiplier classes in one entry
+      }
+    KG = std::max(KG, cnt);
+  }
+  std::vector<int> ent_gen((size_t)ntot * KG, -1), ent_x(ntot, -1), ent_stride(ntot), ent_ystride(ntot), ent_ywarps(ntot);
+  std::vector<cplx> ent_val((size_t)ntot * KG, cmake(0, 0));
+  std::vector<unsigned long long> ent_out(ntot), ent_ysrc(ntot);
+  const int warps_per_role = (S + DUO_SPW - 1) / DUO_SPW;
+  size_t tab_off[DUO_MAXR], con_off[DUO_MAXR], y_off[DUO_MAXR], warp0[DUO_MAXR];
+  size_t tab_total = 0, con_total = 0, y_total = 0;
+  for (int r = 0; r < nroles; ++r) {
+    tab_off[r] = tab_total; tab_total += (size_t)M * 2 * nu[r];
+    con_off[r] = con_total; con_total += (size_t)2 * nu[r] * S;
+    y_off[r] = y_total; y_total += (size_t)warps_per_role * M * 2 * nx[r];
+    warp0[r] = (size_t)r * warps_per_role;
+  }
+  std::vector<double> con_m(con_total, 0.0);
+  std::vector<cplx> con_a(con_total, cmake(0, 0));
+  for (int i = 0; i < ntot; ++i) {
+    const Desc& d = desc[i];
+    ent_x[i] = d.x;
+    ent_out[i] = tab_off[d.role] + (size_t)d.type * nu[d.role] + d.u;
+    ent_stride[i] = 2 * nu[d.role];
+    ent_ysrc[i] = y_off[d.role] + (size_t)d.type * nx[d.role] + (d.x >= 0 ? d.x : 0);
+    ent_ystride[i] = 2 * nx[d.role];
+    ent_ywarps[i] = warps_per_role;
+    if (d.a < 0 || d.b < 0) continue;
+    int cnt = 0, c0 = -1;
+    for (int j = 0; j < J; ++j) {
+      const zc v = AG(j, d.a, d.b);
+      if (std::abs(v) == 0.0) continue;
+      ent_gen[(size_t)i * KG + cnt] = j;
+      ent_val[(size_t)i * KG + cnt] = cmake(v.real(), v.imag());
+      c0 = cls[j];
+      ++cnt;
+    }
+    const size_t cbase = con_off[d.role] + ((size_t)d.type * nu[d.role] + d.u) * S;
+    for (int s = 0; s < S; ++s) {
+      con_m[cbase + s] = c0 >= 0 ? p->h_aug_mcls[(size_t)s * ncls + c0] : 0.0;
+      zc acc(0, 0);
+      for (int j = 0; j < J; ++j)
+        if (has_add[j] && std::abs(AG(j, d.a, d.b)) > 0.0) {
+          const cplx ad = p->h_add[(size_t)s * J + j];
+          acc += zc(ad.x, ad.y) * AG(j, d.a, d.b);
+        }
+      con_a[cbase + s] = cmake(acc.real() * p->d.dt, acc.imag() * p->d.dt);
+    }
+  }
+  // ---- geometry: warps per CTA so that the reverse kernel's shared memory fits
+  int numax = 0;
+  for (int r = 0; r < nroles; ++r) numax = std::max(numax, nu[r]);
+  int wpc = 4;
+  while (wpc > 1 && (size_t)wpc * duo_smem_layout(numax, p->qcap, true).total > 220 * 1024) wpc >>= 1;
+  if ((size_t)wpc * duo_smem_layout(numax, p->qcap, true).total > 220 * 1024) return QOCVL_ERR_UNSUPPORTED;
+  if (p->has_opt("duo_wpc")) wpc = std::max(1, std::min(wpc, p->opt("duo_wpc")));
+  D.nroles = nroles; D.wpc = wpc; D.KG = KG; D.ntot = ntot; D.warps_per_role = warps_per_role;
+  D.smem_fwd = (size_t)wpc * duo_smem_layout(numax, p->qcap, false).total;
+  D.smem_rev = (size_t)wpc * duo_smem_layout(numax, p->qcap, true).total;
+  D.numax = numax;
+  for (int r = 0; r < nroles; ++r) {
+    D.variant[r] = variant[r]; D.nu[r] = nu[r]; D.nx[r] = nx[r]; D.ent0[r] = ent0[r];
+    D.tab_off[r] = tab_off[r]; D.con_off[r] = con_off[r]; D.y_off[r] = y_off[r]; D.warp0[r] = warp0[r];
+  }
+  p->blocks = nroles * ((warps_per_role + wpc - 1) / wpc);
+  p->threads = wpc * 32;
+  p->spb = wpc * DUO_SPW; p->groups = p->spb;
+  // ---- upload
+#define DUO_UP(ptr, vec)                                                                               \
+  do {                                                                                                 \
+    QCUDA(cudaMalloc((void**)&(ptr), std::max<size_t>(1, (vec).size()) * sizeof((vec)[0])));            \
+    if (!(vec).empty())                                                                                \
+      QCUDA(cudaMemcpy((ptr), (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice));  \
+  } while (0)
+  DUO_UP(D.d_con_m, con_m); DUO_UP(D.d_con_a, con_a); DUO_UP(D.d_srow, srow);
+  DUO_UP(D.d_ent_gen, ent_gen); DUO_UP(D.d_ent_val, ent_val); DUO_UP(D.d_ent_x, ent_x);
+  DUO_UP(D.d_ent_out, ent_out); DUO_UP(D.d_ent_stride, ent_stride);
+  DUO_UP(D.d_ent_ysrc, ent_ysrc); DUO_UP(D.d_ent_ystride, ent_ystride); DUO_UP(D.d_ent_ywarps, ent_ywarps);
+  {
+    std::vector<cplx> st(p->h_aug_st.begin(), p->h_aug_st.begin() + N), tg(p->h_aug_tg.begin(), p->h_aug_tg.begin() + N);
+    std::vector<int> pr(p->h_aug_pair.begin(), p->h_aug_pair.begin() + N);
+    const int Lk = (int)p->h_aug_wq.size() / 2;
+    std::vector<double> wq(2 * (size_t)N);
+    for (int r = 0; r < N; ++r) { wq[r] = p->h_aug_wq[r]; wq[N + r] = p->h_aug_wq[Lk + r]; }
+    DUO_UP(D.d_starts, st); DUO_UP(D.d_targets, tg); DUO_UP(D.d_pair, pr); DUO_UP(D.d_wq, wq);
+  }
+#undef DUO_UP
+  QCUDA(cudaMalloc((void**)&D.d_tab, tab_total * sizeof(cplx)));
+  QCUDA(cudaMalloc((void**)&D.d_zfin, (size_t)S * N * sizeof(cplx)));
+  QCUDA(cudaMalloc((void**)&D.d_lam, (size_t)S * N * sizeof(cplx)));
+  if (p->d_ckpt) { cudaFree(p->d_ckpt); p->d_ckpt = nullptr; p->bytes -= p->ckpt_bytes; p->ckpt_bytes = 0; }
+  if (p->d_ypart) { cudaFree(p->d_ypart); p->d_ypart = nullptr; p->bytes -= p->ypart_bytes; p->ypart_bytes = 0; }
+  p->ckpt_bytes = (size_t)nroles * warps_per_role * M * 96 * sizeof(cplx);
+  p->ypart_bytes = y_total * sizeof(cplx);
+  QCUDA(cudaMalloc((void**)&p->d_ckpt, p->ckpt_bytes));
+  QCUDA(cudaMalloc((void**)&p->d_ypart, std::max<size_t>(16, p->ypart_bytes)));
+  p->bytes += p->ckpt_bytes + p->ypart_bytes;
+  QCUDA(cudaFuncSetAttribute(k_duo_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_fwd));
+  QCUDA(cudaFuncSetAttribute(k_duo_reverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_rev));
+  p->aug_store = false;
+  p->aug_parts = nroles * warps_per_role;
+  p->n_parts = 0;
+  p->qcap_apriori = p->qcap;
+  p->use_duo = true;
+  return QOCVL_OK;
+}
+
+int qocvl_duo_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t st) {
+  const DuoState& D = p->duo;
+  const qocvl_desc& d = p->d;
+  if (want_grad && !gwave) return QOCVL_ERR_ARG;
+  DuoArgs q;
+  memset(&q, 0, sizeof(q));
+  q.M = d.n_slices; q.S = p->n_samples; q.C = d.n_chan; q.J = d.n_gen; q.N = p->aug_n;
+  q.nroles = D.nroles; q.wpc = D.wpc; q.qcap = p->qcap_apriori; q.want_grad = want_grad ? 1 : 0; q.KG = D.KG;
+  q.ntot = D.ntot;
+  for (int r = 0; r < D.nroles; ++r) {
+    q.variant[r] = D.variant[r]; q.nu[r] = D.nu[r]; q.nx[r] = D.nx[r]; q.warps[r] = D.warps_per_role;
+    q.tab_off[r] = D.tab_off[r]; q.con_off[r] = D.con_off[r]; q.y_off[r] = D.y_off[r]; q.warp0[r] = D.warp0[r];
+    q.ent0[r] = D.ent0[r];
+  }
+  q.dt = d.dt; q.inv_duration = 1.0 / d.duration; q.w_infid = d.w_infid; q.w_adiab = d.w_adiab;
+  q.inv_fid_norm = 1.0 / d.fid_norm; q.inv_samples = 1.0 / (double)p->global_samples;
+  q.d_const = p->d_const;
+  q.tab = D.d_tab; q.con_m = D.d_con_m; q.con_a = D.d_con_a; q.srow = D.d_srow;
+  q.ent_gen = D.d_ent_gen; q.ent_val = D.d_ent_val; q.ent_x = D.d_ent_x;
+  q.coef = p->d_coef; q.dcoef = p->d_dcoef; q.qdeg = p->d_qdeg;
+  q.starts = D.d_starts; q.targets = D.d_targets; q.pair = D.d_pair; q.wq = D.d_wq;
+  q.ckpt = p->d_ckpt; q.zfin = D.d_zfin; q.lam = D.d_lam; q.ypart = p->d_ypart;
+  q.sample_out = p->d_sample_out; q.gwave = gwave;
+  q.ifact[0] = 1.0;
+  for (int j = 1; j < QOCVL_QMAX + 2; ++j) q.ifact[j] = q.ifact[j - 1] / (double)j;
+  k_duo_tables<<<d.n_slices, 64, 0, st>>>(q, D.d_ent_out, D.d_ent_stride);
+  k_duo_forward<<<p->blocks, p->threads, D.smem_fwd, st>>>(q);
+  k_duo_terminal<<<(q.S + 127) / 128, 128, 0, st>>>(q);
+  p->launches += 3;
+  if (want_grad) {
+    k_duo_reverse<<<p->blocks, p->threads, D.smem_rev, st>>>(q);
+    k_duo_reduce<<<d.n_slices, 256, 0, st>>>(q, D.d_ent_ysrc, D.d_ent_ystride, D.d_ent_ywarps);
+    p->launches += 2;
+  }
+  QCUDA(cudaGetLastError());
+  return QOCVL_OK;
+}

@@ -1,0 +1,431 @@
+// chain_duo.cuh -- the ensemble hot kernels, third generation: every coupled sector of the reduced stacked system on
+// TWO lanes, one warp per scheduler, everything in registers.
+//
+// Same numbers as chain_aug.cu (ST:247-302 / TQ:460-567 and the reverse pass of jax.value_and_grad,
+// TQ:592) on the same reduced stacked system Xaug (chain_aug.cu builds it: reachability + orbit folding; CZ: 12 rows,
+// 36 non-zeros).  What changes is the mapping, driven by the profiles of the older kernels (issue slots
+// ~50 %, FP64 pipe 24-45 % busy, `wait` / `short_scoreboard` the top stalls: every Taylor step paid an exchange round
+// trip per ROW, and half of the issued DFMAs were lane padding):
+//   * A role (connected component of the stacked pattern; CZ: {U|10>, W|10>} and {U|11>}, 6 rows each) is cut into two
+//     TRIPLES of rows, one lane each: a lane keeps its 3 vector elements, its 3x3 own block and the <= 2x2 block that
+//     couples it to the partner lane in REGISTERS.  The sparsity of both blocks is a compile-time mask, so a Taylor
+//     step is a fully unrolled, branch-free sequence of DFMAs (CZ: 11 / 9 complex multiply-adds per lane and step
+//     for 9 useful on average) and the only communication is ONE xor-1 shuffle of the two "send" rows per step.
+//     The host finds the cut and the row order by brute force (<= 720 permutations per role) and picks the cheapest
+//     compiled pattern that covers it; a system with a sector that does not split this way falls back to chain_aug.cu.
+//   * 16 samples x 2 lanes per warp, one role per CTA (role = blockIdx % nroles, uniform for the compiler), 4 warps
+//     per CTA: at 4096 samples that is 512 warps = one warp per scheduler on 128 SMs.  A lone warp per scheduler can
+//     keep the FP64 pipe busy because the unrolled step carries 6 independent accumulation chains.
+//   * Unscaled Taylor powers (u_j = X u_{j-1}, z' = sum_j u_j / j!) and the matching adjoint w_j = tbar_j / j!
+//     (w_{j-1} = lam / (j-1)! + X^dag w_j,  Xbar = sum_j conj(w_j) u_{j-1}^T): one DFMA pair with
+//     a constant operand per row and step instead of a scale and an add.
+//   * HBM carries only the slice checkpoints z_k (192 B per sample and slice, written by the forward kernel, read
+//     back by the reverse kernel): the older kernels streamed every Taylor term (5.2-5.9 KB per unit, 40+ GB per
+//     evaluation), which capped them at the HBM roofline.  The reverse kernel recomputes u_0 .. u_{q-1} into a
+//     per-warp shared-memory slab instead (one mat-vec per term).
+//   * TMA staging of slice batches (north_star (3)): the per-slice entry tables (sample independent, L2 resident) and
+//     the checkpoints of DUO_BT consecutive slices arrive in shared memory through 1-D bulk copies
+//     (cp.async.bulk.shared::cluster.global + mbarrier complete_tx), two stages per warp, issued by one lane one batch
+//     ahead; there is no barrier of any kind between warps.
+//   * The per-sample Xbar entries are scaled by the entry's class multiplier and summed over the warp's 16 samples
+//     with xor shuffles; two lanes per warp write the sums (<= 13 complex per lane type and slice), k_duo_reduce adds
+//     the warps in a fixed order and contracts with d coef / d wave.  Deterministic: no atomics anywhere.
+// Forward sweep, terminal cost / cotangent and reverse sweep are three launches (the cost couples the roles of a
+// sample; the checkpoints live in HBM anyway), plus the table kernel before and the reduction after.
+#pragma once
+#include "common.cuh"
+#include <type_traits>
+
+#define DUO_MAXR 4      // roles per system
+#define DUO_BT 4        // slices per staged batch
+#define DUO_SPW 16      // samples per warp
+#define DUO_NVAR 3      // compiled patterns
+
+struct DuoArgs {
+  int M, S, C, J, N, nroles, wpc, qcap, want_grad, KG;
+  int variant[DUO_MAXR], nu[DUO_MAXR], nx[DUO_MAXR], warps[DUO_MAXR];
+  unsigned long long tab_off[DUO_MAXR], con_off[DUO_MAXR], y_off[DUO_MAXR], warp0[DUO_MAXR];
+  int ent0[DUO_MAXR];   // first (role, type, slot) descriptor of the role
+  int ntot;             // descriptors in total: sum_r 2 nu_r
+  double dt, inv_duration, w_infid, w_adiab, inv_fid_norm, inv_samples;
+  cplx d_const;
+  const cplx* tab;      // role r at tab_off[r]: [M][2 lane types][nu_r]   P_u(k) = dt sum_g coef_kg val_ug
+  const double* con_m;  // role r at con_off[r]: [2][nu_r][S]  class multiplier of the entry for sample s
+  const cplx* con_a;    //                       [2][nu_r][S]  additive-noise part of the entry
+  const int* srow;      // [nroles][2][3]  stacked row of (role, lane type, local row), -1 = padding row
+  const int* ent_gen;   // [ntot][KG] generators of a descriptor (-1 = none)
+  const cplx* ent_val;  // [ntot][KG]
+  const int* ent_x;     // [ntot] index of the descriptor among its lane type's Xbar slots, -1 = not a gradient slot
+  const cplx* coef;     // [M][J]
+  const cplx* dcoef;    // [M][J][C]
+  const int* qdeg;      // [M]
+  const cplx* starts;   // [N]
+  const cplx* targets;  // [N]
+  const int* pair;      // [N]
+  const double* wq;     // [2][N]
+  cplx* ckpt;           // [global warp][M][3][32]
+  cplx* zfin;           // [S][N]
+  cplx* lam;            // [S][N]
+  cplx* ypart;          // role r at y_off[r]: [warps_r][M][2][nx_r]
+  double* sample_out;   // [S][3]
+  double* gwave;        // [M][C]
+  double ifact[QOCVL_QMAX + 2];   // 1 / j!
+};
+
+__host__ __device__ constexpr int duo_popc(unsigned v) { return v == 0 ? 0 : (int)(v & 1u) + duo_popc(v >> 1); }
+
+// Compile-time description of a lane program: TM = 9-bit mask of the 3x3 own block (bit 3 i + i'), CM = 4-bit mask of
+// the 2x2 coupling block (bit 2 g + h: my send row g <- partner's send row h), S0 / S1 = local index of the send rows.
+// Compact slot order of a lane's entries: own block | coupling block as row owner | coupling block as column owner.
+template <int TM_, int CM_, int S0_, int S1_>
+struct DuoPat {
+  static constexpr int TM = TM_, CM = CM_, S0 = S0_, S1 = S1_;
+  static constexpr int NT = duo_popc(TM_), NC = duo_popc(CM_), NU = NT + 2 * NC, NX = NT + NC;
+  __host__ __device__ static constexpr bool ht(int i, int ip) { return (TM_ >> (3 * i + ip)) & 1; }
+  __host__ __device__ static constexpr bool hc(int g, int h) { return (CM_ >> (2 * g + h)) & 1; }
+  __host__ __device__ static constexpr int t(int i, int ip) { return duo_popc(TM_ & ((1u << (3 * i + ip)) - 1u)); }
+  __host__ __device__ static constexpr int c(int g, int h) { return duo_popc(CM_ & ((1u << (2 * g + h)) - 1u)); }
+  __host__ __device__ static constexpr int nr(int g, int h) { return NT + c(g, h); }
+  __host__ __device__ static constexpr int nc(int g, int h) { return NT + NC + c(g, h); }
+  __host__ __device__ static constexpr int send(int g) { return g == 0 ? S0_ : S1_; }
+};
+// The compiled patterns.  0: tridiagonal own block, full coupling, send rows (0, 2)  -- {U psi, W psi} of a 3-level
+// ladder (q lane / p lane; CZ role {U|10>, W|10>}, the state-transfer model).  1: tridiagonal own block, anti-diagonal
+// coupling, send rows (2, 1) -- a 6-cycle-free ladder of two chains (CZ role {U|11>} on its 6 orbit rows).
+// 2: dense own block, full coupling (anything that splits at all).
+typedef DuoPat<0x1BB, 0xF, 0, 2> DuoPat0;   // rows: {0,1} {0,1,2} {1,2}  ->  bits 0,1 | 3,4,5 | 7,8
+typedef DuoPat<0x1BB, 0x6, 2, 1> DuoPat1;
+typedef DuoPat<0x1FF, 0xF, 0, 2> DuoPat2;
+
+// compile-time loop: every index below is a constant expression, so the entry / accumulator arrays stay in registers
+template <int I, int N, class F>
+__device__ __forceinline__ void duo_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    duo_for<I + 1, N>(f);
+  }
+}
+#define DUO_I(v) decltype(v)::value
+
+// ---- small device helpers -----------------------------------------------------------------------------------------
+__device__ __forceinline__ double duo_xchg(double v) {   // partner lane's value (32-bit halves: the CUDA double overload packs with `asm volatile`, which pins the order)
+  const int lo = __shfl_xor_sync(0xffffffffu, __double2loint(v), 1);
+  const int hi = __shfl_xor_sync(0xffffffffu, __double2hiint(v), 1);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ cplx duo_xchg(cplx v) { return cmake(duo_xchg(v.x), duo_xchg(v.y)); }
+__device__ __forceinline__ double duo_xor(double v, int m) {
+  const int lo = __shfl_xor_sync(0xffffffffu, __double2loint(v), m);
+  const int hi = __shfl_xor_sync(0xffffffffu, __double2hiint(v), m);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ unsigned duo_s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void duo_bar_init(unsigned bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void duo_bar_expect(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void duo_bulk(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void duo_bar_wait(unsigned bar, unsigned parity) {
+  unsigned done = 0;
+  while (!done)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+
+// y = X x on my rows: own block, then the coupling block on the partner's send rows (one exchange per step)
+template <class PT>
+__device__ __forceinline__ void duo_mv(const cplx (&e)[PT::NU], const cplx (&x)[3], cplx (&y)[3]) {
+  cplx h[2];
+  h[0] = duo_xchg(x[PT::S0]);
+  h[1] = duo_xchg(x[PT::S1]);
+  duo_for<0, 3>([&](auto i_) {
+    constexpr int i = DUO_I(i_);
+    cplx acc = cmake(0.0, 0.0);
+    duo_for<0, 3>([&](auto ip_) {
+      constexpr int ip = DUO_I(ip_);
+      if constexpr (PT::ht(i, ip)) {
+        constexpr bool first = (PT::TM & ((1u << (3 * i + ip)) - 1u) & (7u << (3 * i))) == 0u;
+        if constexpr (first) acc = cmul(e[PT::t(i, ip)], x[ip]);
+        else acc = cfma(e[PT::t(i, ip)], x[ip], acc);
+      }
+    });
+    y[i] = acc;
+  });
+  duo_for<0, 4>([&](auto gh_) {
+    constexpr int g = DUO_I(gh_) >> 1, hh = DUO_I(gh_) & 1;
+    if constexpr (PT::hc(g, hh)) y[PT::send(g)] = cfma(e[PT::nr(g, hh)], h[hh], y[PT::send(g)]);
+  });
+}
+
+// per-warp shared-memory carve-up (bytes), shared by host and device
+struct DuoSmem {
+  int tab, ck, bars, con_m, con_a, us, total;
+};
+__host__ __device__ inline DuoSmem duo_smem_layout(int nu, int qcap, bool reverse) {
+  DuoSmem s;
+  int o = 0;
+  s.tab = o; o += 2 * DUO_BT * 2 * nu * (int)sizeof(cplx);
+  s.ck = o; o += reverse ? 2 * DUO_BT * 3 * 32 * (int)sizeof(cplx) : 0;
+  s.bars = o; o += 16;
+  s.con_a = o; o += nu * 32 * (int)sizeof(cplx);
+  s.con_m = o; o += nu * 32 * (int)sizeof(double);
+  s.us = o; o += reverse ? qcap * 3 * 32 * (int)sizeof(cplx) : 0;
+  s.total = o;
+  return s;
+}
+
+// =====================================================================================================================
+// Forward sweep of one warp: 16 samples x 2 lanes of role `role`.
+// =====================================================================================================================
+template <class PT>
+__device__ __forceinline__ void duo_forward(const DuoArgs& Q, const int role, unsigned char* smem_raw) {
+  constexpr int NU = PT::NU;
+  const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // uniform for the compiler
+  const int type = lane & 1, sl = lane >> 1;
+  const int wg = (blockIdx.x / Q.nroles) * Q.wpc + warp;          // warp of this role
+  if (wg >= Q.warps[role]) return;
+  const int sample = wg * DUO_SPW + sl;
+  const bool live = sample < Q.S;
+  const int sm = live ? sample : Q.S - 1;
+  const DuoSmem L = duo_smem_layout(NU, Q.qcap, false);
+  unsigned char* base = smem_raw + (size_t)warp * L.total;
+  const cplx* s_tab = (const cplx*)(base + L.tab);
+  cplx* s_a = (cplx*)(base + L.con_a) + lane;
+  double* s_m = (double*)(base + L.con_m) + lane;
+  const unsigned bar0 = duo_s32(base + L.bars), tab0 = duo_s32(base + L.tab);
+  const unsigned row_bytes = 2u * NU * sizeof(cplx);              // both lane types of one slice
+  const cplx* gtab = Q.tab + Q.tab_off[role];
+  const int nb = (Q.M + DUO_BT - 1) / DUO_BT;
+  auto issue = [&](int b) {
+    const int cnt = min(DUO_BT, Q.M - b * DUO_BT);
+    const unsigned bar = bar0 + (b & 1) * 8, bytes = cnt * row_bytes;
+    duo_bar_expect(bar, bytes);
+    duo_bulk(tab0 + (b & 1) * DUO_BT * row_bytes, gtab + (size_t)b * DUO_BT * 2 * NU, bytes, bar);
+  };
+  if (lane == 0) {
+    duo_bar_init(bar0);
+    duo_bar_init(bar0 + 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    issue(0);
+    if (nb > 1) issue(1);
+  }
+  // per-sample constants of my entries: class multiplier and additive-noise part
+  {
+    const double* gm = Q.con_m + Q.con_off[role] + (size_t)type * NU * Q.S + sm;
+    const cplx* ga = Q.con_a + Q.con_off[role] + (size_t)type * NU * Q.S + sm;
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      s_m[u * 32] = gm[(size_t)u * Q.S];
+      s_a[u * 32] = ga[(size_t)u * Q.S];
+    }
+  }
+  int srow[3];
+  cplx z[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    srow[i] = Q.srow[(role * 2 + type) * 3 + i];
+    z[i] = srow[i] >= 0 ? Q.starts[srow[i]] : cmake(0.0, 0.0);
+  }
+  __syncwarp();
+  cplx* ck = Q.ckpt + ((size_t)(Q.warp0[role] + wg) * Q.M) * 96 + lane;
+  int q_next = __ldg(Q.qdeg);
+  for (int b = 0; b < nb; ++b) {
+    duo_bar_wait(bar0 + (b & 1) * 8, (b >> 1) & 1);
+    const int cnt = min(DUO_BT, Q.M - b * DUO_BT);
+    for (int kk = 0; kk < cnt; ++kk) {
+      const int k = b * DUO_BT + kk;
+      const int q = q_next;
+      if (k + 1 < Q.M) q_next = __ldg(Q.qdeg + k + 1);
+      const cplx* row = s_tab + ((size_t)((b & 1) * DUO_BT + kk) * 2 + type) * NU;
+      cplx e[NU];
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const cplx pv = row[u], av = s_a[u * 32];
+        const double mv = s_m[u * 32];
+        e[u] = cmake(fma(mv, pv.x, av.x), fma(mv, pv.y, av.y));
+      }
+      if (Q.want_grad) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ck[((size_t)k * 3 + i) * 32] = z[i];
+      }
+      cplx x[3] = {z[0], z[1], z[2]};
+      for (int j = 1; j <= q; ++j) {
+        cplx y[3];
+        duo_mv<PT>(e, x, y);
+        const double cj = Q.ifact[j];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          x[i] = y[i];
+          z[i].x = fma(cj, y[i].x, z[i].x);
+          z[i].y = fma(cj, y[i].y, z[i].y);
+        }
+      }
+    }
+    __syncwarp();                                          // every lane is done with this stage
+    if (lane == 0 && b + 2 < nb) issue(b + 2);
+  }
+  if (live) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      if (srow[i] >= 0) Q.zfin[(size_t)sample * Q.N + srow[i]] = z[i];
+  }
+}
+
+// =====================================================================================================================
+// Reverse sweep of one warp: recompute the Taylor powers of slice k from its checkpoint, run the adjoint recurrence,
+// accumulate Xbar on my entries, emit the warp's sums.
+// =====================================================================================================================
+template <class PT>
+__device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, unsigned char* smem_raw) {
+  constexpr int NU = PT::NU, NX = PT::NX, NT = PT::NT;
+  const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int type = lane & 1, sl = lane >> 1;
+  const int wg = (blockIdx.x / Q.nroles) * Q.wpc + warp;
+  if (wg >= Q.warps[role]) return;
+  const int sample = wg * DUO_SPW + sl;
+  const bool live = sample < Q.S;
+  const int sm = live ? sample : Q.S - 1;
+  const DuoSmem L = duo_smem_layout(NU, Q.qcap, true);
+  unsigned char* base = smem_raw + (size_t)warp * L.total;
+  const cplx* s_tab = (const cplx*)(base + L.tab);
+  const cplx* s_ck = (const cplx*)(base + L.ck) + lane;
+  cplx* s_a = (cplx*)(base + L.con_a) + lane;
+  double* s_m = (double*)(base + L.con_m) + lane;
+  cplx* s_u = (cplx*)(base + L.us) + lane;
+  const unsigned bar0 = duo_s32(base + L.bars), tab0 = duo_s32(base + L.tab), ck0 = duo_s32(base + L.ck);
+  const unsigned row_bytes = 2u * NU * sizeof(cplx), ck_bytes = 96u * sizeof(cplx);
+  const cplx* gtab = Q.tab + Q.tab_off[role];
+  const cplx* gck = Q.ckpt + ((size_t)(Q.warp0[role] + wg) * Q.M) * 96;
+  const int nb = (Q.M + DUO_BT - 1) / DUO_BT;
+  // batch b covers slices [b BT, b BT + cnt); the sweep visits the batches downwards: visit v = nb - 1 - b
+  auto issue = [&](int b) {
+    const int v = nb - 1 - b, cnt = min(DUO_BT, Q.M - b * DUO_BT);
+    const unsigned bar = bar0 + (v & 1) * 8;
+    duo_bar_expect(bar, cnt * (row_bytes + ck_bytes));
+    duo_bulk(tab0 + (v & 1) * DUO_BT * row_bytes, gtab + (size_t)b * DUO_BT * 2 * NU, cnt * row_bytes, bar);
+    duo_bulk(ck0 + (v & 1) * DUO_BT * ck_bytes, gck + (size_t)b * DUO_BT * 96, cnt * ck_bytes, bar);
+  };
+  if (lane == 0) {
+    duo_bar_init(bar0);
+    duo_bar_init(bar0 + 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    issue(nb - 1);
+    if (nb > 1) issue(nb - 2);
+  }
+  {
+    const double* gm = Q.con_m + Q.con_off[role] + (size_t)type * NU * Q.S + sm;
+    const cplx* ga = Q.con_a + Q.con_off[role] + (size_t)type * NU * Q.S + sm;
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      s_m[u * 32] = gm[(size_t)u * Q.S];
+      s_a[u * 32] = ga[(size_t)u * Q.S];
+    }
+  }
+  cplx w[3];                                               // running cotangent of my rows
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int sr = Q.srow[(role * 2 + type) * 3 + i];
+    w[i] = (sr >= 0 && live) ? Q.lam[(size_t)sample * Q.N + sr] : cmake(0.0, 0.0);
+  }
+  __syncwarp();
+  cplx* yout = Q.ypart + Q.y_off[role] + ((size_t)wg * Q.M) * 2 * NX + (size_t)type * NX;
+  int q_next = __ldg(Q.qdeg + Q.M - 1);
+  for (int v = 0; v < nb; ++v) {
+    const int b = nb - 1 - v;
+    duo_bar_wait(bar0 + (v & 1) * 8, (v >> 1) & 1);
+    const int cnt = min(DUO_BT, Q.M - b * DUO_BT);
+    for (int kk = cnt - 1; kk >= 0; --kk) {
+      const int k = b * DUO_BT + kk;
+      const int q = q_next;
+      if (k > 0) q_next = __ldg(Q.qdeg + k - 1);
+      const cplx* row = s_tab + ((size_t)((v & 1) * DUO_BT + kk) * 2 + type) * NU;
+      cplx e[NU];
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const cplx pv = row[u], av = s_a[u * 32];
+        const double mv = s_m[u * 32];
+        e[u] = cmake(fma(mv, pv.x, av.x), fma(mv, pv.y, av.y));
+      }
+      // ---- recompute u_0 .. u_{q-1}
+      {
+        const cplx* zk = s_ck + (size_t)((v & 1) * DUO_BT + kk) * 96;
+        cplx x[3] = {zk[0], zk[32], zk[64]};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) s_u[i * 32] = x[i];
+        for (int j = 1; j < q; ++j) {
+          cplx y[3];
+          duo_mv<PT>(e, x, y);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            x[i] = y[i];
+            s_u[(j * 3 + i) * 32] = y[i];
+          }
+        }
+      }
+      // ---- adjoint recurrence, descending; Xbar on my own block and on the coupling block I own by column
+      cplx lamk[3], xb[NX];
+      {
+        const double cq = Q.ifact[q];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { lamk[i] = w[i]; w[i] = cscale(w[i], cq); }
+      }
+#pragma unroll
+      for (int x = 0; x < NX; ++x) xb[x] = cmake(0.0, 0.0);
+      cplx u[3] = {s_u[((q - 1) * 3 + 0) * 32], s_u[((q - 1) * 3 + 1) * 32], s_u[((q - 1) * 3 + 2) * 32]};
+      for (int j = q; j >= 1; --j) {
+        cplx wh[2];
+        wh[0] = duo_xchg(w[PT::S0]);
+        wh[1] = duo_xchg(w[PT::S1]);
+        cplx un[3];                                        // next step's powers: in flight during this step
+        {
+          const int jn = j >= 2 ? j - 2 : 0;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) un[i] = s_u[(jn * 3 + i) * 32];
+        }
+        const double cj = Q.ifact[j - 1];
+        cplx wn[3];
+        duo_for<0, 3>([&](auto i_) {
+          constexpr int i = DUO_I(i_);
+          wn[i] = cscale(lamk[i], cj);
+          duo_for<0, 3>([&](auto ip_) {
+            constexpr int ip = DUO_I(ip_);
+            if constexpr (PT::ht(ip, i)) wn[i] = cfma_conj(e[PT::t(ip, i)], w[ip], wn[i]);
+            if constexpr (PT::ht(i, ip)) xb[PT::t(i, ip)] = cfma_conj(w[i], u[ip], xb[PT::t(i, ip)]);
+          });
+        });
+        duo_for<0, 4>([&](auto gh_) {
+          constexpr int g = DUO_I(gh_) >> 1, hh = DUO_I(gh_) & 1;
+          if constexpr (PT::hc(g, hh)) {
+            wn[PT::send(hh)] = cfma_conj(e[PT::nc(g, hh)], wh[g], wn[PT::send(hh)]);
+            xb[NT + PT::c(g, hh)] = cfma_conj(wh[g], u[PT::send(hh)], xb[NT + PT::c(g, hh)]);
+          }
+        });
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { w[i] = wn[i]; u[i] = un[i]; }
+      }
+      // ---- Ybar_x = sum over the warp's samples of m_s * Xbar_x  (lanes 0 / 1 end up with the sums of their type)
+      duo_for<0, NX>([&](auto x_) {
+        constexpr int x = DUO_I(x_);
+        const double mv = s_m[(x < NT ? x : x + PT::NC) * 32];
+        cplx yv = cscale(xb[x], mv);
+#pragma unroll
+        for (int off = 2; off < 32; off <<= 1) {
+          yv.x += duo_xor(yv.x, off);
+          yv.y += duo_xor(yv.y, off);
+        }
+        if (lane < 2) yout[(size_t)k * 2 * NX + x] = yv;
+      });
+    }
+    __syncwarp();
+    if (lane == 0 && v + 2 < nb) issue(nb - 1 - (v + 2));
+  }
+}
+
+typedef void (*duo_fn)(const DuoArgs);
+duo_fn qocvl_duo_forward_kernel();
+duo_fn qocvl_duo_reverse_kernel();

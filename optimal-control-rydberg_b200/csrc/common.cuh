@@ -166,14 +166,19 @@ struct WideLayout {
   void release();
 };
 
-// Launch geometry of the sector-per-warp ensemble kernel (chain_rows.cu): roles = connected components of the stacked
-// pattern; a warp holds spw = 32 / rows samples of one role, a CTA holds G samples of every role.
-struct RowsGeom {
-  int nroles = 0, G = 0, wpc = 0, wmax = 0;
-  int rows[8] = {0}, spw[8] = {0}, w[8] = {0}, wc[8] = {0}, warp0[8] = {0}, warps[8] = {0}, parts[8] = {0};
-  size_t yoff[8] = {0}, cap = 0, total_warps = 0;
-  bool tma = true, split = false;
-  int *d_grow = nullptr, *d_lrow = nullptr;
+// Host state of the two-lanes-per-sector ensemble kernels (chain_duo.cu).
+struct DuoState {
+  int nroles = 0, wpc = 0, KG = 1, ntot = 0, warps_per_role = 0, numax = 0;
+  int variant[4] = {0}, nu[4] = {0}, nx[4] = {0}, ent0[4] = {0};
+  size_t tab_off[4] = {0}, con_off[4] = {0}, y_off[4] = {0}, warp0[4] = {0};
+  size_t smem_fwd = 0, smem_rev = 0;
+  cplx *d_tab = nullptr, *d_con_a = nullptr, *d_ent_val = nullptr, *d_starts = nullptr, *d_targets = nullptr,
+       *d_zfin = nullptr, *d_lam = nullptr;
+  double *d_con_m = nullptr, *d_wq = nullptr;
+  int *d_srow = nullptr, *d_ent_gen = nullptr, *d_ent_x = nullptr, *d_ent_stride = nullptr, *d_ent_ystride = nullptr,
+      *d_ent_ywarps = nullptr, *d_pair = nullptr;
+  unsigned long long *d_ent_out = nullptr, *d_ent_ysrc = nullptr;
+  void release();
 };
 
 struct qocvl_plan {
@@ -256,9 +261,14 @@ struct qocvl_plan {
   WideLayout lwide_a;      // 8 basis columns per CTA: column sweeps of the time-parallel single-sample path
   bool use_wide_tp = false;
   bool use_aug = false;
-  bool use_rows = false;   // ... on the sector-per-warp kernel (chain_rows.cu) instead of the lane-group kernel
-  RowsGeom rg;
-  std::vector<int> h_aug_row_col, h_aug_col_row, h_aug_pair;   // host copies of the stacked pattern ([slot][L]) for chain_rows.cu
+  bool use_duo = false;    // ... on the two-lanes-per-sector kernels (chain_duo.cu) instead of the lane-group kernel
+  DuoState duo;
+  std::vector<std::complex<double>> h_aug_gen;   // [J][aug_n][aug_n] stacked generators (host copy for chain_duo.cu)
+  std::vector<int> h_aug_cls;                    // [J] multiplier class of every generator
+  std::vector<char> h_aug_hasadd;                // [J] generator carries an additive per-sample coefficient
+  std::vector<double> h_aug_mcls, h_aug_wq;      // [S][ncls] class multipliers, [2][L] adiabaticity weights
+  std::vector<cplx> h_aug_st, h_aug_tg;          // [L] stacked start / target kets
+  std::vector<int> h_aug_pair;   // host copy of the partner rows of the stacked vector (chain_duo.cu)
   int c64 = 0;             // qocvl_set_precision: 1 = the ensemble kernel runs in complex64 (reduced stacked system only)
   double taylor_tol() const { return c64 ? QOCVL_TAYLOR_TOL_C64 : QOCVL_TAYLOR_TOL_C128; }
   int aug_n = 0, aug_lpg = 0, aug_nnz = 0, aug_wmax = 0, aug_parts = 0, aug_qs = 0;
@@ -293,9 +303,8 @@ int qocvl_wide_configure(qocvl_plan* p);
 int qocvl_wide_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t st);
 int qocvl_aug_configure(qocvl_plan* p);
 int qocvl_aug_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t st);
-int qocvl_rows_configure(qocvl_plan* p);
-struct AugArgs;
-int qocvl_rows_launch(qocvl_plan* p, const AugArgs& a, bool want_grad, cudaStream_t st);
+int qocvl_duo_configure(qocvl_plan* p);
+int qocvl_duo_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t st);
 int qocvl_build_lane_layout(qocvl_plan* p, const std::vector<std::complex<double>>& blocks, int n, int npad,
                             bool diag_slot, BlockLayout* out);
 int qocvl_build_csr(qocvl_plan* p, const std::vector<std::complex<double>>& blocks, CsrLayout* out);

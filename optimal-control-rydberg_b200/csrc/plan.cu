@@ -162,14 +162,12 @@ extern "C" int qocvl_plan_create(qocvl_plan** out, const qocvl_desc* desc, int d
 extern "C" int qocvl_plan_destroy(qocvl_plan* p) {
   if (!p) return QOCVL_OK;
   cudaSetDevice(p->device);
-  free_layout(p->lu); free_layout(p->lw); p->la.release(); p->lwide.release(); p->lwide_a.release();
+  free_layout(p->lu); free_layout(p->lw); p->la.release(); p->lwide.release(); p->lwide_a.release(); p->duo.release();
   for (CsrLayout* c : {&p->cu, &p->cw}) {
     cudaFree(c->rowptr); cudaFree(c->col); cudaFree(c->erow); cudaFree(c->colptr);
     cudaFree(c->crow); cudaFree(c->ceid); cudaFree(c->egen); cudaFree(c->eval);
   }
   if (p->d_tring) cudaFree(p->d_tring);
-  if (p->rg.d_grow) cudaFree(p->rg.d_grow);
-  if (p->rg.d_lrow) cudaFree(p->rg.d_lrow);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
   void* ptrs[] = {p->d_gdense, p->d_coef_const, p->d_gnorm, p->d_starts, p->d_targets, p->d_mul, p->d_add,
@@ -319,7 +317,7 @@ extern "C" int qocvl_set_shard(qocvl_plan* p, int global_samples) {
 // The library reads no environment variables: everything that changes a plan's behaviour is set on the plan.
 extern "C" int qocvl_set_option(qocvl_plan* p, const char* name, int value) {
   static const char* known[] = {"aug", "store", "spb", "nofold", "force_big", "qcap", "tp", "tp_chunk", "tlocal",
-                                "wide", "wide_store", "wide_spc", "wide_threads", "rows", "rows_tma", "rows_split", "strong_chunks"};
+                                "wide", "wide_store", "wide_spc", "wide_threads", "strong_chunks", "duo", "duo_wpc"};
   if (!p || !name) return QOCVL_ERR_ARG;
   bool ok = false;
   for (const char* k : known) ok = ok || strcmp(k, name) == 0;

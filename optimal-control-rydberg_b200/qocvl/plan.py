@@ -247,7 +247,8 @@ class Plan:
         info = dict(zip(keys, (int(x) for x in buf)))
         info["path"] = ("lane_per_row", "reduced_stacked", "time_parallel", "rows_strided",
                         "reduced_stacked_streamed", "samples_minor_streamed", "samples_minor_recomputed",
-                        "samples_minor_time_parallel", "reduced_rows_streamed", "reduced_rows")[info["path"]]
+                        "samples_minor_time_parallel", "reduced_rows_streamed", "reduced_rows",
+                        "reduced_duo")[info["path"]]
         return info
 
     @property

@@ -1,6 +1,6 @@
 """cfg-3 per-step time of the ensemble kernels under explicit plan options:
 
-    python profiles/rows_probe.py 4096 "" "rows_tma=0" "store=0" "spb=5" "rows=0"
+    python profiles/ensemble_probe.py 4096 "" "duo_wpc=1" "duo=0" "duo=0,store=0"
 
 Each argument after the sample count is one comma-separated option set (qocvl_set_option names); prints ms per
 cost+gradient (CUDA events, 2 warm-up + 3 timed) and the chain-kernel time."""
@@ -23,7 +23,7 @@ M = NT + 2 * pad
 rng = np.random.default_rng(0)
 a, b, c = rng.uniform(-1, 1, (NG, 5)), rng.uniform(-1, 1, (NG, 5)), rng.uniform(0, 0.5, (NG, 5))
 nrng = np.random.default_rng(1234)
-dl, eps = nrng.normal(0.0, 2 * np.pi * 0.1e6, 4096)[:S], nrng.normal(0.0, 0.01, 4096)[:S]
+dl, eps = nrng.normal(0.0, 2 * np.pi * 0.1e6, max(S, 4096))[:S], nrng.normal(0.0, 0.01, max(S, 4096))[:S]
 for spec in sets:
     kv = {k: int(v) for k, v in (item.split("=") for item in spec.split(",") if item)}
     with qocvl.options(**kv):

@@ -1,8 +1,8 @@
 """Smoke-size problems for compute-sanitizer (memcheck / racecheck / synccheck), one kernel family per case:
 
-    compute-sanitizer --tool racecheck python profiles/sanitize_case.py rows_tma
+    compute-sanitizer --tool racecheck python profiles/sanitize_case.py duo
 
-cases: rows_tma, rows_cpasync, rows_recompute (chain_rows.cu), aug, aug_recompute, aug_c64 (chain_aug.cu),
+cases: duo, duo_wpc1 (chain_duo.cu), aug, aug_recompute, aug_c64 (chain_aug.cu),
 tp (chain_small.cu time-parallel single sample), wide, wide_tp (chain_wide.cu), lindblad.
 Each case prints the cost it computed so a sanitizer run that silently did nothing is visible."""
 import os
@@ -14,7 +14,7 @@ for p in (ROOT, os.path.join(ROOT, "optimal-control-rydberg_b200")):
 import numpy as np  # noqa: E402
 import qocvl  # noqa: E402
 
-case = sys.argv[1] if len(sys.argv) > 1 else "rows_tma"
+case = sys.argv[1] if len(sys.argv) > 1 else "duo"
 GAM = [0.1, 1.0 / 118e-9, 1.0 / 1.5e-3, 1.0 / 170e-6]
 
 
@@ -51,8 +51,8 @@ if case == "lindblad":
     print("lindblad module:", [n for n, _ in inspect.getmembers(ql, inspect.isfunction)][:5])
     sys.exit(0)
 builders = {
-    "rows_tma": lambda: cz(7), "rows_cpasync": lambda: cz(7, rows_tma=0), "rows_recompute": lambda: cz(7, store=0),
-    "aug": lambda: cz(7, rows=0), "aug_recompute": lambda: cz(7, rows=0, store=0), "aug_c64": lambda: cz(7),
+    "duo": lambda: cz(7), "duo_wpc1": lambda: cz(7, duo_wpc=1),
+    "aug": lambda: cz(7, duo=0), "aug_recompute": lambda: cz(7, duo=0, store=0), "aug_c64": lambda: cz(7),
     "tp": lambda: cz(1, nt=64), "wide": lambda: chain(9), "wide_tp": lambda: chain(1, nt=80),
 }
 prop, a, b, c = builders[case]()

@@ -235,17 +235,17 @@ def test_reduced_system_with_general_noise_tables(kind):
 
 @pytest.mark.parametrize("n_samples", [70, 3, 1])
 def test_reduced_system_kernels_and_modes_agree(n_samples):
-    """The two ensemble kernels of the reduced stacked system -- chain_rows.cu (one coupled sector per warp, shuffles,
-    unscaled Taylor powers; Taylor terms streamed back by bulk TMA, by per-thread cp.async, or recomputed) and
-    chain_aug.cu (one sample per lane group; streamed or recomputed) -- on a ragged ensemble: five independent code
+    """The two ensemble kernel families of the reduced stacked system -- chain_duo.cu (two lanes per coupled sector,
+    registers only, checkpoints + recomputation, bulk-TMA staged slice batches; 4 warps or 1 warp per CTA) and
+    chain_aug.cu (one sample per lane group; Taylor terms streamed or recomputed) -- on a ragged ensemble: four code
     paths, same numbers."""
     from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL
     po, a, b, c = otq.notebook02_setup(seed=4, n_gauss=6, nt=77)
     args = (6, 77, po.padding, 50e6, po.delta_t, 0.0, po.Vint, po.Delta_i_val, po.Rabi_i_val, po.Rabi_r_val, otq.GAMMAS_CZ)
     dl, rs = ensemble.robust_cz_noise(n_samples)
-    variants = [({"tp": 0}, "reduced_rows_streamed"), ({"tp": 0, "rows_tma": 0}, "reduced_rows_streamed"),
-                ({"tp": 0, "store": 0}, "reduced_rows"), ({"tp": 0, "rows": 0}, "reduced_stacked_streamed"),
-                ({"tp": 0, "rows": 0, "store": 0}, "reduced_stacked")]
+    variants = [({"tp": 0}, "reduced_duo"), ({"tp": 0, "duo_wpc": 1}, "reduced_duo"),
+                ({"tp": 0, "duo": 0}, "reduced_stacked_streamed"),
+                ({"tp": 0, "duo": 0, "store": 0}, "reduced_stacked")]
     outs = []
     for kv, path in variants:
         with env(**kv):
@@ -259,7 +259,7 @@ def test_reduced_system_kernels_and_modes_agree(n_samples):
     for out, (kv, _) in zip(outs[1:], variants[1:]):
         assert np.abs(out[:3] - outs[0][:3]).max() < 1e-13, kv
         assert rel(out[3:], outs[0][3:]) < 1e-10, kv
-    assert np.array_equal(outs[0], outs[1])          # bulk TMA vs cp.async: same arithmetic, bit for bit
+    assert np.array_equal(outs[0], outs[1])          # CTA geometry does not change the arithmetic: bit for bit
 
 
 def _chain_ensemble(n_atoms, nt, n_samples, seed=11, n_gauss=6):

@@ -82,7 +82,7 @@ def test_cfg5_full_size_members_match_dense_oracle_fixture_including_gradient(go
         assert rel(one[3:].reshape(3, 16, 2)[0], gold["ga"][s]) < 1e-8
 
 
-@pytest.mark.parametrize("opts", [{}, {"rows": 0}], ids=["rows_kernel", "lane_group_kernel"])
+@pytest.mark.parametrize("opts", [{}, {"duo": 0}], ids=["two_lane_kernels", "lane_group_kernel"])
 def test_sample_sharding_on_the_real_plan_two_halves_equal_the_whole(opts):
     """qocvl_set_shard / global_samples on the REAL kernels: a 13-sample ensemble evaluated as two 'virtual ranks'
     (7 + 6 samples, each told the global count 13) -- the sum of the two partial results is what the single all-reduce

@@ -365,8 +365,8 @@ def test_match_amplitudes_equals_notebook05_seeding_loop():
 
 
 def test_device_side_optimiser_loop_on_an_ensemble():
-    """The same loop on a robustness ensemble: the reduced ensemble kernel (tables -> sweeps with streamed Taylor terms
-    -> fixed-order reduction) replayed from a CUDA graph must equal eager launches and must descend."""
+    """The same loop on a robustness ensemble: the reduced ensemble kernels (tables -> forward sweep -> terminal cost -> reverse
+    sweep -> fixed-order reduction) replayed from a CUDA graph must equal eager launches and must descend."""
     from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL
     po, a, b, c = otq.notebook02_setup(seed=8, n_gauss=6, nt=77)
     prop = PropagatorVL(6, 77, po.padding, 50e6, po.delta_t, 0.0, po.Vint, po.Delta_i_val, po.Rabi_i_val,
@@ -376,7 +376,7 @@ def test_device_side_optimiser_loop_on_an_ensemble():
     hist_g, ag, bg, cg = prop.optimize(a, b, c, num_iters=12, lr=0.02)
     hist_e, ae, be, ce = prop.optimize(a, b, c, num_iters=12, lr=0.02, use_graph=False)
     prop._plan.check()
-    assert prop._plan.chain_info()["path"] == "reduced_rows_streamed"
+    assert prop._plan.chain_info()["path"] == "reduced_duo"
     assert torch.equal(hist_g, hist_e) and torch.equal(ag, ae) and torch.equal(cg, ce)      # deterministic kernels
     assert float(hist_g[-1]) < float(hist_g[0])
 

@@ -147,12 +147,13 @@ def test_engine_single_optimization_step_equals_the_reference(golden_dir):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("opts", [{}, {"store": 0}, {"rows": 0}, {"rows": 0, "store": 0}],
-                         ids=["default", "recompute", "lane_groups", "lane_groups_recompute"])
-def test_cfg3_full_size_members_match_the_reference(opts, golden_dir):
+@pytest.mark.parametrize("opts,path", [({}, "reduced_duo"), ({"duo": 0}, "reduced_stacked_streamed"),
+                                       ({"duo": 0, "store": 0}, "reduced_stacked")],
+                         ids=["default", "lane_groups", "lane_groups_recompute"])
+def test_cfg3_full_size_members_match_the_reference(opts, path, golden_dir):
     """BASELINE configs[2] at its stated per-sample size (N = 16, nt = 1888, M = 2000): the ensemble kernels on the
     four members the fixture holds -- mean cost / infidelity / adiabaticity / gradient against the mean of the reference
-    source's per-member values -- with streamed and with recomputed Taylor terms, on both ensemble kernels."""
+    source's per-member values -- on the two-lane kernels (default) and, with streamed and with recomputed Taylor terms, on the older ensemble kernels."""
     import qocvl
     gold = load(golden_dir, "ref_cfg3_members")
     nominal, a, b, c = otq.notebook02_setup(seed=0, n_gauss=16, nt=1888)
@@ -163,7 +164,7 @@ def test_cfg3_full_size_members_match_the_reference(opts, golden_dir):
     prop._plan.check()
     info = prop._plan.chain_info()
     assert info["path"].startswith("reduced_"), info
-    assert info["path"].endswith("streamed") == (opts.get("store", 1) != 0), info
+    assert info["path"] == path, info
     assert abs(out[1] - gold["infid"].mean()) < TOL_FID
     assert abs(out[2] - gold["adiab"].mean()) < TOL_ADIAB and abs(out[0] - gold["cost"].mean()) < TOL_ADIAB
     g = out[3:].reshape(3, 16, 5)
