@@ -40,6 +40,10 @@
 #define DUO_BT 4        // slices per staged batch
 #define DUO_SPW 16      // samples per warp
 #define DUO_NVAR 3      // compiled patterns
+#ifndef DUO_UNROLL
+#define DUO_UNROLL 1     // unroll factor of the Taylor loops
+#endif
+constexpr int kDuoUnroll = DUO_UNROLL;
 
 struct DuoArgs {
   int M, S, C, J, N, nroles, wpc, qcap, want_grad, KG;
@@ -137,28 +141,59 @@ __device__ __forceinline__ void duo_bar_wait(unsigned bar, unsigned parity) {
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
 }
 
+// The loops below run COLUMN by column and issue, for one vector element, first every product with its real part and
+// then every product with its imaginary part: consecutive DFMAs share a source register in the same operand slot, which
+// ptxas turns into operand-reuse hits.  That matters because the FP64 pipe of a scheduler is fed one 64-bit register
+// operand per cycle (profiles/micro/dfma_operands.cu: 3.6 cycles per DFMA with three fresh operands and one warp per
+// scheduler, 2.8-2.9 with one operand reused).
+template <bool FIRST>
+__device__ __forceinline__ void duo_fma(double& acc, const double a, const double b) {
+  if constexpr (FIRST) acc = a * b;
+  else acc = fma(a, b, acc);
+}
+
 // y = X x on my rows: own block, then the coupling block on the partner's send rows (one exchange per step)
 template <class PT>
 __device__ __forceinline__ void duo_mv(const cplx (&e)[PT::NU], const cplx (&x)[3], cplx (&y)[3]) {
   cplx h[2];
   h[0] = duo_xchg(x[PT::S0]);
   h[1] = duo_xchg(x[PT::S1]);
-  duo_for<0, 3>([&](auto i_) {
-    constexpr int i = DUO_I(i_);
-    cplx acc = cmake(0.0, 0.0);
-    duo_for<0, 3>([&](auto ip_) {
-      constexpr int ip = DUO_I(ip_);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) y[i] = cmake(0.0, 0.0);
+  duo_for<0, 3>([&](auto ip_) {
+    constexpr int ip = DUO_I(ip_);
+    duo_for<0, 3>([&](auto i_) {
+      constexpr int i = DUO_I(i_);
       if constexpr (PT::ht(i, ip)) {
         constexpr bool first = (PT::TM & ((1u << (3 * i + ip)) - 1u) & (7u << (3 * i))) == 0u;
-        if constexpr (first) acc = cmul(e[PT::t(i, ip)], x[ip]);
-        else acc = cfma(e[PT::t(i, ip)], x[ip], acc);
+        duo_fma<first>(y[i].x, e[PT::t(i, ip)].x, x[ip].x);
+        duo_fma<first>(y[i].y, e[PT::t(i, ip)].y, x[ip].x);
       }
     });
-    y[i] = acc;
+    duo_for<0, 3>([&](auto i_) {
+      constexpr int i = DUO_I(i_);
+      if constexpr (PT::ht(i, ip)) {
+        y[i].x = fma(-e[PT::t(i, ip)].y, x[ip].y, y[i].x);
+        y[i].y = fma(e[PT::t(i, ip)].x, x[ip].y, y[i].y);
+      }
+    });
   });
-  duo_for<0, 4>([&](auto gh_) {
-    constexpr int g = DUO_I(gh_) >> 1, hh = DUO_I(gh_) & 1;
-    if constexpr (PT::hc(g, hh)) y[PT::send(g)] = cfma(e[PT::nr(g, hh)], h[hh], y[PT::send(g)]);
+  duo_for<0, 2>([&](auto hh_) {
+    constexpr int hh = DUO_I(hh_);
+    duo_for<0, 2>([&](auto g_) {
+      constexpr int g = DUO_I(g_);
+      if constexpr (PT::hc(g, hh)) {
+        y[PT::send(g)].x = fma(e[PT::nr(g, hh)].x, h[hh].x, y[PT::send(g)].x);
+        y[PT::send(g)].y = fma(e[PT::nr(g, hh)].y, h[hh].x, y[PT::send(g)].y);
+      }
+    });
+    duo_for<0, 2>([&](auto g_) {
+      constexpr int g = DUO_I(g_);
+      if constexpr (PT::hc(g, hh)) {
+        y[PT::send(g)].x = fma(-e[PT::nr(g, hh)].y, h[hh].y, y[PT::send(g)].x);
+        y[PT::send(g)].y = fma(e[PT::nr(g, hh)].x, h[hh].y, y[PT::send(g)].y);
+      }
+    });
   });
 }
 
@@ -254,6 +289,7 @@ __device__ __forceinline__ void duo_forward(const DuoArgs& Q, const int role, un
         for (int i = 0; i < 3; ++i) ck[((size_t)k * 3 + i) * 32] = z[i];
       }
       cplx x[3] = {z[0], z[1], z[2]};
+#pragma unroll kDuoUnroll
       for (int j = 1; j <= q; ++j) {
         cplx y[3];
         duo_mv<PT>(e, x, y);
@@ -357,6 +393,7 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
         cplx x[3] = {zk[0], zk[32], zk[64]};
 #pragma unroll
         for (int i = 0; i < 3; ++i) s_u[i * 32] = x[i];
+#pragma unroll kDuoUnroll
         for (int j = 1; j < q; ++j) {
           cplx y[3];
           duo_mv<PT>(e, x, y);
@@ -377,6 +414,7 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
 #pragma unroll
       for (int x = 0; x < NX; ++x) xb[x] = cmake(0.0, 0.0);
       cplx u[3] = {s_u[((q - 1) * 3 + 0) * 32], s_u[((q - 1) * 3 + 1) * 32], s_u[((q - 1) * 3 + 2) * 32]};
+#pragma unroll kDuoUnroll
       for (int j = q; j >= 1; --j) {
         cplx wh[2];
         wh[0] = duo_xchg(w[PT::S0]);
@@ -388,22 +426,54 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
           for (int i = 0; i < 3; ++i) un[i] = s_u[(jn * 3 + i) * 32];
         }
         const double cj = Q.ifact[j - 1];
-        cplx wn[3];
-        duo_for<0, 3>([&](auto i_) {
-          constexpr int i = DUO_I(i_);
-          wn[i] = cscale(lamk[i], cj);
-          duo_for<0, 3>([&](auto ip_) {
-            constexpr int ip = DUO_I(ip_);
-            if constexpr (PT::ht(ip, i)) wn[i] = cfma_conj(e[PT::t(ip, i)], w[ip], wn[i]);
-            if constexpr (PT::ht(i, ip)) xb[PT::t(i, ip)] = cfma_conj(w[i], u[ip], xb[PT::t(i, ip)]);
+        cplx wn[3];                                        // w_{j-1} = c_{j-1} lam + X^dag w_j  (conjugated entries)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) wn[i] = cscale(lamk[i], cj);
+        // own block, source element w[ip] at a time: X^dag w (column i of row ip) and Xbar (row ip: conj(w_ip) u_i)
+        duo_for<0, 3>([&](auto ip_) {
+          constexpr int ip = DUO_I(ip_);
+          duo_for<0, 3>([&](auto i_) {           // products with Re w[ip]
+            constexpr int i = DUO_I(i_);
+            if constexpr (PT::ht(ip, i)) {
+              wn[i].x = fma(e[PT::t(ip, i)].x, w[ip].x, wn[i].x);
+              wn[i].y = fma(-e[PT::t(ip, i)].y, w[ip].x, wn[i].y);
+              xb[PT::t(ip, i)].x = fma(w[ip].x, u[i].x, xb[PT::t(ip, i)].x);
+              xb[PT::t(ip, i)].y = fma(w[ip].x, u[i].y, xb[PT::t(ip, i)].y);
+            }
+          });
+          duo_for<0, 3>([&](auto i_) {           // products with Im w[ip]
+            constexpr int i = DUO_I(i_);
+            if constexpr (PT::ht(ip, i)) {
+              wn[i].x = fma(e[PT::t(ip, i)].y, w[ip].y, wn[i].x);
+              wn[i].y = fma(e[PT::t(ip, i)].x, w[ip].y, wn[i].y);
+              xb[PT::t(ip, i)].x = fma(w[ip].y, u[i].y, xb[PT::t(ip, i)].x);
+              xb[PT::t(ip, i)].y = fma(-w[ip].y, u[i].x, xb[PT::t(ip, i)].y);
+            }
           });
         });
-        duo_for<0, 4>([&](auto gh_) {
-          constexpr int g = DUO_I(gh_) >> 1, hh = DUO_I(gh_) & 1;
-          if constexpr (PT::hc(g, hh)) {
-            wn[PT::send(hh)] = cfma_conj(e[PT::nc(g, hh)], wh[g], wn[PT::send(hh)]);
-            xb[NT + PT::c(g, hh)] = cfma_conj(wh[g], u[PT::send(hh)], xb[NT + PT::c(g, hh)]);
-          }
+        // coupling block I own by column: rows = partner's send rows g (halo wh[g]), columns = my send rows hh
+        duo_for<0, 2>([&](auto g_) {
+          constexpr int g = DUO_I(g_);
+          duo_for<0, 2>([&](auto hh_) {
+            constexpr int hh = DUO_I(hh_);
+            if constexpr (PT::hc(g, hh)) {
+              constexpr int i = PT::send(hh);
+              wn[i].x = fma(e[PT::nc(g, hh)].x, wh[g].x, wn[i].x);
+              wn[i].y = fma(-e[PT::nc(g, hh)].y, wh[g].x, wn[i].y);
+              xb[NT + PT::c(g, hh)].x = fma(wh[g].x, u[i].x, xb[NT + PT::c(g, hh)].x);
+              xb[NT + PT::c(g, hh)].y = fma(wh[g].x, u[i].y, xb[NT + PT::c(g, hh)].y);
+            }
+          });
+          duo_for<0, 2>([&](auto hh_) {
+            constexpr int hh = DUO_I(hh_);
+            if constexpr (PT::hc(g, hh)) {
+              constexpr int i = PT::send(hh);
+              wn[i].x = fma(e[PT::nc(g, hh)].y, wh[g].y, wn[i].x);
+              wn[i].y = fma(e[PT::nc(g, hh)].x, wh[g].y, wn[i].y);
+              xb[NT + PT::c(g, hh)].x = fma(wh[g].y, u[i].y, xb[NT + PT::c(g, hh)].x);
+              xb[NT + PT::c(g, hh)].y = fma(-wh[g].y, u[i].x, xb[NT + PT::c(g, hh)].y);
+            }
+          });
         });
 #pragma unroll
         for (int i = 0; i < 3; ++i) { w[i] = wn[i]; u[i] = un[i]; }
