@@ -141,6 +141,25 @@ __device__ __forceinline__ void duo_bar_wait(unsigned bar, unsigned parity) {
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
 }
 
+#ifndef DUO_HALO_SMEM
+#define DUO_HALO_SMEM 0   // 1: the two send rows travel through a double-buffered shared-memory slot instead of shuffles
+#endif
+// h[g] = the partner lane's element S_g.  `xs` = this warp's exchange slab [2 buffers][2 rows][32 lanes], `buf` = step parity.
+template <class PT>
+__device__ __forceinline__ void duo_halo(const cplx (&x)[3], cplx (&h)[2], cplx* xs, const int buf, const int lane) {
+#if DUO_HALO_SMEM
+  cplx* slot = xs + buf * 64;
+  slot[lane] = x[PT::S0];
+  slot[32 + lane] = x[PT::S1];
+  __syncwarp();
+  h[0] = slot[lane ^ 1];
+  h[1] = slot[32 + (lane ^ 1)];
+#else
+  h[0] = duo_xchg(x[PT::S0]);
+  h[1] = duo_xchg(x[PT::S1]);
+#endif
+}
+
 // The loops below run COLUMN by column and issue, for one vector element, first every product with its real part and
 // then every product with its imaginary part: consecutive DFMAs share a source register in the same operand slot, which
 // ptxas turns into operand-reuse hits.  That matters because the FP64 pipe of a scheduler is fed one 64-bit register
@@ -154,10 +173,10 @@ __device__ __forceinline__ void duo_fma(double& acc, const double a, const doubl
 
 // y = X x on my rows: own block, then the coupling block on the partner's send rows (one exchange per step)
 template <class PT>
-__device__ __forceinline__ void duo_mv(const cplx (&e)[PT::NU], const cplx (&x)[3], cplx (&y)[3]) {
+__device__ __forceinline__ void duo_mv(const cplx (&e)[PT::NU], const cplx (&x)[3], cplx (&y)[3], cplx* xs, const int buf,
+                                       const int lane) {
   cplx h[2];
-  h[0] = duo_xchg(x[PT::S0]);
-  h[1] = duo_xchg(x[PT::S1]);
+  duo_halo<PT>(x, h, xs, buf, lane);
 #pragma unroll
   for (int i = 0; i < 3; ++i) y[i] = cmake(0.0, 0.0);
   duo_for<0, 3>([&](auto ip_) {
@@ -199,7 +218,7 @@ __device__ __forceinline__ void duo_mv(const cplx (&e)[PT::NU], const cplx (&x)[
 
 // per-warp shared-memory carve-up (bytes), shared by host and device
 struct DuoSmem {
-  int tab, ck, bars, con_m, con_a, us, total;
+  int tab, ck, bars, xs, con_m, con_a, us, total;
 };
 __host__ __device__ inline DuoSmem duo_smem_layout(int nu, int qcap, bool reverse) {
   DuoSmem s;
@@ -207,9 +226,10 @@ __host__ __device__ inline DuoSmem duo_smem_layout(int nu, int qcap, bool revers
   s.tab = o; o += 2 * DUO_BT * 2 * nu * (int)sizeof(cplx);
   s.ck = o; o += reverse ? 2 * DUO_BT * 3 * 32 * (int)sizeof(cplx) : 0;
   s.bars = o; o += 16;
+  s.xs = o; o += 2 * 2 * 32 * (int)sizeof(cplx);            // halo exchange slab (DUO_HALO_SMEM)
   s.con_a = o; o += nu * 32 * (int)sizeof(cplx);
   s.con_m = o; o += nu * 32 * (int)sizeof(double);
-  s.us = o; o += reverse ? qcap * 3 * 32 * (int)sizeof(cplx) : 0;
+  s.us = o; o += reverse ? (qcap * 96 > 14 * 33 ? qcap * 96 : 14 * 33) * (int)sizeof(cplx) : 0;   // powers | Xbar staging
   s.total = o;
   return s;
 }
@@ -232,6 +252,7 @@ __device__ __forceinline__ void duo_forward(const DuoArgs& Q, const int role, un
   const cplx* s_tab = (const cplx*)(base + L.tab);
   cplx* s_a = (cplx*)(base + L.con_a) + lane;
   double* s_m = (double*)(base + L.con_m) + lane;
+  cplx* s_x = (cplx*)(base + L.xs);
   const unsigned bar0 = duo_s32(base + L.bars), tab0 = duo_s32(base + L.tab);
   const unsigned row_bytes = 2u * NU * sizeof(cplx);              // both lane types of one slice
   const cplx* gtab = Q.tab + Q.tab_off[role];
@@ -292,7 +313,7 @@ __device__ __forceinline__ void duo_forward(const DuoArgs& Q, const int role, un
 #pragma unroll kDuoUnroll
       for (int j = 1; j <= q; ++j) {
         cplx y[3];
-        duo_mv<PT>(e, x, y);
+        duo_mv<PT>(e, x, y, s_x, j & 1, lane);
         const double cj = Q.ifact[j];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -332,6 +353,7 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
   const cplx* s_ck = (const cplx*)(base + L.ck) + lane;
   cplx* s_a = (cplx*)(base + L.con_a) + lane;
   double* s_m = (double*)(base + L.con_m) + lane;
+  cplx* s_x = (cplx*)(base + L.xs);
   cplx* s_u = (cplx*)(base + L.us) + lane;
   const unsigned bar0 = duo_s32(base + L.bars), tab0 = duo_s32(base + L.tab), ck0 = duo_s32(base + L.ck);
   const unsigned row_bytes = 2u * NU * sizeof(cplx), ck_bytes = 96u * sizeof(cplx);
@@ -369,7 +391,8 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
     w[i] = (sr >= 0 && live) ? Q.lam[(size_t)sample * Q.N + sr] : cmake(0.0, 0.0);
   }
   __syncwarp();
-  cplx* yout = Q.ypart + Q.y_off[role] + ((size_t)wg * Q.M) * 2 * NX + (size_t)type * NX;
+  cplx* yout = Q.ypart + Q.y_off[role] + ((size_t)wg * Q.M) * 2 * NX;
+  cplx* s_e = (cplx*)(base + L.us);                       // [NX][33] staging of the per-sample Xbar entries
   int q_next = __ldg(Q.qdeg + Q.M - 1);
   for (int v = 0; v < nb; ++v) {
     const int b = nb - 1 - v;
@@ -396,7 +419,7 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
 #pragma unroll kDuoUnroll
         for (int j = 1; j < q; ++j) {
           cplx y[3];
-          duo_mv<PT>(e, x, y);
+          duo_mv<PT>(e, x, y, s_x, j & 1, lane);
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             x[i] = y[i];
@@ -417,8 +440,7 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
 #pragma unroll kDuoUnroll
       for (int j = q; j >= 1; --j) {
         cplx wh[2];
-        wh[0] = duo_xchg(w[PT::S0]);
-        wh[1] = duo_xchg(w[PT::S1]);
+        duo_halo<PT>(w, wh, s_x, j & 1, lane);
         cplx un[3];                                        // next step's powers: in flight during this step
         {
           const int jn = j >= 2 ? j - 2 : 0;
@@ -478,18 +500,27 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
 #pragma unroll
         for (int i = 0; i < 3; ++i) { w[i] = wn[i]; u[i] = un[i]; }
       }
-      // ---- Ybar_x = sum over the warp's samples of m_s * Xbar_x  (lanes 0 / 1 end up with the sums of their type)
+      // ---- Ybar_x = sum over the warp's samples of m_s * Xbar_x, through shared memory (the slab of the Taylor powers
+      //      is free now): a shuffle tree would cost 16 SHFL per number, and an SM moves only ~0.5-0.75 SHFL per clock
+      //      (profiles/micro/latency.cu) -- it was 10 % of the reverse sweep.  Fixed summation order: deterministic.
+      __syncwarp();                                        // every lane is done with its powers
       duo_for<0, NX>([&](auto x_) {
         constexpr int x = DUO_I(x_);
         const double mv = s_m[(x < NT ? x : x + PT::NC) * 32];
-        cplx yv = cscale(xb[x], mv);
-#pragma unroll
-        for (int off = 2; off < 32; off <<= 1) {
-          yv.x += duo_xor(yv.x, off);
-          yv.y += duo_xor(yv.y, off);
-        }
-        if (lane < 2) yout[(size_t)k * 2 * NX + x] = yv;
+        s_e[x * 33 + lane] = cscale(xb[x], mv);
       });
+      __syncwarp();
+      if (lane < 2 * NX) {                                 // lane = 2 x + lane type: sum its 16 samples
+        const cplx* src = s_e + (lane >> 1) * 33 + (lane & 1);
+        cplx p0 = src[0], p1 = src[2], p2 = src[4], p3 = src[6];
+#pragma unroll
+        for (int sl2 = 4; sl2 < 16; sl2 += 4) {
+          p0 = cadd(p0, src[2 * sl2]); p1 = cadd(p1, src[2 * sl2 + 2]);
+          p2 = cadd(p2, src[2 * sl2 + 4]); p3 = cadd(p3, src[2 * sl2 + 6]);
+        }
+        yout[((size_t)k * 2 + (lane & 1)) * NX + (lane >> 1)] = cadd(cadd(p0, p1), cadd(p2, p3));
+      }
+      __syncwarp();                                        // before the next slice's powers overwrite the slab
     }
     __syncwarp();
     if (lane == 0 && v + 2 < nb) issue(nb - 1 - (v + 2));
