@@ -503,12 +503,13 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
       // ---- Ybar_x = sum over the warp's samples of m_s * Xbar_x, through shared memory (the slab of the Taylor powers
       //      is free now): a shuffle tree would cost 16 SHFL per number, and an SM moves only ~0.5-0.75 SHFL per clock
       //      (profiles/micro/latency.cu) -- it was 10 % of the reverse sweep.  Fixed summation order: deterministic.
-      __syncwarp();                                        // every lane is done with its powers
-      duo_for<0, NX>([&](auto x_) {
-        constexpr int x = DUO_I(x_);
-        const double mv = s_m[(x < NT ? x : x + PT::NC) * 32];
-        s_e[x * 33 + lane] = cscale(xb[x], mv);
+      duo_for<0, NX>([&](auto x_) {                       // (all multiplier loads before the first store: the
+        constexpr int x = DUO_I(x_);                       //  compiler cannot reorder them across possibly aliasing stores)
+        xb[x] = cscale(xb[x], s_m[(x < NT ? x : x + PT::NC) * 32]);
       });
+      __syncwarp();                                        // every lane is done with its powers
+#pragma unroll
+      for (int x = 0; x < NX; ++x) s_e[x * 33 + lane] = xb[x];
       __syncwarp();
       if (lane < 2 * NX) {                                 // lane = 2 x + lane type: sum its 16 samples
         const cplx* src = s_e + (lane >> 1) * 33 + (lane & 1);
