@@ -138,7 +138,9 @@ int qocvl_set_shard(qocvl_plan* plan, int global_samples);
  * kernel: 0 = recompute the Taylor terms instead of streaming them through HBM), "spb" (samples per CTA), "nofold"
  * (1 = no orbit folding), "force_big" (1 = rows-strided kernel for any n), "qcap" (Taylor-degree cap), "tp" (0 = no
  * time-parallel single-sample path), "tp_chunk" (slices per chunk), "tlocal", "wide" (0 = no samples-minor kernel),
- * "wide_store", "wide_spc", "wide_threads", "strong_chunks" (slice-axis chunks per sample of the ensemble path).
+ * "wide_store", "wide_spc", "wide_threads", "strong_chunks" (slice-axis chunks of the time-parallel evaluation of an
+ * ensemble on the two-lane kernels; automatic: 1 above ~1500 samples, up to 16 below), "duo_nomirror" (1 = sweep every
+ * basis column of a chunk propagator).
  * They exist so that every kernel path can be cross-checked against the others on the same plan API.
  * QOCVL_ERR_ARG for an unknown name. */
 int qocvl_set_option(qocvl_plan* plan, const char* name, int value);
@@ -167,7 +169,11 @@ int qocvl_vectors_propagated(const qocvl_plan* plan);
  * QOCVL_AUG=0).  Results are identical either way: only structural zeros are skipped. */
 int qocvl_reduced_rows(const qocvl_plan* plan);
 long long qocvl_launch_count(const qocvl_plan* plan); /* kernels launched so far by this plan */
-double qocvl_flops_per_call(const qocvl_plan* plan, int with_grad); /* executed FP64 flop model */
+/* FP64 flop model of the last evaluation (useful complex multiply-adds on the non-zeros of the propagated system, 8 flops
+ * each).  with_grad: 0 = cost only; 1 = cost + gradient as EXECUTED (including the Taylor powers a checkpointing kernel
+ * recomputes in its reverse sweep); 2 = cost + gradient ALGORITHMIC (forward q + adjoint q + Xbar q per slice: what
+ * SURVEY 8(d) prices, no recomputation); 3 = the reverse sweep's share of 2 (adjoint q + Xbar q). */
+double qocvl_flops_per_call(const qocvl_plan* plan, int with_grad);
 /* Algorithmic HBM bytes of one chain evaluation: checkpoints written then read once, plus the per-warp partial
  * gradient data written by the reverse sweep and read once by the reduction (0 before the first evaluation). */
 double qocvl_hbm_bytes_per_call(const qocvl_plan* plan, int with_grad);
@@ -185,6 +191,12 @@ int qocvl_chain_info(const qocvl_plan* plan, int* out8);
  * of the most recent chain-kernel launch in milliseconds (< 0 if none was timed). */
 int qocvl_set_timing(qocvl_plan* plan, int enabled);
 double qocvl_last_chain_ms(qocvl_plan* plan);
+/* Number of concurrent slice-axis chunks of the configured path (1 = every sample is swept sequentially; > 1 = the
+ * time-parallel evaluation: chunk propagators -> combine -> per-chunk sweeps).  0 before the first evaluation. */
+int qocvl_slice_chunks(const qocvl_plan* plan);
+/* The same for one stage of the most recent timed evaluation: stage 0 = forward-sweep kernel, 1 = reverse-sweep kernel
+ * (ensemble kernels of chain_duo.cu; < 0 when the path that ran has no such stage or nothing was timed). */
+double qocvl_last_stage_ms(qocvl_plan* plan, int stage);
 /* Pure-DFMA microbenchmark (no memory traffic): sustained FP64 FMA throughput of `device` in
  * TFLOP/s, best of `repeats` launches.  This is the FP64 roofline denominator (the driver's
  * MEASURED_PEAKS.json only has HBM and bf16).  Returns < 0 on error. */

@@ -125,9 +125,19 @@ extern "C" double qocvl_flops_per_call(const qocvl_plan* p, int with_grad) {
                       : (p->use_wide ? p->lwide.macs : (double)(p->n_live + 1) * p->cu.nnz + p->cw.nnz);
   const bool stored = (p->use_aug && p->aug_store) || (p->use_wide && p->lwide.store);
   double total = 0.0;
+  // with_grad: 0 cost only / 1 executed cost + gradient (with the recomputed Taylor powers) / 2 algorithmic cost + gradient
+  // (forward q + adjoint q + Xbar q, what a kernel that kept every power would execute) / 3 the reverse sweep's share of 2
   for (int k = 0; k < M; ++k) {
-    total += q[k] * macs;
-    if (with_grad) total += ((stored ? 0 : q[k] - 1) + 2.0 * q[k]) * macs;
+    if (with_grad != 3) total += q[k] * macs;
+    if (with_grad == 1) total += ((stored ? 0 : q[k] - 1) + 2.0 * q[k]) * macs;
+    else if (with_grad >= 2) total += 2.0 * q[k] * macs;
+  }
+  // time-parallel evaluation of a small ensemble (chain_duo.cu, slice-axis chunks): the chunk propagators are executed
+  // work on top of the per-chunk sweeps -- one forward sweep per basis column of every role
+  if (p->use_aug && p->use_duo && p->duo.chunks > 1 && with_grad <= 1) {
+    int cols = 0;
+    for (int r = 0; r < p->duo.nroles; ++r) cols = std::max(cols, p->duo.ncol[r]);
+    for (int k = 0; k < M; ++k) total += (double)(with_grad ? cols : cols - 1) * q[k] * macs;
   }
   // time-parallel path of the wide kernel: the column sweeps (n basis columns pushed forward through every slice) are
   // executed work on top of the per-chunk forward + reverse sweeps
@@ -205,6 +215,7 @@ extern "C" int qocvl_set_timing(qocvl_plan* p, int enabled) {
   if (enabled && !p->ev0) {
     QCUDA(cudaEventCreate(&p->ev0));
     QCUDA(cudaEventCreate(&p->ev1));
+    for (cudaEvent_t& e : p->ev_stage) QCUDA(cudaEventCreate(&e));
   }
   p->timing = enabled != 0;
   p->timed_once = false;
@@ -216,6 +227,21 @@ extern "C" double qocvl_last_chain_ms(qocvl_plan* p) {
   float ms = -1.0f;
   if (cudaEventSynchronize(p->ev1) != cudaSuccess) return -1.0;
   if (cudaEventElapsedTime(&ms, p->ev0, p->ev1) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+
+extern "C" int qocvl_slice_chunks(const qocvl_plan* p) {
+  if (!p || p->groups <= 0) return 0;
+  if (p->use_tp) return p->tp_nchunks;
+  if (p->use_aug && p->use_duo) return p->duo.chunks;
+  return 1;
+}
+
+extern "C" double qocvl_last_stage_ms(qocvl_plan* p, int stage) {
+  if (!p || stage < 0 || stage > 1 || !p->timed_once || !p->stage_timed[stage]) return -1.0;
+  float ms = -1.0f;
+  if (cudaEventSynchronize(p->ev_stage[2 * stage + 1]) != cudaSuccess) return -1.0;
+  if (cudaEventElapsedTime(&ms, p->ev_stage[2 * stage], p->ev_stage[2 * stage + 1]) != cudaSuccess) return -1.0;
   return (double)ms;
 }
 

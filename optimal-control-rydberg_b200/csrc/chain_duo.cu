@@ -55,6 +55,58 @@ __global__ void k_duo_terminal(const DuoArgs Q) {
   }
 }
 
+// Time-parallel evaluation (mode 1 / 2 of the sweeps): walk the chunk propagators of one (sample, role).
+//   dir = +1: z_0 = start kets, zstart[c] = z_c, z_{c+1} = P_c z_c; the last state goes to zfin (-> k_duo_terminal).
+//   dir = -1: lam_C = terminal cotangent, lamend[c] = lam_{c+1}, lam_c = P_c^dag lam_{c+1}   (P_c^dag is exactly what
+//             the reverse sweep applies slice by slice: the adjoint of the same truncated Taylor polynomials).
+// Roles partition the stacked rows and never mix, so each (sample, role) is walked by its own group of 8 lanes (6 live:
+// one local row each, the vector exchanged with shuffles); a role's propagator is a 6x6 block stored by column.
+// Mirrored roles ([[U, 0], [W, U]]): only the independent triple's columns were swept; the dependent triple's own block
+// is the same U.
+__device__ __forceinline__ cplx duo_pfull(const DuoArgs& Q, const cplx* P, const int* colof, int role, int li, int lj) {
+  if (colof[lj] >= 0) return P[colof[lj] * 6 + li];                 // swept column
+  if (Q.mirror[role] && li / 3 == lj / 3) {                          // dependent triple's own block = independent one's
+    const int sh = lj < 3 ? 3 : -3;
+    return P[colof[lj + sh] * 6 + li + sh];
+  }
+  return cmake(0.0, 0.0);
+}
+
+__global__ void __launch_bounds__(128) k_duo_combine(const DuoArgs Q, int dir) {
+  const int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, li = threadIdx.x & 7;
+  const int s = grp / Q.nroles, role = grp % Q.nroles;
+  const bool on = s < Q.S && li < 6;
+  const int sm = s < Q.S ? s : Q.S - 1;
+  const int base = (threadIdx.x & 31) & ~7;                           // first lane of my group inside the warp
+  int colof[6];                                                       // swept column of local row l, or -1
+#pragma unroll
+  for (int l = 0; l < 6; ++l) colof[l] = -1;
+  for (int jc = 0; jc < Q.ncol[role]; ++jc) {
+    const int l = Q.colrow[role * 6 + jc];
+#pragma unroll
+    for (int l2 = 0; l2 < 6; ++l2) if (l2 == l) colof[l2] = jc;
+  }
+  const int myrow = li < 6 ? Q.srow[role * 6 + li] : -1;
+  cplx z = cmake(0.0, 0.0);
+  if (on && myrow >= 0) z = dir > 0 ? Q.starts[myrow] : Q.lam[(size_t)sm * Q.N + myrow];
+  for (int cc = 0; cc < Q.chunks; ++cc) {
+    const int c = dir > 0 ? cc : Q.chunks - 1 - cc;
+    if (on && myrow >= 0) ((dir > 0 ? Q.zstart : Q.lamend) + ((size_t)sm * Q.chunks + c) * Q.N)[myrow] = z;
+    const cplx* P = Q.prop + (((size_t)sm * Q.chunks + c) * Q.nroles + role) * 36;
+    cplx zn = cmake(0.0, 0.0);
+#pragma unroll
+    for (int l = 0; l < 6; ++l) {
+      const cplx zl = cmake(__shfl_sync(0xffffffffu, z.x, base + l), __shfl_sync(0xffffffffu, z.y, base + l));
+      if (li < 6) {
+        if (dir > 0) zn = cfma(duo_pfull(Q, P, colof, role, li, l), zl, zn);          // z'_li = sum_l P[li][l] z_l
+        else zn = cfma_conj(duo_pfull(Q, P, colof, role, l, li), zl, zn);           // lam'_li = sum_l conj(P[l][li]) lam_l
+      }
+    }
+    z = zn;
+  }
+  if (dir > 0 && on && myrow >= 0) Q.zfin[(size_t)sm * Q.N + myrow] = z;
+}
+
 // gwave[k][c] = 2 dt Re sum_x Ybar_x(k) * sum_{g in x} val_xg * dcoef_kgc, with Ybar summed over the per-warp partials
 // in a fixed order (deterministic).  One block of 256 threads per slice: 64 descriptor slots x 4 interleaved parts.
 __global__ void __launch_bounds__(256) k_duo_reduce(const DuoArgs Q, const unsigned long long* __restrict__ ent_ysrc,
@@ -142,7 +194,8 @@ int slot_of(unsigned mask, int bit) { return duo_popc(mask & ((1u << bit) - 1u))
 
 void DuoState::release() {
   void* ptrs[] = {d_tab, d_con_m, d_con_a, d_srow, d_ent_gen, d_ent_val, d_ent_x, d_ent_out, d_ent_stride, d_ent_ysrc,
-                  d_ent_ystride, d_ent_ywarps, d_starts, d_targets, d_pair, d_wq, d_zfin, d_lam};
+                  d_ent_ystride, d_ent_ywarps, d_starts, d_targets, d_pair, d_wq, d_zfin, d_lam, d_colrow, d_prop,
+                  d_zstart, d_lamend};
   for (void* q : ptrs) if (q) cudaFree(q);
   *this = DuoState();
 }
@@ -351,6 +404,42 @@ int qocvl_duo_configure(qocvl_plan* p) {
   p->blocks = nroles * ((warps_per_role + wpc - 1) / wpc);
   p->threads = wpc * 32;
   p->spb = wpc * DUO_SPW; p->groups = p->spb;
+  // ---- time-parallel evaluation of small ensembles: the sweeps are bound by the sequential depth of one sample's
+  //      slices (the evaluation takes the same 8.7 ms for 512 and for 4096 samples), so a small ensemble -- a shard of
+  //      a strong-scaling run -- cuts the slice axis into chunks that run concurrently.  The price is the chunk
+  //      propagators: one forward sweep per basis column of every role (CZ: 3 + 6 instead of 1 + 1).
+  //      A role of the Van Loan form [[T, 0], [C, T]] (the {U psi, W psi} pair: one triple evolves on its own, both
+  //      triples carry the same own block) has the propagator [[U, 0], [W, U]]: only the columns of the independent
+  //      triple are swept, the other three are mirrored by k_duo_combine (mirror[r] = 1 + the independent lane type).
+  std::vector<int> colrow((size_t)nroles * 6, 0);
+  int ncol[DUO_MAXR] = {0}, mirror[DUO_MAXR] = {0};
+  for (int r = 0; r < nroles; ++r) {
+    const int* rows = &srow[(size_t)r * 6];
+    for (int t = 0; t < 2 && !mirror[r]; ++t) {          // is triple t independent of triple 1 - t, with equal own blocks?
+      bool ok = true;
+      for (int i = 0; i < 3 && ok; ++i) {
+        if (rows[t * 3 + i] < 0 || rows[(1 - t) * 3 + i] < 0) { ok = false; break; }
+        for (int ip = 0; ip < 3 && ok; ++ip) {
+          if (pat[(size_t)rows[t * 3 + i] * N + rows[(1 - t) * 3 + ip]]) ok = false;
+          for (int j = 0; j < J && ok; ++j)
+            if (AG(j, rows[t * 3 + i], rows[t * 3 + ip]) != AG(j, rows[(1 - t) * 3 + i], rows[(1 - t) * 3 + ip])) ok = false;
+        }
+      }
+      if (ok) mirror[r] = 1 + t;
+    }
+    if (p->opt("duo_nomirror")) mirror[r] = 0;
+    for (int l = 0; l < 6; ++l)
+      if (rows[l] >= 0 && (!mirror[r] || l / 3 == mirror[r] - 1)) colrow[(size_t)r * 6 + ncol[r]++] = l;
+  }
+  int chunks = 1;
+  if (S <= 2304 && M >= 512) {                          // measured on cfg 3 (profiles/README.md): 16 chunks win up to ~2300 samples
+    while (chunks < 16 && M / (chunks * 2) >= 64) chunks *= 2;
+  }
+  if (p->has_opt("strong_chunks")) chunks = std::max(1, std::min(std::min(64, M / 4), p->opt("strong_chunks")));
+  D.lc = (M + chunks - 1) / chunks;
+  D.chunks = (M + D.lc - 1) / D.lc;
+  D.G = warps_per_role;
+  for (int r = 0; r < nroles; ++r) { D.ncol[r] = ncol[r]; D.mirror[r] = mirror[r]; }
   // ---- upload
 #define DUO_UP(ptr, vec)                                                                               \
   do {                                                                                                 \
@@ -358,7 +447,7 @@ int qocvl_duo_configure(qocvl_plan* p) {
     if (!(vec).empty())                                                                                \
       QCUDA(cudaMemcpy((ptr), (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice));  \
   } while (0)
-  DUO_UP(D.d_con_m, con_m); DUO_UP(D.d_con_a, con_a); DUO_UP(D.d_srow, srow);
+  DUO_UP(D.d_con_m, con_m); DUO_UP(D.d_con_a, con_a); DUO_UP(D.d_srow, srow); DUO_UP(D.d_colrow, colrow);
   DUO_UP(D.d_ent_gen, ent_gen); DUO_UP(D.d_ent_val, ent_val); DUO_UP(D.d_ent_x, ent_x);
   DUO_UP(D.d_ent_out, ent_out); DUO_UP(D.d_ent_stride, ent_stride);
   DUO_UP(D.d_ent_ysrc, ent_ysrc); DUO_UP(D.d_ent_ystride, ent_ystride); DUO_UP(D.d_ent_ywarps, ent_ywarps);
@@ -374,6 +463,12 @@ int qocvl_duo_configure(qocvl_plan* p) {
   QCUDA(cudaMalloc((void**)&D.d_tab, tab_total * sizeof(cplx)));
   QCUDA(cudaMalloc((void**)&D.d_zfin, (size_t)S * N * sizeof(cplx)));
   QCUDA(cudaMalloc((void**)&D.d_lam, (size_t)S * N * sizeof(cplx)));
+  if (D.chunks > 1) {
+    QCUDA(cudaMalloc((void**)&D.d_prop, (size_t)S * D.chunks * nroles * 36 * sizeof(cplx)));
+    QCUDA(cudaMemset(D.d_prop, 0, (size_t)S * D.chunks * nroles * 36 * sizeof(cplx)));
+    QCUDA(cudaMalloc((void**)&D.d_zstart, (size_t)S * D.chunks * N * sizeof(cplx)));
+    QCUDA(cudaMalloc((void**)&D.d_lamend, (size_t)S * D.chunks * N * sizeof(cplx)));
+  }
   if (p->d_ckpt) { cudaFree(p->d_ckpt); p->d_ckpt = nullptr; p->bytes -= p->ckpt_bytes; p->ckpt_bytes = 0; }
   if (p->d_ypart) { cudaFree(p->d_ypart); p->d_ypart = nullptr; p->bytes -= p->ypart_bytes; p->ypart_bytes = 0; }
   p->ckpt_bytes = (size_t)nroles * warps_per_role * M * 96 * sizeof(cplx);
@@ -416,14 +511,50 @@ int qocvl_duo_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t 
   q.sample_out = p->d_sample_out; q.gwave = gwave;
   q.ifact[0] = 1.0;
   for (int j = 1; j < QOCVL_QMAX + 2; ++j) q.ifact[j] = q.ifact[j - 1] / (double)j;
+  q.chunks = D.chunks; q.lc = D.lc; q.G = D.G;
+  for (int r = 0; r < D.nroles; ++r) { q.ncol[r] = D.ncol[r]; q.mirror[r] = D.mirror[r]; }
+  q.colrow = D.d_colrow; q.prop = D.d_prop; q.zstart = D.d_zstart; q.lamend = D.d_lamend;
+  // one sweep launch: `items` work items (warps) per role
+  auto sweep = [&](bool reverse, int mode) {
+    DuoArgs a = q;
+    a.mode = mode;
+    int most = 0;
+    for (int r = 0; r < D.nroles; ++r) {
+      a.warps[r] = D.G * (mode == 0 ? 1 : D.chunks) * (mode == 1 ? D.ncol[r] : 1);
+      most = std::max(most, a.warps[r]);
+    }
+    const int blocks = D.nroles * ((most + D.wpc - 1) / D.wpc);
+    if (reverse) k_duo_reverse<<<blocks, p->threads, D.smem_rev, st>>>(a);
+    else k_duo_forward<<<blocks, p->threads, D.smem_fwd, st>>>(a);
+    p->launches++;
+  };
+  const bool timed = p->timing_now && p->ev_stage[0];
   k_duo_tables<<<d.n_slices, 64, 0, st>>>(q, D.d_ent_out, D.d_ent_stride);
-  k_duo_forward<<<p->blocks, p->threads, D.smem_fwd, st>>>(q);
+  p->launches++;
+  if (D.chunks > 1) {            // chunk propagators -> boundary states -> (terminal cost) -> boundary cotangents
+    sweep(false, 1);
+    k_duo_combine<<<(q.S * q.nroles * 8 + 127) / 128, 128, 0, st>>>(q, +1);
+    p->launches++;
+  } else {
+    if (timed) QCUDA(cudaEventRecord(p->ev_stage[0], st));
+    sweep(false, 0);
+    if (timed) { QCUDA(cudaEventRecord(p->ev_stage[1], st)); p->stage_timed[0] = true; }
+  }
   k_duo_terminal<<<(q.S + 127) / 128, 128, 0, st>>>(q);
-  p->launches += 3;
+  p->launches++;
   if (want_grad) {
-    k_duo_reverse<<<p->blocks, p->threads, D.smem_rev, st>>>(q);
+    if (D.chunks > 1) {
+      k_duo_combine<<<(q.S * q.nroles * 8 + 127) / 128, 128, 0, st>>>(q, -1);
+      p->launches++;
+      if (timed) QCUDA(cudaEventRecord(p->ev_stage[0], st));
+      sweep(false, 2);
+      if (timed) { QCUDA(cudaEventRecord(p->ev_stage[1], st)); p->stage_timed[0] = true; }
+    }
+    if (timed) QCUDA(cudaEventRecord(p->ev_stage[2], st));
+    sweep(true, D.chunks > 1 ? 2 : 0);
+    if (timed) { QCUDA(cudaEventRecord(p->ev_stage[3], st)); p->stage_timed[1] = true; }
     k_duo_reduce<<<d.n_slices, 256, 0, st>>>(q, D.d_ent_ysrc, D.d_ent_ystride, D.d_ent_ywarps);
-    p->launches += 2;
+    p->launches++;
   }
   QCUDA(cudaGetLastError());
   return QOCVL_OK;

@@ -47,6 +47,13 @@ constexpr int kDuoUnroll = DUO_UNROLL;
 
 struct DuoArgs {
   int M, S, C, J, N, nroles, wpc, qcap, want_grad, KG;
+  // Time-parallel evaluation of small ensembles (strong scaling): the slice axis is cut into `chunks` chunks of `lc`
+  // slices.  mode 0: one warp sweeps all slices of its 16 samples.  mode 1: (sample group, chunk, basis column) items
+  // push a unit vector of the role's 6-dimensional space through one chunk -> chunk propagators `prop`.
+  // mode 2: (sample group, chunk) items sweep one chunk between the boundary states / cotangents that k_duo_combine
+  // obtained from the chunk propagators.
+  int mode, chunks, lc, G;
+  int ncol[DUO_MAXR], mirror[DUO_MAXR];   // mirror: 1 + lane type whose own-block propagator is copied to the other triple
   int variant[DUO_MAXR], nu[DUO_MAXR], nx[DUO_MAXR], warps[DUO_MAXR];
   unsigned long long tab_off[DUO_MAXR], con_off[DUO_MAXR], y_off[DUO_MAXR], warp0[DUO_MAXR];
   int ent0[DUO_MAXR];   // first (role, type, slot) descriptor of the role
@@ -71,6 +78,10 @@ struct DuoArgs {
   cplx* zfin;           // [S][N]
   cplx* lam;            // [S][N]
   cplx* ypart;          // role r at y_off[r]: [warps_r][M][2][nx_r]
+  const int* colrow;    // [nroles][6] local row (3 lane type + i) that basis column j of the role excites
+  cplx* prop;           // [S][chunks][nroles][6 columns][6 local rows]  chunk propagators (mode 1 -> k_duo_combine)
+  cplx* zstart;         // [S][chunks][N]  state at the start of chunk c
+  cplx* lamend;         // [S][chunks][N]  cotangent at the end of chunk c
   double* sample_out;   // [S][3]
   double* gwave;        // [M][C]
   double ifact[QOCVL_QMAX + 2];   // 1 / j!
@@ -234,6 +245,23 @@ __host__ __device__ inline DuoSmem duo_smem_layout(int nu, int qcap, bool revers
   return s;
 }
 
+// What a warp of role `role` works on: sample group g, slice range [k0, k1), basis column (mode 1)
+struct DuoItem {
+  int g, c, col, k0, k1;
+};
+__device__ __forceinline__ DuoItem duo_item(const DuoArgs& Q, const int role, const int it) {
+  DuoItem I;
+  I.col = 0; I.c = 0; I.g = it; I.k0 = 0; I.k1 = Q.M;
+  if (Q.mode == 1) {
+    const int nc = Q.ncol[role];
+    I.col = it % nc; I.c = (it / nc) % Q.chunks; I.g = it / (nc * Q.chunks);
+  } else if (Q.mode == 2) {
+    I.c = it % Q.chunks; I.g = it / Q.chunks;
+  }
+  if (Q.mode != 0) { I.k0 = I.c * Q.lc; I.k1 = min(Q.M, I.k0 + Q.lc); }
+  return I;
+}
+
 // =====================================================================================================================
 // Forward sweep of one warp: 16 samples x 2 lanes of role `role`.
 // =====================================================================================================================
@@ -244,7 +272,8 @@ __device__ __forceinline__ void duo_forward(const DuoArgs& Q, const int role, un
   const int type = lane & 1, sl = lane >> 1;
   const int wg = (blockIdx.x / Q.nroles) * Q.wpc + warp;          // warp of this role
   if (wg >= Q.warps[role]) return;
-  const int sample = wg * DUO_SPW + sl;
+  const DuoItem I = duo_item(Q, role, wg);
+  const int sample = I.g * DUO_SPW + sl;
   const bool live = sample < Q.S;
   const int sm = live ? sample : Q.S - 1;
   const DuoSmem L = duo_smem_layout(NU, Q.qcap, false);
@@ -256,12 +285,13 @@ __device__ __forceinline__ void duo_forward(const DuoArgs& Q, const int role, un
   const unsigned bar0 = duo_s32(base + L.bars), tab0 = duo_s32(base + L.tab);
   const unsigned row_bytes = 2u * NU * sizeof(cplx);              // both lane types of one slice
   const cplx* gtab = Q.tab + Q.tab_off[role];
-  const int nb = (Q.M + DUO_BT - 1) / DUO_BT;
+  const int k0 = I.k0, nsl = I.k1 - I.k0;                         // my slices: k0 .. k0 + nsl - 1
+  const int nb = (nsl + DUO_BT - 1) / DUO_BT;
   auto issue = [&](int b) {
-    const int cnt = min(DUO_BT, Q.M - b * DUO_BT);
+    const int cnt = min(DUO_BT, nsl - b * DUO_BT);
     const unsigned bar = bar0 + (b & 1) * 8, bytes = cnt * row_bytes;
     duo_bar_expect(bar, bytes);
-    duo_bulk(tab0 + (b & 1) * DUO_BT * row_bytes, gtab + (size_t)b * DUO_BT * 2 * NU, bytes, bar);
+    duo_bulk(tab0 + (b & 1) * DUO_BT * row_bytes, gtab + (size_t)(k0 + b * DUO_BT) * 2 * NU, bytes, bar);
   };
   if (lane == 0) {
     duo_bar_init(bar0);
@@ -285,18 +315,21 @@ __device__ __forceinline__ void duo_forward(const DuoArgs& Q, const int role, un
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     srow[i] = Q.srow[(role * 2 + type) * 3 + i];
-    z[i] = srow[i] >= 0 ? Q.starts[srow[i]] : cmake(0.0, 0.0);
+    if (Q.mode == 0) z[i] = srow[i] >= 0 ? Q.starts[srow[i]] : cmake(0.0, 0.0);
+    else if (Q.mode == 1) z[i] = cmake(Q.colrow[role * 6 + I.col] == type * 3 + i ? 1.0 : 0.0, 0.0);
+    else z[i] = srow[i] >= 0 ? Q.zstart[((size_t)sm * Q.chunks + I.c) * Q.N + srow[i]] : cmake(0.0, 0.0);
   }
   __syncwarp();
-  cplx* ck = Q.ckpt + ((size_t)(Q.warp0[role] + wg) * Q.M) * 96 + lane;
-  int q_next = __ldg(Q.qdeg);
+  const bool keep = Q.want_grad && Q.mode != 1;
+  cplx* ck = Q.ckpt + ((size_t)(Q.warp0[role] + I.g) * Q.M) * 96 + lane;
+  int q_next = __ldg(Q.qdeg + k0);
   for (int b = 0; b < nb; ++b) {
     duo_bar_wait(bar0 + (b & 1) * 8, (b >> 1) & 1);
-    const int cnt = min(DUO_BT, Q.M - b * DUO_BT);
+    const int cnt = min(DUO_BT, nsl - b * DUO_BT);
     for (int kk = 0; kk < cnt; ++kk) {
-      const int k = b * DUO_BT + kk;
+      const int k = k0 + b * DUO_BT + kk;
       const int q = q_next;
-      if (k + 1 < Q.M) q_next = __ldg(Q.qdeg + k + 1);
+      if (k + 1 < I.k1) q_next = __ldg(Q.qdeg + k + 1);
       const cplx* row = s_tab + ((size_t)((b & 1) * DUO_BT + kk) * 2 + type) * NU;
       cplx e[NU];
 #pragma unroll
@@ -305,7 +338,7 @@ __device__ __forceinline__ void duo_forward(const DuoArgs& Q, const int role, un
         const double mv = s_m[u * 32];
         e[u] = cmake(fma(mv, pv.x, av.x), fma(mv, pv.y, av.y));
       }
-      if (Q.want_grad) {
+      if (keep) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) ck[((size_t)k * 3 + i) * 32] = z[i];
       }
@@ -326,10 +359,15 @@ __device__ __forceinline__ void duo_forward(const DuoArgs& Q, const int role, un
     __syncwarp();                                          // every lane is done with this stage
     if (lane == 0 && b + 2 < nb) issue(b + 2);
   }
-  if (live) {
+  if (live && Q.mode == 0) {
 #pragma unroll
     for (int i = 0; i < 3; ++i)
       if (srow[i] >= 0) Q.zfin[(size_t)sample * Q.N + srow[i]] = z[i];
+  }
+  if (live && Q.mode == 1) {                               // column I.col of the chunk propagator of my role
+    cplx* pc = Q.prop + ((((size_t)sample * Q.chunks + I.c) * Q.nroles + role) * 6 + I.col) * 6 + type * 3;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) pc[i] = z[i];
   }
 }
 
@@ -344,7 +382,8 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
   const int type = lane & 1, sl = lane >> 1;
   const int wg = (blockIdx.x / Q.nroles) * Q.wpc + warp;
   if (wg >= Q.warps[role]) return;
-  const int sample = wg * DUO_SPW + sl;
+  const DuoItem I = duo_item(Q, role, wg);
+  const int sample = I.g * DUO_SPW + sl;
   const bool live = sample < Q.S;
   const int sm = live ? sample : Q.S - 1;
   const DuoSmem L = duo_smem_layout(NU, Q.qcap, true);
@@ -358,15 +397,16 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
   const unsigned bar0 = duo_s32(base + L.bars), tab0 = duo_s32(base + L.tab), ck0 = duo_s32(base + L.ck);
   const unsigned row_bytes = 2u * NU * sizeof(cplx), ck_bytes = 96u * sizeof(cplx);
   const cplx* gtab = Q.tab + Q.tab_off[role];
-  const cplx* gck = Q.ckpt + ((size_t)(Q.warp0[role] + wg) * Q.M) * 96;
-  const int nb = (Q.M + DUO_BT - 1) / DUO_BT;
+  const cplx* gck = Q.ckpt + ((size_t)(Q.warp0[role] + I.g) * Q.M) * 96;
+  const int k0 = I.k0, nsl = I.k1 - I.k0;
+  const int nb = (nsl + DUO_BT - 1) / DUO_BT;
   // batch b covers slices [b BT, b BT + cnt); the sweep visits the batches downwards: visit v = nb - 1 - b
   auto issue = [&](int b) {
-    const int v = nb - 1 - b, cnt = min(DUO_BT, Q.M - b * DUO_BT);
+    const int v = nb - 1 - b, cnt = min(DUO_BT, nsl - b * DUO_BT);
     const unsigned bar = bar0 + (v & 1) * 8;
     duo_bar_expect(bar, cnt * (row_bytes + ck_bytes));
-    duo_bulk(tab0 + (v & 1) * DUO_BT * row_bytes, gtab + (size_t)b * DUO_BT * 2 * NU, cnt * row_bytes, bar);
-    duo_bulk(ck0 + (v & 1) * DUO_BT * ck_bytes, gck + (size_t)b * DUO_BT * 96, cnt * ck_bytes, bar);
+    duo_bulk(tab0 + (v & 1) * DUO_BT * row_bytes, gtab + (size_t)(k0 + b * DUO_BT) * 2 * NU, cnt * row_bytes, bar);
+    duo_bulk(ck0 + (v & 1) * DUO_BT * ck_bytes, gck + (size_t)(k0 + b * DUO_BT) * 96, cnt * ck_bytes, bar);
   };
   if (lane == 0) {
     duo_bar_init(bar0);
@@ -388,20 +428,21 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const int sr = Q.srow[(role * 2 + type) * 3 + i];
-    w[i] = (sr >= 0 && live) ? Q.lam[(size_t)sample * Q.N + sr] : cmake(0.0, 0.0);
+    const cplx* lsrc = Q.mode == 2 ? Q.lamend + ((size_t)sm * Q.chunks + I.c) * Q.N : Q.lam + (size_t)sm * Q.N;
+    w[i] = (sr >= 0 && live) ? lsrc[sr] : cmake(0.0, 0.0);
   }
   __syncwarp();
-  cplx* yout = Q.ypart + Q.y_off[role] + ((size_t)wg * Q.M) * 2 * NX;
+  cplx* yout = Q.ypart + Q.y_off[role] + ((size_t)I.g * Q.M) * 2 * NX;
   cplx* s_e = (cplx*)(base + L.us);                       // [NX][33] staging of the per-sample Xbar entries
-  int q_next = __ldg(Q.qdeg + Q.M - 1);
+  int q_next = __ldg(Q.qdeg + I.k1 - 1);
   for (int v = 0; v < nb; ++v) {
     const int b = nb - 1 - v;
     duo_bar_wait(bar0 + (v & 1) * 8, (v >> 1) & 1);
-    const int cnt = min(DUO_BT, Q.M - b * DUO_BT);
+    const int cnt = min(DUO_BT, nsl - b * DUO_BT);
     for (int kk = cnt - 1; kk >= 0; --kk) {
-      const int k = b * DUO_BT + kk;
+      const int k = k0 + b * DUO_BT + kk;
       const int q = q_next;
-      if (k > 0) q_next = __ldg(Q.qdeg + k - 1);
+      if (k > k0) q_next = __ldg(Q.qdeg + k - 1);
       const cplx* row = s_tab + ((size_t)((v & 1) * DUO_BT + kk) * 2 + type) * NU;
       cplx e[NU];
 #pragma unroll

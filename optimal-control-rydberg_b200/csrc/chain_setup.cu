@@ -235,6 +235,8 @@ int qocvl_launch_chain(qocvl_plan* p, bool want_grad, double* out3, double* gwav
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) timing = false;
   }
+  p->timing_now = timing;
+  p->stage_timed[0] = p->stage_timed[1] = false;
   if (timing) QCUDA(cudaEventRecord(p->ev0, st));
   if (p->use_tp) rc = qocvl_tp_launch(p, want_grad, gwave, st);
   else if (p->use_aug) rc = qocvl_aug_launch(p, want_grad, gwave, st);

@@ -169,14 +169,15 @@ struct WideLayout {
 // Host state of the two-lanes-per-sector ensemble kernels (chain_duo.cu).
 struct DuoState {
   int nroles = 0, wpc = 0, KG = 1, ntot = 0, warps_per_role = 0, numax = 0;
+  int chunks = 1, lc = 0, G = 0, ncol[4] = {0}, mirror[4] = {0};   // time-parallel evaluation of small ensembles (slice-axis chunks)
   int variant[4] = {0}, nu[4] = {0}, nx[4] = {0}, ent0[4] = {0};
   size_t tab_off[4] = {0}, con_off[4] = {0}, y_off[4] = {0}, warp0[4] = {0};
   size_t smem_fwd = 0, smem_rev = 0;
   cplx *d_tab = nullptr, *d_con_a = nullptr, *d_ent_val = nullptr, *d_starts = nullptr, *d_targets = nullptr,
-       *d_zfin = nullptr, *d_lam = nullptr;
+       *d_zfin = nullptr, *d_lam = nullptr, *d_prop = nullptr, *d_zstart = nullptr, *d_lamend = nullptr;
   double *d_con_m = nullptr, *d_wq = nullptr;
   int *d_srow = nullptr, *d_ent_gen = nullptr, *d_ent_x = nullptr, *d_ent_stride = nullptr, *d_ent_ystride = nullptr,
-      *d_ent_ywarps = nullptr, *d_pair = nullptr;
+      *d_ent_ywarps = nullptr, *d_pair = nullptr, *d_colrow = nullptr;
   unsigned long long *d_ent_out = nullptr, *d_ent_ysrc = nullptr;
   void release();
 };
@@ -241,6 +242,9 @@ struct qocvl_plan {
   // optional kernel timing
   bool timing = false, timed_once = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_stage[4] = {nullptr, nullptr, nullptr, nullptr};   // forward sweep start / end, reverse sweep start / end
+  bool timing_now = false;   // this launch is being timed (not inside a graph capture)
+  bool stage_timed[2] = {false, false};
   // chain launch geometry
   int spb = 1, groups = 0, threads = 0, blocks = 0;
   bool tlocal = true;      // Taylor terms of the reverse sweep in thread-local (L1) instead of shared memory

@@ -54,6 +54,8 @@ SIGNATURES = {
     "qocvl_flops_per_call": (C.c_double, [_P, C.c_int]),
     "qocvl_set_timing": (C.c_int, [_P, C.c_int]),
     "qocvl_last_chain_ms": (C.c_double, [_P]),
+    "qocvl_last_stage_ms": (C.c_double, [_P, C.c_int]),
+    "qocvl_slice_chunks": (C.c_int, [_P]),
     "qocvl_measure_fp64_peak": (C.c_double, [C.c_int, C.c_int]),
     "qocvl_measure_fp64_peak_reg": (C.c_double, [C.c_int, C.c_int]),
     "qocvl_lindblad_propagate": (C.c_int, [C.c_int] * 7 + [_D] * 6 + [C.c_double, _D, _D]),

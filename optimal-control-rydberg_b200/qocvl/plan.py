@@ -265,5 +265,16 @@ class Plan:
     def last_chain_ms(self):
         return float(self._lib.qocvl_last_chain_ms(self._h))
 
+    @property
+    def slice_chunks(self):
+        """Concurrent slice-axis chunks of the configured path (1 = sequential sweep per sample)."""
+        return int(self._lib.qocvl_slice_chunks(self._h))
+
+    def last_stage_ms(self, stage):
+        """Duration of one kernel of the last timed evaluation: 0 = forward sweep, 1 = reverse sweep (< 0: not timed)."""
+        return float(self._lib.qocvl_last_stage_ms(self._h, int(stage)))
+
     def flops_per_call(self, with_grad=True):
-        return float(self._lib.qocvl_flops_per_call(self._h, 1 if with_grad else 0))
+        """with_grad: False / 0 cost only, True / 1 executed cost + gradient, 2 algorithmic (no recomputation), 3 the
+        reverse sweep's share of 2 (include/qocvl.h)."""
+        return float(self._lib.qocvl_flops_per_call(self._h, int(with_grad)))

@@ -237,15 +237,20 @@ def test_reduced_system_with_general_noise_tables(kind):
 def test_reduced_system_kernels_and_modes_agree(n_samples):
     """The two ensemble kernel families of the reduced stacked system -- chain_duo.cu (two lanes per coupled sector,
     registers only, checkpoints + recomputation, bulk-TMA staged slice batches; 4 warps or 1 warp per CTA) and
-    chain_aug.cu (one sample per lane group; Taylor terms streamed or recomputed) -- on a ragged ensemble: four code
-    paths, same numbers."""
+    chain_aug.cu (one sample per lane group; Taylor terms streamed or recomputed) -- on a ragged ensemble, plus the
+    time-parallel form of the two-lane kernels: seven code paths, same numbers."""
     from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL
     po, a, b, c = otq.notebook02_setup(seed=4, n_gauss=6, nt=77)
     args = (6, 77, po.padding, 50e6, po.delta_t, 0.0, po.Vint, po.Delta_i_val, po.Rabi_i_val, po.Rabi_r_val, otq.GAMMAS_CZ)
     dl, rs = ensemble.robust_cz_noise(n_samples)
     variants = [({"tp": 0}, "reduced_duo"), ({"tp": 0, "duo_wpc": 1}, "reduced_duo"),
                 ({"tp": 0, "duo": 0}, "reduced_stacked_streamed"),
-                ({"tp": 0, "duo": 0, "store": 0}, "reduced_stacked")]
+                ({"tp": 0, "duo": 0, "store": 0}, "reduced_stacked"),
+                # time-parallel evaluation (what small shards of a strong-scaling run use): slice axis cut into chunks
+                # (chunk propagators -> boundary states / cotangents -> per-chunk sweeps); 7 does not divide M = 81
+                ({"tp": 0, "strong_chunks": 4}, "reduced_duo"), ({"tp": 0, "strong_chunks": 7}, "reduced_duo"),
+                # ... with every basis column swept (no mirroring of the Van Loan pair's own-block propagator)
+                ({"tp": 0, "strong_chunks": 4, "duo_nomirror": 1}, "reduced_duo")]
     outs = []
     for kv, path in variants:
         with env(**kv):
@@ -255,6 +260,7 @@ def test_reduced_system_kernels_and_modes_agree(n_samples):
             cost_only = float(prop.target(a, b, c))
             prop._plan.check()
             assert prop._plan.chain_info()["path"] == path, kv
+            assert prop._plan.slice_chunks == kv.get("strong_chunks", 1)
             assert abs(cost_only - outs[-1][0]) < 1e-14
     for out, (kv, _) in zip(outs[1:], variants[1:]):
         assert np.abs(out[:3] - outs[0][:3]).max() < 1e-13, kv
