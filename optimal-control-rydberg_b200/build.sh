@@ -22,5 +22,5 @@ done
 [ "$fail" -eq 0 ] || exit 1
 objs=()
 for u in "${UNITS[@]}"; do objs+=("$OBJ/$u.o"); done
-"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC -o "$OUT" "${objs[@]}" -lcudart
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC -o "$OUT" "${objs[@]}" -lcudart -ldl
 echo "built $OUT"

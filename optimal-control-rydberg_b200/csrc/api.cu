@@ -1,6 +1,14 @@
 // api.cu -- hot-path entry points of the C-ABI (include/qocvl.h): each composes the kernels of
 // pulse.cu, chain.cu and dense.cu on the caller's stream.  No host synchronisation here.
 #include "common.cuh"
+#include <nvtx3/nvToolsExt.h>
+
+// NVTX ranges around the four stages of an evaluation: visible in Nsight Systems / Compute timelines,
+// a no-op (one predictable branch inside the header-only NVTX v3 shim) when no tool is attached.
+struct QocvlRange {
+  explicit QocvlRange(const char* name) { nvtxRangePushA(name); }
+  ~QocvlRange() { nvtxRangePop(); }
+};
 
 static int check_ready(qocvl_plan* p) {
   if (!p) return QOCVL_ERR_ARG;
@@ -67,8 +75,9 @@ extern "C" int qocvl_cost(qocvl_plan* p, const double* abc, double* out3, void* 
   if (rc) return rc;
   if (!abc || !out3) return QOCVL_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  if ((rc = qocvl_launch_pulse_forward(p, abc, st))) return rc;
-  if ((rc = qocvl_launch_coefficients(p, p->d_wave, st))) return rc;
+  { QocvlRange r("qocvl:pulse_map"); if ((rc = qocvl_launch_pulse_forward(p, abc, st))) return rc; }
+  { QocvlRange r("qocvl:coefficients"); if ((rc = qocvl_launch_coefficients(p, p->d_wave, st))) return rc; }
+  QocvlRange r("qocvl:chain_forward");
   return qocvl_launch_chain(p, false, out3, nullptr, st);
 }
 
@@ -77,9 +86,16 @@ extern "C" int qocvl_cost_grad(qocvl_plan* p, const double* abc, double* out, vo
   if (rc) return rc;
   if (!abc || !out) return QOCVL_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  if ((rc = qocvl_launch_pulse_forward(p, abc, st))) return rc;
-  if ((rc = qocvl_launch_coefficients(p, p->d_wave, st))) return rc;
-  if ((rc = qocvl_launch_chain(p, true, out, p->d_gwave, st))) return rc;
+  { QocvlRange r("qocvl:pulse_map"); if ((rc = qocvl_launch_pulse_forward(p, abc, st))) return rc; }
+  { QocvlRange r("qocvl:coefficients"); if ((rc = qocvl_launch_coefficients(p, p->d_wave, st))) return rc; }
+  {
+    QocvlRange r("qocvl:chain_forward_reverse");
+    p->lean_now = true;                                    // d cost / d wave only feeds the pulse-map VJP below
+    rc = qocvl_launch_chain(p, true, out, p->d_gwave, st);
+    p->lean_now = false;
+    if (rc) return rc;
+  }
+  QocvlRange r("qocvl:pulse_map_vjp");
   return qocvl_launch_pulse_vjp(p, abc, p->d_gwave, out + 3, st);
 }
 

@@ -2,6 +2,7 @@
 // every role, the tables, the launch sequence; and the three small kernels around the sweeps
 // (k_duo_tables, k_duo_terminal, k_duo_reduce).
 #include "chain_duo.cuh"
+#include "model.cuh"
 #include <algorithm>
 #include <cmath>
 #include <numeric>
@@ -158,12 +159,12 @@ __global__ void __launch_bounds__(256) k_duo_reduce(const DuoArgs Q, const unsig
   }
 }
 
-__global__ void __launch_bounds__(128, 1) k_duo_forward(const DuoArgs Q) {
+__global__ void __launch_bounds__(128, 3) k_duo_forward(const DuoArgs Q) {
   extern __shared__ __align__(128) unsigned char duo_smem[];
   const int role = blockIdx.x % Q.nroles;
   switch (Q.variant[role]) {
-    case 0: duo_forward<DuoPat0>(Q, role, duo_smem); break;
-    case 1: duo_forward<DuoPat1>(Q, role, duo_smem); break;
+    case 0: case 3: duo_forward<DuoPat0>(Q, role, duo_smem); break;   // (the forward sweep has no Xbar: lean = full)
+    case 1: case 4: duo_forward<DuoPat1>(Q, role, duo_smem); break;
     default: duo_forward<DuoPat2>(Q, role, duo_smem); break;
   }
 }
@@ -174,6 +175,8 @@ __global__ void __launch_bounds__(128, 1) k_duo_reverse(const DuoArgs Q) {
   switch (Q.variant[role]) {
     case 0: duo_reverse<DuoPat0>(Q, role, duo_smem); break;
     case 1: duo_reverse<DuoPat1>(Q, role, duo_smem); break;
+    case 3: duo_reverse<DuoPat3>(Q, role, duo_smem); break;
+    case 4: duo_reverse<DuoPat4>(Q, role, duo_smem); break;
     default: duo_reverse<DuoPat2>(Q, role, duo_smem); break;
   }
 }
@@ -182,17 +185,21 @@ __global__ void __launch_bounds__(128, 1) k_duo_reverse(const DuoArgs Q) {
 // Host
 // ---------------------------------------------------------------------------------------------------
 namespace {
-struct PatInfo { unsigned tm, cm; int s0, s1, nt, nc; };
+struct PatInfo { unsigned tm, cm, xm; int s0, s1, nt, nc, lean; };   // lean: the pattern's twin without diagonal Xbar, or -1
 const PatInfo kPat[DUO_NVAR] = {
-    {(unsigned)DuoPat0::TM, (unsigned)DuoPat0::CM, DuoPat0::S0, DuoPat0::S1, DuoPat0::NT, DuoPat0::NC},
-    {(unsigned)DuoPat1::TM, (unsigned)DuoPat1::CM, DuoPat1::S0, DuoPat1::S1, DuoPat1::NT, DuoPat1::NC},
-    {(unsigned)DuoPat2::TM, (unsigned)DuoPat2::CM, DuoPat2::S0, DuoPat2::S1, DuoPat2::NT, DuoPat2::NC}};
+    {(unsigned)DuoPat0::TM, (unsigned)DuoPat0::CM, (unsigned)DuoPat0::XM, DuoPat0::S0, DuoPat0::S1, DuoPat0::NT, DuoPat0::NC, 3},
+    {(unsigned)DuoPat1::TM, (unsigned)DuoPat1::CM, (unsigned)DuoPat1::XM, DuoPat1::S0, DuoPat1::S1, DuoPat1::NT, DuoPat1::NC, 4},
+    {(unsigned)DuoPat2::TM, (unsigned)DuoPat2::CM, (unsigned)DuoPat2::XM, DuoPat2::S0, DuoPat2::S1, DuoPat2::NT, DuoPat2::NC, -1},
+    {(unsigned)DuoPat3::TM, (unsigned)DuoPat3::CM, (unsigned)DuoPat3::XM, DuoPat3::S0, DuoPat3::S1, DuoPat3::NT, DuoPat3::NC, -1},
+    {(unsigned)DuoPat4::TM, (unsigned)DuoPat4::CM, (unsigned)DuoPat4::XM, DuoPat4::S0, DuoPat4::S1, DuoPat4::NT, DuoPat4::NC, -1}};
+const int kSearchVariants = 3;                            // the cut search only considers the full patterns
 
 // compact slot index of a bit inside a mask
 int slot_of(unsigned mask, int bit) { return duo_popc(mask & ((1u << bit) - 1u)); }
 }  // namespace
 
 void DuoState::release() {
+  for (void* q : {(void*)d_ent_x_lean, (void*)d_ent_ystride_lean, (void*)d_ent_ysrc_lean}) if (q) cudaFree(q);
   void* ptrs[] = {d_tab, d_con_m, d_con_a, d_srow, d_ent_gen, d_ent_val, d_ent_x, d_ent_out, d_ent_stride, d_ent_ysrc,
                   d_ent_ystride, d_ent_ywarps, d_starts, d_targets, d_pair, d_wq, d_zfin, d_lam, d_colrow, d_prop,
                   d_zstart, d_lamend};
@@ -266,7 +273,7 @@ int qocvl_duo_configure(qocvl_plan* p) {
     std::vector<int> best_perm;
     std::vector<int> perm = rows;
     do {
-      for (int v = 0; v < DUO_NVAR; ++v) {
+      for (int v = 0; v < kSearchVariants; ++v) {
         const PatInfo& pi = kPat[v];
         const int cost = pi.nt + pi.nc;
         if (cost >= best_cost) continue;
@@ -386,6 +393,51 @@ int qocvl_duo_configure(qocvl_plan* p) {
       con_a[cbase + s] = cmake(acc.real() * p->d.dt, acc.imag() * p->d.dt);
     }
   }
+  // ---- lean twin (pulse-map path): a role drops the Xbar of its own-block DIAGONAL when none of those entries has a
+  //      generator whose coefficient depends on a live pulse channel (qocvl_model_gen_channels / _dead_channels)
+  bool has_lean = false;
+  int variant_lean[DUO_MAXR], nx_lean[DUO_MAXR];
+  std::vector<int> ent_x_lean = ent_x, ent_ystride_lean = ent_ystride;
+  std::vector<unsigned long long> ent_ysrc_lean = ent_ysrc;
+  {
+    const unsigned dead = p->opt("duo_nolean") ? 0u : qocvl_model_dead_channels(p->d.model);
+    for (int r = 0; r < nroles; ++r) {
+      variant_lean[r] = variant[r]; nx_lean[r] = nx[r];
+      const int lv = kPat[variant[r]].lean;
+      if (lv < 0 || dead == 0u) continue;
+      const PatInfo &pf = kPat[variant[r]], &pl = kPat[lv];
+      bool ok = true;
+      for (int i = ent0[r]; i < ent0[r] + 2 * nu[r] && ok; ++i) {
+        const Desc& d = desc[i];
+        if (d.u >= pf.nt || d.a < 0 || d.b < 0) continue;                  // own-block entries only
+        int bit = 0;                                                       // bit of entry slot d.u inside TM
+        for (int b2 = 0, cnt = 0; b2 < 9; ++b2)
+          if ((pf.tm >> b2) & 1u) { if (cnt == d.u) bit = b2; ++cnt; }
+        if ((pl.xm >> bit) & 1u) continue;                                 // kept in the lean pattern
+        for (int j = 0; j < J; ++j)
+          if (std::abs(AG(j, d.a, d.b)) > 0.0 && (qocvl_model_gen_channels(p->d.model, j) & ~dead)) ok = false;
+      }
+      if (!ok) continue;
+      has_lean = true;
+      variant_lean[r] = lv;
+      nx_lean[r] = duo_popc(pl.xm) + pl.nc;
+      for (int i = ent0[r]; i < ent0[r] + 2 * nu[r]; ++i) {
+        const Desc& d = desc[i];
+        int x = -1;
+        if (d.u < pf.nt) {
+          int bit = 0;
+          for (int b2 = 0, cnt = 0; b2 < 9; ++b2)
+            if ((pf.tm >> b2) & 1u) { if (cnt == d.u) bit = b2; ++cnt; }
+          if ((pl.xm >> bit) & 1u) x = slot_of(pl.xm, bit);
+        } else if (d.x >= 0) {
+          x = d.x - pf.nt + duo_popc(pl.xm);                               // column-owner coupling slots follow
+        }
+        ent_x_lean[i] = x;
+        ent_ystride_lean[i] = 2 * nx_lean[r];
+        ent_ysrc_lean[i] = y_off[r] + (size_t)d.type * nx_lean[r] + (x >= 0 ? x : 0);
+      }
+    }
+  }
   // ---- geometry: warps per CTA so that the reverse kernel's shared memory fits
   int numax = 0;
   for (int r = 0; r < nroles; ++r) numax = std::max(numax, nu[r]);
@@ -451,6 +503,9 @@ int qocvl_duo_configure(qocvl_plan* p) {
   DUO_UP(D.d_ent_gen, ent_gen); DUO_UP(D.d_ent_val, ent_val); DUO_UP(D.d_ent_x, ent_x);
   DUO_UP(D.d_ent_out, ent_out); DUO_UP(D.d_ent_stride, ent_stride);
   DUO_UP(D.d_ent_ysrc, ent_ysrc); DUO_UP(D.d_ent_ystride, ent_ystride); DUO_UP(D.d_ent_ywarps, ent_ywarps);
+  D.has_lean = has_lean;
+  for (int r = 0; r < nroles; ++r) { D.variant_lean[r] = variant_lean[r]; D.nx_lean[r] = nx_lean[r]; }
+  DUO_UP(D.d_ent_x_lean, ent_x_lean); DUO_UP(D.d_ent_ysrc_lean, ent_ysrc_lean); DUO_UP(D.d_ent_ystride_lean, ent_ystride_lean);
   {
     std::vector<cplx> st(p->h_aug_st.begin(), p->h_aug_st.begin() + N), tg(p->h_aug_tg.begin(), p->h_aug_tg.begin() + N);
     std::vector<int> pr(p->h_aug_pair.begin(), p->h_aug_pair.begin() + N);
@@ -514,6 +569,14 @@ int qocvl_duo_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t 
   q.chunks = D.chunks; q.lc = D.lc; q.G = D.G;
   for (int r = 0; r < D.nroles; ++r) { q.ncol[r] = D.ncol[r]; q.mirror[r] = D.mirror[r]; }
   q.colrow = D.d_colrow; q.prop = D.d_prop; q.zstart = D.d_zstart; q.lamend = D.d_lamend;
+  // pulse-map path: the reverse sweep and the reduction skip what only a dead channel would consume
+  const bool lean = want_grad && p->lean_now && D.has_lean;
+  const unsigned long long* ysrc = lean ? D.d_ent_ysrc_lean : D.d_ent_ysrc;
+  const int* ystride = lean ? D.d_ent_ystride_lean : D.d_ent_ystride;
+  if (lean) {
+    q.ent_x = D.d_ent_x_lean;
+    for (int r = 0; r < D.nroles; ++r) { q.variant[r] = D.variant_lean[r]; q.nx[r] = D.nx_lean[r]; }
+  }
   // one sweep launch: `items` work items (warps) per role
   auto sweep = [&](bool reverse, int mode) {
     DuoArgs a = q;
@@ -553,7 +616,7 @@ int qocvl_duo_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t 
     if (timed) QCUDA(cudaEventRecord(p->ev_stage[2], st));
     sweep(true, D.chunks > 1 ? 2 : 0);
     if (timed) { QCUDA(cudaEventRecord(p->ev_stage[3], st)); p->stage_timed[1] = true; }
-    k_duo_reduce<<<d.n_slices, 256, 0, st>>>(q, D.d_ent_ysrc, D.d_ent_ystride, D.d_ent_ywarps);
+    k_duo_reduce<<<d.n_slices, 256, 0, st>>>(q, ysrc, ystride, D.d_ent_ywarps);
     p->launches++;
   }
   QCUDA(cudaGetLastError());

@@ -39,7 +39,7 @@
 #define DUO_MAXR 4      // roles per system
 #define DUO_BT 4        // slices per staged batch
 #define DUO_SPW 16      // samples per warp
-#define DUO_NVAR 3      // compiled patterns
+#define DUO_NVAR 5      // compiled patterns
 #ifndef DUO_UNROLL
 #define DUO_UNROLL 1     // unroll factor of the Taylor loops
 #endif
@@ -92,10 +92,26 @@ __host__ __device__ constexpr int duo_popc(unsigned v) { return v == 0 ? 0 : (in
 // Compile-time description of a lane program: TM = 9-bit mask of the 3x3 own block (bit 3 i + i'), CM = 4-bit mask of
 // the 2x2 coupling block (bit 2 g + h: my send row g <- partner's send row h), S0 / S1 = local index of the send rows.
 // Compact slot order of a lane's entries: own block | coupling block as row owner | coupling block as column owner.
-template <int TM_, int CM_, int S0_, int S1_>
+// XM = the own-block entries whose Xbar is accumulated (entries whose coefficient depends on no live pulse channel --
+// the CZ model's diagonal on the pulse-map path, where the detuning channel is a forced constant -- need none).
+__host__ __device__ constexpr int duo_nth_bit(unsigned mask, int n) {   // position of the n-th set bit
+  int pos = 0;
+  while (pos < 32) {
+    if ((mask >> pos) & 1u) { if (n == 0) return pos; --n; }
+    ++pos;
+  }
+  return 0;
+}
+template <int TM_, int CM_, int S0_, int S1_, int XM_ = TM_>
 struct DuoPat {
-  static constexpr int TM = TM_, CM = CM_, S0 = S0_, S1 = S1_;
-  static constexpr int NT = duo_popc(TM_), NC = duo_popc(CM_), NU = NT + 2 * NC, NX = NT + NC;
+  static constexpr int TM = TM_, CM = CM_, S0 = S0_, S1 = S1_, XM = XM_;
+  static constexpr int NT = duo_popc(TM_), NC = duo_popc(CM_), NU = NT + 2 * NC, NXT = duo_popc(XM_), NX = NXT + NC;
+  __host__ __device__ static constexpr bool hx(int i, int ip) { return (XM_ >> (3 * i + ip)) & 1; }
+  __host__ __device__ static constexpr int xt(int i, int ip) { return duo_popc(XM_ & ((1u << (3 * i + ip)) - 1u)); }
+  // entry slot (multiplier) of Xbar slot x
+  __host__ __device__ static constexpr int ux(int x) {
+    return x < NXT ? duo_popc(TM_ & ((1u << duo_nth_bit(XM_, x)) - 1u)) : x - NXT + NT + NC;
+  }
   __host__ __device__ static constexpr bool ht(int i, int ip) { return (TM_ >> (3 * i + ip)) & 1; }
   __host__ __device__ static constexpr bool hc(int g, int h) { return (CM_ >> (2 * g + h)) & 1; }
   __host__ __device__ static constexpr int t(int i, int ip) { return duo_popc(TM_ & ((1u << (3 * i + ip)) - 1u)); }
@@ -111,6 +127,8 @@ struct DuoPat {
 typedef DuoPat<0x1BB, 0xF, 0, 2> DuoPat0;   // rows: {0,1} {0,1,2} {1,2}  ->  bits 0,1 | 3,4,5 | 7,8
 typedef DuoPat<0x1BB, 0x6, 2, 1> DuoPat1;
 typedef DuoPat<0x1FF, 0xF, 0, 2> DuoPat2;
+typedef DuoPat<0x1BB, 0xF, 0, 2, 0x0AA> DuoPat3;   // patterns 0 / 1 without Xbar on the diagonal
+typedef DuoPat<0x1BB, 0x6, 2, 1, 0x0AA> DuoPat4;
 
 // compile-time loop: every index below is a constant expression, so the entry / accumulator arrays stay in registers
 template <int I, int N, class F>
@@ -377,7 +395,7 @@ __device__ __forceinline__ void duo_forward(const DuoArgs& Q, const int role, un
 // =====================================================================================================================
 template <class PT>
 __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, unsigned char* smem_raw) {
-  constexpr int NU = PT::NU, NX = PT::NX, NT = PT::NT;
+  constexpr int NU = PT::NU, NX = PT::NX;
   const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int type = lane & 1, sl = lane >> 1;
   const int wg = (blockIdx.x / Q.nroles) * Q.wpc + warp;
@@ -500,8 +518,10 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
             if constexpr (PT::ht(ip, i)) {
               wn[i].x = fma(e[PT::t(ip, i)].x, w[ip].x, wn[i].x);
               wn[i].y = fma(-e[PT::t(ip, i)].y, w[ip].x, wn[i].y);
-              xb[PT::t(ip, i)].x = fma(w[ip].x, u[i].x, xb[PT::t(ip, i)].x);
-              xb[PT::t(ip, i)].y = fma(w[ip].x, u[i].y, xb[PT::t(ip, i)].y);
+              if constexpr (PT::hx(ip, i)) {
+                xb[PT::xt(ip, i)].x = fma(w[ip].x, u[i].x, xb[PT::xt(ip, i)].x);
+                xb[PT::xt(ip, i)].y = fma(w[ip].x, u[i].y, xb[PT::xt(ip, i)].y);
+              }
             }
           });
           duo_for<0, 3>([&](auto i_) {           // products with Im w[ip]
@@ -509,8 +529,10 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
             if constexpr (PT::ht(ip, i)) {
               wn[i].x = fma(e[PT::t(ip, i)].y, w[ip].y, wn[i].x);
               wn[i].y = fma(e[PT::t(ip, i)].x, w[ip].y, wn[i].y);
-              xb[PT::t(ip, i)].x = fma(w[ip].y, u[i].y, xb[PT::t(ip, i)].x);
-              xb[PT::t(ip, i)].y = fma(-w[ip].y, u[i].x, xb[PT::t(ip, i)].y);
+              if constexpr (PT::hx(ip, i)) {
+                xb[PT::xt(ip, i)].x = fma(w[ip].y, u[i].y, xb[PT::xt(ip, i)].x);
+                xb[PT::xt(ip, i)].y = fma(-w[ip].y, u[i].x, xb[PT::xt(ip, i)].y);
+              }
             }
           });
         });
@@ -523,8 +545,8 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
               constexpr int i = PT::send(hh);
               wn[i].x = fma(e[PT::nc(g, hh)].x, wh[g].x, wn[i].x);
               wn[i].y = fma(-e[PT::nc(g, hh)].y, wh[g].x, wn[i].y);
-              xb[NT + PT::c(g, hh)].x = fma(wh[g].x, u[i].x, xb[NT + PT::c(g, hh)].x);
-              xb[NT + PT::c(g, hh)].y = fma(wh[g].x, u[i].y, xb[NT + PT::c(g, hh)].y);
+              xb[PT::NXT + PT::c(g, hh)].x = fma(wh[g].x, u[i].x, xb[PT::NXT + PT::c(g, hh)].x);
+              xb[PT::NXT + PT::c(g, hh)].y = fma(wh[g].x, u[i].y, xb[PT::NXT + PT::c(g, hh)].y);
             }
           });
           duo_for<0, 2>([&](auto hh_) {
@@ -533,8 +555,8 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
               constexpr int i = PT::send(hh);
               wn[i].x = fma(e[PT::nc(g, hh)].y, wh[g].y, wn[i].x);
               wn[i].y = fma(e[PT::nc(g, hh)].x, wh[g].y, wn[i].y);
-              xb[NT + PT::c(g, hh)].x = fma(wh[g].y, u[i].y, xb[NT + PT::c(g, hh)].x);
-              xb[NT + PT::c(g, hh)].y = fma(-wh[g].y, u[i].x, xb[NT + PT::c(g, hh)].y);
+              xb[PT::NXT + PT::c(g, hh)].x = fma(wh[g].y, u[i].y, xb[PT::NXT + PT::c(g, hh)].x);
+              xb[PT::NXT + PT::c(g, hh)].y = fma(-wh[g].y, u[i].x, xb[PT::NXT + PT::c(g, hh)].y);
             }
           });
         });
@@ -546,7 +568,7 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
       //      (profiles/micro/latency.cu) -- it was 10 % of the reverse sweep.  Fixed summation order: deterministic.
       duo_for<0, NX>([&](auto x_) {                       // (all multiplier loads before the first store: the
         constexpr int x = DUO_I(x_);                       //  compiler cannot reorder them across possibly aliasing stores)
-        xb[x] = cscale(xb[x], s_m[(x < NT ? x : x + PT::NC) * 32]);
+        xb[x] = cscale(xb[x], s_m[PT::ux(x) * 32]);
       });
       __syncwarp();                                        // every lane is done with its powers
 #pragma unroll

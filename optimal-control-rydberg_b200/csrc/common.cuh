@@ -171,6 +171,11 @@ struct DuoState {
   int nroles = 0, wpc = 0, KG = 1, ntot = 0, warps_per_role = 0, numax = 0;
   int chunks = 1, lc = 0, G = 0, ncol[4] = {0}, mirror[4] = {0};   // time-parallel evaluation of small ensembles (slice-axis chunks)
   int variant[4] = {0}, nu[4] = {0}, nx[4] = {0}, ent0[4] = {0};
+  // "lean" twin of the reverse sweep: no Xbar on own-block entries that only a dead pulse channel would consume
+  bool has_lean = false;
+  int variant_lean[4] = {0}, nx_lean[4] = {0};
+  int *d_ent_x_lean = nullptr, *d_ent_ystride_lean = nullptr;
+  unsigned long long* d_ent_ysrc_lean = nullptr;
   size_t tab_off[4] = {0}, con_off[4] = {0}, y_off[4] = {0}, warp0[4] = {0};
   size_t smem_fwd = 0, smem_rev = 0;
   cplx *d_tab = nullptr, *d_con_a = nullptr, *d_ent_val = nullptr, *d_starts = nullptr, *d_targets = nullptr,
@@ -244,6 +249,7 @@ struct qocvl_plan {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_stage[4] = {nullptr, nullptr, nullptr, nullptr};   // forward sweep start / end, reverse sweep start / end
   bool timing_now = false;   // this launch is being timed (not inside a graph capture)
+  bool lean_now = false;     // this evaluation feeds the pulse-map VJP: gradients of dead channels are not needed
   bool stage_timed[2] = {false, false};
   // chain launch geometry
   int spb = 1, groups = 0, threads = 0, blocks = 0;

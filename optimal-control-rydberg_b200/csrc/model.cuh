@@ -90,6 +90,21 @@ __host__ __device__ inline void qocvl_model_coefficients(const ModelParams& mp, 
   }
 }
 
+// Which physical-amplitude channels the coefficient of generator g depends on (bit c = channel c): the sparsity of dc
+// above.  Used to skip gradient work that only a dead channel would consume.
+__host__ __device__ inline unsigned qocvl_model_gen_channels(int model, int g) {
+  if (model == QOCVL_MODEL_CHAIN) return g < 2 ? 1u << g : 0u;
+  if (g < 2) return 0u;                                   // drift pieces
+  if (g >= 7) return 0x1Eu;                               // projector weights: channels 1-4
+  if (model == QOCVL_MODEL_TWO_QUBIT) return g == 2 ? 0x1u : (g <= 4 ? 0x6u : 0x18u);
+  return 1u << (g - 2);                                   // state transfer: one channel per Hamiltonian piece
+}
+// Channels whose gradient the pulse map discards (abc -> wave -> cost path only): the two-qubit model forces its detuning
+// channel to -1 (TQ:364, quirk q2), so d cost / d wave[:, 0] never reaches the parameters.
+__host__ __device__ inline unsigned qocvl_model_dead_channels(int model) {
+  return model == QOCVL_MODEL_TWO_QUBIT ? 0x1u : 0u;
+}
+
 // Sparse twin of qocvl_slice_norm below (same bound, O(nnz) instead of O(n^2 J)): column sums through
 // the CSC views of the two block families.  *_colptr [n+1], *_ceid [nnz] (entry id in row order),
 // *_egen / *_eval [nnz][kc].

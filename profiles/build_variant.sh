@@ -9,5 +9,5 @@ mkdir -p "$PKG/build/variants"
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC "$@" -c "$PKG/csrc/chain_duo.cu" -o "$PKG/build/variants/chain_duo_$name.o"
 objs=()
 for o in "$PKG"/build/*.o; do [ "$(basename "$o")" = chain_duo.o ] || objs+=("$o"); done
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC -o "$PKG/build/variants/libqocvl_$name.so" "${objs[@]}" "$PKG/build/variants/chain_duo_$name.o" -lcudart
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC -o "$PKG/build/variants/libqocvl_$name.so" "${objs[@]}" "$PKG/build/variants/chain_duo_$name.o" -lcudart -ldl
 echo "built $PKG/build/variants/libqocvl_$name.so"

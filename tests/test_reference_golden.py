@@ -147,9 +147,10 @@ def test_engine_single_optimization_step_equals_the_reference(golden_dir):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("opts,path", [({}, "reduced_duo"), ({"duo": 0}, "reduced_stacked_streamed"),
+@pytest.mark.parametrize("opts,path", [({}, "reduced_duo"), ({"strong_chunks": 1}, "reduced_duo"),
+                                       ({"duo": 0}, "reduced_stacked_streamed"),
                                        ({"duo": 0, "store": 0}, "reduced_stacked")],
-                         ids=["default", "lane_groups", "lane_groups_recompute"])
+                         ids=["default_time_parallel", "sequential_sweeps", "lane_groups", "lane_groups_recompute"])
 def test_cfg3_full_size_members_match_the_reference(opts, path, golden_dir):
     """BASELINE configs[2] at its stated per-sample size (N = 16, nt = 1888, M = 2000): the ensemble kernels on the
     four members the fixture holds -- mean cost / infidelity / adiabaticity / gradient against the mean of the reference
@@ -165,6 +166,7 @@ def test_cfg3_full_size_members_match_the_reference(opts, path, golden_dir):
     info = prop._plan.chain_info()
     assert info["path"].startswith("reduced_"), info
     assert info["path"] == path, info
+    assert prop._plan.slice_chunks == (16 if opts == {} else 1)   # 4 samples x 2000 slices: 16 concurrent chunks by default
     assert abs(out[1] - gold["infid"].mean()) < TOL_FID
     assert abs(out[2] - gold["adiab"].mean()) < TOL_ADIAB and abs(out[0] - gold["cost"].mean()) < TOL_ADIAB
     g = out[3:].reshape(3, 16, 5)
