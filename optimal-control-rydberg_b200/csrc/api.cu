@@ -143,10 +143,13 @@ extern "C" double qocvl_flops_per_call(const qocvl_plan* p, int with_grad) {
   double total = 0.0;
   // with_grad: 0 cost only / 1 executed cost + gradient (with the recomputed Taylor powers) / 2 algorithmic cost + gradient
   // (forward q + adjoint q + Xbar q, what a kernel that kept every power would execute) / 3 the reverse sweep's share of 2
+  // (the lean reverse sweep of chain_duo.cu accumulates Xbar only on the entries a live pulse channel reaches: those
+  //  multiply-adds are neither executed nor needed, so they are not counted either way)
+  const double macs_x = (p->use_aug && p->use_duo && p->duo.last_lean) ? (double)p->duo.nnz_x_lean : macs;
   for (int k = 0; k < M; ++k) {
     if (with_grad != 3) total += q[k] * macs;
-    if (with_grad == 1) total += ((stored ? 0 : q[k] - 1) + 2.0 * q[k]) * macs;
-    else if (with_grad >= 2) total += 2.0 * q[k] * macs;
+    if (with_grad == 1) total += (stored ? 0 : q[k] - 1) * macs + q[k] * (macs + macs_x);
+    else if (with_grad >= 2) total += q[k] * (macs + macs_x);
   }
   // time-parallel evaluation of a small ensemble (chain_duo.cu, slice-axis chunks): the chunk propagators are executed
   // work on top of the per-chunk sweeps -- one forward sweep per basis column of every role

@@ -200,7 +200,7 @@ int slot_of(unsigned mask, int bit) { return duo_popc(mask & ((1u << bit) - 1u))
 
 void DuoState::release() {
   for (void* q : {(void*)d_ent_x_lean, (void*)d_ent_ystride_lean, (void*)d_ent_ysrc_lean}) if (q) cudaFree(q);
-  void* ptrs[] = {d_tab, d_con_m, d_con_a, d_srow, d_ent_gen, d_ent_val, d_ent_x, d_ent_out, d_ent_stride, d_ent_ysrc,
+  void* ptrs[] = {d_tab, d_con_a, d_srow, d_ent_gen, d_ent_val, d_ent_x, d_ent_out, d_ent_stride, d_ent_ysrc,
                   d_ent_ystride, d_ent_ywarps, d_starts, d_targets, d_pair, d_wq, d_zfin, d_lam, d_colrow, d_prop,
                   d_zstart, d_lamend};
   for (void* q : ptrs) if (q) cudaFree(q);
@@ -305,6 +305,7 @@ int qocvl_duo_configure(qocvl_plan* p) {
   const std::vector<char>& has_add = p->h_aug_hasadd;
   const int ncls = p->la.ncls;
   if ((int)cls.size() != J || (int)p->h_aug_mcls.size() != S * ncls) return QOCVL_ERR_STATE;
+  if (ncls > 2) return QOCVL_ERR_UNSUPPORTED;           // the lane programs select between 1 and ONE per-sample multiplier
   // ---- descriptors: (role, lane type, slot) -> stacked (row, col), generators, class, additive generators
   struct Desc { int role, type, u, a, b, x; };
   std::vector<Desc> desc;
@@ -361,7 +362,7 @@ int qocvl_duo_configure(qocvl_plan* p) {
     y_off[r] = y_total; y_total += (size_t)warps_per_role * M * 2 * nx[r];
     warp0[r] = (size_t)r * warps_per_role;
   }
-  std::vector<double> con_m(con_total, 0.0);
+  unsigned clsmask[2 * DUO_MAXR] = {0}, amask[2 * DUO_MAXR] = {0};
   std::vector<cplx> con_a(con_total, cmake(0, 0));
   for (int i = 0; i < ntot; ++i) {
     const Desc& d = desc[i];
@@ -383,7 +384,6 @@ int qocvl_duo_configure(qocvl_plan* p) {
     }
     const size_t cbase = con_off[d.role] + ((size_t)d.type * nu[d.role] + d.u) * S;
     for (int s = 0; s < S; ++s) {
-      con_m[cbase + s] = c0 >= 0 ? p->h_aug_mcls[(size_t)s * ncls + c0] : 0.0;
       zc acc(0, 0);
       for (int j = 0; j < J; ++j)
         if (has_add[j] && std::abs(AG(j, d.a, d.b)) > 0.0) {
@@ -391,7 +391,9 @@ int qocvl_duo_configure(qocvl_plan* p) {
           acc += zc(ad.x, ad.y) * AG(j, d.a, d.b);
         }
       con_a[cbase + s] = cmake(acc.real() * p->d.dt, acc.imag() * p->d.dt);
+      if (acc != zc(0, 0)) amask[d.role * 2 + d.type] |= 1u << d.u;
     }
+    if (c0 > 0) clsmask[d.role * 2 + d.type] |= 1u << d.u;
   }
   // ---- lean twin (pulse-map path): a role drops the Xbar of its own-block DIAGONAL when none of those entries has a
   //      generator whose coefficient depends on a live pulse channel (qocvl_model_gen_channels / _dead_channels)
@@ -499,11 +501,15 @@ int qocvl_duo_configure(qocvl_plan* p) {
     if (!(vec).empty())                                                                                \
       QCUDA(cudaMemcpy((ptr), (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice));  \
   } while (0)
-  DUO_UP(D.d_con_m, con_m); DUO_UP(D.d_con_a, con_a); DUO_UP(D.d_srow, srow); DUO_UP(D.d_colrow, colrow);
+  for (int i = 0; i < 2 * DUO_MAXR; ++i) { D.clsmask[i] = clsmask[i]; D.amask[i] = amask[i]; }
+  DUO_UP(D.d_con_a, con_a); DUO_UP(D.d_srow, srow); DUO_UP(D.d_colrow, colrow);
   DUO_UP(D.d_ent_gen, ent_gen); DUO_UP(D.d_ent_val, ent_val); DUO_UP(D.d_ent_x, ent_x);
   DUO_UP(D.d_ent_out, ent_out); DUO_UP(D.d_ent_stride, ent_stride);
   DUO_UP(D.d_ent_ysrc, ent_ysrc); DUO_UP(D.d_ent_ystride, ent_ystride); DUO_UP(D.d_ent_ywarps, ent_ywarps);
   D.has_lean = has_lean;
+  D.nnz_x_lean = 0;
+  for (int i = 0; i < ntot; ++i)
+    if (ent_x_lean[i] >= 0 && desc[i].a >= 0 && desc[i].b >= 0 && pat[(size_t)desc[i].a * N + desc[i].b]) D.nnz_x_lean++;
   for (int r = 0; r < nroles; ++r) { D.variant_lean[r] = variant_lean[r]; D.nx_lean[r] = nx_lean[r]; }
   DUO_UP(D.d_ent_x_lean, ent_x_lean); DUO_UP(D.d_ent_ysrc_lean, ent_ysrc_lean); DUO_UP(D.d_ent_ystride_lean, ent_ystride_lean);
   {
@@ -558,7 +564,9 @@ int qocvl_duo_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t 
   q.dt = d.dt; q.inv_duration = 1.0 / d.duration; q.w_infid = d.w_infid; q.w_adiab = d.w_adiab;
   q.inv_fid_norm = 1.0 / d.fid_norm; q.inv_samples = 1.0 / (double)p->global_samples;
   q.d_const = p->d_const;
-  q.tab = D.d_tab; q.con_m = D.d_con_m; q.con_a = D.d_con_a; q.srow = D.d_srow;
+  q.tab = D.d_tab; q.con_a = D.d_con_a; q.srow = D.d_srow;
+  q.mcls = p->la.mcls; q.ncls = p->la.ncls;
+  for (int i = 0; i < 2 * DUO_MAXR; ++i) { q.clsmask[i] = D.clsmask[i]; q.amask[i] = D.amask[i]; }
   q.ent_gen = D.d_ent_gen; q.ent_val = D.d_ent_val; q.ent_x = D.d_ent_x;
   q.coef = p->d_coef; q.dcoef = p->d_dcoef; q.qdeg = p->d_qdeg;
   q.starts = D.d_starts; q.targets = D.d_targets; q.pair = D.d_pair; q.wq = D.d_wq;
@@ -571,6 +579,7 @@ int qocvl_duo_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t 
   q.colrow = D.d_colrow; q.prop = D.d_prop; q.zstart = D.d_zstart; q.lamend = D.d_lamend;
   // pulse-map path: the reverse sweep and the reduction skip what only a dead channel would consume
   const bool lean = want_grad && p->lean_now && D.has_lean;
+  if (want_grad) p->duo.last_lean = lean;
   const unsigned long long* ysrc = lean ? D.d_ent_ysrc_lean : D.d_ent_ysrc;
   const int* ystride = lean ? D.d_ent_ystride_lean : D.d_ent_ystride;
   if (lean) {

@@ -61,7 +61,9 @@ struct DuoArgs {
   double dt, inv_duration, w_infid, w_adiab, inv_fid_norm, inv_samples;
   cplx d_const;
   const cplx* tab;      // role r at tab_off[r]: [M][2 lane types][nu_r]   P_u(k) = dt sum_g coef_kg val_ug
-  const double* con_m;  // role r at con_off[r]: [2][nu_r][S]  class multiplier of the entry for sample s
+  const double* mcls;   // [S][ncls] per-sample multiplier of every generator class (class 0 = 1)
+  int ncls;
+  unsigned clsmask[2 * DUO_MAXR], amask[2 * DUO_MAXR];   // per (role, lane type): entries of class 1 / with an additive part
   const cplx* con_a;    //                       [2][nu_r][S]  additive-noise part of the entry
   const int* srow;      // [nroles][2][3]  stacked row of (role, lane type, local row), -1 = padding row
   const int* ent_gen;   // [ntot][KG] generators of a descriptor (-1 = none)
@@ -247,7 +249,7 @@ __device__ __forceinline__ void duo_mv(const cplx (&e)[PT::NU], const cplx (&x)[
 
 // per-warp shared-memory carve-up (bytes), shared by host and device
 struct DuoSmem {
-  int tab, ck, bars, xs, con_m, con_a, us, total;
+  int tab, ck, bars, xs, con_a, us, total;
 };
 __host__ __device__ inline DuoSmem duo_smem_layout(int nu, int qcap, bool reverse) {
   DuoSmem s;
@@ -257,7 +259,6 @@ __host__ __device__ inline DuoSmem duo_smem_layout(int nu, int qcap, bool revers
   s.bars = o; o += 16;
   s.xs = o; o += 2 * 2 * 32 * (int)sizeof(cplx);            // halo exchange slab (DUO_HALO_SMEM)
   s.con_a = o; o += nu * 32 * (int)sizeof(cplx);
-  s.con_m = o; o += nu * 32 * (int)sizeof(double);
   s.us = o; o += reverse ? (qcap * 96 > 14 * 33 ? qcap * 96 : 14 * 33) * (int)sizeof(cplx) : 0;   // powers | Xbar staging
   s.total = o;
   return s;
@@ -294,11 +295,12 @@ __device__ __forceinline__ void duo_forward(const DuoArgs& Q, const int role, un
   const int sample = I.g * DUO_SPW + sl;
   const bool live = sample < Q.S;
   const int sm = live ? sample : Q.S - 1;
+  const double m1 = Q.ncls > 1 ? Q.mcls[(size_t)sm * Q.ncls + 1] : 1.0;
   const DuoSmem L = duo_smem_layout(NU, Q.qcap, false);
   unsigned char* base = smem_raw + (size_t)warp * L.total;
   const cplx* s_tab = (const cplx*)(base + L.tab);
   cplx* s_a = (cplx*)(base + L.con_a) + lane;
-  double* s_m = (double*)(base + L.con_m) + lane;
+  const unsigned cmask = Q.clsmask[role * 2 + type], amask = Q.amask[role * 2 + type];
   cplx* s_x = (cplx*)(base + L.xs);
   const unsigned bar0 = duo_s32(base + L.bars), tab0 = duo_s32(base + L.tab);
   const unsigned row_bytes = 2u * NU * sizeof(cplx);              // both lane types of one slice
@@ -320,13 +322,10 @@ __device__ __forceinline__ void duo_forward(const DuoArgs& Q, const int role, un
   }
   // per-sample constants of my entries: class multiplier and additive-noise part
   {
-    const double* gm = Q.con_m + Q.con_off[role] + (size_t)type * NU * Q.S + sm;
     const cplx* ga = Q.con_a + Q.con_off[role] + (size_t)type * NU * Q.S + sm;
 #pragma unroll
-    for (int u = 0; u < NU; ++u) {
-      s_m[u * 32] = gm[(size_t)u * Q.S];
-      s_a[u * 32] = ga[(size_t)u * Q.S];
-    }
+    for (int u = 0; u < NU; ++u)
+      if ((amask >> u) & 1u) s_a[u * 32] = ga[(size_t)u * Q.S];
   }
   int srow[3];
   cplx z[3];
@@ -349,11 +348,12 @@ __device__ __forceinline__ void duo_forward(const DuoArgs& Q, const int role, un
       const int q = q_next;
       if (k + 1 < I.k1) q_next = __ldg(Q.qdeg + k + 1);
       const cplx* row = s_tab + ((size_t)((b & 1) * DUO_BT + kk) * 2 + type) * NU;
-      cplx e[NU];
-#pragma unroll
+      cplx e[NU];                                          // entry = A_u(s) + m_u(s) P_u(k); m_u is 1 or the sample's class-1
+#pragma unroll                                              // multiplier, A_u exists on few entries (additive noise)
       for (int u = 0; u < NU; ++u) {
-        const cplx pv = row[u], av = s_a[u * 32];
-        const double mv = s_m[u * 32];
+        const cplx pv = row[u];
+        const double mv = ((cmask >> u) & 1u) ? m1 : 1.0;
+        const cplx av = ((amask >> u) & 1u) ? s_a[u * 32] : cmake(0.0, 0.0);
         e[u] = cmake(fma(mv, pv.x, av.x), fma(mv, pv.y, av.y));
       }
       if (keep) {
@@ -404,12 +404,13 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
   const int sample = I.g * DUO_SPW + sl;
   const bool live = sample < Q.S;
   const int sm = live ? sample : Q.S - 1;
+  const double m1 = Q.ncls > 1 ? Q.mcls[(size_t)sm * Q.ncls + 1] : 1.0;
   const DuoSmem L = duo_smem_layout(NU, Q.qcap, true);
   unsigned char* base = smem_raw + (size_t)warp * L.total;
   const cplx* s_tab = (const cplx*)(base + L.tab);
   const cplx* s_ck = (const cplx*)(base + L.ck) + lane;
   cplx* s_a = (cplx*)(base + L.con_a) + lane;
-  double* s_m = (double*)(base + L.con_m) + lane;
+  const unsigned cmask = Q.clsmask[role * 2 + type], amask = Q.amask[role * 2 + type];
   cplx* s_x = (cplx*)(base + L.xs);
   cplx* s_u = (cplx*)(base + L.us) + lane;
   const unsigned bar0 = duo_s32(base + L.bars), tab0 = duo_s32(base + L.tab), ck0 = duo_s32(base + L.ck);
@@ -434,13 +435,10 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
     if (nb > 1) issue(nb - 2);
   }
   {
-    const double* gm = Q.con_m + Q.con_off[role] + (size_t)type * NU * Q.S + sm;
     const cplx* ga = Q.con_a + Q.con_off[role] + (size_t)type * NU * Q.S + sm;
 #pragma unroll
-    for (int u = 0; u < NU; ++u) {
-      s_m[u * 32] = gm[(size_t)u * Q.S];
-      s_a[u * 32] = ga[(size_t)u * Q.S];
-    }
+    for (int u = 0; u < NU; ++u)
+      if ((amask >> u) & 1u) s_a[u * 32] = ga[(size_t)u * Q.S];
   }
   cplx w[3];                                               // running cotangent of my rows
 #pragma unroll
@@ -462,11 +460,12 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
       const int q = q_next;
       if (k > k0) q_next = __ldg(Q.qdeg + k - 1);
       const cplx* row = s_tab + ((size_t)((v & 1) * DUO_BT + kk) * 2 + type) * NU;
-      cplx e[NU];
-#pragma unroll
+      cplx e[NU];                                          // entry = A_u(s) + m_u(s) P_u(k); m_u is 1 or the sample's class-1
+#pragma unroll                                              // multiplier, A_u exists on few entries (additive noise)
       for (int u = 0; u < NU; ++u) {
-        const cplx pv = row[u], av = s_a[u * 32];
-        const double mv = s_m[u * 32];
+        const cplx pv = row[u];
+        const double mv = ((cmask >> u) & 1u) ? m1 : 1.0;
+        const cplx av = ((amask >> u) & 1u) ? s_a[u * 32] : cmake(0.0, 0.0);
         e[u] = cmake(fma(mv, pv.x, av.x), fma(mv, pv.y, av.y));
       }
       // ---- recompute u_0 .. u_{q-1}
@@ -568,7 +567,7 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
       //      (profiles/micro/latency.cu) -- it was 10 % of the reverse sweep.  Fixed summation order: deterministic.
       duo_for<0, NX>([&](auto x_) {                       // (all multiplier loads before the first store: the
         constexpr int x = DUO_I(x_);                       //  compiler cannot reorder them across possibly aliasing stores)
-        xb[x] = cscale(xb[x], s_m[PT::ux(x) * 32]);
+        xb[x] = cscale(xb[x], ((cmask >> PT::ux(x)) & 1u) ? m1 : 1.0);
       });
       __syncwarp();                                        // every lane is done with its powers
 #pragma unroll

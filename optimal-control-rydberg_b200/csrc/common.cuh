@@ -172,7 +172,8 @@ struct DuoState {
   int chunks = 1, lc = 0, G = 0, ncol[4] = {0}, mirror[4] = {0};   // time-parallel evaluation of small ensembles (slice-axis chunks)
   int variant[4] = {0}, nu[4] = {0}, nx[4] = {0}, ent0[4] = {0};
   // "lean" twin of the reverse sweep: no Xbar on own-block entries that only a dead pulse channel would consume
-  bool has_lean = false;
+  bool has_lean = false, last_lean = false;
+  int nnz_x_lean = 0;        // entries of the stacked system whose Xbar the lean reverse sweep accumulates
   int variant_lean[4] = {0}, nx_lean[4] = {0};
   int *d_ent_x_lean = nullptr, *d_ent_ystride_lean = nullptr;
   unsigned long long* d_ent_ysrc_lean = nullptr;
@@ -180,7 +181,8 @@ struct DuoState {
   size_t smem_fwd = 0, smem_rev = 0;
   cplx *d_tab = nullptr, *d_con_a = nullptr, *d_ent_val = nullptr, *d_starts = nullptr, *d_targets = nullptr,
        *d_zfin = nullptr, *d_lam = nullptr, *d_prop = nullptr, *d_zstart = nullptr, *d_lamend = nullptr;
-  double *d_con_m = nullptr, *d_wq = nullptr;
+  double* d_wq = nullptr;
+  unsigned clsmask[8] = {0}, amask[8] = {0};   // per (role, lane type): entries of class 1 / with an additive-noise part
   int *d_srow = nullptr, *d_ent_gen = nullptr, *d_ent_x = nullptr, *d_ent_stride = nullptr, *d_ent_ystride = nullptr,
       *d_ent_ywarps = nullptr, *d_pair = nullptr, *d_colrow = nullptr;
   unsigned long long *d_ent_out = nullptr, *d_ent_ysrc = nullptr;
