@@ -173,7 +173,9 @@ long long qocvl_launch_count(const qocvl_plan* plan); /* kernels launched so far
 /* FP64 flop model of the last evaluation (useful complex multiply-adds on the non-zeros of the propagated system, 8 flops
  * each).  with_grad: 0 = cost only; 1 = cost + gradient as EXECUTED (including the Taylor powers a checkpointing kernel
  * recomputes in its reverse sweep); 2 = cost + gradient ALGORITHMIC (forward q + adjoint q + Xbar q per slice: what
- * SURVEY 8(d) prices, no recomputation); 3 = the reverse sweep's share of 2 (adjoint q + Xbar q). */
+ * SURVEY 8(d) prices, no recomputation); 3 = the reverse sweep's share of 2 (adjoint q + Xbar q); 4 = 2 with Xbar counted
+ * on every entry (modes 1-3 do not count the Xbar updates that qocvl_cost_grad skips because only a pulse channel the
+ * model's pulse map discards would consume them). */
 double qocvl_flops_per_call(const qocvl_plan* plan, int with_grad);
 /* Algorithmic HBM bytes of one chain evaluation: checkpoints written then read once, plus the per-warp partial
  * gradient data written by the reverse sweep and read once by the reduction (0 before the first evaluation). */

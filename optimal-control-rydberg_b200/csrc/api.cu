@@ -145,7 +145,8 @@ extern "C" double qocvl_flops_per_call(const qocvl_plan* p, int with_grad) {
   // (forward q + adjoint q + Xbar q, what a kernel that kept every power would execute) / 3 the reverse sweep's share of 2
   // (the lean reverse sweep of chain_duo.cu accumulates Xbar only on the entries a live pulse channel reaches: those
   //  multiply-adds are neither executed nor needed, so they are not counted either way)
-  const double macs_x = (p->use_aug && p->use_duo && p->duo.last_lean) ? (double)p->duo.nnz_x_lean : macs;
+  // (with_grad = 4: mode 2 with Xbar counted on EVERY entry -- SURVEY's M2 figure, the basis of round 1's roofline fraction)
+  const double macs_x = (p->use_aug && p->use_duo && p->duo.last_lean && with_grad != 4) ? (double)p->duo.nnz_x_lean : macs;
   for (int k = 0; k < M; ++k) {
     if (with_grad != 3) total += q[k] * macs;
     if (with_grad == 1) total += (stored ? 0 : q[k] - 1) * macs + q[k] * (macs + macs_x);
