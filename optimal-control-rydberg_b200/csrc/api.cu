@@ -56,6 +56,7 @@ extern "C" int qocvl_exponentials(qocvl_plan* p, const double* abc, double* out,
   cudaStream_t st = (cudaStream_t)stream;
   if ((rc = qocvl_launch_pulse_forward(p, abc, st))) return rc;
   if ((rc = qocvl_launch_coefficients(p, p->d_wave, st))) return rc;
+  if (2 * p->d.n > 32) return qocvl_launch_block_expm(p, (cplx*)out, st);      // block-triangular pairs + DMMA GEMMs
   return qocvl_launch_dense_expm(p, (cplx*)out, st);
 }
 
@@ -66,6 +67,7 @@ extern "C" int qocvl_propagate(qocvl_plan* p, const double* abc, double* out, vo
   cudaStream_t st = (cudaStream_t)stream;
   if ((rc = qocvl_launch_pulse_forward(p, abc, st))) return rc;
   if ((rc = qocvl_launch_coefficients(p, p->d_wave, st))) return rc;
+  if (2 * p->d.n > 32) return qocvl_launch_block_propagate(p, (cplx*)out, st);
   if ((rc = qocvl_launch_dense_expm(p, nullptr, st))) return rc;   // into the plan's slice buffer
   return qocvl_launch_dense_tree(p, p->d_dense_a, (cplx*)out, st);
 }

@@ -244,6 +244,8 @@ struct qocvl_plan {
   double* d_greg = nullptr;   // [nt][C]
   double* d_graw = nullptr;   // [nt][C]
   double* d_out3 = nullptr;   // [3]
+  cplx *d_gblk_u = nullptr, *d_gblk_w = nullptr;   // [J][n][n] dense generator blocks (dense_blocks.cu, n > 16)
+  cplx* d_blk_work = nullptr;                      // its per-batch workspace
   cplx* d_dense_a = nullptr;  // [M][2n][2n] ping
   cplx* d_dense_b = nullptr;  // [M/2+1][2n][2n] pong
   // optional kernel timing
@@ -323,3 +325,6 @@ int qocvl_build_csr(qocvl_plan* p, const std::vector<std::complex<double>>& bloc
 // dense.cu
 int qocvl_launch_dense_expm(qocvl_plan* p, cplx* out, cudaStream_t st);
 int qocvl_launch_dense_tree(qocvl_plan* p, cplx* slices, cplx* out, cudaStream_t st);
+// dense_blocks.cu (n > 16: block-triangular pairs, batched DMMA complex GEMM)
+int qocvl_launch_block_expm(qocvl_plan* p, cplx* out, cudaStream_t st);
+int qocvl_launch_block_propagate(qocvl_plan* p, cplx* out, cudaStream_t st);

@@ -168,6 +168,7 @@ extern "C" int qocvl_plan_destroy(qocvl_plan* p) {
     cudaFree(c->crow); cudaFree(c->ceid); cudaFree(c->egen); cudaFree(c->eval);
   }
   if (p->d_tring) cudaFree(p->d_tring);
+  for (void* q : {(void*)p->d_gblk_u, (void*)p->d_gblk_w, (void*)p->d_blk_work}) if (q) cudaFree(q);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
   for (cudaEvent_t e : p->ev_stage) if (e) cudaEventDestroy(e);
@@ -187,6 +188,7 @@ extern "C" int qocvl_set_generators(qocvl_plan* p, const double* gens_u, const d
   QCUDA(cudaSetDevice(p->device));
   const int n = p->d.n, J = p->d.n_gen, D = 2 * n;
   const size_t blk = (size_t)J * n * n;
+  for (cplx** q : {&p->d_gblk_u, &p->d_gblk_w}) if (*q) { cudaFree(*q); *q = nullptr; }   // dense blocks: rebuilt on use
   p->h_gu.resize(blk); p->h_gw.resize(blk); p->h_coef_const.resize(J);
   for (size_t i = 0; i < blk; ++i) {
     p->h_gu[i] = zc(gens_u[2 * i], gens_u[2 * i + 1]);

@@ -100,12 +100,31 @@ def test_big_kernel_equals_lane_kernel_on_cz():
     assert rel(out_big[3:], out_small[3:]) < 1e-10
 
 
-def test_dense_api_is_unsupported_for_large_n():
-    import qocvl
-    po, a, b, c = obc.chain_setup(n_atoms=7, n_gauss=4, nt=16)
+@pytest.mark.parametrize("n_atoms,nt", [(7, 16), (8, 21), (10, 6)])
+def test_dense_api_for_large_n_block_triangular_dmma_path(n_atoms, nt):
+    """exponentials() / propagate() (ST:247-283 / TQ:460-535) for n > 16 (n = 34, 55, 144): dense_blocks.cu keeps every
+    matrix as its (u, w) block pair -- 3 n x n products instead of 8 -- and multiplies on FP64 tensor cores
+    (k_zgemm_dmma).  Against the dense oracle's Pade-13 exponentials and the reference's halving product order (odd
+    slice counts fold the leftover), and against the engine's own cost: chain cost == cost read off the dense propagator."""
+    import torch
+    from oracle.state_transfer import halving_flags, ordered_product
+    po, a, b, c = obc.chain_setup(n_atoms=n_atoms, n_gauss=4, nt=nt)
     prop = make_chain(po)
-    with pytest.raises(qocvl.QocvlError, match="not supported"):
-        prop.exponentials(a, b, c)
+    n = po.dim
+    assert 2 * n > 32
+    ex = np_(prop.exponentials(a, b, c))
+    w = po.waves(torch.tensor(a), torch.tensor(b), torch.tensor(c))
+    want = po._dense_steps(w, 0, nt).numpy()
+    assert ex.shape == want.shape == (nt, 2 * n, 2 * n)
+    assert np.abs(ex - want).max() < 1e-12
+    assert np.abs(ex[:, n:, :n]).max() == 0.0 and np.abs(ex[:, :n, :n] - ex[:, n:, n:]).max() == 0.0
+    vl = np_(prop.propagate(a, b, c))
+    assert np.abs(vl - ordered_product(want, halving_flags(nt))).max() < 1e-11
+    out = np_(prop.cost_and_grad_packed(prop._pack(a, b, c)))
+    final = vl[:n, po.i_g]
+    infid = 1.0 - abs(final[po.i_z]) ** 2
+    adiab = (1.0 - np.vdot(final, vl[:n, n + po.i_g]) / po.duration).real
+    assert abs(out[1] - infid) < 1e-11 and abs(out[2] - adiab) < 1e-11
 
 
 def env(**kv):
