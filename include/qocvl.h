@@ -29,7 +29,7 @@ enum {
   QOCVL_ERR_CUDA = 2,       /* a CUDA runtime call failed; qocvl_last_cuda_error() has the text */
   QOCVL_ERR_STATE = 3,      /* generators / cost / noise not set yet */
   QOCVL_ERR_NORM = 4,       /* |X_k| bound too large for the Taylor propagator: refine delta_t */
-  QOCVL_ERR_UNSUPPORTED = 5 /* e.g. dense exponentials for n > 32 */
+  QOCVL_ERR_UNSUPPORTED = 5 /* e.g. complex64 on a path that has no complex64 kernel */
 };
 
 enum { QOCVL_MODEL_STATE_TRANSFER = 0, QOCVL_MODEL_TWO_QUBIT = 1, QOCVL_MODEL_CHAIN = 2 };
@@ -106,7 +106,9 @@ int qocvl_physical_amplitudes_vjp(qocvl_plan* plan, const double* abc, const dou
 /* ST:229-245 / TQ:406-455 return_auxiliary_amplitudes: -> aux [M][J-2] complex. */
 int qocvl_auxiliary_amplitudes(qocvl_plan* plan, const double* abc, double* aux, void* stream);
 
-/* ST:247-256 / TQ:460-484 exponentials: -> [M][2n][2n] complex (dense, nominal sample). */
+/* ST:247-256 / TQ:460-484 exponentials: -> [M][2n][2n] complex (dense, nominal sample).  2n <= 32: one CTA per slice in
+ * shared memory; larger n: block-triangular (u, w) pairs multiplied by a batched FP64 tensor-core (DMMA) complex GEMM --
+ * that path synchronises the stream (it sizes the scaling on the host) and is not graph-capturable. */
 int qocvl_exponentials(qocvl_plan* plan, const double* abc, double* out, void* stream);
 
 /* ST:258-283 / TQ:489-535 propagate: -> [2n][2n] complex; same product order as the reference. */
