@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(256) k_duo_reduce(const DuoArgs Q, const unsig
   }
 }
 
+// (three CTAs per SM: the (sample group, chunk, column) items of the time-parallel form are many)
 __global__ void __launch_bounds__(128, 3) k_duo_forward(const DuoArgs Q) {
   extern __shared__ __align__(128) unsigned char duo_smem[];
   const int role = blockIdx.x % Q.nroles;
