@@ -490,6 +490,7 @@ int qocvl_duo_configure(qocvl_plan* p) {
   if (S <= 2304 && M >= 512) {                          // measured on cfg 3 (profiles/README.md): 16 chunks win up to ~2300 samples
     while (chunks < 16 && M / (chunks * 2) >= 64) chunks *= 2;
   }
+  if (S == 1 && M >= 32) chunks = std::max(1, std::min(32, M / 16));   // one sample (notebooks 01 / 02): ~16 slices per chunk
   if (p->has_opt("strong_chunks")) chunks = std::max(1, std::min(std::min(64, M / 4), p->opt("strong_chunks")));
   D.lc = (M + chunks - 1) / chunks;
   D.chunks = (M + D.lc - 1) / D.lc;

@@ -192,14 +192,23 @@ int qocvl_chain_configure(qocvl_plan* p) {
   // a single sample has no ensemble parallelism: cut the slice axis into concurrent chunks instead
   p->use_tp = !p->use_big && p->n_samples == 1 && d.n_slices >= 32 && !p->c64;
   if (p->has_opt("tp")) p->use_tp = p->use_tp && p->opt("tp") != 0;
+  // ... unless the two-lane kernels take the system: their time-parallel form (chain_duo.cu, chunks of ~16 slices) is
+  // 15-25 % faster on the reference's notebook problems.  chain_small.cu's path stays for systems they do not take and
+  // whenever it is asked for (tp = 1 / tp_chunk).
+  const bool tp_asked = p->has_opt("tp_chunk") || (p->has_opt("tp") && p->opt("tp") == 1);
+  const bool single_on_duo = p->use_tp && !tp_asked && p->opt("duo", 1) != 0 && p->opt("aug", 1) != 0 && !p->opt("force_big");
   // ensembles: the reduced stacked system (chain_aug.cu) whenever it fits its kernel
   p->use_aug = false;
   int rc = QOCVL_ERR_UNSUPPORTED;
-  bool try_aug = !p->use_tp && !p->opt("force_big");
+  bool try_aug = (!p->use_tp || single_on_duo) && !p->opt("force_big");
   if (p->has_opt("aug")) try_aug = try_aug && p->opt("aug") != 0;
   if (try_aug) {
     rc = qocvl_aug_configure(p);
     if (rc != QOCVL_OK && rc != QOCVL_ERR_UNSUPPORTED) { p->groups = 0; return rc; }
+    if (single_on_duo) {
+      if (p->use_aug && p->use_duo) p->use_tp = false;
+      else p->use_aug = false;                    // (the lane-group kernel is no match for one sample)
+    }
   }
   // complex64 exists only on the reduced stacked system: anything else fails loudly instead of running in fp64
   if (p->c64 && !p->use_aug) { p->groups = 0; return QOCVL_ERR_UNSUPPORTED; }

@@ -282,12 +282,38 @@ def test_reduced_system_kernels_and_modes_agree(n_samples):
             cost_only = float(prop.target(a, b, c))
             prop._plan.check()
             assert prop._plan.chain_info()["path"] == path, kv
-            assert prop._plan.slice_chunks == kv.get("strong_chunks", 1)
+            assert prop._plan.slice_chunks == kv.get("strong_chunks", 1 if n_samples > 1 or "duo" in kv else 5)   # one sample: M / 16
             assert abs(cost_only - outs[-1][0]) < 1e-14
     for out, (kv, _) in zip(outs[1:], variants[1:]):
         assert np.abs(out[:3] - outs[0][:3]).max() < 1e-13, kv
         assert rel(out[3:], outs[0][3:]) < 1e-10, kv
     assert np.array_equal(outs[0], outs[1])          # CTA geometry does not change the arithmetic: bit for bit
+
+
+def test_profiling_hooks_of_the_two_lane_kernels():
+    """qocvl_last_stage_ms / qocvl_flops_per_call modes / qocvl_hbm_bytes_per_call / qocvl_slice_chunks on a small CZ
+    ensemble: the per-kernel event timings are positive and nest inside the chain's, the flop models are ordered
+    (executed >= M2 on every entry >= needed >= the reverse sweep's share > 0), and the design bytes are the checkpoints
+    (written once, read once) plus the per-warp gradient partials."""
+    from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL
+    po, a, b, c = otq.notebook02_setup(seed=4, n_gauss=6, nt=77)
+    prop = PropagatorVL(6, 77, po.padding, 50e6, po.delta_t, 0.0, po.Vint, po.Delta_i_val, po.Rabi_i_val, po.Rabi_r_val,
+                        otq.GAMMAS_CZ)
+    dl, rs = ensemble.robust_cz_noise(40)
+    prop.set_ensemble(del_total=dl, rabi_scale=rs)
+    plan = prop._plan
+    plan.set_timing(True)
+    for _ in range(2):
+        prop.cost_and_grad_packed(prop._pack(a, b, c))
+    plan.check()
+    assert plan.chain_info()["path"] == "reduced_duo" and plan.slice_chunks == 1
+    total, fwd, rev = plan.last_chain_ms(), plan.last_stage_ms(0), plan.last_stage_ms(1)
+    assert fwd > 0 and rev > 0 and fwd + rev <= total * 1.001
+    executed, needed, rev_share, m2 = (plan.flops_per_call(m) for m in (1, 2, 3, 4))
+    assert executed > m2 > needed > rev_share > 0
+    M, warps = 81, 3                                     # 40 samples = 3 warps of 16 per role
+    ckpt = 2 * warps * M * 96 * 16                       # 2 roles x warps x slices x (3 rows x 32 lanes) complex
+    assert plan.hbm_bytes_per_call(True) >= 2 * ckpt and plan.hbm_bytes_per_call(True) < 2 * ckpt * 1.5
 
 
 def _chain_ensemble(n_atoms, nt, n_samples, seed=11, n_gauss=6):
