@@ -500,9 +500,9 @@ def run_gpu(args):
                                     "adiabaticity": abs(float(o64[2] - result_main[2]))},
                "grad_max_rel_diff_vs_c128": float(np.abs(o64[3:] - result_main[3:]).max() / np.abs(result_main[3:]).max()),
                "stated_bounds": "cost 5e-5 absolute, gradient 1e-2 of its largest entry (include/qocvl.h)",
-               "note": "same workload on the lane-group kernel of chain_aug.cu in complex64 (state, Taylor terms, HBM stream "
-                       "and exchange in fp32, Taylor remainder 2^-26); pulse map, coefficients, cost and gradient reduction "
-                       "in fp64"}
+               "note": "same workload, same kernels (chain_duo.cu) instantiated for float2: state, Taylor powers, entries, "
+                       "checkpoints and Xbar accumulators in fp32, Taylor remainder 2^-26; pulse map, coefficients, cost, "
+                       "terminal cotangent, sample sums and gradient reduction in fp64"}
         prop.set_precision("complex128")
 
     parity, cpu_baseline, configs = None, None, None

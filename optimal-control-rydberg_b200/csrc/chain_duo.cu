@@ -11,6 +11,7 @@ typedef std::complex<double> zc;
 
 // P_u(k) = dt * sum_g coef_kg * val_ug for every (role, lane type, slot): the sample-independent part of the slice
 // generators, once per evaluation.  One block per slice.
+template <typename CT>
 __global__ void k_duo_tables(const DuoArgs Q, const unsigned long long* __restrict__ ent_out,
                              const int* __restrict__ ent_stride) {
   const int k = blockIdx.x;
@@ -20,7 +21,8 @@ __global__ void k_duo_tables(const DuoArgs Q, const unsigned long long* __restri
       const int g = Q.ent_gen[d * Q.KG + i];
       if (g >= 0) acc = cfma(Q.coef[(size_t)k * Q.J + g], Q.ent_val[d * Q.KG + i], acc);
     }
-    ((cplx*)Q.tab)[ent_out[d] + (size_t)k * ent_stride[d]] = cscale(acc, Q.dt);
+    // (stored in the sweep's own type: a conversion inside the sweep would sit right behind the staged load)
+    ((CT*)Q.tab)[ent_out[d] + (size_t)k * ent_stride[d]] = duo_from<CT>(cscale(acc, Q.dt));
   }
 }
 
@@ -160,25 +162,27 @@ __global__ void __launch_bounds__(256) k_duo_reduce(const DuoArgs Q, const unsig
 }
 
 // (three CTAs per SM: the (sample group, chunk, column) items of the time-parallel form are many)
+template <typename CT>
 __global__ void __launch_bounds__(128, 3) k_duo_forward(const DuoArgs Q) {
   extern __shared__ __align__(128) unsigned char duo_smem[];
   const int role = blockIdx.x % Q.nroles;
   switch (Q.variant[role]) {
-    case 0: case 3: duo_forward<DuoPat0>(Q, role, duo_smem); break;   // (the forward sweep has no Xbar: lean = full)
-    case 1: case 4: duo_forward<DuoPat1>(Q, role, duo_smem); break;
-    default: duo_forward<DuoPat2>(Q, role, duo_smem); break;
+    case 0: case 3: duo_forward<DuoPat0, CT>(Q, role, duo_smem); break;   // (the forward sweep has no Xbar: lean = full)
+    case 1: case 4: duo_forward<DuoPat1, CT>(Q, role, duo_smem); break;
+    default: duo_forward<DuoPat2, CT>(Q, role, duo_smem); break;
   }
 }
 
+template <typename CT>
 __global__ void __launch_bounds__(128, 1) k_duo_reverse(const DuoArgs Q) {
   extern __shared__ __align__(128) unsigned char duo_smem[];
   const int role = blockIdx.x % Q.nroles;
   switch (Q.variant[role]) {
-    case 0: duo_reverse<DuoPat0>(Q, role, duo_smem); break;
-    case 1: duo_reverse<DuoPat1>(Q, role, duo_smem); break;
-    case 3: duo_reverse<DuoPat3>(Q, role, duo_smem); break;
-    case 4: duo_reverse<DuoPat4>(Q, role, duo_smem); break;
-    default: duo_reverse<DuoPat2>(Q, role, duo_smem); break;
+    case 0: duo_reverse<DuoPat0, CT>(Q, role, duo_smem); break;
+    case 1: duo_reverse<DuoPat1, CT>(Q, role, duo_smem); break;
+    case 3: duo_reverse<DuoPat3, CT>(Q, role, duo_smem); break;
+    case 4: duo_reverse<DuoPat4, CT>(Q, role, duo_smem); break;
+    default: duo_reverse<DuoPat2, CT>(Q, role, duo_smem); break;
   }
 }
 
@@ -215,7 +219,7 @@ int qocvl_duo_configure(qocvl_plan* p) {
   DuoState& D = p->duo;
   D.release();
   p->use_duo = false;
-  if (p->c64) return QOCVL_ERR_UNSUPPORTED;
+  const int esz = p->c64 ? (int)sizeof(cplxf) : (int)sizeof(cplx);   // element of the sweeps (qocvl_set_precision)
   const int N = p->aug_n, J = p->d.n_gen, M = p->d.n_slices, S = p->n_samples;
   const std::vector<zc>& aug = p->h_aug_gen;
   if ((int)aug.size() != J * N * N || N < 1) return QOCVL_ERR_UNSUPPORTED;
@@ -445,12 +449,12 @@ int qocvl_duo_configure(qocvl_plan* p) {
   int numax = 0;
   for (int r = 0; r < nroles; ++r) numax = std::max(numax, nu[r]);
   int wpc = 4;
-  while (wpc > 1 && (size_t)wpc * duo_smem_layout(numax, p->qcap, true).total > 220 * 1024) wpc >>= 1;
-  if ((size_t)wpc * duo_smem_layout(numax, p->qcap, true).total > 220 * 1024) return QOCVL_ERR_UNSUPPORTED;
+  while (wpc > 1 && (size_t)wpc * duo_smem_layout(numax, p->qcap, true, esz).total > 220 * 1024) wpc >>= 1;
+  if ((size_t)wpc * duo_smem_layout(numax, p->qcap, true, esz).total > 220 * 1024) return QOCVL_ERR_UNSUPPORTED;
   if (p->has_opt("duo_wpc")) wpc = std::max(1, std::min(wpc, p->opt("duo_wpc")));
   D.nroles = nroles; D.wpc = wpc; D.KG = KG; D.ntot = ntot; D.warps_per_role = warps_per_role;
-  D.smem_fwd = (size_t)wpc * duo_smem_layout(numax, p->qcap, false).total;
-  D.smem_rev = (size_t)wpc * duo_smem_layout(numax, p->qcap, true).total;
+  D.smem_fwd = (size_t)wpc * duo_smem_layout(numax, p->qcap, false, esz).total;
+  D.smem_rev = (size_t)wpc * duo_smem_layout(numax, p->qcap, true, esz).total;
   D.numax = numax;
   for (int r = 0; r < nroles; ++r) {
     D.variant[r] = variant[r]; D.nu[r] = nu[r]; D.nx[r] = nx[r]; D.ent0[r] = ent0[r];
@@ -534,13 +538,18 @@ int qocvl_duo_configure(qocvl_plan* p) {
   }
   if (p->d_ckpt) { cudaFree(p->d_ckpt); p->d_ckpt = nullptr; p->bytes -= p->ckpt_bytes; p->ckpt_bytes = 0; }
   if (p->d_ypart) { cudaFree(p->d_ypart); p->d_ypart = nullptr; p->bytes -= p->ypart_bytes; p->ypart_bytes = 0; }
-  p->ckpt_bytes = (size_t)nroles * warps_per_role * M * 96 * sizeof(cplx);
+  p->ckpt_bytes = (size_t)nroles * warps_per_role * M * 96 * esz;
   p->ypart_bytes = y_total * sizeof(cplx);
   QCUDA(cudaMalloc((void**)&p->d_ckpt, p->ckpt_bytes));
   QCUDA(cudaMalloc((void**)&p->d_ypart, std::max<size_t>(16, p->ypart_bytes)));
   p->bytes += p->ckpt_bytes + p->ypart_bytes;
-  QCUDA(cudaFuncSetAttribute(k_duo_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_fwd));
-  QCUDA(cudaFuncSetAttribute(k_duo_reverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_rev));
+  if (p->c64) {
+    QCUDA(cudaFuncSetAttribute(k_duo_forward<cplxf>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_fwd));
+    QCUDA(cudaFuncSetAttribute(k_duo_reverse<cplxf>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_rev));
+  } else {
+    QCUDA(cudaFuncSetAttribute(k_duo_forward<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_fwd));
+    QCUDA(cudaFuncSetAttribute(k_duo_reverse<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_rev));
+  }
   p->aug_store = false;
   p->aug_parts = nroles * warps_per_role;
   p->n_parts = 0;
@@ -572,10 +581,12 @@ int qocvl_duo_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t 
   q.ent_gen = D.d_ent_gen; q.ent_val = D.d_ent_val; q.ent_x = D.d_ent_x;
   q.coef = p->d_coef; q.dcoef = p->d_dcoef; q.qdeg = p->d_qdeg;
   q.starts = D.d_starts; q.targets = D.d_targets; q.pair = D.d_pair; q.wq = D.d_wq;
-  q.ckpt = p->d_ckpt; q.zfin = D.d_zfin; q.lam = D.d_lam; q.ypart = p->d_ypart;
+  q.ckpt = p->d_ckpt;                                   // (elements of the sweeps' type: the kernels cast)
+  q.zfin = D.d_zfin; q.lam = D.d_lam; q.ypart = p->d_ypart;
   q.sample_out = p->d_sample_out; q.gwave = gwave;
   q.ifact[0] = 1.0;
   for (int j = 1; j < QOCVL_QMAX + 2; ++j) q.ifact[j] = q.ifact[j - 1] / (double)j;
+  for (int j = 0; j < QOCVL_QMAX + 2; ++j) q.ifactf[j] = (float)q.ifact[j];
   q.chunks = D.chunks; q.lc = D.lc; q.G = D.G;
   for (int r = 0; r < D.nroles; ++r) { q.ncol[r] = D.ncol[r]; q.mirror[r] = D.mirror[r]; }
   q.colrow = D.d_colrow; q.prop = D.d_prop; q.zstart = D.d_zstart; q.lamend = D.d_lamend;
@@ -598,24 +609,48 @@ int qocvl_duo_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t 
       most = std::max(most, a.warps[r]);
     }
     const int blocks = D.nroles * ((most + D.wpc - 1) / D.wpc);
-    if (reverse) k_duo_reverse<<<blocks, p->threads, D.smem_rev, st>>>(a);
-    else k_duo_forward<<<blocks, p->threads, D.smem_fwd, st>>>(a);
+    if (p->c64) {
+      if (reverse) k_duo_reverse<cplxf><<<blocks, p->threads, D.smem_rev, st>>>(a);
+      else k_duo_forward<cplxf><<<blocks, p->threads, D.smem_fwd, st>>>(a);
+    } else {
+      if (reverse) k_duo_reverse<cplx><<<blocks, p->threads, D.smem_rev, st>>>(a);
+      else k_duo_forward<cplx><<<blocks, p->threads, D.smem_fwd, st>>>(a);
+    }
     p->launches++;
   };
   const bool timed = p->timing_now && p->ev_stage[0];
-  k_duo_tables<<<d.n_slices, 64, 0, st>>>(q, D.d_ent_out, D.d_ent_stride);
+  // "debug_sync" option: synchronise after every launch and name the kernel that failed (diagnostic only)
+  const bool dbg = p->opt("debug_sync") != 0;
+#define DUO_DBG(name)                                                                     \
+  do {                                                                                    \
+    if (dbg) {                                                                            \
+      cudaError_t e_ = cudaStreamSynchronize(st);                                         \
+      if (e_ == cudaSuccess) e_ = cudaGetLastError();                                     \
+      if (e_ != cudaSuccess) {                                                            \
+        g_qocvl_cuda_error = std::string(name) + ": " + cudaGetErrorString(e_);           \
+        return QOCVL_ERR_CUDA;                                                            \
+      }                                                                                   \
+    }                                                                                     \
+  } while (0)
+  if (p->c64) k_duo_tables<cplxf><<<d.n_slices, 64, 0, st>>>(q, D.d_ent_out, D.d_ent_stride);
+  else k_duo_tables<cplx><<<d.n_slices, 64, 0, st>>>(q, D.d_ent_out, D.d_ent_stride);
   p->launches++;
+  DUO_DBG("k_duo_tables");
   if (D.chunks > 1) {            // chunk propagators -> boundary states -> (terminal cost) -> boundary cotangents
     sweep(false, 1);
+    DUO_DBG("k_duo_forward (chunk propagators)");
     k_duo_combine<<<(q.S * q.nroles * 8 + 127) / 128, 128, 0, st>>>(q, +1);
     p->launches++;
+    DUO_DBG("k_duo_combine (+1)");
   } else {
     if (timed) QCUDA(cudaEventRecord(p->ev_stage[0], st));
     sweep(false, 0);
     if (timed) { QCUDA(cudaEventRecord(p->ev_stage[1], st)); p->stage_timed[0] = true; }
+    DUO_DBG("k_duo_forward");
   }
   k_duo_terminal<<<(q.S + 127) / 128, 128, 0, st>>>(q);
   p->launches++;
+  DUO_DBG("k_duo_terminal");
   if (want_grad) {
     if (D.chunks > 1) {
       k_duo_combine<<<(q.S * q.nroles * 8 + 127) / 128, 128, 0, st>>>(q, -1);
@@ -625,8 +660,10 @@ int qocvl_duo_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t 
       if (timed) { QCUDA(cudaEventRecord(p->ev_stage[1], st)); p->stage_timed[0] = true; }
     }
     if (timed) QCUDA(cudaEventRecord(p->ev_stage[2], st));
+    DUO_DBG("k_duo_combine (-1) / k_duo_forward (chunks)");
     sweep(true, D.chunks > 1 ? 2 : 0);
     if (timed) { QCUDA(cudaEventRecord(p->ev_stage[3], st)); p->stage_timed[1] = true; }
+    DUO_DBG("k_duo_reverse");
     k_duo_reduce<<<d.n_slices, 256, 0, st>>>(q, ysrc, ystride, D.d_ent_ywarps);
     p->launches++;
   }

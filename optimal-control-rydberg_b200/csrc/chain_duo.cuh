@@ -87,6 +87,7 @@ struct DuoArgs {
   double* sample_out;   // [S][3]
   double* gwave;        // [M][C]
   double ifact[QOCVL_QMAX + 2];   // 1 / j!
+  float ifactf[QOCVL_QMAX + 2];   // the same for the complex64 sweeps
 };
 
 __host__ __device__ constexpr int duo_popc(unsigned v) { return v == 0 ? 0 : (int)(v & 1u) + duo_popc(v >> 1); }
@@ -142,6 +143,22 @@ __device__ __forceinline__ void duo_for(F&& f) {
 }
 #define DUO_I(v) decltype(v)::value
 
+// ---- arithmetic type of the sweeps: CT = double2 (complex128, the parity path) or float2 (the optional complex64 mode:
+//      state, Taylor powers, entries, checkpoints and the Xbar accumulators in fp32; tables written in fp32 by
+//      k_duo_tables; cost, terminal cotangent, boundary states, the sample sums and the reduction stay fp64)
+template <typename CT> struct DuoReal;
+template <> struct DuoReal<cplx> { typedef double R; };
+template <> struct DuoReal<cplxf> { typedef float R; };
+__device__ __forceinline__ cplx duo_mk(double re, double im, cplx*) { return cmake(re, im); }
+__device__ __forceinline__ cplxf duo_mk(double re, double im, cplxf*) { return cmakef((float)re, (float)im); }
+template <typename CT> __device__ __forceinline__ CT duo_from(const cplx v) { return duo_mk(v.x, v.y, (CT*)nullptr); }
+__device__ __forceinline__ double duo_ifact(const DuoArgs& Q, int j, double*) { return Q.ifact[j]; }
+__device__ __forceinline__ float duo_ifact(const DuoArgs& Q, int j, float*) { return Q.ifactf[j]; }
+__device__ __forceinline__ cplx duo_to_d(const cplx v) { return v; }
+__device__ __forceinline__ cplx duo_to_d(const cplxf v) { return cmake((double)v.x, (double)v.y); }
+__device__ __forceinline__ float duo_xchg(float v) { return __shfl_xor_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ cplxf duo_xchg(cplxf v) { return cmakef(duo_xchg(v.x), duo_xchg(v.y)); }
+
 // ---- small device helpers -----------------------------------------------------------------------------------------
 __device__ __forceinline__ double duo_xchg(double v) {   // partner lane's value (32-bit halves: the CUDA double overload packs with `asm volatile`, which pins the order)
   const int lo = __shfl_xor_sync(0xffffffffu, __double2loint(v), 1);
@@ -176,10 +193,10 @@ __device__ __forceinline__ void duo_bar_wait(unsigned bar, unsigned parity) {
 #define DUO_HALO_SMEM 0   // 1: the two send rows travel through a double-buffered shared-memory slot instead of shuffles
 #endif
 // h[g] = the partner lane's element S_g.  `xs` = this warp's exchange slab [2 buffers][2 rows][32 lanes], `buf` = step parity.
-template <class PT>
-__device__ __forceinline__ void duo_halo(const cplx (&x)[3], cplx (&h)[2], cplx* xs, const int buf, const int lane) {
+template <class PT, typename CT>
+__device__ __forceinline__ void duo_halo(const CT (&x)[3], CT (&h)[2], CT* xs, const int buf, const int lane) {
 #if DUO_HALO_SMEM
-  cplx* slot = xs + buf * 64;
+  CT* slot = xs + buf * 64;
   slot[lane] = x[PT::S0];
   slot[32 + lane] = x[PT::S1];
   __syncwarp();
@@ -196,20 +213,20 @@ __device__ __forceinline__ void duo_halo(const cplx (&x)[3], cplx (&h)[2], cplx*
 // ptxas turns into operand-reuse hits.  That matters because the FP64 pipe of a scheduler is fed one 64-bit register
 // operand per cycle (profiles/micro/dfma_operands.cu: 3.6 cycles per DFMA with three fresh operands and one warp per
 // scheduler, 2.8-2.9 with one operand reused).
-template <bool FIRST>
-__device__ __forceinline__ void duo_fma(double& acc, const double a, const double b) {
+template <bool FIRST, typename R>
+__device__ __forceinline__ void duo_fma(R& acc, const R a, const R b) {
   if constexpr (FIRST) acc = a * b;
   else acc = fma(a, b, acc);
 }
 
 // y = X x on my rows: own block, then the coupling block on the partner's send rows (one exchange per step)
-template <class PT>
-__device__ __forceinline__ void duo_mv(const cplx (&e)[PT::NU], const cplx (&x)[3], cplx (&y)[3], cplx* xs, const int buf,
+template <class PT, typename CT>
+__device__ __forceinline__ void duo_mv(const CT (&e)[PT::NU], const CT (&x)[3], CT (&y)[3], CT* xs, const int buf,
                                        const int lane) {
-  cplx h[2];
+  CT h[2];
   duo_halo<PT>(x, h, xs, buf, lane);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) y[i] = cmake(0.0, 0.0);
+  for (int i = 0; i < 3; ++i) y[i] = duo_mk(0.0, 0.0, (CT*)nullptr);
   duo_for<0, 3>([&](auto ip_) {
     constexpr int ip = DUO_I(ip_);
     duo_for<0, 3>([&](auto i_) {
@@ -251,16 +268,17 @@ __device__ __forceinline__ void duo_mv(const cplx (&e)[PT::NU], const cplx (&x)[
 struct DuoSmem {
   int tab, ck, bars, xs, con_a, us, total;
 };
-__host__ __device__ inline DuoSmem duo_smem_layout(int nu, int qcap, bool reverse) {
+__host__ __device__ inline DuoSmem duo_smem_layout(int nu, int qcap, bool reverse, int esz) {   // esz = sizeof(CT)
   DuoSmem s;
   int o = 0;
-  s.tab = o; o += 2 * DUO_BT * 2 * nu * (int)sizeof(cplx);
-  s.ck = o; o += reverse ? 2 * DUO_BT * 3 * 32 * (int)sizeof(cplx) : 0;
+  s.tab = o; o += 2 * DUO_BT * 2 * nu * esz;
+  s.ck = o; o += reverse ? 2 * DUO_BT * 3 * 32 * esz : 0;
   s.bars = o; o += 16;
-  s.xs = o; o += 2 * 2 * 32 * (int)sizeof(cplx);            // halo exchange slab (DUO_HALO_SMEM)
-  s.con_a = o; o += nu * 32 * (int)sizeof(cplx);
-  s.us = o; o += reverse ? (qcap * 96 > 14 * 33 ? qcap * 96 : 14 * 33) * (int)sizeof(cplx) : 0;   // powers | Xbar staging
-  s.total = o;
+  s.xs = o; o += 2 * 2 * 32 * esz;                          // halo exchange slab (DUO_HALO_SMEM)
+  s.con_a = o; o += nu * 32 * esz;
+  const int powers = qcap * 96 * esz, staging = 14 * 33 * (int)sizeof(cplx);   // powers | Xbar staging (always fp64)
+  s.us = o; o += reverse ? (powers > staging ? powers : staging) : 0;
+  s.total = (o + 15) / 16 * 16;
   return s;
 }
 
@@ -285,9 +303,10 @@ __device__ __forceinline__ DuoItem duo_item(const DuoArgs& Q, const int role, co
 // Forward sweep of one warp: 16 samples x 2 lanes of role `role`.
 // =====================================================================================================================
 // (Tried: the next slice's table values prefetched into a second register set -- 218 registers, 2.39 instead of 2.12 ms.)
-template <class PT>
+template <class PT, typename CT>
 __device__ __forceinline__ void duo_forward(const DuoArgs& Q, const int role, unsigned char* smem_raw) {
   constexpr int NU = PT::NU;
+  typedef typename DuoReal<CT>::R R;
   const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // uniform for the compiler
   const int type = lane & 1, sl = lane >> 1;
   const int wg = (blockIdx.x / Q.nroles) * Q.wpc + warp;          // warp of this role
@@ -296,16 +315,16 @@ __device__ __forceinline__ void duo_forward(const DuoArgs& Q, const int role, un
   const int sample = I.g * DUO_SPW + sl;
   const bool live = sample < Q.S;
   const int sm = live ? sample : Q.S - 1;
-  const double m1 = Q.ncls > 1 ? Q.mcls[(size_t)sm * Q.ncls + 1] : 1.0;
-  const DuoSmem L = duo_smem_layout(NU, Q.qcap, false);
+  const R m1 = (R)(Q.ncls > 1 ? Q.mcls[(size_t)sm * Q.ncls + 1] : 1.0);
+  const DuoSmem L = duo_smem_layout(NU, Q.qcap, false, (int)sizeof(CT));
   unsigned char* base = smem_raw + (size_t)warp * L.total;
-  const cplx* s_tab = (const cplx*)(base + L.tab);
-  cplx* s_a = (cplx*)(base + L.con_a) + lane;
+  const CT* s_tab = (const CT*)(base + L.tab);
+  CT* s_a = (CT*)(base + L.con_a) + lane;
   const unsigned cmask = Q.clsmask[role * 2 + type], amask = Q.amask[role * 2 + type];
-  cplx* s_x = (cplx*)(base + L.xs);
+  CT* s_x = (CT*)(base + L.xs);
   const unsigned bar0 = duo_s32(base + L.bars), tab0 = duo_s32(base + L.tab);
-  const unsigned row_bytes = 2u * NU * sizeof(cplx);              // both lane types of one slice
-  const cplx* gtab = Q.tab + Q.tab_off[role];
+  const unsigned row_bytes = 2u * NU * sizeof(CT);              // both lane types of one slice
+  const CT* gtab = (const CT*)Q.tab + Q.tab_off[role];
   const int k0 = I.k0, nsl = I.k1 - I.k0;                         // my slices: k0 .. k0 + nsl - 1
   const int nb = (nsl + DUO_BT - 1) / DUO_BT;
   auto issue = [&](int b) {
@@ -326,20 +345,21 @@ __device__ __forceinline__ void duo_forward(const DuoArgs& Q, const int role, un
     const cplx* ga = Q.con_a + Q.con_off[role] + (size_t)type * NU * Q.S + sm;
 #pragma unroll
     for (int u = 0; u < NU; ++u)
-      if ((amask >> u) & 1u) s_a[u * 32] = ga[(size_t)u * Q.S];
+      if ((amask >> u) & 1u) s_a[u * 32] = duo_from<CT>(ga[(size_t)u * Q.S]);
   }
+  const CT czero = duo_mk(0.0, 0.0, (CT*)nullptr);
   int srow[3];
-  cplx z[3];
+  CT z[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     srow[i] = Q.srow[(role * 2 + type) * 3 + i];
-    if (Q.mode == 0) z[i] = srow[i] >= 0 ? Q.starts[srow[i]] : cmake(0.0, 0.0);
-    else if (Q.mode == 1) z[i] = cmake(Q.colrow[role * 6 + I.col] == type * 3 + i ? 1.0 : 0.0, 0.0);
-    else z[i] = srow[i] >= 0 ? Q.zstart[((size_t)sm * Q.chunks + I.c) * Q.N + srow[i]] : cmake(0.0, 0.0);
+    if (Q.mode == 0) z[i] = srow[i] >= 0 ? duo_from<CT>(Q.starts[srow[i]]) : czero;
+    else if (Q.mode == 1) z[i] = duo_mk(Q.colrow[role * 6 + I.col] == type * 3 + i ? 1.0 : 0.0, 0.0, (CT*)nullptr);
+    else z[i] = srow[i] >= 0 ? duo_from<CT>(Q.zstart[((size_t)sm * Q.chunks + I.c) * Q.N + srow[i]]) : czero;
   }
   __syncwarp();
   const bool keep = Q.want_grad && Q.mode != 1;
-  cplx* ck = Q.ckpt + ((size_t)(Q.warp0[role] + I.g) * Q.M) * 96 + lane;
+  CT* ck = (CT*)Q.ckpt + ((size_t)(Q.warp0[role] + I.g) * Q.M) * 96 + lane;
   int q_next = __ldg(Q.qdeg + k0);
   for (int b = 0; b < nb; ++b) {
     duo_bar_wait(bar0 + (b & 1) * 8, (b >> 1) & 1);
@@ -348,25 +368,25 @@ __device__ __forceinline__ void duo_forward(const DuoArgs& Q, const int role, un
       const int k = k0 + b * DUO_BT + kk;
       const int q = q_next;
       if (k + 1 < I.k1) q_next = __ldg(Q.qdeg + k + 1);
-      const cplx* row = s_tab + ((size_t)((b & 1) * DUO_BT + kk) * 2 + type) * NU;
-      cplx e[NU];                                          // entry = A_u(s) + m_u(s) P_u(k); m_u is 1 or the sample's class-1
+      const CT* row = s_tab + ((size_t)((b & 1) * DUO_BT + kk) * 2 + type) * NU;
+      CT e[NU];                                            // entry = A_u(s) + m_u(s) P_u(k); m_u is 1 or the sample's class-1
 #pragma unroll                                              // multiplier, A_u exists on few entries (additive noise)
       for (int u = 0; u < NU; ++u) {
-        const cplx pv = row[u];
-        const double mv = ((cmask >> u) & 1u) ? m1 : 1.0;
-        const cplx av = ((amask >> u) & 1u) ? s_a[u * 32] : cmake(0.0, 0.0);
-        e[u] = cmake(fma(mv, pv.x, av.x), fma(mv, pv.y, av.y));
+        const CT pv = row[u];
+        const R mv = ((cmask >> u) & 1u) ? m1 : (R)1;
+        const CT av = ((amask >> u) & 1u) ? s_a[u * 32] : czero;
+        e[u].x = fma(mv, pv.x, av.x); e[u].y = fma(mv, pv.y, av.y);
       }
       if (keep) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) ck[((size_t)k * 3 + i) * 32] = z[i];
       }
-      cplx x[3] = {z[0], z[1], z[2]};
+      CT x[3] = {z[0], z[1], z[2]};
 #pragma unroll kDuoUnroll
       for (int j = 1; j <= q; ++j) {
-        cplx y[3];
+        CT y[3];
         duo_mv<PT>(e, x, y, s_x, j & 1, lane);
-        const double cj = Q.ifact[j];
+        const R cj = duo_ifact(Q, j, (R*)nullptr);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           x[i] = y[i];
@@ -381,12 +401,12 @@ __device__ __forceinline__ void duo_forward(const DuoArgs& Q, const int role, un
   if (live && Q.mode == 0) {
 #pragma unroll
     for (int i = 0; i < 3; ++i)
-      if (srow[i] >= 0) Q.zfin[(size_t)sample * Q.N + srow[i]] = z[i];
+      if (srow[i] >= 0) Q.zfin[(size_t)sample * Q.N + srow[i]] = duo_to_d(z[i]);
   }
   if (live && Q.mode == 1) {                               // column I.col of the chunk propagator of my role
     cplx* pc = Q.prop + ((((size_t)sample * Q.chunks + I.c) * Q.nroles + role) * 6 + I.col) * 6 + type * 3;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) pc[i] = z[i];
+    for (int i = 0; i < 3; ++i) pc[i] = duo_to_d(z[i]);
   }
 }
 
@@ -394,9 +414,10 @@ __device__ __forceinline__ void duo_forward(const DuoArgs& Q, const int role, un
 // Reverse sweep of one warp: recompute the Taylor powers of slice k from its checkpoint, run the adjoint recurrence,
 // accumulate Xbar on my entries, emit the warp's sums.
 // =====================================================================================================================
-template <class PT>
+template <class PT, typename CT>
 __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, unsigned char* smem_raw) {
   constexpr int NU = PT::NU, NX = PT::NX;
+  typedef typename DuoReal<CT>::R R;
   const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int type = lane & 1, sl = lane >> 1;
   const int wg = (blockIdx.x / Q.nroles) * Q.wpc + warp;
@@ -405,19 +426,20 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
   const int sample = I.g * DUO_SPW + sl;
   const bool live = sample < Q.S;
   const int sm = live ? sample : Q.S - 1;
-  const double m1 = Q.ncls > 1 ? Q.mcls[(size_t)sm * Q.ncls + 1] : 1.0;
-  const DuoSmem L = duo_smem_layout(NU, Q.qcap, true);
+  const R m1 = (R)(Q.ncls > 1 ? Q.mcls[(size_t)sm * Q.ncls + 1] : 1.0);
+  const DuoSmem L = duo_smem_layout(NU, Q.qcap, true, (int)sizeof(CT));
   unsigned char* base = smem_raw + (size_t)warp * L.total;
-  const cplx* s_tab = (const cplx*)(base + L.tab);
-  const cplx* s_ck = (const cplx*)(base + L.ck) + lane;
-  cplx* s_a = (cplx*)(base + L.con_a) + lane;
+  const CT* s_tab = (const CT*)(base + L.tab);
+  const CT* s_ck = (const CT*)(base + L.ck) + lane;
+  CT* s_a = (CT*)(base + L.con_a) + lane;
   const unsigned cmask = Q.clsmask[role * 2 + type], amask = Q.amask[role * 2 + type];
-  cplx* s_x = (cplx*)(base + L.xs);
-  cplx* s_u = (cplx*)(base + L.us) + lane;
+  CT* s_x = (CT*)(base + L.xs);
+  CT* s_u = (CT*)(base + L.us) + lane;
+  const CT czero = duo_mk(0.0, 0.0, (CT*)nullptr);
   const unsigned bar0 = duo_s32(base + L.bars), tab0 = duo_s32(base + L.tab), ck0 = duo_s32(base + L.ck);
-  const unsigned row_bytes = 2u * NU * sizeof(cplx), ck_bytes = 96u * sizeof(cplx);
-  const cplx* gtab = Q.tab + Q.tab_off[role];
-  const cplx* gck = Q.ckpt + ((size_t)(Q.warp0[role] + I.g) * Q.M) * 96;
+  const unsigned row_bytes = 2u * NU * sizeof(CT), ck_bytes = 96u * sizeof(CT);
+  const CT* gtab = (const CT*)Q.tab + Q.tab_off[role];
+  const CT* gck = (const CT*)Q.ckpt + ((size_t)(Q.warp0[role] + I.g) * Q.M) * 96;
   const int k0 = I.k0, nsl = I.k1 - I.k0;
   const int nb = (nsl + DUO_BT - 1) / DUO_BT;
   // batch b covers slices [b BT, b BT + cnt); the sweep visits the batches downwards: visit v = nb - 1 - b
@@ -439,14 +461,14 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
     const cplx* ga = Q.con_a + Q.con_off[role] + (size_t)type * NU * Q.S + sm;
 #pragma unroll
     for (int u = 0; u < NU; ++u)
-      if ((amask >> u) & 1u) s_a[u * 32] = ga[(size_t)u * Q.S];
+      if ((amask >> u) & 1u) s_a[u * 32] = duo_from<CT>(ga[(size_t)u * Q.S]);
   }
-  cplx w[3];                                               // running cotangent of my rows
+  CT w[3];                                                 // running cotangent of my rows
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const int sr = Q.srow[(role * 2 + type) * 3 + i];
     const cplx* lsrc = Q.mode == 2 ? Q.lamend + ((size_t)sm * Q.chunks + I.c) * Q.N : Q.lam + (size_t)sm * Q.N;
-    w[i] = (sr >= 0 && live) ? lsrc[sr] : cmake(0.0, 0.0);
+    w[i] = (sr >= 0 && live) ? duo_from<CT>(lsrc[sr]) : czero;
   }
   __syncwarp();
   cplx* yout = Q.ypart + Q.y_off[role] + ((size_t)I.g * Q.M) * 2 * NX;
@@ -455,10 +477,10 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
   // The table values and the checkpoint of the NEXT slice to be visited are loaded right after the adjoint loop of the
   // current one -- into the entry registers, which are dead by then -- so that they arrive behind the Xbar staging
   // instead of in front of the recomputation.
-  cplx e[NU], xk[3];
+  CT e[NU], xk[3];
   auto prefetch = [&](int vv, int kk2) {
-    const cplx* row = s_tab + ((size_t)((vv & 1) * DUO_BT + kk2) * 2 + type) * NU;
-    const cplx* zk = s_ck + (size_t)((vv & 1) * DUO_BT + kk2) * 96;
+    const CT* row = s_tab + ((size_t)((vv & 1) * DUO_BT + kk2) * 2 + type) * NU;
+    const CT* zk = s_ck + (size_t)((vv & 1) * DUO_BT + kk2) * 96;
 #pragma unroll
     for (int u = 0; u < NU; ++u) e[u] = row[u];
     xk[0] = zk[0]; xk[1] = zk[32]; xk[2] = zk[64];
@@ -474,19 +496,19 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
       if (k > k0) q_next = __ldg(Q.qdeg + k - 1);
 #pragma unroll                                              // entry = A_u(s) + m_u(s) P_u(k); m_u is 1 or the sample's class-1
       for (int u = 0; u < NU; ++u) {                       // multiplier, A_u exists on few entries (additive noise)
-        const cplx pv = e[u];
-        const double mv = ((cmask >> u) & 1u) ? m1 : 1.0;
-        const cplx av = ((amask >> u) & 1u) ? s_a[u * 32] : cmake(0.0, 0.0);
-        e[u] = cmake(fma(mv, pv.x, av.x), fma(mv, pv.y, av.y));
+        const CT pv = e[u];
+        const R mv = ((cmask >> u) & 1u) ? m1 : (R)1;
+        const CT av = ((amask >> u) & 1u) ? s_a[u * 32] : czero;
+        e[u].x = fma(mv, pv.x, av.x); e[u].y = fma(mv, pv.y, av.y);
       }
       // ---- recompute u_0 .. u_{q-1}
       {
-        cplx x[3] = {xk[0], xk[1], xk[2]};
+        CT x[3] = {xk[0], xk[1], xk[2]};
 #pragma unroll
         for (int i = 0; i < 3; ++i) s_u[i * 32] = x[i];
 #pragma unroll kDuoUnroll
         for (int j = 1; j < q; ++j) {
-          cplx y[3];
+          CT y[3];
           duo_mv<PT>(e, x, y, s_x, j & 1, lane);
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
@@ -496,27 +518,27 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
         }
       }
       // ---- adjoint recurrence, descending; Xbar on my own block and on the coupling block I own by column
-      cplx lamk[3], xb[NX];
+      CT lamk[3], xb[NX];
       {
-        const double cq = Q.ifact[q];
+        const R cq = duo_ifact(Q, q, (R*)nullptr);
 #pragma unroll
         for (int i = 0; i < 3; ++i) { lamk[i] = w[i]; w[i] = cscale(w[i], cq); }
       }
 #pragma unroll
-      for (int x = 0; x < NX; ++x) xb[x] = cmake(0.0, 0.0);
-      cplx u[3] = {s_u[((q - 1) * 3 + 0) * 32], s_u[((q - 1) * 3 + 1) * 32], s_u[((q - 1) * 3 + 2) * 32]};
+      for (int x = 0; x < NX; ++x) xb[x] = czero;
+      CT u[3] = {s_u[((q - 1) * 3 + 0) * 32], s_u[((q - 1) * 3 + 1) * 32], s_u[((q - 1) * 3 + 2) * 32]};
 #pragma unroll kDuoUnroll
       for (int j = q; j >= 1; --j) {
-        cplx wh[2];
+        CT wh[2];
         duo_halo<PT>(w, wh, s_x, j & 1, lane);
-        cplx un[3];                                        // next step's powers: in flight during this step
+        CT un[3];                                          // next step's powers: in flight during this step
         {
           const int jn = j >= 2 ? j - 2 : 0;
 #pragma unroll
           for (int i = 0; i < 3; ++i) un[i] = s_u[(jn * 3 + i) * 32];
         }
-        const double cj = Q.ifact[j - 1];
-        cplx wn[3];                                        // w_{j-1} = c_{j-1} lam + X^dag w_j  (conjugated entries)
+        const R cj = duo_ifact(Q, j - 1, (R*)nullptr);
+        CT wn[3];                                          // w_{j-1} = c_{j-1} lam + X^dag w_j  (conjugated entries)
 #pragma unroll
         for (int i = 0; i < 3; ++i) wn[i] = cscale(lamk[i], cj);
         // own block, source element w[ip] at a time: X^dag w (column i of row ip) and Xbar (row ip: conj(w_ip) u_i)
@@ -583,11 +605,11 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
       //      (profiles/micro/latency.cu) -- it was 10 % of the reverse sweep.  Fixed summation order: deterministic.
       duo_for<0, NX>([&](auto x_) {                       // (all multiplier loads before the first store: the
         constexpr int x = DUO_I(x_);                       //  compiler cannot reorder them across possibly aliasing stores)
-        xb[x] = cscale(xb[x], ((cmask >> PT::ux(x)) & 1u) ? m1 : 1.0);
+        xb[x] = cscale(xb[x], ((cmask >> PT::ux(x)) & 1u) ? m1 : (R)1);
       });
       __syncwarp();                                        // every lane is done with its powers
 #pragma unroll
-      for (int x = 0; x < NX; ++x) s_e[x * 33 + lane] = xb[x];
+      for (int x = 0; x < NX; ++x) s_e[x * 33 + lane] = duo_to_d(xb[x]);
       __syncwarp();
       if (lane < 2 * NX) {                                 // lane = 2 x + lane type: sum its 16 samples
         const cplx* src = s_e + (lane >> 1) * 33 + (lane & 1);

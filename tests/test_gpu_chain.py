@@ -496,15 +496,17 @@ def test_complex64_ensemble_within_stated_bounds_of_oracle_and_of_complex128():
     prop.set_ensemble(del_total=dl, rabi_scale=rs)
     full = np_(prop.cost_and_grad_packed(prop._pack(a, b, c))).copy()
     outs = {}
-    for flag in (1, 0):                                    # streamed terms / checkpoints + recomputation
-        with env(QOCVL_STORE=flag):
+    # two-lane kernels in fp32 (default) / lane-group kernel with streamed terms / with checkpoints + recomputation
+    for flag, (kv, path) in enumerate([({}, "reduced_duo"), ({"duo": 0}, "reduced_stacked_streamed"),
+                                       ({"duo": 0, "store": 0}, "reduced_stacked")]):
+        with env(**kv):
             p64 = PropagatorVL(*args)
             p64.set_precision("complex64")
             assert p64._plan.precision == "complex64"
             p64.set_ensemble(del_total=dl, rabi_scale=rs)
             outs[flag] = np_(p64.cost_and_grad_packed(p64._pack(a, b, c))).copy()
             p64._plan.check()
-            assert p64._plan.chain_info()["path"] == ("reduced_stacked_streamed" if flag else "reduced_stacked")
+            assert p64._plan.chain_info()["path"] == path
     n = 8 * 5
     for out in outs.values():
         assert np.abs(out[:3] - np.array(ref[:3])).max() < TOL_C64_COST          # vs the CPU oracle
@@ -512,17 +514,16 @@ def test_complex64_ensemble_within_stated_bounds_of_oracle_and_of_complex128():
         for i, r in enumerate(ref[3:6]):
             assert rel(out[3 + i * n:3 + (i + 1) * n], np.asarray(r).ravel()) < TOL_C64_GRAD_REL
         assert np.abs(out - full).max() > 0.0                                    # it really is another arithmetic
-    # both modes of the complex64 kernel see the same terms up to fp32 rounding
-    assert np.abs(outs[1][:3] - outs[0][:3]).max() < TOL_C64_COST
-    # switching back gives the complex128 numbers bit for bit
+    # the complex64 kernels see the same terms up to fp32 rounding
+    assert np.abs(outs[1][:3] - outs[0][:3]).max() < TOL_C64_COST and np.abs(outs[2][:3] - outs[1][:3]).max() < TOL_C64_COST
+    # switching back gives the complex128 numbers
     p64.set_precision("complex128")
-    with env(QOCVL_STORE=0):
-        back = np_(p64.cost_and_grad_packed(p64._pack(a, b, c))).copy()
+    back = np_(p64.cost_and_grad_packed(p64._pack(a, b, c))).copy()
     assert np.abs(back[:3] - full[:3]).max() < 1e-13 and rel(back[3:], full[3:]) < 1e-10
 
 
 def test_complex64_single_sample_and_state_transfer():
-    """One sample (no time-parallel path in complex64: the reduced kernel takes it) and the 5-level model."""
+    """One sample (the time-parallel form of the two-lane kernels, in fp32) and the 5-level model."""
     from oracle import autograd_ref, state_transfer as ost
     from quantum_optimal_control.state_transfer.propagator_vl import PropagatorVL as StVL
     from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL as TqVL
@@ -536,7 +537,7 @@ def test_complex64_single_sample_and_state_transfer():
         engine.set_precision("complex64")
         cost, grads = engine.target_and_grad(*ctrl)
         engine._plan.check()
-        assert engine._plan.chain_info()["path"].startswith("reduced_stacked")
+        assert engine._plan.chain_info()["path"] == "reduced_duo" and engine._plan.slice_chunks > 1
         ref = autograd_ref.value_and_grad(model, *ctrl)
         assert abs(float(cost) - ref[0]) < TOL_C64_COST
         for mine, r in zip(grads, ref[3:]):
@@ -573,7 +574,7 @@ def test_complex64_optimiser_loop_replays_from_a_graph_and_tracks_complex128():
     hist_g, ag, bg, cg = prop.optimize(a, b, c, num_iters=12, lr=0.02)
     hist_e, ae, be, ce = prop.optimize(a, b, c, num_iters=12, lr=0.02, use_graph=False)
     prop._plan.check()
-    assert prop._plan.precision == "complex64" and prop._plan.chain_info()["path"] == "reduced_stacked_streamed"
+    assert prop._plan.precision == "complex64" and prop._plan.chain_info()["path"] == "reduced_duo"
     assert torch.equal(hist_g, hist_e) and torch.equal(ag, ae) and torch.equal(cg, ce)
     assert float(hist_g[-1]) < float(hist_g[0])
     assert float((hist_g - hist_128).abs().max()) < TOL_C64_COST
