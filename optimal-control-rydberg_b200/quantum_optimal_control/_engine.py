@@ -210,18 +210,22 @@ class EngineBase:
 
     # -- the optimiser loop of the notebooks, kept on the device ------------------------------------------
     def optimize(self, ctrl_a, ctrl_b, ctrl_c, num_iters, lr, masks=None, use_graph=True, method="gd",
-                 betas=(0.9, 0.999), eps=1e-8):
+                 betas=(0.9, 0.999), eps=1e-8, history=8):
         """``num_iters`` plain gradient-descent steps (notebook 01 cell 9, notebook 02 cell 13:
         ``ctrl -= lr * grad`` with the cost recorded BEFORE each update, TQ:580-600) without a host
         synchronisation per step.  ``masks`` = optional (mask_a, mask_b, mask_c) multiplied into the
         gradients (notebook 04 cells 5, 12: frozen columns).  One step is captured in a CUDA graph and
         replayed; the cost history stays on the device.  ``method="adam"`` replaces the update by Adam (Kingma & Ba;
         bias-corrected moments, the masks multiply the final step so frozen entries stay frozen) -- the reference only
-        has plain descent; same loop, same graph capture.
+        has plain descent; same loop, same graph capture.  ``method="lbfgs"``: limited-memory BFGS direction (two-loop
+        recursion over the last ``history`` (s, y) pairs, initial scaling s.y / y.y, pairs with s.y <= 0 skipped, the
+        first step is plain descent) with the fixed step ``lr`` instead of a line search, so that the whole step stays on
+        the device and inside the same CUDA graph; the pair buffers are shifted, not indexed, and empty slots carry
+        rho = 0, which makes every replay the same launch sequence.
 
         Returns (cost_history [num_iters] CUDA tensor, a, b, c) with a, b, c CUDA tensors [input_dim, C]."""
-        if method not in ("gd", "adam"):
-            raise ValueError("method must be 'gd' or 'adam'")
+        if method not in ("gd", "adam", "lbfgs"):
+            raise ValueError("method must be 'gd', 'adam' or 'lbfgs'")
         dev = self.device
         abc = self._pack(ctrl_a, ctrl_b, ctrl_c).clone()
         n = 3 * self.input_dim * self.num_ctrls
@@ -238,12 +242,51 @@ class EngineBase:
         pow1 = torch.ones(1, dtype=torch.float64, device=dev)      # beta1^t, beta2^t kept on the device (graph replay)
         pow2 = torch.ones(1, dtype=torch.float64, device=dev)
 
+        hm = max(1, int(history))
+        nflat = abc.numel()
+        s_buf = torch.zeros(hm, nflat, dtype=torch.float64, device=dev)     # newest pair in row 0
+        y_buf = torch.zeros(hm, nflat, dtype=torch.float64, device=dev)
+        rho = torch.zeros(hm, dtype=torch.float64, device=dev)
+        x_prev, g_prev = torch.zeros(nflat, dtype=torch.float64, device=dev), torch.zeros(nflat, dtype=torch.float64, device=dev)
+        have_prev = torch.zeros(1, dtype=torch.float64, device=dev)
+        mask_flat = (scale != 0).to(torch.float64).reshape(-1)
+
+        def lbfgs_direction(g):
+            # new pair from the previous iterate (ignored on the first step and when the curvature condition fails)
+            s_new, y_new = (abc.reshape(-1) - x_prev) * have_prev, (g - g_prev) * have_prev
+            sy = (s_new * y_new).sum()     # (no cuBLAS inside the captured step: plain reductions)
+            ok = (sy > 1e-300).to(torch.float64)
+            s_buf.copy_(torch.roll(s_buf, 1, 0)); y_buf.copy_(torch.roll(y_buf, 1, 0)); rho.copy_(torch.roll(rho, 1, 0))
+            s_buf[0].copy_(s_new * ok); y_buf[0].copy_(y_new * ok)
+            rho[0:1].copy_((ok / torch.where(sy > 1e-300, sy, torch.ones_like(sy))).reshape(1))
+            x_prev.copy_(abc.reshape(-1)); g_prev.copy_(g); have_prev.fill_(1.0)
+            q = g.clone()
+            alphas = []
+            for i in range(hm):                           # newest to oldest
+                a_i = rho[i] * (s_buf[i] * q).sum()
+                q = q - a_i * y_buf[i]
+                alphas.append(a_i)
+            # initial Hessian scaling from the newest VALID pair (1 when there is none)
+            yy = (y_buf * y_buf).sum(1)
+            gam_all = torch.where(rho > 0, 1.0 / (rho * torch.where(yy > 0, yy, torch.ones_like(yy))), torch.zeros_like(rho))
+            first = torch.cumsum((rho > 0).to(torch.float64), 0)
+            pick = ((rho > 0) & (first == 1)).to(torch.float64)
+            gamma = (gam_all * pick).sum() + (1.0 - pick.sum())
+            r = gamma * q
+            for i in reversed(range(hm)):                 # oldest to newest
+                b_i = rho[i] * (y_buf[i] * r).sum()
+                r = r + s_buf[i] * (alphas[i] - b_i)
+            return r
+
         def one_step():
             self.cost_and_grad_packed(abc, out)
             hist.index_copy_(0, step_idx, out[0:1])
             g = out[3:].view_as(abc)
             if method == "gd":
                 abc.sub_(scale * g)
+            elif method == "lbfgs":
+                d = lbfgs_direction(g.reshape(-1) * mask_flat)
+                abc.sub_(scale * d.view_as(abc))
             else:
                 m1.mul_(betas[0]).add_(g, alpha=1.0 - betas[0])
                 m2.mul_(betas[1]).addcmul_(g, g, value=1.0 - betas[1])

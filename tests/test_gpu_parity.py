@@ -404,4 +404,49 @@ def test_device_side_adam_matches_a_host_adam_loop():
     assert np.array_equal(fc.cpu().numpy(), np.asarray(c, float))
     assert float(hist[-1]) < float(hist[0])
     with pytest.raises(ValueError):
-        prop.optimize(a, b, c, num_iters=2, lr=0.01, method="lbfgs")
+        prop.optimize(a, b, c, num_iters=2, lr=0.01, method="newton")
+
+
+def test_device_side_lbfgs_matches_a_host_two_loop_recursion():
+    """optimize(method="lbfgs") (optional): the graph-replayed device loop equals eager launches bit for bit
+    and a NumPy two-loop recursion (same pair policy: newest first, s.y <= 0 skipped, gamma = s.y / y.y, fixed step)
+    driven by the engine's own gradients; frozen entries stay frozen; it descends further than plain descent with the
+    notebook's step in the same number of evaluations."""
+    from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL
+    po, a, b, c = otq.notebook02_setup(seed=12, n_gauss=5, nt=60)
+    prop = PropagatorVL(5, 60, po.padding, 50e6, po.delta_t, 0.0, po.Vint, po.Delta_i_val, po.Rabi_i_val,
+                        po.Rabi_r_val, otq.GAMMAS_CZ)
+    masks = (np.ones((5, 5)), np.ones((5, 5)), np.zeros((5, 5)))          # widths frozen
+    iters, lr, hm = 10, 0.5, 4
+    hist, fa, fb, fc = prop.optimize(a, b, c, num_iters=iters, lr=lr, masks=masks, method="lbfgs", history=hm)
+    hist_e, ea, eb, ec = prop.optimize(a, b, c, num_iters=iters, lr=lr, masks=masks, method="lbfgs", history=hm,
+                                       use_graph=False)
+    assert torch.equal(hist, hist_e) and torch.equal(fa, ea) and torch.equal(fb, eb)
+    x = np.stack([a, b, c]).astype(float)
+    mk = np.stack(masks).reshape(-1)
+    slots, costs, x_prev, g_prev = [], [], None, None
+    for _ in range(iters):
+        cost, (ga, gb, gc) = prop.target_and_grad(x[0], x[1], x[2])
+        g = np.stack([ga.cpu().numpy(), gb.cpu().numpy(), gc.cpu().numpy()]).reshape(-1) * mk
+        costs.append(float(cost))
+        if x_prev is not None:
+            s_new, y_new = x.reshape(-1) - x_prev, g - g_prev
+            # a pair that fails the curvature condition still takes a slot of the window (as an empty one)
+            slots.insert(0, (s_new, y_new, 1.0 / (s_new @ y_new)) if s_new @ y_new > 1e-300 else None)
+            del slots[hm:]
+        pairs = [p_ for p_ in slots if p_ is not None]
+        x_prev, g_prev = x.reshape(-1).copy(), g.copy()
+        q, alphas = g.copy(), []
+        for s_i, y_i, r_i in pairs:
+            a_i = r_i * (s_i @ q)
+            q -= a_i * y_i
+            alphas.append(a_i)
+        r = q * ((pairs[0][0] @ pairs[0][1]) / (pairs[0][1] @ pairs[0][1]) if pairs else 1.0)
+        for (s_i, y_i, r_i), a_i in zip(reversed(pairs), reversed(alphas)):
+            r += s_i * (a_i - r_i * (y_i @ r))
+        x = x - lr * (mk * r).reshape(x.shape)
+    assert np.abs(hist.cpu().numpy() - np.array(costs)).max() < 1e-9
+    assert np.abs(fa.cpu().numpy() - x[0]).max() < 1e-8 and np.abs(fb.cpu().numpy() - x[1]).max() < 1e-8
+    assert np.array_equal(fc.cpu().numpy(), np.asarray(c, float))
+    hist_gd, *_ = prop.optimize(a, b, c, num_iters=iters, lr=0.02, masks=masks)
+    assert float(hist[-1]) < float(hist[0]) and float(hist[-1]) < float(hist_gd[-1])
