@@ -290,6 +290,36 @@ def test_reduced_system_kernels_and_modes_agree(n_samples):
     assert np.array_equal(outs[0], outs[1])          # CTA geometry does not change the arithmetic: bit for bit
 
 
+@pytest.mark.parametrize("n_atoms", [2, 3, 4])
+def test_two_lane_kernels_on_other_small_systems(n_atoms):
+    """The cut search of chain_duo.cu on systems other than the reference's two models: blockade chains of 2-4 atoms
+    (n = 3, 5, 8).  n = 3 is a star graph (its {U psi, W psi} pair needs a row order the search has to find); n = 5 and
+    n = 8 have sectors of more than 6 rows and must fall back.  Whatever path is chosen agrees with the lane-group kernel
+    and with the dense oracle."""
+    po, a, b, c = obc.chain_setup(n_atoms=n_atoms, n_gauss=4, nt=40)
+    rng = np.random.default_rng(5)
+    dl, rs = rng.normal(0, 2 * np.pi * 0.1e6, 7), 1 + rng.normal(0, 0.01, 7)
+    outs, paths = [], []
+    for kv in ({}, {"duo": 0}, {"strong_chunks": 3}):
+        with env(**kv):
+            prop = make_chain(po)
+            prop.set_ensemble(del_total=dl, rabi_scale=rs)
+            outs.append(np_(prop.cost_and_grad_packed(prop._pack(a, b, c))).copy())
+            prop._plan.check()
+            paths.append(prop._plan.chain_info()["path"])
+    assert paths[0] == ("reduced_duo" if n_atoms == 2 else paths[1])
+    for out in outs[1:]:
+        assert np.abs(out[:3] - outs[0][:3]).max() < 1e-13 and rel(out[3:], outs[0][3:]) < 1e-10
+    acc = None
+    for d, s in zip(dl, rs):
+        member, *_ = obc.chain_setup(n_atoms=n_atoms, n_gauss=4, nt=40, del_offset=float(d), rabi_scale=float(s))
+        vals = [np.asarray(x, float) for x in member.value_and_grad(a, b, c)]
+        acc = vals if acc is None else [x + y for x, y in zip(acc, vals)]
+    ref = [x / len(dl) for x in acc]
+    assert np.abs(outs[0][:3] - np.array(ref[:3])).max() < 1e-10
+    assert rel(outs[0][3:11], ref[3].ravel()) < 1e-8
+
+
 def test_profiling_hooks_of_the_two_lane_kernels():
     """qocvl_last_stage_ms / qocvl_flops_per_call modes / qocvl_hbm_bytes_per_call / qocvl_slice_chunks on a small CZ
     ensemble: the per-kernel event timings are positive and nest inside the chain's, the flop models are ordered
