@@ -142,7 +142,9 @@ int qocvl_set_shard(qocvl_plan* plan, int global_samples);
  * time-parallel single-sample path), "tp_chunk" (slices per chunk), "tlocal", "wide" (0 = no samples-minor kernel),
  * "wide_store", "wide_spc", "wide_threads", "strong_chunks" (slice-axis chunks of the time-parallel evaluation of an
  * ensemble on the two-lane kernels; automatic: 1 above ~1500 samples, up to 16 below), "duo_nomirror" (1 = sweep every
- * basis column of a chunk propagator), "duo_nolean" (1 = qocvl_cost_grad accumulates the gradient of every matrix entry,
+ * basis column of a chunk propagator), "duo_cols" (1 = three basis columns per work item of the chunk-propagator sweep instead of one),
+ * "debug_sync" (1 = synchronise after every launch of the two-lane path and name the kernel that failed),
+ * "duo_nolean" (1 = qocvl_cost_grad accumulates the gradient of every matrix entry,
  * also of those only a pulse channel that the model's pulse map discards would consume).
  * They exist so that every kernel path can be cross-checked against the others on the same plan API.
  * QOCVL_ERR_ARG for an unknown name. */

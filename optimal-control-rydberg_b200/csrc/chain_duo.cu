@@ -173,6 +173,18 @@ __global__ void __launch_bounds__(128, 3) k_duo_forward(const DuoArgs Q) {
   }
 }
 
+// chunk propagators: DUO_COLS basis columns per item (two CTAs per SM)
+template <typename CT>
+__global__ void __launch_bounds__(128, 2) k_duo_forward_cols(const DuoArgs Q) {
+  extern __shared__ __align__(128) unsigned char duo_smem[];
+  const int role = blockIdx.x % Q.nroles;
+  switch (Q.variant[role]) {
+    case 0: case 3: duo_forward_cols<DuoPat0, CT, DUO_COLS>(Q, role, duo_smem); break;
+    case 1: case 4: duo_forward_cols<DuoPat1, CT, DUO_COLS>(Q, role, duo_smem); break;
+    default: duo_forward_cols<DuoPat2, CT, DUO_COLS>(Q, role, duo_smem); break;
+  }
+}
+
 template <typename CT>
 __global__ void __launch_bounds__(128, 1) k_duo_reverse(const DuoArgs Q) {
   extern __shared__ __align__(128) unsigned char duo_smem[];
@@ -545,9 +557,11 @@ int qocvl_duo_configure(qocvl_plan* p) {
   p->bytes += p->ckpt_bytes + p->ypart_bytes;
   if (p->c64) {
     QCUDA(cudaFuncSetAttribute(k_duo_forward<cplxf>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_fwd));
+    QCUDA(cudaFuncSetAttribute(k_duo_forward_cols<cplxf>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_fwd));
     QCUDA(cudaFuncSetAttribute(k_duo_reverse<cplxf>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_rev));
   } else {
     QCUDA(cudaFuncSetAttribute(k_duo_forward<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_fwd));
+    QCUDA(cudaFuncSetAttribute(k_duo_forward_cols<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_fwd));
     QCUDA(cudaFuncSetAttribute(k_duo_reverse<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_rev));
   }
   p->aug_store = false;
@@ -587,7 +601,7 @@ int qocvl_duo_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t 
   q.ifact[0] = 1.0;
   for (int j = 1; j < QOCVL_QMAX + 2; ++j) q.ifact[j] = q.ifact[j - 1] / (double)j;
   for (int j = 0; j < QOCVL_QMAX + 2; ++j) q.ifactf[j] = (float)q.ifact[j];
-  q.chunks = D.chunks; q.lc = D.lc; q.G = D.G;
+  q.chunks = D.chunks; q.lc = D.lc; q.G = D.G; q.cpi = 1;
   for (int r = 0; r < D.nroles; ++r) { q.ncol[r] = D.ncol[r]; q.mirror[r] = D.mirror[r]; }
   q.colrow = D.d_colrow; q.prop = D.d_prop; q.zstart = D.d_zstart; q.lamend = D.d_lamend;
   // pulse-map path: the reverse sweep and the reduction skip what only a dead channel would consume
@@ -603,17 +617,23 @@ int qocvl_duo_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t 
   auto sweep = [&](bool reverse, int mode) {
     DuoArgs a = q;
     a.mode = mode;
+    // (several basis columns per item share the entry registers, but measured SLOWER: 0.95 vs 0.87 ms at 512 samples --
+    //  a third of the warps, 214 registers; kept behind "duo_cols" = 1 as a cross-check)
+    const bool cols = mode == 1 && p->opt("duo_cols", 0) != 0;
+    a.cpi = cols ? DUO_COLS : 1;
     int most = 0;
     for (int r = 0; r < D.nroles; ++r) {
-      a.warps[r] = D.G * (mode == 0 ? 1 : D.chunks) * (mode == 1 ? D.ncol[r] : 1);
+      a.warps[r] = D.G * (mode == 0 ? 1 : D.chunks) * (mode == 1 ? (D.ncol[r] + a.cpi - 1) / a.cpi : 1);
       most = std::max(most, a.warps[r]);
     }
     const int blocks = D.nroles * ((most + D.wpc - 1) / D.wpc);
     if (p->c64) {
       if (reverse) k_duo_reverse<cplxf><<<blocks, p->threads, D.smem_rev, st>>>(a);
+      else if (cols) k_duo_forward_cols<cplxf><<<blocks, p->threads, D.smem_fwd, st>>>(a);
       else k_duo_forward<cplxf><<<blocks, p->threads, D.smem_fwd, st>>>(a);
     } else {
       if (reverse) k_duo_reverse<cplx><<<blocks, p->threads, D.smem_rev, st>>>(a);
+      else if (cols) k_duo_forward_cols<cplx><<<blocks, p->threads, D.smem_fwd, st>>>(a);
       else k_duo_forward<cplx><<<blocks, p->threads, D.smem_fwd, st>>>(a);
     }
     p->launches++;

@@ -53,6 +53,7 @@ struct DuoArgs {
   // mode 2: (sample group, chunk) items sweep one chunk between the boundary states / cotangents that k_duo_combine
   // obtained from the chunk propagators.
   int mode, chunks, lc, G;
+  int cpi;                // mode 1: basis columns swept by one item (DUO_COLS on the multi-column kernel, else 1)
   int ncol[DUO_MAXR], mirror[DUO_MAXR];   // mirror: 1 + lane type whose own-block propagator is copied to the other triple
   int variant[DUO_MAXR], nu[DUO_MAXR], nx[DUO_MAXR], warps[DUO_MAXR];
   unsigned long long tab_off[DUO_MAXR], con_off[DUO_MAXR], y_off[DUO_MAXR], warp0[DUO_MAXR];
@@ -290,8 +291,8 @@ __device__ __forceinline__ DuoItem duo_item(const DuoArgs& Q, const int role, co
   DuoItem I;
   I.col = 0; I.c = 0; I.g = it; I.k0 = 0; I.k1 = Q.M;
   if (Q.mode == 1) {
-    const int nc = Q.ncol[role];
-    I.col = it % nc; I.c = (it / nc) % Q.chunks; I.g = it / (nc * Q.chunks);
+    const int nc = (Q.ncol[role] + Q.cpi - 1) / Q.cpi;    // column groups of the role
+    I.col = (it % nc) * Q.cpi; I.c = (it / nc) % Q.chunks; I.g = it / (nc * Q.chunks);
   } else if (Q.mode == 2) {
     I.c = it % Q.chunks; I.g = it / Q.chunks;
   }
@@ -407,6 +408,152 @@ __device__ __forceinline__ void duo_forward(const DuoArgs& Q, const int role, un
     cplx* pc = Q.prop + ((((size_t)sample * Q.chunks + I.c) * Q.nroles + role) * 6 + I.col) * 6 + type * 3;
 #pragma unroll
     for (int i = 0; i < 3; ++i) pc[i] = duo_to_d(z[i]);
+  }
+}
+
+// =====================================================================================================================
+// Chunk propagators (mode 1), NC basis columns per item: the columns share the matrix entries, so the mat-vec issues NC
+// consecutive DFMAs per entry component with the SAME entry register (operand-reuse hits: 2.3-2.9 instead of 3.0-3.6
+// cycles per DFMA), and the per-slice entry assembly is paid once for NC columns.
+// =====================================================================================================================
+#define DUO_COLS 3
+template <class PT, typename CT, int NC>
+__device__ __forceinline__ void duo_forward_cols(const DuoArgs& Q, const int role, unsigned char* smem_raw) {
+  constexpr int NU = PT::NU;
+  typedef typename DuoReal<CT>::R R;
+  const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int type = lane & 1, sl = lane >> 1;
+  const int wg = (blockIdx.x / Q.nroles) * Q.wpc + warp;
+  if (wg >= Q.warps[role]) return;
+  const DuoItem I = duo_item(Q, role, wg);
+  const int sample = I.g * DUO_SPW + sl;
+  const bool live = sample < Q.S;
+  const int sm = live ? sample : Q.S - 1;
+  const R m1 = (R)(Q.ncls > 1 ? Q.mcls[(size_t)sm * Q.ncls + 1] : 1.0);
+  const DuoSmem L = duo_smem_layout(NU, Q.qcap, false, (int)sizeof(CT));
+  unsigned char* base = smem_raw + (size_t)warp * L.total;
+  const CT* s_tab = (const CT*)(base + L.tab);
+  CT* s_a = (CT*)(base + L.con_a) + lane;
+  const unsigned cmask = Q.clsmask[role * 2 + type], amask = Q.amask[role * 2 + type];
+  const unsigned bar0 = duo_s32(base + L.bars), tab0 = duo_s32(base + L.tab);
+  const unsigned row_bytes = 2u * NU * sizeof(CT);
+  const CT* gtab = (const CT*)Q.tab + Q.tab_off[role];
+  const int k0 = I.k0, nsl = I.k1 - I.k0;
+  const int nb = (nsl + DUO_BT - 1) / DUO_BT;
+  auto issue = [&](int b) {
+    const int cnt = min(DUO_BT, nsl - b * DUO_BT);
+    const unsigned bar = bar0 + (b & 1) * 8, bytes = cnt * row_bytes;
+    duo_bar_expect(bar, bytes);
+    duo_bulk(tab0 + (b & 1) * DUO_BT * row_bytes, gtab + (size_t)(k0 + b * DUO_BT) * 2 * NU, bytes, bar);
+  };
+  if (lane == 0) {
+    duo_bar_init(bar0);
+    duo_bar_init(bar0 + 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    issue(0);
+    if (nb > 1) issue(1);
+  }
+  {
+    const cplx* ga = Q.con_a + Q.con_off[role] + (size_t)type * NU * Q.S + sm;
+#pragma unroll
+    for (int u = 0; u < NU; ++u)
+      if ((amask >> u) & 1u) s_a[u * 32] = duo_from<CT>(ga[(size_t)u * Q.S]);
+  }
+  const CT czero = duo_mk(0.0, 0.0, (CT*)nullptr);
+  CT z[NC][3];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const bool one = I.col + c < Q.ncol[role] && Q.colrow[role * 6 + min(I.col + c, 5)] == type * 3 + i;
+      z[c][i] = duo_mk(one ? 1.0 : 0.0, 0.0, (CT*)nullptr);
+    }
+  __syncwarp();
+  int q_next = __ldg(Q.qdeg + k0);
+  for (int b = 0; b < nb; ++b) {
+    duo_bar_wait(bar0 + (b & 1) * 8, (b >> 1) & 1);
+    const int cnt = min(DUO_BT, nsl - b * DUO_BT);
+    for (int kk = 0; kk < cnt; ++kk) {
+      const int k = k0 + b * DUO_BT + kk;
+      const int q = q_next;
+      if (k + 1 < I.k1) q_next = __ldg(Q.qdeg + k + 1);
+      const CT* row = s_tab + ((size_t)((b & 1) * DUO_BT + kk) * 2 + type) * NU;
+      CT e[NU];
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const CT pv = row[u];
+        const R mv = ((cmask >> u) & 1u) ? m1 : (R)1;
+        const CT av = ((amask >> u) & 1u) ? s_a[u * 32] : czero;
+        e[u].x = fma(mv, pv.x, av.x); e[u].y = fma(mv, pv.y, av.y);
+      }
+      CT x[NC][3];
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) x[c][i] = z[c][i];
+      for (int j = 1; j <= q; ++j) {
+        CT h[NC][2], y[NC][3];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { h[c][0] = duo_xchg(x[c][PT::S0]); h[c][1] = duo_xchg(x[c][PT::S1]); }
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+          for (int i = 0; i < 3; ++i) y[c][i] = czero;
+        duo_for<0, 3>([&](auto ip_) {
+          constexpr int ip = DUO_I(ip_);
+          duo_for<0, 3>([&](auto i_) {
+            constexpr int i = DUO_I(i_);
+            if constexpr (PT::ht(i, ip)) {
+              constexpr bool first = (PT::TM & ((1u << (3 * i + ip)) - 1u) & (7u << (3 * i))) == 0u;
+              const CT ev = e[PT::t(i, ip)];
+#pragma unroll
+              for (int c = 0; c < NC; ++c) duo_fma<first>(y[c][i].x, ev.x, x[c][ip].x);
+#pragma unroll
+              for (int c = 0; c < NC; ++c) duo_fma<first>(y[c][i].y, ev.y, x[c][ip].x);
+#pragma unroll
+              for (int c = 0; c < NC; ++c) y[c][i].x = fma(-ev.y, x[c][ip].y, y[c][i].x);
+#pragma unroll
+              for (int c = 0; c < NC; ++c) y[c][i].y = fma(ev.x, x[c][ip].y, y[c][i].y);
+            }
+          });
+        });
+        duo_for<0, 4>([&](auto gh_) {
+          constexpr int g = DUO_I(gh_) >> 1, hh = DUO_I(gh_) & 1;
+          if constexpr (PT::hc(g, hh)) {
+            constexpr int i = PT::send(g);
+            const CT ev = e[PT::nr(g, hh)];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) y[c][i].x = fma(ev.x, h[c][hh].x, y[c][i].x);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) y[c][i].y = fma(ev.y, h[c][hh].x, y[c][i].y);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) y[c][i].x = fma(-ev.y, h[c][hh].y, y[c][i].x);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) y[c][i].y = fma(ev.x, h[c][hh].y, y[c][i].y);
+          }
+        });
+        const R cj = duo_ifact(Q, j, (R*)nullptr);
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            x[c][i] = y[c][i];
+            z[c][i].x = fma(cj, y[c][i].x, z[c][i].x);
+            z[c][i].y = fma(cj, y[c][i].y, z[c][i].y);
+          }
+      }
+    }
+    __syncwarp();
+    if (lane == 0 && b + 2 < nb) issue(b + 2);
+  }
+  if (live) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      if (I.col + c < Q.ncol[role]) {
+        cplx* pc = Q.prop + ((((size_t)sample * Q.chunks + I.c) * Q.nroles + role) * 6 + I.col + c) * 6 + type * 3;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) pc[i] = duo_to_d(z[c][i]);
+      }
   }
 }
 

@@ -257,7 +257,7 @@ def test_reduced_system_kernels_and_modes_agree(n_samples):
     """The two ensemble kernel families of the reduced stacked system -- chain_duo.cu (two lanes per coupled sector,
     registers only, checkpoints + recomputation, bulk-TMA staged slice batches; 4 warps or 1 warp per CTA) and
     chain_aug.cu (one sample per lane group; Taylor terms streamed or recomputed) -- on a ragged ensemble, plus the
-    time-parallel form of the two-lane kernels: eight code paths, same numbers."""
+    time-parallel form of the two-lane kernels: nine code paths, same numbers."""
     from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL
     po, a, b, c = otq.notebook02_setup(seed=4, n_gauss=6, nt=77)
     args = (6, 77, po.padding, 50e6, po.delta_t, 0.0, po.Vint, po.Delta_i_val, po.Rabi_i_val, po.Rabi_r_val, otq.GAMMAS_CZ)
@@ -270,6 +270,8 @@ def test_reduced_system_kernels_and_modes_agree(n_samples):
                 ({"tp": 0, "strong_chunks": 4}, "reduced_duo"), ({"tp": 0, "strong_chunks": 7}, "reduced_duo"),
                 # ... with every basis column swept (no mirroring of the Van Loan pair's own-block propagator)
                 ({"tp": 0, "strong_chunks": 4, "duo_nomirror": 1}, "reduced_duo"),
+                # ... three basis columns per item in the chunk-propagator sweep (shared entry registers)
+                ({"tp": 0, "strong_chunks": 4, "duo_cols": 1}, "reduced_duo"),
                 # Xbar accumulated on every entry (default: not on the CZ model's diagonal, whose coefficient only depends
                 # on the detuning channel that the pulse map forces to a constant, TQ:364)
                 ({"tp": 0, "duo_nolean": 1}, "reduced_duo")]
