@@ -201,6 +201,12 @@ double qocvl_last_chain_ms(qocvl_plan* plan);
 /* Number of concurrent slice-axis chunks of the configured path (1 = every sample is swept sequentially; > 1 = the
  * time-parallel evaluation: chunk propagators -> combine -> per-chunk sweeps).  0 before the first evaluation. */
 int qocvl_slice_chunks(const qocvl_plan* plan);
+/* Taylor degrees of the last evaluation, per role (independent diagonal block of the propagated system) of the two-lane
+ * ensemble kernels, which pick the degree per role and slice from the role's own norm bound (option "duo_roleq": 2 =
+ * min(1-norm, 2-norm) bound [default], 1 = 1-norm bound, 0 = one degree per slice for the whole system):
+ * out[r * n_slices + k] for r < return value (the number of roles, <= 4).  Returns 0 when the configured path has one
+ * degree per slice for the whole system (then out[k] holds it).  `out` has room for 4 * n_slices ints.  Synchronises. */
+int qocvl_role_degrees(const qocvl_plan* plan, int* out);
 /* The same for one stage of the most recent timed evaluation: stage 0 = forward-sweep kernel, 1 = reverse-sweep kernel
  * (ensemble kernels of chain_duo.cu; < 0 when the path that ran has no such stage or nothing was timed). */
 double qocvl_last_stage_ms(qocvl_plan* plan, int stage);

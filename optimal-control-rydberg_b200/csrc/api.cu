@@ -149,17 +149,36 @@ extern "C" double qocvl_flops_per_call(const qocvl_plan* p, int with_grad) {
   //  multiply-adds are neither executed nor needed, so they are not counted either way)
   // (with_grad = 4: mode 2 with Xbar counted on EVERY entry -- SURVEY's M2 figure, the basis of round 1's roofline fraction)
   const double macs_x = (p->use_aug && p->use_duo && p->duo.last_lean && with_grad != 4) ? (double)p->duo.nnz_x_lean : macs;
-  for (int k = 0; k < M; ++k) {
-    if (with_grad != 3) total += q[k] * macs;
-    if (with_grad == 1) total += (stored ? 0 : q[k] - 1) * macs + q[k] * (macs + macs_x);
-    else if (with_grad >= 2) total += q[k] * (macs + macs_x);
+  // two-lane kernels with per-role Taylor degrees: every role counts its own non-zeros at its own degrees
+  const bool role_q = p->use_aug && p->use_duo && p->duo.role_q;
+  std::vector<int> qr;
+  if (role_q) {
+    qr.resize((size_t)4 * M);
+    if (cudaMemcpy(qr.data(), p->duo.d_qdeg_role, qr.size() * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 0.0;
+  }
+  const int nparts = role_q ? p->duo.nroles : 1;
+  for (int r = 0; r < nparts; ++r) {
+    const double m_r = role_q ? (double)p->duo.nnz_role[r] : macs;
+    const double mx_r = role_q ? ((p->duo.last_lean && with_grad != 4) ? (double)p->duo.nnz_x_lean_role[r] : m_r) : macs_x;
+    const int* qq = role_q ? &qr[(size_t)r * M] : q.data();
+    for (int k = 0; k < M; ++k) {
+      if (with_grad != 3) total += qq[k] * m_r;
+      if (with_grad == 1) total += (stored ? 0 : qq[k] - 1) * m_r + qq[k] * (m_r + mx_r);
+      else if (with_grad >= 2) total += qq[k] * (m_r + mx_r);
+    }
   }
   // time-parallel evaluation of a small ensemble (chain_duo.cu, slice-axis chunks): the chunk propagators are executed
   // work on top of the per-chunk sweeps -- one forward sweep per basis column of every role
   if (p->use_aug && p->use_duo && p->duo.chunks > 1 && with_grad <= 1) {
     int cols = 0;
     for (int r = 0; r < p->duo.nroles; ++r) cols = std::max(cols, p->duo.ncol[r]);
-    for (int k = 0; k < M; ++k) total += (double)(with_grad ? cols : cols - 1) * q[k] * macs;
+    if (role_q) {           // one sweep of the role's block per swept basis column, at the role's degrees
+      for (int r = 0; r < p->duo.nroles; ++r)
+        for (int k = 0; k < M; ++k)
+          total += (double)(with_grad ? p->duo.ncol[r] : p->duo.ncol[r] - 1) * qr[(size_t)r * M + k] * p->duo.nnz_role[r];
+    } else {
+      for (int k = 0; k < M; ++k) total += (double)(with_grad ? cols : cols - 1) * q[k] * macs;
+    }
   }
   // time-parallel path of the wide kernel: the column sweeps (n basis columns pushed forward through every slice) are
   // executed work on top of the per-chunk forward + reverse sweeps
@@ -257,6 +276,18 @@ extern "C" int qocvl_slice_chunks(const qocvl_plan* p) {
   if (p->use_tp) return p->tp_nchunks;
   if (p->use_aug && p->use_duo) return p->duo.chunks;
   return 1;
+}
+
+extern "C" int qocvl_role_degrees(const qocvl_plan* p, int* out) {
+  if (!p || !out || p->groups <= 0) return 0;
+  const int M = p->d.n_slices;
+  const bool role_q = p->use_aug && p->use_duo && p->duo.role_q;
+  cudaSetDevice(p->device);
+  cudaDeviceSynchronize();
+  const int nr = role_q ? p->duo.nroles : 1;
+  if (cudaMemcpy(out, role_q ? p->duo.d_qdeg_role : p->d_qdeg, (size_t)nr * M * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return 0;
+  return role_q ? nr : 0;
 }
 
 extern "C" double qocvl_last_stage_ms(qocvl_plan* p, int stage) {

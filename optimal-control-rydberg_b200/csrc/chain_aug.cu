@@ -804,6 +804,12 @@ int qocvl_aug_configure(qocvl_plan* p) {
   p->use_duo = false;
   p->h_aug_gen = aug; p->h_aug_cls = cls; p->h_aug_hasadd = has_add; p->h_aug_mcls = mcls; p->h_aug_wq = wq;
   p->h_aug_st = st; p->h_aug_tg = tg;
+  // basis states behind every stacked row (its orbit): chain_duo.cu bounds the norm of a role by their columns
+  p->aug_p0 = off[nv];                                  // first stacked row of p = W psi
+  p->h_aug_members.assign(N, std::vector<int>());
+  for (int v = 0; v <= nv; ++v)
+    for (int i = 0; i < n; ++i)
+      if (sec[v].rep_of.size() == (size_t)n && sec[v].rep_of[i] >= 0) p->h_aug_members[off[v] + sec[v].rep_of[i]].push_back(i);
   if (p->opt("duo", 1) != 0) {
     const int rc = qocvl_duo_configure(p);
     if (rc == QOCVL_OK) { p->use_aug = true; return QOCVL_OK; }

@@ -217,7 +217,7 @@ int slot_of(unsigned mask, int bit) { return duo_popc(mask & ((1u << bit) - 1u))
 
 void DuoState::release() {
   for (void* q : {(void*)d_ent_x_lean, (void*)d_ent_ystride_lean, (void*)d_ent_ysrc_lean}) if (q) cudaFree(q);
-  void* ptrs[] = {d_tab, d_con_a, d_srow, d_ent_gen, d_ent_val, d_ent_x, d_ent_out, d_ent_stride, d_ent_ysrc,
+  void* ptrs[] = {d_colrole, d_qdeg_role, d_tab, d_con_a, d_srow, d_ent_gen, d_ent_val, d_ent_x, d_ent_out, d_ent_stride, d_ent_ysrc,
                   d_ent_ystride, d_ent_ywarps, d_starts, d_targets, d_pair, d_wq, d_zfin, d_lam, d_colrow, d_prop,
                   d_zstart, d_lamend};
   for (void* q : ptrs) if (q) cudaFree(q);
@@ -527,7 +527,31 @@ int qocvl_duo_configure(qocvl_plan* p) {
   D.has_lean = has_lean;
   D.nnz_x_lean = 0;
   for (int i = 0; i < ntot; ++i)
-    if (ent_x_lean[i] >= 0 && desc[i].a >= 0 && desc[i].b >= 0 && pat[(size_t)desc[i].a * N + desc[i].b]) D.nnz_x_lean++;
+    if (ent_x_lean[i] >= 0 && desc[i].a >= 0 && desc[i].b >= 0 && pat[(size_t)desc[i].a * N + desc[i].b]) {
+      D.nnz_x_lean++;
+      D.nnz_x_lean_role[desc[i].role]++;
+    }
+  // ---- per-role Taylor degrees: the roles are the diagonal blocks of the stacked system, so the remainder of a role's
+  //      series is bounded by the norm of ITS block -- the column sums of the basis states its rows stand for
+  //      (k_coefficients, model.cuh::qocvl_slice_norm_csr).  CZ: the {U psi, W psi} pair has half the norm of U|11>.
+  {
+    std::vector<unsigned char> colrole(2 * (size_t)p->d.n, 0);   // [q part | p part][basis state]
+    bool ok = (int)p->h_aug_members.size() == N && p->opt("duo_roleq", 2) != 0;
+    for (int r = 0; r < nroles && ok; ++r)
+      for (int row : comp[r]) {
+        if (row < 0) continue;
+        if (p->h_aug_members[row].empty()) ok = false;
+        for (int b : p->h_aug_members[row]) colrole[(row >= p->aug_p0 ? p->d.n : 0) + b] |= (unsigned char)(1u << r);
+        for (int c2 : comp[r])
+          if (c2 >= 0 && pat[(size_t)row * N + c2]) D.nnz_role[r]++;
+      }
+    D.role_q = ok;
+    if (ok) {
+      DUO_UP(D.d_colrole, colrole);
+      QCUDA(cudaMalloc((void**)&D.d_qdeg_role, (size_t)DUO_MAXR * M * sizeof(int)));
+      QCUDA(cudaMemset(D.d_qdeg_role, 0, (size_t)DUO_MAXR * M * sizeof(int)));
+    }
+  }
   for (int r = 0; r < nroles; ++r) { D.variant_lean[r] = variant_lean[r]; D.nx_lean[r] = nx_lean[r]; }
   DUO_UP(D.d_ent_x_lean, ent_x_lean); DUO_UP(D.d_ent_ysrc_lean, ent_ysrc_lean); DUO_UP(D.d_ent_ystride_lean, ent_ystride_lean);
   {
@@ -593,7 +617,8 @@ int qocvl_duo_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t 
   q.mcls = p->la.mcls; q.ncls = p->la.ncls;
   for (int i = 0; i < 2 * DUO_MAXR; ++i) { q.clsmask[i] = D.clsmask[i]; q.amask[i] = D.amask[i]; }
   q.ent_gen = D.d_ent_gen; q.ent_val = D.d_ent_val; q.ent_x = D.d_ent_x;
-  q.coef = p->d_coef; q.dcoef = p->d_dcoef; q.qdeg = p->d_qdeg;
+  q.coef = p->d_coef; q.dcoef = p->d_dcoef;
+  q.qdeg = D.role_q ? D.d_qdeg_role : p->d_qdeg; q.qstride = D.role_q ? d.n_slices : 0;   // [role][M] or one row for all
   q.starts = D.d_starts; q.targets = D.d_targets; q.pair = D.d_pair; q.wq = D.d_wq;
   q.ckpt = p->d_ckpt;                                   // (elements of the sweeps' type: the kernels cast)
   q.zfin = D.d_zfin; q.lam = D.d_lam; q.ypart = p->d_ypart;

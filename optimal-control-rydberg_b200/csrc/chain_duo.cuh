@@ -72,7 +72,8 @@ struct DuoArgs {
   const int* ent_x;     // [ntot] index of the descriptor among its lane type's Xbar slots, -1 = not a gradient slot
   const cplx* coef;     // [M][J]
   const cplx* dcoef;    // [M][J][C]
-  const int* qdeg;      // [M]
+  const int* qdeg;      // [nroles][M] Taylor degree of every role and slice (qstride = M), or [M] for all roles (qstride = 0)
+  int qstride;
   const cplx* starts;   // [N]
   const cplx* targets;  // [N]
   const int* pair;      // [N]
@@ -361,14 +362,15 @@ __device__ __forceinline__ void duo_forward(const DuoArgs& Q, const int role, un
   __syncwarp();
   const bool keep = Q.want_grad && Q.mode != 1;
   CT* ck = (CT*)Q.ckpt + ((size_t)(Q.warp0[role] + I.g) * Q.M) * 96 + lane;
-  int q_next = __ldg(Q.qdeg + k0);
+  const int* qd = Q.qdeg + (size_t)role * Q.qstride;
+  int q_next = __ldg(qd + k0);
   for (int b = 0; b < nb; ++b) {
     duo_bar_wait(bar0 + (b & 1) * 8, (b >> 1) & 1);
     const int cnt = min(DUO_BT, nsl - b * DUO_BT);
     for (int kk = 0; kk < cnt; ++kk) {
       const int k = k0 + b * DUO_BT + kk;
       const int q = q_next;
-      if (k + 1 < I.k1) q_next = __ldg(Q.qdeg + k + 1);
+      if (k + 1 < I.k1) q_next = __ldg(qd + k + 1);
       const CT* row = s_tab + ((size_t)((b & 1) * DUO_BT + kk) * 2 + type) * NU;
       CT e[NU];                                            // entry = A_u(s) + m_u(s) P_u(k); m_u is 1 or the sample's class-1
 #pragma unroll                                              // multiplier, A_u exists on few entries (additive noise)
@@ -469,14 +471,15 @@ __device__ __forceinline__ void duo_forward_cols(const DuoArgs& Q, const int rol
       z[c][i] = duo_mk(one ? 1.0 : 0.0, 0.0, (CT*)nullptr);
     }
   __syncwarp();
-  int q_next = __ldg(Q.qdeg + k0);
+  const int* qd = Q.qdeg + (size_t)role * Q.qstride;
+  int q_next = __ldg(qd + k0);
   for (int b = 0; b < nb; ++b) {
     duo_bar_wait(bar0 + (b & 1) * 8, (b >> 1) & 1);
     const int cnt = min(DUO_BT, nsl - b * DUO_BT);
     for (int kk = 0; kk < cnt; ++kk) {
       const int k = k0 + b * DUO_BT + kk;
       const int q = q_next;
-      if (k + 1 < I.k1) q_next = __ldg(Q.qdeg + k + 1);
+      if (k + 1 < I.k1) q_next = __ldg(qd + k + 1);
       const CT* row = s_tab + ((size_t)((b & 1) * DUO_BT + kk) * 2 + type) * NU;
       CT e[NU];
 #pragma unroll
@@ -620,7 +623,8 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
   __syncwarp();
   cplx* yout = Q.ypart + Q.y_off[role] + ((size_t)I.g * Q.M) * 2 * NX;
   cplx* s_e = (cplx*)(base + L.us);                       // [NX][33] staging of the per-sample Xbar entries
-  int q_next = __ldg(Q.qdeg + I.k1 - 1);
+  const int* qd = Q.qdeg + (size_t)role * Q.qstride;
+  int q_next = __ldg(qd + I.k1 - 1);
   // The table values and the checkpoint of the NEXT slice to be visited are loaded right after the adjoint loop of the
   // current one -- into the entry registers, which are dead by then -- so that they arrive behind the Xbar staging
   // instead of in front of the recomputation.
@@ -640,7 +644,7 @@ __device__ __forceinline__ void duo_reverse(const DuoArgs& Q, const int role, un
     for (int kk = cnt - 1; kk >= 0; --kk) {
       const int k = k0 + b * DUO_BT + kk;
       const int q = q_next;
-      if (k > k0) q_next = __ldg(Q.qdeg + k - 1);
+      if (k > k0) q_next = __ldg(qd + k - 1);
 #pragma unroll                                              // entry = A_u(s) + m_u(s) P_u(k); m_u is 1 or the sample's class-1
       for (int u = 0; u < NU; ++u) {                       // multiplier, A_u exists on few entries (additive noise)
         const CT pv = e[u];

@@ -186,6 +186,12 @@ struct DuoState {
   int *d_srow = nullptr, *d_ent_gen = nullptr, *d_ent_x = nullptr, *d_ent_stride = nullptr, *d_ent_ystride = nullptr,
       *d_ent_ywarps = nullptr, *d_pair = nullptr, *d_colrow = nullptr;
   unsigned long long *d_ent_out = nullptr, *d_ent_ysrc = nullptr;
+  // per-role Taylor degrees: colrole[b] = bit mask of the roles whose sectors contain basis state b; k_coefficients
+  // writes qdeg_role[role][M] from the column sums of those states ("duo_roleq" = 0: every role runs the global degree)
+  unsigned char* d_colrole = nullptr;
+  int* d_qdeg_role = nullptr;
+  bool role_q = false;
+  int nnz_role[4] = {0}, nnz_x_lean_role[4] = {0};   // non-zeros / lean Xbar entries of every role (flop model)
   void release();
 };
 
@@ -283,6 +289,8 @@ struct qocvl_plan {
   std::vector<double> h_aug_mcls, h_aug_wq;      // [S][ncls] class multipliers, [2][L] adiabaticity weights
   std::vector<cplx> h_aug_st, h_aug_tg;          // [L] stacked start / target kets
   std::vector<int> h_aug_pair;   // host copy of the partner rows of the stacked vector (chain_duo.cu)
+  int aug_p0 = 0;                                // first stacked row that belongs to p = W psi (rows before: U x_v)
+  std::vector<std::vector<int>> h_aug_members;   // [aug_n] basis states a stacked row stands for (its orbit)
   int c64 = 0;             // qocvl_set_precision: 1 = the ensemble kernel runs in complex64 (reduced stacked system only)
   double taylor_tol() const { return c64 ? QOCVL_TAYLOR_TOL_C64 : QOCVL_TAYLOR_TOL_C128; }
   int aug_n = 0, aug_lpg = 0, aug_nnz = 0, aug_wmax = 0, aug_parts = 0, aug_qs = 0;

@@ -113,7 +113,8 @@ __host__ __device__ inline double qocvl_slice_norm_csr(const ModelParams& mp, co
                                                       const cplx* u_eval, int u_kc, const int* w_colptr,
                                                       const int* w_ceid, const int* w_egen, const cplx* w_eval,
                                                       int w_kc, const double* gcol, const double* mulmax,
-                                                      const double* addmax) {
+                                                      const double* addmax, const unsigned char* colrole = nullptr,
+                                                      int nroles = 0, double* role_nrm = nullptr) {
   const int n = mp.n, J = mp.J;
   double wgt[QOCVL_MAX_GEN];
   for (int j = 0; j < J; ++j)
@@ -147,6 +148,11 @@ __host__ __device__ inline double qocvl_slice_norm_csr(const ModelParams& mp, co
       s += sqrt(re * re + im * im);
     }
     nrm = fmax(nrm, s);
+    // per-role bound (chain_duo.cu): the roles are the diagonal blocks of the propagated system, so the Taylor
+    // remainder of a role is bounded by the columns of ITS basis states alone
+    if (colrole)
+      for (int r = 0; r < nroles; ++r)
+        if (((colrole[b] | colrole[n + b]) >> r) & 1u) role_nrm[r] = fmax(role_nrm[r], s * mp.dt);
   }
   return nrm * mp.dt;
 }

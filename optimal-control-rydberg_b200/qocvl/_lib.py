@@ -56,6 +56,7 @@ SIGNATURES = {
     "qocvl_last_chain_ms": (C.c_double, [_P]),
     "qocvl_last_stage_ms": (C.c_double, [_P, C.c_int]),
     "qocvl_slice_chunks": (C.c_int, [_P]),
+    "qocvl_role_degrees": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "qocvl_measure_fp64_peak": (C.c_double, [C.c_int, C.c_int]),
     "qocvl_measure_fp64_peak_reg": (C.c_double, [C.c_int, C.c_int]),
     "qocvl_lindblad_propagate": (C.c_int, [C.c_int] * 7 + [_D] * 6 + [C.c_double, _D, _D]),

@@ -270,6 +270,25 @@ class Plan:
         """Concurrent slice-axis chunks of the configured path (1 = sequential sweep per sample)."""
         return int(self._lib.qocvl_slice_chunks(self._h))
 
+    def role_degrees(self):
+        """Taylor degrees of the last evaluation: int array [roles, M] for the two-lane kernels (one row per role: every
+        role runs the degree its own norm bound asks for), [1, M] for paths with one degree per slice."""
+        import ctypes
+        import numpy as np
+        m = int(self.desc.n_slices)
+        buf = (ctypes.c_int * (4 * m))()
+        n = int(self._lib.qocvl_role_degrees(self._h, buf))
+        return np.ctypeslib.as_array(buf)[: max(n, 1) * m].reshape(max(n, 1), m).copy()
+
+    def role_degree_means(self):
+        """{'per_role': mean degree of every role (two-lane kernels; [] otherwise), 'global': mean of the one degree per slice}."""
+        import ctypes
+        m = int(self.desc.n_slices)
+        buf = (ctypes.c_int * (4 * m))()
+        n = int(self._lib.qocvl_role_degrees(self._h, buf))
+        q = [sum(buf[r * m:(r + 1) * m]) / m for r in range(max(n, 1))]
+        return {"per_role": q if n else [], "global": None if n else q[0]}
+
     def last_stage_ms(self, stage):
         """Duration of one kernel of the last timed evaluation: 0 = forward sweep, 1 = reverse sweep (< 0: not timed)."""
         return float(self._lib.qocvl_last_stage_ms(self._h, int(stage)))

@@ -44,5 +44,6 @@ for spec in sets:
     ms = e0.elapsed_time(e1) / 3
     info = prop._plan.chain_info()
     print(f"S={S} opts[{spec}] {ms:.3f} ms/step  chain {prop._plan.last_chain_ms():.3f} ms  {M * S / ms * 1e3:.3e} units/s  "
-          f"path {info['path']} threads {info['threads']} ctas {info['ctas']} cost {float(out[0]):.12f}", flush=True)
+          f"path {info['path']} threads {info['threads']} ctas {info['ctas']} cost {float(out[0]):.12f} "
+          f"fwd {prop._plan.last_stage_ms(0):.3f} rev {prop._plan.last_stage_ms(1):.3f} ms  degrees {prop._plan.role_degree_means()}", flush=True)
     del prop
