@@ -7,7 +7,7 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 OUT="$HERE/libqocvl.so"
 OBJ="$HERE/build"
 mkdir -p "$OBJ"
-UNITS=(plan pulse_map chain_small chain_aug chain_duo chain_big chain_wide chain_wide_b13 chain_wide_b24 chain_setup dense dense_blocks api lindblad)
+UNITS=(plan pulse_map chain_small chain_aug chain_duo chain_big chain_wide chain_wide_b13 chain_wide_b24 chain_wide_b13f chain_wide_b24f chain_setup dense dense_blocks api lindblad)
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC ${QOCVL_PTXAS_V:+-Xptxas -v})
 pids=()
 for u in "${UNITS[@]}"; do

@@ -208,7 +208,7 @@ extern "C" double qocvl_hbm_bytes_per_call(const qocvl_plan* p, int with_grad) {
     return 2.0 * slots * S * p->aug_n * (p->c64 ? sizeof(cplxf) : sizeof(cplx)) + 2.0 * (double)p->ypart_bytes;
   }
   if (p->use_wide) {   // streamed Taylor terms (or checkpoints + the recompute ring) written once, read once
-    const double vs = 2.0 * (p->d.n + 1) * p->lwide.spc * sizeof(cplx) * (p->use_wide_tp ? 1 : p->blocks);   // every slice once
+    const double vs = 2.0 * (p->d.n + 1) * p->lwide.spc * (p->c64 ? sizeof(cplxf) : sizeof(cplx)) * (p->use_wide_tp ? 1 : p->blocks);   // every slice once
     std::vector<int> q(p->d.n_slices);
     cudaSetDevice(p->device);
     cudaDeviceSynchronize();

@@ -210,8 +210,9 @@ int qocvl_chain_configure(qocvl_plan* p) {
       else p->use_aug = false;                    // (the lane-group kernel is no match for one sample)
     }
   }
-  // complex64 exists only on the reduced stacked system: anything else fails loudly instead of running in fp64
-  if (p->c64 && !p->use_aug) { p->groups = 0; return QOCVL_ERR_UNSUPPORTED; }
+  // complex64 exists on the reduced stacked system and on the samples-minor kernel of the large Hilbert spaces
+  // (chain_wide.cu): anything else fails loudly instead of running in fp64
+  if (p->c64 && !p->use_aug && !p->use_big) { p->groups = 0; return QOCVL_ERR_UNSUPPORTED; }
   p->use_wide = false;
   if (!p->use_aug && p->use_big) {          // large Hilbert spaces: the samples-minor kernel when it takes the problem
     bool try_wide = true;
@@ -221,6 +222,7 @@ int qocvl_chain_configure(qocvl_plan* p) {
       if (rc != QOCVL_OK && rc != QOCVL_ERR_UNSUPPORTED) { p->groups = 0; return rc; }
     }
   }
+  if (p->c64 && !p->use_aug && !p->use_wide) { p->groups = 0; return QOCVL_ERR_UNSUPPORTED; }
   if (!p->use_aug && !p->use_wide) {
     rc = p->use_big ? qocvl_big_configure(p) : qocvl_small_configure(p);
     if (rc) { p->groups = 0; return rc; }

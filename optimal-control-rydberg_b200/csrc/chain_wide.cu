@@ -38,15 +38,16 @@ static int wide_upload(T** dst, const std::vector<T>& src) {
 
 // dynamic shared memory of one CTA: vectors, per-slice coefficients, reduction scratch and the generator tables
 static size_t wide_smem_bytes(int n, int J, int C, int spc, int threads, int nb_c, int nd_c, int ngroups,
-                              size_t ent_fwd, size_t ent_rev, bool dreal) {
+                              size_t ent_fwd, size_t ent_rev, bool dreal, size_t esz) {
   const int rw = 32 / spc, nslot = nb_c + nd_c;
   const size_t vs = (size_t)WIDE_NVP * n * spc;
-  size_t cplx_count = 2 * vs + 2 * (size_t)J * spc + (size_t)J * spc + (size_t)J * C +
+  const size_t sweep_bytes = (2 * vs + 2 * (size_t)J * spc) * esz;     // vectors and per-slice coefficients: the sweeps' type
+  size_t cplx_count = (size_t)J * spc + (size_t)J * C +
                       (size_t)(threads / 32) * nslot * spc + (size_t)nslot * spc +
                       (dreal ? 0 : (size_t)nd_c * ngroups * rw);
   size_t dbl_count = (size_t)J * spc + (size_t)(threads / 32) * 3 * spc + 2 * (size_t)spc +
                      (dreal ? (size_t)nd_c * ngroups * rw : 0);
-  return cplx_count * sizeof(cplx) + dbl_count * sizeof(double) + 2 * (size_t)nb_c * ngroups * sizeof(int2) +
+  return sweep_bytes + cplx_count * sizeof(cplx) + dbl_count * sizeof(double) + 2 * (size_t)nb_c * ngroups * sizeof(int2) +
          (((ent_fwd + 7) & ~(size_t)7) + ((ent_rev + 7) & ~(size_t)7)) * sizeof(unsigned short) +
          (((size_t)ngroups * rw + 15) & ~(size_t)15);
 }
@@ -63,13 +64,13 @@ static int wide_threads_for(const qocvl_plan* p, int spc, int ngroups) {
   if (ngroups <= 8 * 12) return 384;
   return 256;
 }
-static wide_kernel_t wide_pick(int spc, int items, int threads, int nb, int nd, bool simple, bool fwd = false) {
+static wide_kernel_t wide_pick(int c64, int spc, int items, int threads, int nb, int nd, bool simple, bool fwd = false) {
   if (fwd) {
     if (spc != 8 || threads != 384) return nullptr;
-    return simple ? qocvl_wide_pick_b13_fwd(items) : qocvl_wide_pick_b24_fwd(items);
+    return simple ? qocvl_wide_pick_b13_fwd(items, c64) : qocvl_wide_pick_b24_fwd(items, c64);
   }
-  if (simple) return qocvl_wide_pick_b13(spc, items, threads);
-  if (nb <= WIDE_MAXB && nd <= WIDE_MAXD) return qocvl_wide_pick_b24(spc, items, threads);
+  if (simple) return qocvl_wide_pick_b13(spc, items, threads, c64);
+  if (nb <= WIDE_MAXB && nd <= WIDE_MAXD) return qocvl_wide_pick_b24(spc, items, threads, c64);
   return nullptr;
 }
 
@@ -207,10 +208,10 @@ static int wide_build(qocvl_plan* p, int spc_request, WideLayout& L, bool fwd = 
     nwarps = std::min(max_threads / 32, T.ngroups);
     items = (T.ngroups + nwarps - 1) / nwarps;
     nwarps = (T.ngroups + items - 1) / items;              // fewest warps that still need `items` passes
-    kern = wide_pick(spc, items, max_threads, nb, nd, simple, fwd);
+    kern = wide_pick(p->c64, spc, items, max_threads, nb, nd, simple, fwd);
     // (n + 1 rows per vector: row n is the zero row the padding entries of uniform-valued blocks read)
     smem = wide_smem_bytes(n + 1, J, d.n_chan, spc, max_threads, nb_c, nd_c, T.ngroups, T.col[0].size(),
-                           T.col[1].size(), dreal);
+                           T.col[1].size(), dreal, p->c64 ? sizeof(cplxf) : sizeof(cplx));
     if (kern && smem <= 227 * 1024) break;
     if (spc == 1) return QOCVL_ERR_UNSUPPORTED;
     spc = 1;
@@ -407,7 +408,7 @@ int qocvl_wide_configure(qocvl_plan* p) {
   p->blocks = ctas;
   p->spb = spc; p->groups = 1;
   p->n_parts = (size_t)ctas;
-  const size_t vs = (size_t)WIDE_NVP * (n + 1) * spc * sizeof(cplx);
+  const size_t vs = (size_t)WIDE_NVP * (n + 1) * spc * (p->c64 ? sizeof(cplxf) : sizeof(cplx));   // elements of the sweeps' type
   const size_t stream_bytes = (size_t)ctas * cta_slices * p->qcap * vs;
   size_t free_b = 0, total_b = 0;
   QCUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -456,7 +457,7 @@ int qocvl_wide_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t
   WideArgs a;
   wide_fill_args(p, L, a);
   a.want_grad = want_grad ? 1 : 0; a.store = L.store ? 1 : 0;
-  wide_kernel_t kern = wide_pick(L.spc, L.items, L.max_threads, L.nb, L.nd, L.simple);
+  wide_kernel_t kern = wide_pick(p->c64, L.spc, L.items, L.max_threads, L.nb, L.nd, L.simple);
   if (!p->use_wide_tp) {
     kern<<<p->blocks, p->threads, p->chain_smem, st>>>(a);
     p->launches++;
@@ -468,7 +469,7 @@ int qocvl_wide_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t
   WideArgs pa;
   wide_fill_args(p, LA, pa);
   pa.mode = 1; pa.want_grad = 0; pa.store = 0;
-  wide_pick(LA.spc, LA.items, LA.max_threads, LA.nb, LA.nd, LA.simple, LA.fwd)<<<p->tp_blocks_a, LA.threads, LA.smem, st>>>(pa);
+  wide_pick(p->c64, LA.spc, LA.items, LA.max_threads, LA.nb, LA.nd, LA.simple, LA.fwd)<<<p->tp_blocks_a, LA.threads, LA.smem, st>>>(pa);
   WideCombineArgs c;
   c.n = p->d.n; c.n_chunks = p->tp_nchunks; c.want_grad = want_grad ? 1 : 0;
   c.inv_duration = a.inv_duration; c.w_infid = a.w_infid; c.w_adiab = a.w_adiab; c.inv_fid_norm = a.inv_fid_norm;

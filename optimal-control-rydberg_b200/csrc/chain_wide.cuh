@@ -53,12 +53,26 @@ __device__ __forceinline__ cplx ld_stream(const cplx* p) {
   return v;
 }
 __device__ __forceinline__ void st_stream(cplx* p, cplx v) { __stcs(reinterpret_cast<double2*>(p), v); }
+__device__ __forceinline__ cplxf ld_stream(const cplxf* p) { return __ldcs(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ void st_stream(cplxf* p, cplxf v) { __stcs(reinterpret_cast<float2*>(p), v); }
+// arithmetic type of the sweeps: CT = cplx (complex128, the parity path) or cplxf (the optional complex64 mode: vectors,
+// Taylor terms, the HBM stream / checkpoints and the per-slice Ybar accumulators in fp32; coefficients, cost, terminal
+// cotangents, chunk boundaries and every reduction stay fp64)
+template <typename CT> struct WideReal;
+template <> struct WideReal<cplx> { typedef double R; };
+template <> struct WideReal<cplxf> { typedef float R; };
+__device__ __forceinline__ cplx wide_mk(double re, double im, cplx*) { return cmake(re, im); }
+__device__ __forceinline__ cplxf wide_mk(double re, double im, cplxf*) { return cmakef((float)re, (float)im); }
+template <typename CT> __device__ __forceinline__ CT wide_from(const cplx v) { return wide_mk(v.x, v.y, (CT*)nullptr); }
+__device__ __forceinline__ cplx wide_to_d(const cplx v) { return v; }
+__device__ __forceinline__ cplx wide_to_d(const cplxf v) { return cmake((double)v.x, (double)v.y); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // FWD = true compiles the forward sweep only (mode 1, the column sweeps of the time-parallel path): without the
 // cotangent / gradient state it needs few enough registers for two CTAs per SM when a thread owns <= 4 rows.
-template <int SPC, int ITEMS, int THREADS, int NB, int ND, bool SIMPLE, bool FWD = false>
+template <typename CT, int SPC, int ITEMS, int THREADS, int NB, int ND, bool SIMPLE, bool FWD = false>
 __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_wide(const WideArgs P) {
+  typedef typename WideReal<CT>::R R;
   constexpr int NVP = WIDE_NVP, NV = NVP - 1, VA = 0;   // vectors: q (index 0, also psi of the adiabaticity term), p
   constexpr int RW = 32 / SPC, NSLOT = NB + ND;   // compiled generator-block counts (off-diagonal, diagonal)
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -75,12 +89,13 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
   const int nact = mode == 0 ? min(SPC, P.S - cta * SPC) : (mode == 1 ? min(SPC, n - colbase) : 1);
   const int nr = n + 1;                                  // row n of every vector stays zero (read by padding entries)
   const int VS = NVP * nr * SPC;                         // elements of one "all vectors" buffer
-  const cplx czero = cmake(0, 0);
+  const CT czero = wide_mk(0.0, 0.0, (CT*)nullptr);
+  const cplx dzero = cmake(0, 0);
 
-  // ---- shared memory
-  cplx* carve = (cplx*)smem_raw;
-  cplx* s_buf = carve; carve += 2 * VS;                  // Taylor term / cotangent term, double buffered
-  cplx* s_cs = carve; carve += 2 * J * SPC;              // dt * (coef_kg * mul_sg + add_sg), double buffered by slice
+  // ---- shared memory (the sweeps' own type first, then the fp64 tables)
+  CT* s_buf = (CT*)smem_raw;                             // Taylor term / cotangent term, double buffered
+  CT* s_cs = s_buf + 2 * VS;                             // dt * (coef_kg * mul_sg + add_sg), double buffered by slice
+  cplx* carve = (cplx*)(s_cs + 2 * J * SPC);
   cplx* s_add = carve; carve += J * SPC;
   cplx* s_dco = carve; carve += J * C;
   cplx* s_scr = carve; carve += (size_t)(THREADS / 32) * NSLOT * SPC;
@@ -104,7 +119,7 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
   }
   auto diag_value = [&](int d, int g) {
     const int idx = (d * P.ngroups + g) * RW + rw;
-    return P.dreal ? cmake(s_dvr[idx], 0.0) : s_dvc[idx];
+    return P.dreal ? wide_mk(s_dvr[idx], 0.0, (CT*)nullptr) : wide_from<CT>(s_dvc[idx]);
   };
 
   // ---- owned rows
@@ -127,11 +142,14 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
   auto load_cs = [&](int k, int b) {
     for (int i = tid; i < J * SPC; i += blockDim.x) {
       const int g = i / SPC;
-      s_cs[b * J * SPC + i] = cscale(cadd(cscale(P.coef[(size_t)k * J + g], s_mul[i]), s_add[i]), P.dt);
+      s_cs[b * J * SPC + i] = wide_from<CT>(cscale(cadd(cscale(P.coef[(size_t)k * J + g], s_mul[i]), s_add[i]), P.dt));
     }
   };
   // coefficients of this thread's sample for the generator blocks of the slice, in registers
-  cplx csb[NB], csd[ND];
+  CT csb[NB], csd[ND];
+  CT bvl[NB];                                            // common value of every uniform-valued block
+#pragma unroll
+  for (int x = 0; x < NB; ++x) bvl[x] = wide_from<CT>(P.bval[x]);
   auto coefficients = [&](int b) {
 #pragma unroll
     for (int x = 0; x < NB; ++x) csb[x] = (x < P.nb) ? s_cs[(b * J + P.bgen[x]) * SPC + s] : czero;
@@ -139,25 +157,25 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
     for (int x = 0; x < ND; ++x) csd[x] = (x < P.nd) ? s_cs[(b * J + P.dgen[x]) * SPC + s] : czero;
   };
 
-  cplx z[ITEMS][NVP];      // forward: state; reverse: cotangent lambda
+  CT z[ITEMS][NVP];        // forward: state; reverse: cotangent lambda
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
-    z[i][0] = (row[i] >= 0) ? P.starts[row[i]] : czero;
+    z[i][0] = (row[i] >= 0) ? wide_from<CT>(P.starts[row[i]]) : czero;
     z[i][NV] = czero;
-    if (mode == 1) z[i][0] = (row[i] == colbase + min(s, nact - 1)) ? cmake(1.0, 0.0) : czero;   // basis column
+    if (mode == 1) z[i][0] = (row[i] == colbase + min(s, nact - 1)) ? wide_mk(1.0, 0.0, (CT*)nullptr) : czero;   // basis column
     if (mode == 2 && row[i] >= 0) {
-      z[i][0] = P.tp_zc[((size_t)chunk * NVP + 0) * n + row[i]];
-      z[i][NV] = P.tp_zc[((size_t)chunk * NVP + NV) * n + row[i]];
+      z[i][0] = wide_from<CT>(P.tp_zc[((size_t)chunk * NVP + 0) * n + row[i]]);
+      z[i][NV] = wide_from<CT>(P.tp_zc[((size_t)chunk * NVP + NV) * n + row[i]]);
     }
   }
   // sum of the gathered elements of one list (4 pre-scaled 16-bit indices per 8-byte load): q and p, or q only
-  auto gather_sum = [&](const cplx* ts, const unsigned short* list, int chunks, bool both, cplx& sq, cplx& sp) {
+  auto gather_sum = [&](const CT* ts, const unsigned short* list, int chunks, bool both, CT& sq, CT& sp) {
     if (both) {
 #pragma unroll 2
       for (int e = 0; e < chunks; ++e) {
         const uint2 c4 = *reinterpret_cast<const uint2*>(list + 4 * e);
-        const cplx* p0 = ts + (c4.x & 0xffffu); const cplx* p1 = ts + (c4.x >> 16);
-        const cplx* p2 = ts + (c4.y & 0xffffu); const cplx* p3 = ts + (c4.y >> 16);
+        const CT* p0 = ts + (c4.x & 0xffffu); const CT* p1 = ts + (c4.x >> 16);
+        const CT* p2 = ts + (c4.y & 0xffffu); const CT* p3 = ts + (c4.y >> 16);
         sq = cadd(sq, cadd(cadd(p0[0], p1[0]), cadd(p2[0], p3[0])));
         sp = cadd(sp, cadd(cadd(p0[SPC], p1[SPC]), cadd(p2[SPC], p3[SPC])));
       }
@@ -170,16 +188,16 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
     }
   };
   // one forward Taylor step of one owned row:  y = (X t)[row] / j
-  auto forward_item = [&](int i, const cplx* t, double invj, cplx* y) {
+  auto forward_item = [&](int i, const CT* t, R invj, CT* y) {
     const int r = row[i], g = i * nwarps + warp;
-    const cplx* ts = t + s;                      // element (row, q) of this thread's sample; p follows SPC later
-    const cplx tq = t[at(VA, r)], tp = t[at(NV, r)];
-    cplx accq = czero, accp = czero;
+    const CT* ts = t + s;                        // element (row, q) of this thread's sample; p follows SPC later
+    const CT tq = t[at(VA, r)], tp = t[at(NV, r)];
+    CT accq = czero, accp = czero;
     if (SIMPLE) {          // one off-diagonal block, uniform value, acting on q and p (checked on the host)
       const int2 co = s_fco[g];
-      cplx sq = czero, sp = czero;
+      CT sq = czero, sp = czero;
       gather_sum(ts, s_fcol + co.y + rw * 4 * co.x, co.x, true, sq, sp);
-      const cplx c = cmul(csb[0], P.bval[0]);
+      const CT c = cmul(csb[0], bvl[0]);
       accq = cmul(c, sq);
       accp = cmul(c, sp);
     } else {
@@ -189,16 +207,16 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
         const int2 co = s_fco[bb * P.ngroups + g];            // {4-entry chunks per row, offset of the group's lists}
         const unsigned short* list = s_fcol + co.y + rw * 4 * co.x;
         const bool both = (P.bfam[bb] == 0);     // u blocks act on q and p, w blocks map q into p
-        cplx sq = czero, sp = czero;
+        CT sq = czero, sp = czero;
         if (P.buni[bb]) {                        // one common value: plain sums, scaled once
           gather_sum(ts, list, co.x, both, sq, sp);
-          sq = cmul(P.bval[bb], sq);
-          sp = cmul(P.bval[bb], sp);
+          sq = cmul(bvl[bb], sq);
+          sp = cmul(bvl[bb], sp);
         } else {
           const cplx* ev = P.fwd_val + co.y + rw * 4 * co.x;
 #pragma unroll 2
           for (int e = 0; e < 4 * co.x; ++e) {
-            const cplx val = __ldg(&ev[e]);
+            const CT val = wide_from<CT>(__ldg(&ev[e]));
             const int col = list[e];
             sq = cfma(val, ts[col], sq);
             if (both) sp = cfma(val, ts[col + SPC], sp);
@@ -213,7 +231,7 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
       if ((dm >> d) & 1u) {
-        const cplx c = cmul(csd[d], diag_value(d, g));
+        const CT c = cmul(csd[d], diag_value(d, g));
         if (P.dfam[d] == 0) { accq = cfma(c, tq, accq); accp = cfma(c, tp, accp); }
         else accp = cfma(c, tq, accp);
       }
@@ -223,8 +241,8 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
   };
 
   const size_t ring_slices = P.store ? (size_t)nslices : 1;
-  cplx* ring = P.ring + (size_t)cta * ring_slices * P.qcap * VS;
-  cplx* ckpt = P.store ? nullptr : P.ckpt + (size_t)cta * nslices * VS;
+  CT* ring = (CT*)P.ring + (size_t)cta * ring_slices * P.qcap * VS;    // (elements of the sweeps' type)
+  CT* ckpt = P.store ? nullptr : (CT*)P.ckpt + (size_t)cta * nslices * VS;
 
   // =================================== forward sweep ===================================
   load_cs(k_begin, k_begin & 1);
@@ -234,7 +252,7 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
     if (k + 1 < k_end) load_cs(k + 1, b ^ 1);
     coefficients(b);
     const int kl = k - k_begin;
-    cplx* t0 = (P.store ? ring + (size_t)kl * P.qcap * VS : ckpt + (size_t)kl * VS);
+    CT* t0 = (P.store ? ring + (size_t)kl * P.qcap * VS : ckpt + (size_t)kl * VS);
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
       if (row[i] < 0) continue;
@@ -247,15 +265,15 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
     __syncthreads();
     int cur = 0;
     for (int j = 1; j <= q; ++j) {
-      const cplx* t = s_buf + cur * VS;
-      cplx* y = s_buf + (cur ^ 1) * VS;
-      const double invj = 1.0 / (double)j;
-      cplx* rj = ring + ((size_t)kl * P.qcap + j) * VS;
+      const CT* t = s_buf + cur * VS;
+      CT* y = s_buf + (cur ^ 1) * VS;
+      const R invj = (R)(1.0 / (double)j);
+      CT* rj = ring + ((size_t)kl * P.qcap + j) * VS;
       const bool keep = (j < q);
 #pragma unroll
       for (int i = 0; i < ITEMS; ++i) {
         if (row[i] < 0) continue;
-        cplx yy[NVP];
+        CT yy[NVP];
         forward_item(i, t, invj, yy);
 #pragma unroll
         for (int v = 0; v < NVP; ++v) {
@@ -277,8 +295,8 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
       for (int i = 0; i < ITEMS; ++i) {
         if (row[i] < 0) continue;
         const size_t o = ((size_t)chunk * n + colbase + s) * n + row[i];
-        P.tp_uc[o] = z[i][0];
-        P.tp_wc[o] = z[i][NV];
+        P.tp_uc[o] = wide_to_d(z[i][0]);
+        P.tp_wc[o] = wide_to_d(z[i][NV]);
       }
     }
     return;
@@ -289,7 +307,7 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
       if (row[i] < 0) continue;
-      const cplx y = P.targets[row[i]], zq = z[i][0], zp = z[i][NV];
+      const cplx y = P.targets[row[i]], zq = wide_to_d(z[i][0]), zp = wide_to_d(z[i][NV]);
       red[0] += y.x * zq.x + y.y * zq.y;
       red[1] += y.x * zq.y - y.y * zq.x;
       red[2] += zq.x * zp.x + zq.y * zp.y;
@@ -324,8 +342,8 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
       if (row[i] < 0) continue;
-      z[i][0] = P.tp_lc[((size_t)(chunk + 1) * NVP + 0) * n + row[i]];
-      z[i][NV] = P.tp_lc[((size_t)(chunk + 1) * NVP + NV) * n + row[i]];
+      z[i][0] = wide_from<CT>(P.tp_lc[((size_t)(chunk + 1) * NVP + 0) * n + row[i]]);
+      z[i][NV] = wide_from<CT>(P.tp_lc[((size_t)(chunk + 1) * NVP + NV) * n + row[i]]);
     }
   } else {
     const double ca = -0.5 * P.w_adiab * P.inv_duration * P.inv_samples;
@@ -334,9 +352,9 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
       if (row[i] < 0) continue;
-      const cplx zq = z[i][0], zp = z[i][NV];
-      z[i][0] = cadd(cscale(cmul(dsum, P.targets[row[i]]), cf), cscale(zp, ca));
-      z[i][NV] = cscale(zq, ca);
+      const cplx zq = wide_to_d(z[i][0]), zp = wide_to_d(z[i][NV]);
+      z[i][0] = wide_from<CT>(cadd(cscale(cmul(dsum, P.targets[row[i]]), cf), cscale(zp, ca)));
+      z[i][NV] = wide_from<CT>(cscale(zq, ca));
     }
   }
 
@@ -347,31 +365,31 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
     const int q = P.qdeg[k], b = k & 1, qprev = k > k_begin ? P.qdeg[k - 1] : 0, kl = k - k_begin;
     if (k > k_begin) load_cs(k - 1, b ^ 1);
     coefficients(b);
-    cplx* rk = ring + (P.store ? (size_t)kl * P.qcap * VS : 0);
+    CT* rk = ring + (P.store ? (size_t)kl * P.qcap * VS : 0);
     int cur = 0;
     if (!P.store) {
       // ---- recompute the forward terms t_0 .. t_{q-1} of this slice into the ring (own elements)
-      const cplx* ck = ckpt + (size_t)kl * VS;
+      const CT* ck = ckpt + (size_t)kl * VS;
 #pragma unroll
       for (int i = 0; i < ITEMS; ++i) {
         if (row[i] < 0) continue;
 #pragma unroll
         for (int v = 0; v < NVP; ++v) {
-          const cplx zz = ld_stream(&ck[at(v, row[i])]);
+          const CT zz = ld_stream(&ck[at(v, row[i])]);
           s_buf[at(v, row[i])] = zz;
           st_stream(&rk[at(v, row[i])], zz);
         }
       }
       __syncthreads();
       for (int j = 1; j < q; ++j) {
-        const cplx* t = s_buf + cur * VS;
-        cplx* y = s_buf + (cur ^ 1) * VS;
-        cplx* rj = rk + (size_t)j * VS;
+        const CT* t = s_buf + cur * VS;
+        CT* y = s_buf + (cur ^ 1) * VS;
+        CT* rj = rk + (size_t)j * VS;
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
           if (row[i] < 0) continue;
-          cplx yy[NVP];
-          forward_item(i, t, 1.0 / (double)j, yy);
+          CT yy[NVP];
+          forward_item(i, t, (R)(1.0 / (double)j), yy);
 #pragma unroll
           for (int v = 0; v < NVP; ++v) { y[at(v, row[i])] = yy[v]; st_stream(&rj[at(v, row[i])], yy[v]); }
         }
@@ -389,38 +407,38 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
     __syncthreads();
     // (the previous slice's readers of s_dco / s_ysum are past this barrier)
     for (int i = tid; i < J * C; i += blockDim.x) s_dco[i] = P.dcoef[(size_t)k * J * C + i];
-    cplx yb[NB], yd[ND];   // Ybar of every generator block: sum_j <G^dag tb_j , t_{j-1}> / j
+    CT yb[NB], yd[ND];     // Ybar of every generator block: sum_j <G^dag tb_j , t_{j-1}> / j
 #pragma unroll
     for (int bb = 0; bb < NB; ++bb) yb[bb] = czero;
 #pragma unroll
     for (int d = 0; d < ND; ++d) yd[d] = czero;
     for (int j = q; j >= 1; --j) {
-      const cplx* t = s_buf + cur * VS;
-      cplx* y = s_buf + (cur ^ 1) * VS;
-      const double invj = 1.0 / (double)j;
-      const cplx* rj = rk + (size_t)(j - 1) * VS;
+      const CT* t = s_buf + cur * VS;
+      CT* y = s_buf + (cur ^ 1) * VS;
+      const R invj = (R)(1.0 / (double)j);
+      const CT* rj = rk + (size_t)(j - 1) * VS;
 #pragma unroll
       for (int i = 0; i < ITEMS; ++i) {
         const int c = row[i], g = i * nwarps + warp;
         if (c < 0) continue;
-        const cplx fq_raw = ld_stream(&rj[at(VA, c)]);             // own elements of t_{j-1}, used after the gathers
-        const cplx fp_raw = ld_stream(&rj[at(NV, c)]);
+        const CT fq_raw = ld_stream(&rj[at(VA, c)]);               // own elements of t_{j-1}, used after the gathers
+        const CT fp_raw = ld_stream(&rj[at(NV, c)]);
         if (j > 2) {                                                // pull the terms of step j-2 from HBM into L2
           prefetch_l2(&rj[at(VA, c) - 2 * VS]);
           prefetch_l2(&rj[at(NV, c) - 2 * VS]);
         } else if (P.store && k > k_begin && qprev - 3 + j >= 0) {       // ... or the top terms of the next slice to process
-          const cplx* nx = rk - (size_t)P.qcap * VS + (size_t)(qprev - 3 + j) * VS;
+          const CT* nx = rk - (size_t)P.qcap * VS + (size_t)(qprev - 3 + j) * VS;
           prefetch_l2(&nx[at(VA, c)]);
           prefetch_l2(&nx[at(NV, c)]);
         }
-        const cplx bq = t[at(VA, c)], bp = t[at(NV, c)];           // own elements of tb_j
-        cplx accq = czero, accp = czero;
-        cplx sqb[NB], spb[NB];                                      // (G^dag tb_q)[c], (G^dag tb_p)[c] per block
+        const CT bq = t[at(VA, c)], bp = t[at(NV, c)];             // own elements of tb_j
+        CT accq = czero, accp = czero;
+        CT sqb[NB], spb[NB];                                        // (G^dag tb_q)[c], (G^dag tb_p)[c] per block
         if (SIMPLE) {
           const int2 co = s_rco[g];
-          cplx sq = czero, sp = czero;
+          CT sq = czero, sp = czero;
           gather_sum(t + s, s_rcol + co.y + rw * 4 * co.x, co.x, true, sq, sp);
-          const cplx vc = cconj(P.bval[0]);
+          const CT vc = cconj(bvl[0]);
           sq = cmul(vc, sq);
           sp = cmul(vc, sp);
           accq = cfma_conj(csb[0], sq, accq);
@@ -434,19 +452,19 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
             const int2 co = s_rco[bb * P.ngroups + g];
             const unsigned short* list = s_rcol + co.y + rw * 4 * co.x;
             const bool both = (P.bfam[bb] == 0);   // w blocks: (G_w^dag tb_p)[c] feeds q
-            cplx sq = czero, sp = czero;
+            CT sq = czero, sp = czero;
             if (P.buni[bb]) {
               if (both) gather_sum(t + s, list, co.x, true, sq, sp);
               else gather_sum(t + s + SPC, list, co.x, false, sp, sq);
-              const cplx vc = cconj(P.bval[bb]);
+              const CT vc = cconj(bvl[bb]);
               sq = cmul(vc, sq);
               sp = cmul(vc, sp);
             } else {
               const cplx* ev = P.rev_val + co.y + rw * 4 * co.x;
-              const cplx* ts = t + s;
+              const CT* ts = t + s;
 #pragma unroll 2
               for (int e = 0; e < 4 * co.x; ++e) {
-                const cplx val = __ldg(&ev[e]);
+                const CT val = wide_from<CT>(__ldg(&ev[e]));
                 const int a = list[e];
                 sp = cfma_conj(val, ts[a + SPC], sp);
                 if (both) sq = cfma_conj(val, ts[a], sq);
@@ -458,7 +476,7 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
           }
         }
         }
-        const cplx fq = cscale(fq_raw, invj), fp = cscale(fp_raw, invj);
+        const CT fq = cscale(fq_raw, invj), fp = cscale(fp_raw, invj);
 #pragma unroll
         for (int bb = 0; bb < NB; ++bb) {
           if (bb < P.nb) {
@@ -467,14 +485,14 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
           }
         }
         // diagonal blocks: Ybar_d += dval * (conj(tb_q) f_q + conj(tb_p) f_p)  (u)   |   dval * conj(tb_p) f_q  (w)
-        const cplx wsum = cfma_conj(bp, fp, cfma_conj(bq, fq, czero));
-        const cplx wpq = cfma_conj(bp, fq, czero);
+        const CT wsum = cfma_conj(bp, fp, cfma_conj(bq, fq, czero));
+        const CT wpq = cfma_conj(bp, fq, czero);
         const unsigned dm = s_dmask[g * RW + rw];
 #pragma unroll
         for (int d = 0; d < ND; ++d) {
           if ((dm >> d) & 1u) {
-            const cplx dv = diag_value(d, g);
-            const cplx cc = cmul(csd[d], dv);
+            const CT dv = diag_value(d, g);
+            const CT cc = cmul(csd[d], dv);
             if (P.dfam[d] == 0) {
               accq = cfma_conj(cc, bq, accq); accp = cfma_conj(cc, bp, accp);
               yd[d] = cfma(dv, wsum, yd[d]);
@@ -484,7 +502,7 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
             }
           }
         }
-        const cplx nq = cadd(z[i][0], cscale(accq, invj)), np = cadd(z[i][NV], cscale(accp, invj));
+        const CT nq = cadd(z[i][0], cscale(accq, invj)), np = cadd(z[i][NV], cscale(accp, invj));
         if (j > 1) { y[at(VA, c)] = nq; y[at(NV, c)] = np; }
         else { z[i][0] = nq; z[i][NV] = np; }
       }
@@ -500,12 +518,12 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
       if (rw == 0) s_scr[(warp * NSLOT + x) * SPC + s] = v;
     };
 #pragma unroll
-    for (int bb = 0; bb < NB; ++bb) warp_partial(yb[bb], bb);
+    for (int bb = 0; bb < NB; ++bb) warp_partial(wide_to_d(yb[bb]), bb);
 #pragma unroll
-    for (int dd = 0; dd < ND; ++dd) warp_partial(yd[dd], NB + dd);
+    for (int dd = 0; dd < ND; ++dd) warp_partial(wide_to_d(yd[dd]), NB + dd);
     __syncthreads();
     if (tid < NSLOT * SPC) {
-      cplx a = czero;
+      cplx a = dzero;
       for (int w = 0; w < nwarps; ++w) a = cadd(a, s_scr[w * NSLOT * SPC + tid]);
       s_ysum[tid] = a;
     }
@@ -530,36 +548,41 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
 }
 
 typedef void (*wide_kernel_t)(const WideArgs);
-template <int NB, int ND, bool SIMPLE>
+template <typename CT, int NB, int ND, bool SIMPLE>
 static inline wide_kernel_t wide_pick_blocks(int spc, int items, int threads) {
   if (spc == 8 && threads == 512) {
-    if (items <= 2) return k_chain_wide<8, 2, 512, NB, ND, SIMPLE>;
-    if (items <= 4) return k_chain_wide<8, 4, 512, NB, ND, SIMPLE>;
+    if (items <= 2) return k_chain_wide<CT, 8, 2, 512, NB, ND, SIMPLE>;
+    if (items <= 4) return k_chain_wide<CT, 8, 4, 512, NB, ND, SIMPLE>;
     return nullptr;
   }
   if (spc == 8 && threads == 384) {
-    if (items <= 8) return k_chain_wide<8, 8, 384, NB, ND, SIMPLE>;
+    if (items <= 8) return k_chain_wide<CT, 8, 8, 384, NB, ND, SIMPLE>;
     return nullptr;
   }
   if (spc == 8 && threads == 256) {
-    if (items <= 14) return k_chain_wide<8, 14, 256, NB, ND, SIMPLE>;
+    if (items <= 14) return k_chain_wide<CT, 8, 14, 256, NB, ND, SIMPLE>;
     return nullptr;
   }
   if (spc == 1) {
-    if (items <= 1) return k_chain_wide<1, 1, 512, NB, ND, SIMPLE>;
-    if (items <= 2) return k_chain_wide<1, 2, 512, NB, ND, SIMPLE>;
+    if (items <= 1) return k_chain_wide<CT, 1, 1, 512, NB, ND, SIMPLE>;
+    if (items <= 2) return k_chain_wide<CT, 1, 2, 512, NB, ND, SIMPLE>;
   }
   return nullptr;
 }
 // forward-only column sweeps (8 basis columns per CTA, 384 threads)
-template <int NB, int ND, bool SIMPLE>
+template <typename CT, int NB, int ND, bool SIMPLE>
 static inline wide_kernel_t wide_pick_blocks_fwd(int items) {
-  if (items <= 4) return k_chain_wide<8, 4, 384, NB, ND, SIMPLE, true>;
-  if (items <= 8) return k_chain_wide<8, 8, 384, NB, ND, SIMPLE, true>;
+  if (items <= 4) return k_chain_wide<CT, 8, 4, 384, NB, ND, SIMPLE, true>;
+  if (items <= 8) return k_chain_wide<CT, 8, 8, 384, NB, ND, SIMPLE, true>;
   return nullptr;
 }
 
-wide_kernel_t qocvl_wide_pick_b13_fwd(int items);
-wide_kernel_t qocvl_wide_pick_b24_fwd(int items);
-wide_kernel_t qocvl_wide_pick_b13(int spc, int items, int threads);   // one uniform-valued off-diagonal u block, <= 3 diagonal blocks
-wide_kernel_t qocvl_wide_pick_b24(int spc, int items, int threads);   // <= 2 off-diagonal, <= 4 diagonal blocks
+// (c64 = 1: the complex64 instantiations, compiled in chain_wide_b13f.cu / chain_wide_b24f.cu)
+wide_kernel_t qocvl_wide_pick_b13_fwd(int items, int c64);
+wide_kernel_t qocvl_wide_pick_b24_fwd(int items, int c64);
+wide_kernel_t qocvl_wide_pick_b13(int spc, int items, int threads, int c64);   // one uniform-valued off-diagonal u block, <= 3 diagonal blocks
+wide_kernel_t qocvl_wide_pick_b24(int spc, int items, int threads, int c64);   // <= 2 off-diagonal, <= 4 diagonal blocks
+wide_kernel_t qocvl_wide_pick_b13f_fwd(int items);
+wide_kernel_t qocvl_wide_pick_b24f_fwd(int items);
+wide_kernel_t qocvl_wide_pick_b13f(int spc, int items, int threads);
+wide_kernel_t qocvl_wide_pick_b24f(int spc, int items, int threads);

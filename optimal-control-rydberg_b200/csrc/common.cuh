@@ -47,6 +47,7 @@ __host__ __device__ __forceinline__ cplxf cmul(cplxf a, cplxf b) {
   return cmakef(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 __host__ __device__ __forceinline__ cplxf cscale(cplxf a, float s) { return cmakef(a.x * s, a.y * s); }
+__host__ __device__ __forceinline__ cplxf cconj(cplxf a) { return cmakef(a.x, -a.y); }
 __device__ __forceinline__ cplxf cfma(cplxf a, cplxf b, cplxf acc) {
   acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x);
   acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(a.y, b.x, acc.y);

@@ -25,14 +25,24 @@ else:
     units = 4000
 a, b, c = rng.uniform(-1, 1, (16, 2)), rng.uniform(-1, 1, (16, 2)), rng.uniform(0, 0.5, (16, 2))
 abc = prop._pack(a, b, c)
-for _ in range(2):
+full = None
+for precision in (["complex128", "complex64"] if "c64" in sys.argv[3:] else ["complex128"]):   # 3rd argument "c64": both modes
+    prop.set_precision(precision)
+    for _ in range(2):
+        out = prop.cost_and_grad_packed(abc)
+    prop._plan.check()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     out = prop.cost_and_grad_packed(abc)
-prop._plan.check()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-out = prop.cost_and_grad_packed(abc)
-e1.record()
-torch.cuda.synchronize()
-ms = e0.elapsed_time(e1)
-print(which, f"{ms:.2f} ms, {units / ms * 1e3:.3e} units/s, cost {float(out[0]):.6f}, taylor cap {prop._plan.taylor_cap}",
-      prop._plan.chain_info())
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    res = out.detach().cpu().numpy().copy()
+    extra = ""
+    if full is None:
+        full = res
+    else:
+        extra = (f" | vs complex128: cost {abs(res[0] - full[0]):.2e}, gradient max-rel "
+                 f"{np.abs(res[3:] - full[3:]).max() / np.abs(full[3:]).max():.2e}")
+    print(which, precision, f"{ms:.2f} ms, {units / ms * 1e3:.3e} units/s, cost {float(out[0]):.6f}, taylor cap {prop._plan.taylor_cap}",
+          prop._plan.chain_info(), extra, flush=True)

@@ -639,19 +639,55 @@ def test_complex64_single_sample_and_state_transfer():
             assert rel(np_(mine), r) < TOL_C64_GRAD_REL
 
 
-def test_complex64_fails_loudly_where_the_reduced_kernel_does_not_apply():
-    """Large Hilbert spaces have no complex64 kernel: the evaluation raises instead of running in fp64."""
+@pytest.mark.parametrize("n_atoms,nt,n_samples,kv", [(7, 40, 19, {}), (7, 40, 19, {"QOCVL_WIDE_STORE": 0}),
+                                                    (10, 40, 9, {}), (8, 100, 1, {}), (8, 100, 1, {"QOCVL_TP": 0}),
+                                                    (7, 36, 3, {})])
+def test_complex64_on_large_hilbert_spaces(n_atoms, nt, n_samples, kv):
+    """The complex64 instantiation of the samples-minor kernel (chain_wide.cuh<cplxf>: vectors, Taylor terms, the HBM
+    stream / checkpoints and the per-slice Ybar accumulators in fp32; coefficients, cost, cotangents at the chunk
+    boundaries and every reduction in fp64) on blockade chains with n = 34, 55, 144: ensembles (streamed and recomputed
+    terms), a ragged small ensemble on the one-sample-per-CTA variant, and ONE sample on the time-parallel and the
+    sequential form -- all within the stated bounds of the complex128 result of the same kernel."""
+    po, a, b, c, dl, rs = _chain_ensemble(n_atoms, nt, n_samples, seed=5)
+    if n_samples == 1:
+        dl = rs = None
+    with env(**kv):
+        prop = make_chain(po)
+        if dl is not None:
+            prop.set_ensemble(del_total=dl, rabi_scale=rs)
+        full = np_(prop.cost_and_grad_packed(prop._pack(a, b, c))).copy()
+        path128 = prop._plan.chain_info()["path"]
+        prop.set_precision("complex64")
+        out = np_(prop.cost_and_grad_packed(prop._pack(a, b, c))).copy()
+        cost_only = float(prop.target(a, b, c))
+        prop._plan.check()
+        assert prop._plan.precision == "complex64" and prop._plan.chain_info()["path"] == path128
+        assert path128.startswith("samples_minor")
+        assert np.abs(out - full).max() > 0.0                               # it really is another arithmetic
+        assert np.abs(out[:3] - full[:3]).max() < TOL_C64_COST and abs(cost_only - full[0]) < TOL_C64_COST
+        n = 6 * 2
+        for i in range(3):
+            assert rel(out[3 + i * n:3 + (i + 1) * n], full[3 + i * n:3 + (i + 1) * n]) < TOL_C64_GRAD_REL
+        prop.set_precision("complex128")                                    # switching back gives the complex128 numbers
+        back = np_(prop.cost_and_grad_packed(prop._pack(a, b, c))).copy()
+        assert np.array_equal(back, full)
+
+
+def test_complex64_fails_loudly_where_no_complex64_kernel_exists():
+    """The one-CTA-per-sample fallback of the large-Hilbert-space path has no complex64 instantiation: the evaluation
+    raises instead of running in fp64."""
     from qocvl import QocvlError
     po, a, b, c = obc.chain_setup(n_atoms=7, n_gauss=6, nt=64)      # dim 34: q and p together exceed 32 rows
-    prop = make_chain(po)
-    prop.set_precision("complex64")
-    with pytest.raises(QocvlError):
-        prop.target_and_grad(a, b, c)
-    with pytest.raises(ValueError):
-        prop.set_precision("complex32")
-    prop.set_precision("complex128")                                # and the plan is still usable afterwards
-    cost, _ = prop.target_and_grad(a, b, c)
-    assert abs(float(cost) - po.value_and_grad(a, b, c)[0]) < 1e-10
+    with env(QOCVL_WIDE=0):
+        prop = make_chain(po)
+        prop.set_precision("complex64")
+        with pytest.raises(QocvlError):
+            prop.target_and_grad(a, b, c)
+        with pytest.raises(ValueError):
+            prop.set_precision("complex32")
+        prop.set_precision("complex128")                            # and the plan is still usable afterwards
+        cost, _ = prop.target_and_grad(a, b, c)
+        assert abs(float(cost) - po.value_and_grad(a, b, c)[0]) < 1e-10
 
 
 def test_complex64_optimiser_loop_replays_from_a_graph_and_tracks_complex128():
