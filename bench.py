@@ -399,6 +399,11 @@ def run_gpu(args):
                       "the diagonal depends on the detuning channel the pulse map forces to a constant, TQ:364); padding, "
                       "scaling, table work and the recomputed Taylor powers are NOT counted",
         "kernel_ms": dom_ms,
+        "taylor_degrees": dict(plan.role_degree_means(),
+                               note="mean Taylor degree per role (independent diagonal block of the propagated system: "
+                                    "{U psi, W psi} of |10>, U|11>) of the two-lane kernels: every role runs the degree its "
+                                    "own norm bound asks for, min(1-norm, Collatz-Wielandt 2-norm bound) -- remainder "
+                                    "|X|^(q+1)/(q+1)! <= 2^-55 (c64: 2^-26); the flop counts above use these degrees"),
         "kernel_share_of_step": dom_ms * args.steps / elapsed_ms if dom_ms > 0 else None,
         "evaluation": {
             "kernels": "k_duo_tables, k_duo_forward, k_duo_terminal, k_duo_reverse, k_duo_reduce"

@@ -100,7 +100,7 @@ __global__ void k_coefficients(ModelParams mp, int M, const double* __restrict__
                                const double* __restrict__ mulmax, const double* __restrict__ addmax, int qcap,
                                double taylor_tol, cplx* __restrict__ coef, cplx* __restrict__ dcoef, int* __restrict__ qdeg,
                                int* __restrict__ flag, const unsigned char* __restrict__ colrole, int nroles,
-                               int* __restrict__ qdeg_role) {
+                               int* __restrict__ qdeg_role, int do_norm) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= M) return;
   const int J = mp.J, C = mp.C;
@@ -111,6 +111,7 @@ __global__ void k_coefficients(ModelParams mp, int M, const double* __restrict__
     coef[(size_t)k * J + j] = co[j];
     for (int c = 0; c < C; ++c) dcoef[((size_t)k * J + j) * C + c] = dc[j][c];
   }
+  if (!do_norm) return;                        // the norms and degrees come from k_slice_degrees (one warp per slice)
   double role_nrm[4] = {0.0, 0.0, 0.0, 0.0};   // (DUO_MAXR roles)
   const double nrm = qocvl_slice_norm_csr(mp, co, nt.u_colptr, nt.u_ceid, nt.u_egen, nt.u_eval, nt.u_kc,
                                           nt.w_colptr, nt.w_ceid, nt.w_egen, nt.w_eval, nt.w_kc, nt.gcol,
@@ -142,16 +143,19 @@ __global__ void k_coefficients(ModelParams mp, int M, const double* __restrict__
 // roles are diagonal blocks and one iteration on the union serves them all).  A few power steps make v the Perron vector
 // and the bound tight: for the reference's models | |Y| |_2 = |Y|_2 to 3 digits and the bound is 0.78 of the 1-norm
 // (CZ: mean degree 9.9 -> 9.4 and 11.9 -> 11.0).  Rigorous for every v, so the iteration count only affects tightness.
-// One warp per slice, lane = basis state: the magnitudes N_e go to shared memory once, y = N v runs over the rows (CSR
-// view) and t = N^T y over the columns (CSC view) of the lane's state.
+// One warp per slice, lane = basis state (n <= 32): the kernel also computes what k_coefficients computes serially for
+// larger systems -- the whole-system 1-norm bound, its degree, the poison-and-flag rule -- so that the pulse-map stage
+// of a single-sample evaluation is not dominated by a serial norm loop.  The magnitudes N_e go to shared memory once;
+// column sums (1-norms) and t = N^T y run over the columns (CSC view), y = N v over the rows (CSR view) of the lane's state.
 #define QOCVL_N2_EMAX_U 160
 #define QOCVL_N2_EMAX_W 96
 #define QOCVL_N2_STEPS 5
-__global__ void __launch_bounds__(128) k_role_degrees(int n, int J, double dt, int M, const cplx* __restrict__ coef,
-                                                      NormTables nt, const double* __restrict__ mulmax,
-                                                      const double* __restrict__ addmax,
-                                                      const unsigned char* __restrict__ colrole, int nroles,
-                                                      double taylor_tol, int* __restrict__ qdeg_role) {
+__global__ void __launch_bounds__(128) k_slice_degrees(int n, int J, double dt, int M, cplx* __restrict__ coef,
+                                                       NormTables nt, const double* __restrict__ mulmax,
+                                                       const double* __restrict__ addmax, int qcap, double taylor_tol,
+                                                       int* __restrict__ qdeg, int* __restrict__ flag,
+                                                       const unsigned char* __restrict__ colrole, int nroles, int norm2,
+                                                       int* __restrict__ qdeg_role) {
   __shared__ double s_mu[4][QOCVL_N2_EMAX_U], s_mw[4][QOCVL_N2_EMAX_W], s_v[4][64], s_y[4][64];
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, k = blockIdx.x * 4 + wl;
   if (k >= M) return;
@@ -179,55 +183,83 @@ __global__ void __launch_bounds__(128) k_role_degrees(int n, int J, double dt, i
       (fam ? mw : mu)[e] = (sqrt(re * re + im * im) + dev) * dt;
     }
   }
+  __syncwarp();
   const bool on = lane < n;
-  const unsigned rq = on ? colrole[lane] : 0u, rp = on ? colrole[n + lane] : 0u;   // roles of my state's q / p element
-  double vq = rq ? 1.0 : 0.0, vp = rp ? 1.0 : 0.0;
   const int ur0 = on ? nt.u_rowptr[lane] : 0, ur1 = on ? nt.u_rowptr[lane + 1] : 0;
   const int wr0 = on ? nt.w_rowptr[lane] : 0, wr1 = on ? nt.w_rowptr[lane + 1] : 0;
   const int uc0 = on ? nt.u_colptr[lane] : 0, uc1 = on ? nt.u_colptr[lane + 1] : 0;
   const int wc0 = on ? nt.w_colptr[lane] : 0, wc1 = on ? nt.w_colptr[lane + 1] : 0;
-  for (int it = 0; it <= QOCVL_N2_STEPS; ++it) {
-    __syncwarp();
-    sv[lane] = vq; sv[32 + lane] = vp;
-    __syncwarp();
-    double yq = 0.0, yp = 0.0;                             // y = N v:  y_q = |A| v_q,  y_p = |B| v_q + |A| v_p
-    for (int e = ur0; e < ur1; ++e) {
-      const int c = nt.u_col[e];
-      yq = fma(mu[e], sv[c], yq); yp = fma(mu[e], sv[32 + c], yp);
+  // ---- 1-norm bounds: column n + b of [[A, B], [0, A]] sums |A_ab| + |B_ab| (qocvl_slice_norm_csr's bound, in parallel)
+  double colsum = 0.0;
+  for (int i = uc0; i < uc1; ++i) colsum += mu[nt.u_ceid[i]];
+  for (int i = wc0; i < wc1; ++i) colsum += mw[nt.w_ceid[i]];
+  double nrm = colsum;
+  for (int off = 16; off > 0; off >>= 1) nrm = fmax(nrm, __shfl_xor_sync(0xffffffffu, nrm, off));
+  const bool isnan_ = !(nrm == nrm) || !(co[0].x == co[0].x);
+  int q = qocvl_taylor_degree(nrm, taylor_tol);
+  const bool bad = isnan_ || !(nrm <= QOCVL_NORM_MAX) || q > qcap;   // also catches NaN pulses
+  if (bad) q = 2;
+  if (lane == 0) {
+    if (bad) {
+      atomicOr(flag, 1);
+      // fail loudly: poison the slice so the cost and gradient come out NaN instead of silently wrong
+      coef[(size_t)k * J] = cmake(nan(""), nan(""));
     }
-    for (int e = wr0; e < wr1; ++e) yp = fma(mw[e], sv[nt.w_col[e]], yp);
-    sy[lane] = rq ? yq : 0.0; sy[32 + lane] = rp ? yp : 0.0;   // rows outside every role do not exist in the propagated system
-    __syncwarp();
-    double tq = 0.0, tp = 0.0;                             // t = N^T y:  t_q = |A|^T y_q + |B|^T y_p,  t_p = |A|^T y_p
-    for (int i = uc0; i < uc1; ++i) {
-      const double m = mu[nt.u_ceid[i]];
-      const int r = nt.u_crow[i];
-      tq = fma(m, sy[r], tq); tp = fma(m, sy[32 + r], tp);
-    }
-    for (int i = wc0; i < wc1; ++i) tq = fma(mw[nt.w_ceid[i]], sy[32 + nt.w_crow[i]], tq);
-    if (!rq) tq = 0.0;
-    if (!rp) tp = 0.0;
-    if (it == QOCVL_N2_STEPS) {
-      for (int r = 0; r < nroles; ++r) {
-        double best = fmax(((rq >> r) & 1u) ? tq / vq : 0.0, ((rp >> r) & 1u) ? tp / vp : 0.0);
-        for (int off = 16; off > 0; off >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, off));
-        if (lane == 0) {
-          const double n2 = sqrt(best) * (1.0 + 1e-12);    // (rounding of the iteration itself)
-          if (n2 == n2) {
-            const int q2 = qocvl_taylor_degree(n2, taylor_tol);
-            int* dst = qdeg_role + (size_t)r * M + k;
-            if (q2 < *dst) *dst = q2;
-          }
-        }
+    qdeg[k] = q;
+  }
+  if (!colrole) return;
+  const unsigned rq = on ? colrole[lane] : 0u, rp = on ? colrole[n + lane] : 0u;   // roles of my state's q / p element
+  double role_n1[4];
+  for (int r = 0; r < nroles; ++r) {
+    double v = (((rq | rp) >> r) & 1u) ? colsum : 0.0;
+    for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+    role_n1[r] = v;
+  }
+  double role_n2[4] = {1e300, 1e300, 1e300, 1e300};
+  if (norm2 && !bad) {
+    double vq = rq ? 1.0 : 0.0, vp = rp ? 1.0 : 0.0;
+    for (int it = 0; it <= QOCVL_N2_STEPS; ++it) {
+      __syncwarp();
+      sv[lane] = vq; sv[32 + lane] = vp;
+      __syncwarp();
+      double yq = 0.0, yp = 0.0;                           // y = N v:  y_q = |A| v_q,  y_p = |B| v_q + |A| v_p
+      for (int e = ur0; e < ur1; ++e) {
+        const int c = nt.u_col[e];
+        yq = fma(mu[e], sv[c], yq); yp = fma(mu[e], sv[32 + c], yp);
       }
-    } else {
-      double mx = fmax(tq, tp);
-      for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-      const double inv = mx > 0.0 ? 1.0 / mx : 0.0;
-      if (rq) vq = fmax(tq * inv, 1e-3);                   // next positive vector (the bound needs v > 0)
-      if (rp) vp = fmax(tp * inv, 1e-3);
+      for (int e = wr0; e < wr1; ++e) yp = fma(mw[e], sv[nt.w_col[e]], yp);
+      sy[lane] = rq ? yq : 0.0; sy[32 + lane] = rp ? yp : 0.0;   // rows outside every role do not exist in the propagated system
+      __syncwarp();
+      double tq = 0.0, tp = 0.0;                           // t = N^T y:  t_q = |A|^T y_q + |B|^T y_p,  t_p = |A|^T y_p
+      for (int i = uc0; i < uc1; ++i) {
+        const double m = mu[nt.u_ceid[i]];
+        const int r = nt.u_crow[i];
+        tq = fma(m, sy[r], tq); tp = fma(m, sy[32 + r], tp);
+      }
+      for (int i = wc0; i < wc1; ++i) tq = fma(mw[nt.w_ceid[i]], sy[32 + nt.w_crow[i]], tq);
+      if (!rq) tq = 0.0;
+      if (!rp) tp = 0.0;
+      if (it == QOCVL_N2_STEPS) {
+        for (int r = 0; r < nroles; ++r) {
+          double best = fmax(((rq >> r) & 1u) ? tq / vq : 0.0, ((rp >> r) & 1u) ? tp / vp : 0.0);
+          for (int off = 16; off > 0; off >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, off));
+          const double n2 = sqrt(best) * (1.0 + 1e-12);    // (rounding of the iteration itself)
+          if (n2 == n2) role_n2[r] = n2;
+        }
+      } else {
+        double mx = fmax(tq, tp);
+        for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        const double inv = mx > 0.0 ? 1.0 / mx : 0.0;
+        if (rq) vq = fmax(tq * inv, 1e-3);                 // next positive vector (the bound needs v > 0)
+        if (rp) vp = fmax(tp * inv, 1e-3);
+      }
     }
   }
+  // every role -- a diagonal block of the propagated system -- gets the degree ITS norm needs
+  // (CZ: the {U psi, W psi} pair has half the norm of U|11>)
+  if (lane == 0)
+    for (int r = 0; r < nroles; ++r)
+      qdeg_role[(size_t)r * M + k] = bad ? 2 : min(q, qocvl_taylor_degree(fmin(role_n1[r], role_n2[r]), taylor_tol));
 }
 
 // aux[k][0..J-3] = coef[k][2..J-1]   (ST:244-245, TQ:452-455)
@@ -328,16 +360,18 @@ int qocvl_launch_coefficients(qocvl_plan* p, const double* wave, cudaStream_t st
                    p->cw.colptr, p->cw.ceid, p->cw.egen, p->cw.eval, p->cw.kc, p->d_gnorm,
                    p->cu.crow, p->cw.crow, p->cu.rowptr, p->cu.col, p->cw.rowptr, p->cw.col};
   const bool role_q = p->use_aug && p->use_duo && p->duo.role_q;   // per-role Taylor degrees of the two-lane kernels
+  // small systems: norms, degrees and the poison rule by one warp per slice (k_slice_degrees) instead of one thread
+  const bool warp_norms = d.n <= 32 && p->cu.nnz <= QOCVL_N2_EMAX_U && p->cw.nnz <= QOCVL_N2_EMAX_W;
   k_coefficients<<<(d.n_slices + 63) / 64, 64, 0, st>>>(mp, d.n_slices, wave, p->d_coef_const, nt, p->d_mulmax,
                                                        p->d_addmax, p->qcap, p->taylor_tol(), p->d_coef, p->d_dcoef, p->d_qdeg,
                                                        p->d_flag, role_q ? p->duo.d_colrole : nullptr, role_q ? p->duo.nroles : 0,
-                                                       p->duo.d_qdeg_role);
+                                                       p->duo.d_qdeg_role, warp_norms ? 0 : 1);
   p->launches++;
-  // 2-norm bounds of the roles ("duo_roleq" = 2, the default) when the tables fit the kernel's shared memory
-  if (role_q && p->opt("duo_roleq", 2) >= 2 && d.n <= 32 && p->cu.nnz <= QOCVL_N2_EMAX_U && p->cw.nnz <= QOCVL_N2_EMAX_W) {
-    k_role_degrees<<<(d.n_slices + 3) / 4, 128, 0, st>>>(d.n, d.n_gen, d.dt, d.n_slices, p->d_coef, nt, p->d_mulmax,
-                                                        p->d_addmax, p->duo.d_colrole, p->duo.nroles, p->taylor_tol(),
-                                                        p->duo.d_qdeg_role);
+  if (warp_norms) {         // ("duo_roleq" = 2, the default: per-role degrees from min(1-norm, 2-norm bound); 1: 1-norm only)
+    k_slice_degrees<<<(d.n_slices + 3) / 4, 128, 0, st>>>(d.n, d.n_gen, d.dt, d.n_slices, p->d_coef, nt, p->d_mulmax,
+                                                         p->d_addmax, p->qcap, p->taylor_tol(), p->d_qdeg, p->d_flag,
+                                                         role_q ? p->duo.d_colrole : nullptr, role_q ? p->duo.nroles : 0,
+                                                         p->opt("duo_roleq", 2) >= 2 ? 1 : 0, p->duo.d_qdeg_role);
     p->launches++;
   }
   QCUDA(cudaGetLastError());
