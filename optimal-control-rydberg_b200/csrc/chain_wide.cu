@@ -361,6 +361,197 @@ __global__ void __launch_bounds__(1024) k_wide_combine(const WideCombineArgs A) 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Taylor degrees of the samples-minor kernel: one CTA per slice computes, for the whole propagated system
+// [[A, B], [0, A]] (q = U psi and p = W psi on every basis state),
+//   * the 1-norm bound k_coefficients computes serially (column sums of |nominal entry| + entrywise noise-deviation
+//     bound) and its degree; the poison-and-flag rule lives here when k_coefficients skips its norm loop;
+//   * a phase shift  phi_k = midpoint of the range of Im diag(X_k):  the sweeps run the Taylor series of
+//     Y_k = X_k - i phi_k I  (exp(X_k) = e^{i phi_k} exp(Y_k); the phases of all slices commute with everything and are
+//     applied once, to the target kets: k_wide_phase).  For the blockade chains the diagonal is the detuning times the
+//     excitation number (0 .. N/2): the shift halves its contribution to the norm;
+//   * a 2-norm bound of the shifted generator:  |Y(s)|_2 <= | |Y(s)| |_2 <= |N|_2 = sqrt(rho(N^T N))
+//     <= sqrt(max_i (N^T N v)_i / v_i)  for ANY positive v (Collatz-Wielandt; N >= |Y(s)| entrywise for every noise
+//     sample).  A few power steps make the bound tight; it is rigorous whatever v is.
+// The degree is the one min(1-norm, 2-norm bound) of Y_k asks for (cfg 5: mean degree 15.2 -> 13.1).
+// ---------------------------------------------------------------------------------------------------
+struct WideNormArgs {
+  int n, J, M, qcap, fresh, do_shift, u_kc, w_kc;
+  double dt, tol;
+  cplx* coef;
+  const int *u_rowptr, *u_col, *u_colptr, *u_crow, *u_ceid, *u_egen;
+  const int *w_rowptr, *w_col, *w_colptr, *w_crow, *w_ceid, *w_egen;
+  const cplx *u_eval, *w_eval;
+  const double *mulmax, *addmax;
+  int *qdeg, *flag;
+  double* shift;
+};
+#define WIDE_NORM_THREADS 256
+#define WIDE_NORM_STEPS 5
+
+__device__ __forceinline__ double wide_block_max(double v, double* red, int tid) {
+  for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  double r = red[0];
+  for (int w = 1; w < WIDE_NORM_THREADS / 32; ++w) r = fmax(r, red[w]);
+  return r;
+}
+
+__global__ void __launch_bounds__(WIDE_NORM_THREADS) k_wide_degrees(const WideNormArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red[WIDE_NORM_THREADS / 32];
+  const int n = A.n, J = A.J, k = blockIdx.x, tid = threadIdx.x, T = WIDE_NORM_THREADS;
+  const int nu = A.u_rowptr[n], nw = A.w_rowptr[n];
+  double* mu = (double*)smem_raw;            // [nu] off-diagonal magnitudes of A (diagonal entries: 0, see dmag)
+  double* mw = mu + nu;                      // [nw]
+  double* dre = mw + nw;                     // [n] Re, Im of the nominal diagonal of A (times dt), its deviation bound
+  double* dim = dre + n;
+  double* ddev = dim + n;
+  double* dmag = ddev + n;                   // [n] |shifted diagonal| + deviation
+  double* vq = dmag + n;                     // [n] each
+  double *vp = vq + n, *yq = vp + n, *yp = yq + n;
+  cplx co[QOCVL_MAX_GEN];
+  double wgt[QOCVL_MAX_GEN];
+  for (int j = 0; j < J; ++j) {
+    co[j] = A.coef[(size_t)k * J + j];
+    wgt[j] = sqrt(co[j].x * co[j].x + co[j].y * co[j].y) * A.mulmax[J + j] + A.addmax[j];
+  }
+  for (int r = tid; r < n; r += T) { dre[r] = 0.0; dim[r] = 0.0; ddev[r] = 0.0; }
+  __syncthreads();
+  for (int r = tid; r < n; r += T) {                       // magnitudes, row by row (the row's diagonal entry apart)
+    for (int fam = 0; fam < 2; ++fam) {
+      const int e0 = fam ? A.w_rowptr[r] : A.u_rowptr[r], e1 = fam ? A.w_rowptr[r + 1] : A.u_rowptr[r + 1];
+      const int kc = fam ? A.w_kc : A.u_kc;
+      const int *egen = fam ? A.w_egen : A.u_egen, *col = fam ? A.w_col : A.u_col;
+      const cplx* eval = fam ? A.w_eval : A.u_eval;
+      for (int e = e0; e < e1; ++e) {
+        double re = 0, im = 0, dev = 0;
+        for (int c = 0; c < kc; ++c) {
+          const int g = egen[e * kc + c];
+          if (g >= 0) {
+            const cplx v = eval[e * kc + c];
+            re += co[g].x * v.x - co[g].y * v.y; im += co[g].x * v.y + co[g].y * v.x;
+            dev += wgt[g] * sqrt(v.x * v.x + v.y * v.y);
+          }
+        }
+        if (!fam && col[e] == r) { dre[r] = re * A.dt; dim[r] = im * A.dt; ddev[r] = dev * A.dt; mu[e] = 0.0; }
+        else (fam ? mw : mu)[e] = (sqrt(re * re + im * im) + dev) * A.dt;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- unshifted 1-norm bound (qocvl_slice_norm_csr's) and the poison rule
+  double cs = 0.0, lo = 1e300, hi = -1e300;
+  for (int b = tid; b < n; b += T) {
+    double sum = sqrt(dre[b] * dre[b] + dim[b] * dim[b]) + ddev[b];
+    for (int i = A.u_colptr[b]; i < A.u_colptr[b + 1]; ++i) sum += mu[A.u_ceid[i]];
+    for (int i = A.w_colptr[b]; i < A.w_colptr[b + 1]; ++i) sum += mw[A.w_ceid[i]];
+    cs = fmax(cs, sum);
+    lo = fmin(lo, dim[b]); hi = fmax(hi, dim[b]);
+  }
+  const double nrm_u = wide_block_max(cs, red, tid);
+  int q_u = qocvl_taylor_degree(nrm_u, A.tol);
+  const bool bad = !(nrm_u == nrm_u) || !(co[0].x == co[0].x) || !(nrm_u <= QOCVL_NORM_MAX) || q_u > A.qcap;
+  if (bad) {                                               // (uniform: every thread sees the same nrm_u)
+    if (tid == 0) {
+      if (A.fresh) {
+        atomicOr(A.flag, 1);
+        A.coef[(size_t)k * J] = cmake(nan(""), nan(""));   // fail loudly: NaN cost and gradient, never silently wrong
+        A.qdeg[k] = 2;
+      }
+      A.shift[k] = 0.0;
+    }
+    return;
+  }
+  // ---- phase shift: midpoint of the range of Im diag
+  const double dhi = wide_block_max(hi, red, tid), dlo = -wide_block_max(-lo, red, tid);
+  const double phi = A.do_shift ? 0.5 * (dhi + dlo) : 0.0;
+  for (int r = tid; r < n; r += T) {
+    const double im = dim[r] - phi;
+    dmag[r] = sqrt(dre[r] * dre[r] + im * im) + ddev[r];
+    vq[r] = 1.0; vp[r] = 1.0;
+  }
+  __syncthreads();
+  // ---- shifted 1-norm
+  cs = 0.0;
+  for (int b = tid; b < n; b += T) {
+    double sum = dmag[b];
+    for (int i = A.u_colptr[b]; i < A.u_colptr[b + 1]; ++i) sum += mu[A.u_ceid[i]];
+    for (int i = A.w_colptr[b]; i < A.w_colptr[b + 1]; ++i) sum += mw[A.w_ceid[i]];
+    cs = fmax(cs, sum);
+  }
+  const double n1 = wide_block_max(cs, red, tid);
+  // ---- Collatz-Wielandt bound of | N |_2,  N = [[|A|, 0], [|B|, |A|]] acting on (v_q, v_p)
+  double best = 0.0;
+  for (int it = 0; it <= WIDE_NORM_STEPS; ++it) {
+    for (int r = tid; r < n; r += T) {                     // y = N v:  y_q = |A| v_q,  y_p = |B| v_q + |A| v_p
+      double aq = dmag[r] * vq[r], ap = dmag[r] * vp[r];
+      for (int e = A.u_rowptr[r]; e < A.u_rowptr[r + 1]; ++e) {
+        const int c = A.u_col[e];
+        aq = fma(mu[e], vq[c], aq); ap = fma(mu[e], vp[c], ap);
+      }
+      for (int e = A.w_rowptr[r]; e < A.w_rowptr[r + 1]; ++e) ap = fma(mw[e], vq[A.w_col[e]], ap);
+      yq[r] = aq; yp[r] = ap;
+    }
+    __syncthreads();
+    double mx = 0.0, ratio = 0.0, tq_[4], tp_[4];          // t = N^T y  (rows b = tid, tid + T, ...: at most 4 per thread here)
+    int cnt = 0;
+    for (int b = tid; b < n; b += T, ++cnt) {
+      double tq = dmag[b] * yq[b], tp = dmag[b] * yp[b];
+      for (int i = A.u_colptr[b]; i < A.u_colptr[b + 1]; ++i) {
+        const double m = mu[A.u_ceid[i]];
+        const int r = A.u_crow[i];
+        tq = fma(m, yq[r], tq); tp = fma(m, yp[r], tp);
+      }
+      for (int i = A.w_colptr[b]; i < A.w_colptr[b + 1]; ++i) tq = fma(mw[A.w_ceid[i]], yp[A.w_crow[i]], tq);
+      ratio = fmax(ratio, fmax(tq / vq[b], tp / vp[b]));
+      mx = fmax(mx, fmax(tq, tp));
+      if (cnt < 4) { tq_[cnt] = tq; tp_[cnt] = tp; }
+    }
+    if (it == WIDE_NORM_STEPS) { best = wide_block_max(ratio, red, tid); break; }
+    mx = wide_block_max(mx, red, tid);                     // (its barriers also separate the reads of v from the writes)
+    const double inv = mx > 0.0 ? 1.0 / mx : 0.0;
+    cnt = 0;
+    for (int b = tid; b < n; b += T, ++cnt) {              // next positive vector (the bound needs v > 0)
+      vq[b] = fmax(tq_[cnt] * inv, 1e-3); vp[b] = fmax(tp_[cnt] * inv, 1e-3);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    double nb = n1;
+    const double n2 = sqrt(best) * (1.0 + 1e-12);
+    if (n2 == n2 && n2 > 0.0) nb = fmin(nb, n2);
+    int q = qocvl_taylor_degree(nb, A.tol);
+    if (q > q_u) q = q_u;
+    if (!A.fresh && A.qdeg[k] < q) q = A.qdeg[k];          // (k_coefficients already ran its own rule: keep a poisoned slice's 2)
+    A.qdeg[k] = q;
+    A.shift[k] = phi;
+  }
+}
+
+// Accumulated phase of the shifts: exp(X_M) ... exp(X_1) = e^{i Phi} exp(Y_M) ... exp(Y_1), Phi = sum_k phi_k.  The sweeps
+// propagate z~ = e^{-i Phi} z; the cost reads z only through <y, z> (and q^dag p, which is phase free), so the target kets
+// are rotated instead, y~ = e^{-i Phi} y: <y~, z~> = <y, z>, and the terminal cotangent the kernels derive from y~ is
+// the cotangent of z~.  One block, fixed summation order (deterministic).
+__global__ void __launch_bounds__(256) k_wide_phase(int M, int count, const double* __restrict__ shift,
+                                                    const cplx* __restrict__ targets, cplx* __restrict__ rot) {
+  __shared__ double part[256];
+  double acc = 0.0;
+  for (int k = threadIdx.x; k < M; k += 256) acc += shift[k];
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) part[threadIdx.x] += part[threadIdx.x + off];
+    __syncthreads();
+  }
+  double sn, cs;
+  sincos(-part[0], &sn, &cs);
+  const cplx ph = cmake(cs, sn);
+  for (int i = threadIdx.x; i < count; i += 256) rot[i] = cmul(ph, targets[i]);
+}
+
 // Build the tables of the wide kernel.  QOCVL_ERR_UNSUPPORTED when the problem does not fit it (the caller then
 // falls back to the one-CTA-per-sample kernel).
 int qocvl_wide_configure(qocvl_plan* p) {
@@ -424,6 +615,22 @@ int qocvl_wide_configure(qocvl_plan* p) {
   }
   p->bytes += p->ckpt_bytes + p->tring_bytes;
   L.store = store;
+  // ---- Taylor degrees by k_wide_degrees (phase shift + 2-norm bound) when its tables fit shared memory ("wide_norms" = 0:
+  //      the serial 1-norm rule of k_coefficients, no shift)
+  {
+    const size_t need = ((size_t)p->cu.nnz + p->cw.nnz + 8 * (size_t)n) * sizeof(double);
+    p->wide_norms = need <= 200 * 1024 && n <= 4 * WIDE_NORM_THREADS && p->opt("wide_norms", 1) != 0;
+    p->wide_norm_smem = p->wide_norms ? need : 0;
+    if (p->wide_norms && need > 48 * 1024)
+      QCUDA(cudaFuncSetAttribute(k_wide_degrees, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    if (p->d_wide_shift) { cudaFree(p->d_wide_shift); p->d_wide_shift = nullptr; }
+    if (p->d_targets_rot) { cudaFree(p->d_targets_rot); p->d_targets_rot = nullptr; }
+    if (p->wide_norms) {
+      QCUDA(cudaMalloc((void**)&p->d_wide_shift, (size_t)M * sizeof(double)));
+      QCUDA(cudaMemset(p->d_wide_shift, 0, (size_t)M * sizeof(double)));
+      QCUDA(cudaMalloc((void**)&p->d_targets_rot, (size_t)n * sizeof(cplx)));
+    }
+  }
   p->use_wide = true;
   return QOCVL_OK;
 }
@@ -444,7 +651,8 @@ static void wide_fill_args(const qocvl_plan* p, const WideLayout& L, WideArgs& a
   a.fwd_val = L.fwd_val; a.fwd_col = L.fwd_col; a.rev_val = L.rev_val; a.rev_col = L.rev_col;
   a.dval = L.dval; a.dval_re = L.dval_re; a.dmask = L.dmask;
   a.coef = p->d_coef; a.dcoef = p->d_dcoef; a.qdeg = p->d_qdeg; a.mul = p->d_mul; a.add = p->d_add;
-  a.starts = p->d_starts; a.targets = p->d_targets;
+  a.starts = p->d_starts; a.targets = p->wide_norms ? p->d_targets_rot : p->d_targets;
+  a.shift = p->wide_norms ? p->d_wide_shift : nullptr;
   a.ring = p->d_tring; a.ckpt = p->d_ckpt;
   a.sample_out = p->d_sample_out; a.gw_partial = p->d_gw_partial;
   a.chunk_len = p->tp_chunk; a.n_chunks = p->tp_nchunks; a.ctas_per_chunk = (d.n + 7) / 8;
@@ -454,6 +662,23 @@ static void wide_fill_args(const qocvl_plan* p, const WideLayout& L, WideArgs& a
 // gwave: [M][C] device buffer; the time-parallel path writes d cost / d wave into it directly
 int qocvl_wide_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t st) {
   const WideLayout& L = p->lwide;
+  if (p->wide_norms) {
+    WideNormArgs na;
+    memset(&na, 0, sizeof(na));
+    na.n = p->d.n; na.J = p->d.n_gen; na.M = p->d.n_slices; na.qcap = p->qcap;
+    na.fresh = p->wide_norms_fresh ? 1 : 0;                 // k_coefficients skipped its norm loop for this evaluation
+    na.do_shift = p->opt("wide_shift", 1) != 0 ? 1 : 0;
+    na.u_kc = p->cu.kc; na.w_kc = p->cw.kc; na.dt = p->d.dt; na.tol = p->taylor_tol();
+    na.coef = p->d_coef;
+    na.u_rowptr = p->cu.rowptr; na.u_col = p->cu.col; na.u_colptr = p->cu.colptr; na.u_crow = p->cu.crow;
+    na.u_ceid = p->cu.ceid; na.u_egen = p->cu.egen; na.u_eval = p->cu.eval;
+    na.w_rowptr = p->cw.rowptr; na.w_col = p->cw.col; na.w_colptr = p->cw.colptr; na.w_crow = p->cw.crow;
+    na.w_ceid = p->cw.ceid; na.w_egen = p->cw.egen; na.w_eval = p->cw.eval;
+    na.mulmax = p->d_mulmax; na.addmax = p->d_addmax; na.qdeg = p->d_qdeg; na.flag = p->d_flag; na.shift = p->d_wide_shift;
+    k_wide_degrees<<<p->d.n_slices, WIDE_NORM_THREADS, p->wide_norm_smem, st>>>(na);
+    k_wide_phase<<<1, 256, 0, st>>>(p->d.n_slices, p->d.n, p->d_wide_shift, p->d_targets, p->d_targets_rot);
+    p->launches += 2;
+  }
   WideArgs a;
   wide_fill_args(p, L, a);
   a.want_grad = want_grad ? 1 : 0; a.store = L.store ? 1 : 0;
@@ -474,7 +699,7 @@ int qocvl_wide_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t
   c.n = p->d.n; c.n_chunks = p->tp_nchunks; c.want_grad = want_grad ? 1 : 0;
   c.inv_duration = a.inv_duration; c.w_infid = a.w_infid; c.w_adiab = a.w_adiab; c.inv_fid_norm = a.inv_fid_norm;
   c.inv_samples = a.inv_samples; c.d_const = a.d_const;
-  c.uc = p->d_tp_uc; c.wc = p->d_tp_wc; c.starts = p->d_starts; c.targets = p->d_targets;
+  c.uc = p->d_tp_uc; c.wc = p->d_tp_wc; c.starts = p->d_starts; c.targets = a.targets;
   c.zc = p->d_tp_zc; c.lc = p->d_tp_lc; c.sample_out = p->d_sample_out;
   const int cthreads = 1024, parts = std::max(1, cthreads / p->d.n);
   const size_t csmem = (size_t)(2 + 2 * parts) * p->d.n * sizeof(cplx) + 3 * 32 * sizeof(double);

@@ -34,7 +34,8 @@ struct WideArgs {
   const double* mul;      // [S][J]
   const cplx* add;        // [S][J]
   const cplx* starts;     // [1][n]
-  const cplx* targets;    // [1][n]
+  const cplx* targets;    // [1][n]  (rotated by the accumulated phase of the shifts when `shift` is set)
+  const double* shift;    // [M] phi_k: the sweeps apply X_k - i phi_k I (null: no shift)
   // time-parallel single-sample path: mode 1 = CTA propagates 8 basis columns through one chunk of slices (forward
   // only) and writes the columns of the chunk's Van Loan blocks U_c, W_c; mode 2 = CTA runs the forward + reverse
   // sweep of one chunk between the boundary states / cotangents k_wide_combine stitched together; mode 0 = ensemble.
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
   CT bvl[NB];                                            // common value of every uniform-valued block
 #pragma unroll
   for (int x = 0; x < NB; ++x) bvl[x] = wide_from<CT>(P.bval[x]);
+  CT csh = czero;                                        // -i phi_k: diagonal shift of the slice (see k_wide_degrees)
   auto coefficients = [&](int b) {
 #pragma unroll
     for (int x = 0; x < NB; ++x) csb[x] = (x < P.nb) ? s_cs[(b * J + P.bgen[x]) * SPC + s] : czero;
@@ -192,14 +194,14 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
     const int r = row[i], g = i * nwarps + warp;
     const CT* ts = t + s;                        // element (row, q) of this thread's sample; p follows SPC later
     const CT tq = t[at(VA, r)], tp = t[at(NV, r)];
-    CT accq = czero, accp = czero;
+    CT accq = cmul(csh, tq), accp = cmul(csh, tp);       // the shift's diagonal
     if (SIMPLE) {          // one off-diagonal block, uniform value, acting on q and p (checked on the host)
       const int2 co = s_fco[g];
       CT sq = czero, sp = czero;
       gather_sum(ts, s_fcol + co.y + rw * 4 * co.x, co.x, true, sq, sp);
       const CT c = cmul(csb[0], bvl[0]);
-      accq = cmul(c, sq);
-      accp = cmul(c, sp);
+      accq = cfma(c, sq, accq);
+      accp = cfma(c, sp, accp);
     } else {
 #pragma unroll
     for (int bb = 0; bb < NB; ++bb) {
@@ -251,6 +253,7 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
     const int q = P.qdeg[k], b = k & 1;
     if (k + 1 < k_end) load_cs(k + 1, b ^ 1);
     coefficients(b);
+    if (P.shift) csh = wide_mk(0.0, -P.shift[k], (CT*)nullptr);
     const int kl = k - k_begin;
     CT* t0 = (P.store ? ring + (size_t)kl * P.qcap * VS : ckpt + (size_t)kl * VS);
 #pragma unroll
@@ -365,6 +368,7 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
     const int q = P.qdeg[k], b = k & 1, qprev = k > k_begin ? P.qdeg[k - 1] : 0, kl = k - k_begin;
     if (k > k_begin) load_cs(k - 1, b ^ 1);
     coefficients(b);
+    if (P.shift) csh = wide_mk(0.0, -P.shift[k], (CT*)nullptr);
     CT* rk = ring + (P.store ? (size_t)kl * P.qcap * VS : 0);
     int cur = 0;
     if (!P.store) {
@@ -432,7 +436,7 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
           prefetch_l2(&nx[at(NV, c)]);
         }
         const CT bq = t[at(VA, c)], bp = t[at(NV, c)];             // own elements of tb_j
-        CT accq = czero, accp = czero;
+        CT accq = cfma_conj(csh, bq, czero), accp = cfma_conj(csh, bp, czero);   // (X - i phi)^dag: the shift's diagonal
         CT sqb[NB], spb[NB];                                        // (G^dag tb_q)[c], (G^dag tb_p)[c] per block
         if (SIMPLE) {
           const int2 co = s_rco[g];

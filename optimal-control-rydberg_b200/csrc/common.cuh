@@ -216,6 +216,12 @@ struct qocvl_plan {
   std::vector<double> h_gcol;   // [J][n] column sums of |G_u| + |G_w| (entrywise-abs norm bound)
   BlockLayout lu, lw;      // lane-per-row tables (n <= 16 only)
   CsrLayout cu, cw;        // CSR / CSC tables (any n): big-n kernel, norm bounds
+  // samples-minor kernel (chain_wide.cu): per-slice phase shift phi_k of the generator (X_k - i phi_k I is what the
+  // Taylor series sees; the accumulated phase goes into the rotated target kets) and its degree kernel's shared memory
+  double* d_wide_shift = nullptr;      // [M]
+  cplx* d_targets_rot = nullptr;       // [n_live][n]
+  size_t wide_norm_smem = 0;           // 0: k_wide_degrees not available for this system (serial norms of k_coefficients)
+  bool wide_norms = false, wide_norms_fresh = false;   // fresh: k_coefficients left norms / degrees / poison rule to k_wide_degrees
   cplx* d_gdense = nullptr;   // [J][2n][2n] dense generators (for exponentials())
   cplx* d_coef_const = nullptr;  // [J]
   double* d_gnorm = nullptr;  // [J][n] column sums of |G_u| + |G_w|

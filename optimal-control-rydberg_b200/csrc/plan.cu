@@ -174,7 +174,7 @@ extern "C" int qocvl_plan_destroy(qocvl_plan* p) {
   for (cudaEvent_t e : p->ev_stage) if (e) cudaEventDestroy(e);
   void* ptrs[] = {p->d_gdense, p->d_coef_const, p->d_gnorm, p->d_starts, p->d_targets, p->d_mul, p->d_add,
                   p->d_mulmax, p->d_addmax, p->d_taps, p->d_raw, p->d_reg, p->d_wave, p->d_coef, p->d_dcoef,
-                  p->d_qdeg, p->d_flag, p->d_ckpt, p->d_sample_out, p->d_gw_partial, p->d_gwave, p->d_greg,
+                  p->d_qdeg, p->d_flag, p->d_wide_shift, p->d_targets_rot, p->d_ckpt, p->d_sample_out, p->d_gw_partial, p->d_gwave, p->d_greg,
                   p->d_graw, p->d_out3, p->d_dense_a, p->d_dense_b, p->d_aug_starts, p->d_aug_targets,
                   p->d_aug_pair, p->d_aug_wq, p->d_ypart, p->d_tp_uc, p->d_tp_wc, p->d_tp_zc, p->d_tp_lc};
   for (void* q : ptrs) if (q) cudaFree(q);
@@ -320,7 +320,7 @@ extern "C" int qocvl_set_shard(qocvl_plan* p, int global_samples) {
 // The library reads no environment variables: everything that changes a plan's behaviour is set on the plan.
 extern "C" int qocvl_set_option(qocvl_plan* p, const char* name, int value) {
   static const char* known[] = {"aug", "store", "spb", "nofold", "force_big", "qcap", "tp", "tp_chunk", "tlocal",
-                                "wide", "wide_store", "wide_spc", "wide_threads", "strong_chunks", "duo", "duo_wpc", "duo_nomirror", "duo_nolean", "duo_cols", "duo_roleq", "debug_sync"};
+                                "wide", "wide_store", "wide_spc", "wide_threads", "strong_chunks", "duo", "duo_wpc", "duo_nomirror", "duo_nolean", "duo_cols", "duo_roleq", "wide_norms", "wide_shift", "debug_sync"};
   if (!p || !name) return QOCVL_ERR_ARG;
   bool ok = false;
   for (const char* k : known) ok = ok || strcmp(k, name) == 0;

@@ -362,10 +362,14 @@ int qocvl_launch_coefficients(qocvl_plan* p, const double* wave, cudaStream_t st
   const bool role_q = p->use_aug && p->use_duo && p->duo.role_q;   // per-role Taylor degrees of the two-lane kernels
   // small systems: norms, degrees and the poison rule by one warp per slice (k_slice_degrees) instead of one thread
   const bool warp_norms = d.n <= 32 && p->cu.nnz <= QOCVL_N2_EMAX_U && p->cw.nnz <= QOCVL_N2_EMAX_W;
+  // large systems on the samples-minor kernel: k_wide_degrees (one CTA per slice, launched by qocvl_wide_launch) owns the
+  // norms once the path is configured; the very first evaluation still runs the serial rule here
+  const bool wide_norms = !warp_norms && p->groups > 0 && p->use_wide && p->wide_norms;
   k_coefficients<<<(d.n_slices + 63) / 64, 64, 0, st>>>(mp, d.n_slices, wave, p->d_coef_const, nt, p->d_mulmax,
                                                        p->d_addmax, p->qcap, p->taylor_tol(), p->d_coef, p->d_dcoef, p->d_qdeg,
                                                        p->d_flag, role_q ? p->duo.d_colrole : nullptr, role_q ? p->duo.nroles : 0,
-                                                       p->duo.d_qdeg_role, warp_norms ? 0 : 1);
+                                                       p->duo.d_qdeg_role, (warp_norms || wide_norms) ? 0 : 1);
+  p->wide_norms_fresh = wide_norms;
   p->launches++;
   if (warp_norms) {         // ("duo_roleq" = 2, the default: per-role degrees from min(1-norm, 2-norm bound); 1: 1-norm only)
     k_slice_degrees<<<(d.n_slices + 3) / 4, 128, 0, st>>>(d.n, d.n_gen, d.dt, d.n_slices, p->d_coef, nt, p->d_mulmax,

@@ -459,6 +459,57 @@ def test_samples_minor_kernel_streamed_equals_recomputed_and_any_geometry(thread
         assert rel(out[3:], ref[3:]) < 1e-10
 
 
+@pytest.mark.parametrize("n_atoms,nt,n_samples", [(7, 40, 11), (10, 40, 9), (8, 100, 1), (12, 12, 8)])
+def test_samples_minor_kernel_phase_shift_and_two_norm_degrees(n_atoms, nt, n_samples):
+    """k_wide_degrees: the sweeps of the samples-minor kernel run the Taylor series of X_k - i phi_k I (phi_k = midpoint
+    of the range of Im diag X_k; the accumulated phase goes into the rotated target kets) at the degree the 2-norm bound
+    of the SHIFTED generator asks for.  Same numbers as the serial 1-norm rule without shift ("wide_norms" = 0) and as the
+    unshifted 2-norm rule ("wide_shift" = 0), fewer Taylor terms; ensembles, one sample (time-parallel form), n = 377."""
+    po, a, b, c, dl, rs = _chain_ensemble(n_atoms, nt, n_samples, seed=3, n_gauss=4 if n_atoms == 12 else 6)
+    if n_samples == 1:
+        dl = rs = None
+    outs, degs = [], []
+    for kv in ({"QOCVL_WIDE_NORMS": 0}, {"QOCVL_WIDE_SHIFT": 0}, {}):
+        with env(**kv):
+            prop = make_chain(po)
+            if dl is not None:
+                prop.set_ensemble(del_total=dl, rabi_scale=rs)
+            for _ in range(2):                                  # (the second evaluation runs with k_coefficients' norm loop off)
+                out = np_(prop.cost_and_grad_packed(prop._pack(a, b, c))).copy()
+            cost_only = float(prop.target(a, b, c))
+            prop._plan.check()
+            assert prop._plan.chain_info()["path"].startswith("samples_minor")
+            assert abs(cost_only - out[0]) < 1e-13
+            outs.append(out)
+            degs.append(prop._plan.role_degrees()[0])
+    for out in outs[1:]:
+        assert np.abs(out[:3] - outs[0][:3]).max() < 1e-12 and rel(out[3:], outs[0][3:]) < 1e-9
+    assert (degs[2] <= degs[1]).all() and (degs[1] <= degs[0]).all() and degs[2].sum() < degs[0].sum()
+    # rigour: the degree covers the true 2-norm of every member's shifted generator
+    def need(nrm, tol=2.0 ** -55):
+        term, q = 1.0, 0
+        while q < 40:
+            q += 1
+            term *= nrm / q
+            if q >= 2 and term * nrm / (q + 1) <= tol:
+                return q
+        return 40
+    if n_atoms <= 8:
+        w = po.waves(*(torch.tensor(x) for x in (a, b, c))).numpy()
+        hx, nn = po.h_drive.real, po.h_number.real
+        n, M = po.dim, po.no_of_steps
+        for d_, s_ in zip(dl if dl is not None else [0.0], rs if rs is not None else [1.0]):
+            for k in range(M):
+                ham0 = po.Rabi_max * w[k, 0] * hx - po.Delta_max * w[k, 1] * nn          # nominal: defines the shift
+                dg = -np.diag(ham0) * po.delta_t                                        # Im diag of X = -i dt H
+                phi = 0.5 * (dg.max() + dg.min())
+                ham = s_ * po.Rabi_max * w[k, 0] * hx - (po.Delta_max * w[k, 1] + d_) * nn
+                pen = np.zeros((n, n)); pen[po.i_g, po.i_g] = 1 - k / M; pen[po.i_z, po.i_z] = k / M
+                y = -1j * po.delta_t * ham - 1j * phi * np.eye(n)
+                x = np.block([[y, po.delta_t * pen], [np.zeros((n, n)), y]])
+                assert degs[2][k] >= need(np.linalg.norm(x, 2)), k
+
+
 def test_samples_minor_kernel_dim377_against_dense_oracle_sample():
     """cfg 5 Hilbert space (12 atoms, n = 377) on a short grid: ensemble of 8 = one full CTA; the ensemble mean must
     equal the mean of the dense torch oracle evaluated member by member for the cost, and the one-CTA-per-sample
