@@ -21,8 +21,43 @@ __global__ void k_duo_tables(const DuoArgs Q, const unsigned long long* __restri
       const int g = Q.ent_gen[d * Q.KG + i];
       if (g >= 0) acc = cfma(Q.coef[(size_t)k * Q.J + g], Q.ent_val[d * Q.KG + i], acc);
     }
+    acc = cscale(acc, Q.dt);
+    if (Q.phi && Q.ent_srole[d] >= 0) acc.y -= Q.phi[(size_t)Q.ent_srole[d] * Q.M + k];   // Y = X - i phi_role I
     // (stored in the sweep's own type: a conversion inside the sweep would sit right behind the staged load)
-    ((CT*)Q.tab)[ent_out[d] + (size_t)k * ent_stride[d]] = duo_from<CT>(cscale(acc, Q.dt));
+    ((CT*)Q.tab)[ent_out[d] + (size_t)k * ent_stride[d]] = duo_from<CT>(acc);
+  }
+}
+
+// Accumulated phase of the per-role shifts: the sweeps propagate z~ = e^{-i Phi_r} z on the rows of role r, Phi_r =
+// sum_k phi_r(k).  The cost reads z only through <y, z> (and q^dag p inside one role: phase free), so the role's target
+// kets are rotated instead, y~ = e^{-i Phi_r} y: <y~, z~> = <y, z>, and the terminal cotangent k_duo_terminal derives from
+// y~ is the cotangent of z~.  One block, fixed summation order (deterministic).
+__global__ void __launch_bounds__(256) k_duo_phase(int M, int N, int nroles, const double* __restrict__ phi,
+                                                   const int* __restrict__ rowrole, const cplx* __restrict__ targets,
+                                                   cplx* __restrict__ rot) {
+  __shared__ double part[256];
+  __shared__ double total[DUO_MAXR];
+  for (int r = 0; r < nroles; ++r) {
+    double acc = 0.0;
+    for (int k = threadIdx.x; k < M; k += 256) acc += phi[(size_t)r * M + k];
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+      if (threadIdx.x < off) part[threadIdx.x] += part[threadIdx.x + off];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) total[r] = part[0];
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < N; i += 256) {
+    const int r = rowrole[i];
+    cplx y = targets[i];
+    if (r >= 0) {
+      double sn, cs;
+      sincos(-total[r], &sn, &cs);
+      y = cmul(cmake(cs, sn), y);
+    }
+    rot[i] = y;
   }
 }
 
@@ -217,7 +252,7 @@ int slot_of(unsigned mask, int bit) { return duo_popc(mask & ((1u << bit) - 1u))
 
 void DuoState::release() {
   for (void* q : {(void*)d_ent_x_lean, (void*)d_ent_ystride_lean, (void*)d_ent_ysrc_lean}) if (q) cudaFree(q);
-  void* ptrs[] = {d_colrole, d_qdeg_role, d_tab, d_con_a, d_srow, d_ent_gen, d_ent_val, d_ent_x, d_ent_out, d_ent_stride, d_ent_ysrc,
+  void* ptrs[] = {d_phi, d_rowrole, d_ent_srole, d_targets_rot, d_colrole, d_qdeg_role, d_tab, d_con_a, d_srow, d_ent_gen, d_ent_val, d_ent_x, d_ent_out, d_ent_stride, d_ent_ysrc,
                   d_ent_ystride, d_ent_ywarps, d_starts, d_targets, d_pair, d_wq, d_zfin, d_lam, d_colrow, d_prop,
                   d_zstart, d_lamend};
   for (void* q : ptrs) if (q) cudaFree(q);
@@ -536,7 +571,7 @@ int qocvl_duo_configure(qocvl_plan* p) {
   //      (k_coefficients, model.cuh::qocvl_slice_norm_csr).  CZ: the {U psi, W psi} pair has half the norm of U|11>.
   {
     std::vector<unsigned char> colrole(2 * (size_t)p->d.n, 0);   // [q part | p part][basis state]
-    bool ok = (int)p->h_aug_members.size() == N && p->opt("duo_roleq", 2) != 0;
+    bool ok = (int)p->h_aug_members.size() == N && p->opt("duo_roleq", 3) != 0;
     for (int r = 0; r < nroles && ok; ++r)
       for (int row : comp[r]) {
         if (row < 0) continue;
@@ -550,6 +585,29 @@ int qocvl_duo_configure(qocvl_plan* p) {
       DUO_UP(D.d_colrole, colrole);
       QCUDA(cudaMalloc((void**)&D.d_qdeg_role, (size_t)DUO_MAXR * M * sizeof(int)));
       QCUDA(cudaMemset(D.d_qdeg_role, 0, (size_t)DUO_MAXR * M * sizeof(int)));
+    }
+    // ---- phase shift per role: needs one role per basis state (the shift of a state's diagonal is its role's) and
+    //      diagonal entries without a per-sample multiplier (entry = A + m P would scale the shift with m)
+    //      (complex128 only: in fp32 the rotating frame costs accuracy -- without the shift the dominant amplitudes sit
+    //      on states with an exactly zero diagonal and are never multiplied; measured 10x the adiabaticity error)
+    bool shift = ok && p->opt("duo_roleq", 3) >= 3 && !p->c64;
+    for (int b = 0; b < p->d.n && shift; ++b) shift = duo_popc((unsigned)(colrole[b] | colrole[p->d.n + b])) <= 1;
+    std::vector<int> rowrole(N, -1), ent_srole(ntot, -1);
+    for (int r = 0; r < nroles; ++r)
+      for (int row : comp[r]) if (row >= 0) rowrole[row] = r;
+    for (int i = 0; i < ntot && shift; ++i) {
+      const Desc& d = desc[i];
+      if (d.a < 0 || d.a != d.b || d.u >= kPat[variant[d.role]].nt) continue;       // own-block diagonal entries only
+      ent_srole[i] = d.role;
+      if ((clsmask[d.role * 2 + d.type] >> d.u) & 1u) shift = false;
+    }
+    // every row of a role needs its diagonal slot in the pattern (all compiled patterns have the full diagonal)
+    D.shift_on = shift;
+    if (shift) {
+      DUO_UP(D.d_rowrole, rowrole); DUO_UP(D.d_ent_srole, ent_srole);
+      QCUDA(cudaMalloc((void**)&D.d_phi, (size_t)DUO_MAXR * M * sizeof(double)));
+      QCUDA(cudaMemset(D.d_phi, 0, (size_t)DUO_MAXR * M * sizeof(double)));
+      QCUDA(cudaMalloc((void**)&D.d_targets_rot, (size_t)N * sizeof(cplx)));
     }
   }
   for (int r = 0; r < nroles; ++r) { D.variant_lean[r] = variant_lean[r]; D.nx_lean[r] = nx_lean[r]; }
@@ -619,7 +677,8 @@ int qocvl_duo_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t 
   q.ent_gen = D.d_ent_gen; q.ent_val = D.d_ent_val; q.ent_x = D.d_ent_x;
   q.coef = p->d_coef; q.dcoef = p->d_dcoef;
   q.qdeg = D.role_q ? D.d_qdeg_role : p->d_qdeg; q.qstride = D.role_q ? d.n_slices : 0;   // [role][M] or one row for all
-  q.starts = D.d_starts; q.targets = D.d_targets; q.pair = D.d_pair; q.wq = D.d_wq;
+  q.starts = D.d_starts; q.targets = D.shift_on ? D.d_targets_rot : D.d_targets; q.pair = D.d_pair; q.wq = D.d_wq;
+  q.phi = D.shift_on ? D.d_phi : nullptr; q.ent_srole = D.d_ent_srole;
   q.ckpt = p->d_ckpt;                                   // (elements of the sweeps' type: the kernels cast)
   q.zfin = D.d_zfin; q.lam = D.d_lam; q.ypart = p->d_ypart;
   q.sample_out = p->d_sample_out; q.gwave = gwave;
@@ -681,6 +740,11 @@ int qocvl_duo_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t 
   else k_duo_tables<cplx><<<d.n_slices, 64, 0, st>>>(q, D.d_ent_out, D.d_ent_stride);
   p->launches++;
   DUO_DBG("k_duo_tables");
+  if (D.shift_on) {
+    k_duo_phase<<<1, 256, 0, st>>>(q.M, q.N, q.nroles, D.d_phi, D.d_rowrole, D.d_targets, D.d_targets_rot);
+    p->launches++;
+    DUO_DBG("k_duo_phase");
+  }
   if (D.chunks > 1) {            // chunk propagators -> boundary states -> (terminal cost) -> boundary cotangents
     sweep(false, 1);
     DUO_DBG("k_duo_forward (chunk propagators)");

@@ -72,6 +72,8 @@ struct DuoArgs {
   const int* ent_x;     // [ntot] index of the descriptor among its lane type's Xbar slots, -1 = not a gradient slot
   const cplx* coef;     // [M][J]
   const cplx* dcoef;    // [M][J][C]
+  const double* phi;    // [nroles][M] phase shift of every role and slice (null: none), see k_slice_degrees
+  const int* ent_srole; // [ntot] role whose shift the descriptor carries (own-block diagonal entries), -1 = none
   const int* qdeg;      // [nroles][M] Taylor degree of every role and slice (qstride = M), or [M] for all roles (qstride = 0)
   int qstride;
   const cplx* starts;   // [N]

@@ -1,6 +1,8 @@
 // common.cuh -- shared definitions for the qocvl sm_100a kernels (plan layout, complex helpers).
 #pragma once
 #include <cuda_runtime.h>
+#include <cmath>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -61,7 +63,8 @@ __device__ __forceinline__ cplxf cfma_conj(cplxf a, cplxf b, cplxf acc) {
 
 // Smallest q with  nrm^(q+1)/(q+1)! <= tol.  complex128: tol = 2^-55 = u/4 (u = fp64 unit round-off: a smaller
 // remainder is not representable next to the O(1) state; the oracle's twin rule,
-// oracle/vector_model.py::taylor_degree, uses the stricter 2^-60).  complex64: 2^-26 = u_fp32/4.
+// oracle/vector_model.py::taylor_degree, uses the stricter 2^-60).  complex64: 2^-26 = u_fp32/4
+// (measured with the tight per-role bounds: the actual remainder is ~1e-11 per slice, profiles/c64_shift_probe.py).
 #define QOCVL_TAYLOR_TOL_C128 2.7755575615628914e-17  // 2^-55
 #define QOCVL_TAYLOR_TOL_C64 1.4901161193847656e-08   // 2^-26
 __host__ __device__ inline int qocvl_taylor_degree(double nrm, double tol = QOCVL_TAYLOR_TOL_C128) {
@@ -193,6 +196,12 @@ struct DuoState {
   int* d_qdeg_role = nullptr;
   bool role_q = false;
   int nnz_role[4] = {0}, nnz_x_lean_role[4] = {0};   // non-zeros / lean Xbar entries of every role (flop model)
+  // per-role phase shift ("duo_roleq" = 3, the default): k_slice_degrees writes phi[role][M], k_duo_tables subtracts
+  // i phi from the role's diagonal entries, k_duo_phase rotates the role's target kets by the accumulated phase
+  bool shift_on = false;
+  double* d_phi = nullptr;
+  int *d_rowrole = nullptr, *d_ent_srole = nullptr;   // [N] role of a stacked row; [ntot] role if the descriptor is a diagonal entry, else -1
+  cplx* d_targets_rot = nullptr;
   void release();
 };
 
@@ -299,7 +308,11 @@ struct qocvl_plan {
   int aug_p0 = 0;                                // first stacked row that belongs to p = W psi (rows before: U x_v)
   std::vector<std::vector<int>> h_aug_members;   // [aug_n] basis states a stacked row stands for (its orbit)
   int c64 = 0;             // qocvl_set_precision: 1 = the ensemble kernel runs in complex64 (reduced stacked system only)
-  double taylor_tol() const { return c64 ? QOCVL_TAYLOR_TOL_C64 : QOCVL_TAYLOR_TOL_C128; }
+  // ("taylor_tol_exp" = e: remainder tolerance 2^-e instead of the precision's default)
+  double taylor_tol() const {
+    if (has_opt("taylor_tol_exp")) return ldexp(1.0, -std::max(8, std::min(70, opt("taylor_tol_exp"))));
+    return c64 ? QOCVL_TAYLOR_TOL_C64 : QOCVL_TAYLOR_TOL_C128;
+  }
   int aug_n = 0, aug_lpg = 0, aug_nnz = 0, aug_wmax = 0, aug_parts = 0, aug_qs = 0;
   bool aug_store = false;         // Taylor terms streamed through HBM instead of recomputed in the reverse sweep
   cplx* d_ypart = nullptr;        // [warps][M][column contributions][aug_lpg] per-warp sums of m * Xbar (c64: float2)

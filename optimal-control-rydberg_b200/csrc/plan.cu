@@ -320,7 +320,7 @@ extern "C" int qocvl_set_shard(qocvl_plan* p, int global_samples) {
 // The library reads no environment variables: everything that changes a plan's behaviour is set on the plan.
 extern "C" int qocvl_set_option(qocvl_plan* p, const char* name, int value) {
   static const char* known[] = {"aug", "store", "spb", "nofold", "force_big", "qcap", "tp", "tp_chunk", "tlocal",
-                                "wide", "wide_store", "wide_spc", "wide_threads", "strong_chunks", "duo", "duo_wpc", "duo_nomirror", "duo_nolean", "duo_cols", "duo_roleq", "wide_norms", "wide_shift", "debug_sync"};
+                                "wide", "wide_store", "wide_spc", "wide_threads", "strong_chunks", "duo", "duo_wpc", "duo_nomirror", "duo_nolean", "duo_cols", "duo_roleq", "wide_norms", "wide_shift", "taylor_tol_exp", "debug_sync"};
   if (!p || !name) return QOCVL_ERR_ARG;
   bool ok = false;
   for (const char* k : known) ok = ok || strcmp(k, name) == 0;

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(128) k_slice_degrees(int n, int J, double dt, 
                                                        const double* __restrict__ addmax, int qcap, double taylor_tol,
                                                        int* __restrict__ qdeg, int* __restrict__ flag,
                                                        const unsigned char* __restrict__ colrole, int nroles, int norm2,
-                                                       int* __restrict__ qdeg_role) {
+                                                       int* __restrict__ qdeg_role, double* __restrict__ phi) {
   __shared__ double s_mu[4][QOCVL_N2_EMAX_U], s_mw[4][QOCVL_N2_EMAX_W], s_v[4][64], s_y[4][64];
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, k = blockIdx.x * 4 + wl;
   if (k >= M) return;
@@ -209,6 +209,42 @@ __global__ void __launch_bounds__(128) k_slice_degrees(int n, int J, double dt, 
   }
   if (!colrole) return;
   const unsigned rq = on ? colrole[lane] : 0u, rp = on ? colrole[n + lane] : 0u;   // roles of my state's q / p element
+  // ---- phase shift per role (phi != null): the sweeps of role r run the Taylor series of  Y = X - i phi_r I  with
+  //      phi_r = midpoint of the range of Im diag(X) over the role's states (exp(X) = e^{i phi} exp(Y); the phases of
+  //      all slices go into the role's target kets, k_duo_phase).  From here on the diagonal lives in `dmag`.
+  int ed = -1;                                             // my state's diagonal entry in A
+  for (int e = ur0; e < ur1; ++e) if (nt.u_col[e] == lane) ed = e;
+  double dre = 0.0, dim = 0.0, ddev = 0.0;
+  if (ed >= 0) {
+    for (int c = 0; c < nt.u_kc; ++c) {
+      const int g = nt.u_egen[ed * nt.u_kc + c];
+      if (g >= 0) {
+        const cplx v = nt.u_eval[ed * nt.u_kc + c];
+        dre += co[g].x * v.x - co[g].y * v.y; dim += co[g].x * v.y + co[g].y * v.x;
+        ddev += wgt[g] * sqrt(v.x * v.x + v.y * v.y);
+      }
+    }
+    dre *= dt; dim *= dt; ddev *= dt;
+  }
+  double myphi = 0.0;
+  for (int r = 0; r < nroles; ++r) {
+    const bool in = ((rq | rp) >> r) & 1u;
+    double hi = in ? dim : -1e300, lo = in ? -dim : -1e300;
+    for (int off = 16; off > 0; off >>= 1) {
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+      lo = fmax(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+    }
+    const double ph = (phi && !bad && hi > -1e299) ? 0.5 * (hi - lo) : 0.0;
+    if (in) myphi = ph;                                    // (the host enables the shift only if a state has ONE role)
+    if (phi && lane == 0) phi[(size_t)r * M + k] = ph;
+  }
+  __syncwarp();
+  if (ed >= 0) mu[ed] = 0.0;
+  __syncwarp();
+  const double dmag = sqrt(dre * dre + (dim - myphi) * (dim - myphi)) + ddev;
+  colsum = dmag;                                           // column sums of the shifted generator
+  for (int i = uc0; i < uc1; ++i) colsum += mu[nt.u_ceid[i]];
+  for (int i = wc0; i < wc1; ++i) colsum += mw[nt.w_ceid[i]];
   double role_n1[4];
   for (int r = 0; r < nroles; ++r) {
     double v = (((rq | rp) >> r) & 1u) ? colsum : 0.0;
@@ -222,7 +258,7 @@ __global__ void __launch_bounds__(128) k_slice_degrees(int n, int J, double dt, 
       __syncwarp();
       sv[lane] = vq; sv[32 + lane] = vp;
       __syncwarp();
-      double yq = 0.0, yp = 0.0;                           // y = N v:  y_q = |A| v_q,  y_p = |B| v_q + |A| v_p
+      double yq = dmag * vq, yp = dmag * vp;               // y = N v:  y_q = |A| v_q,  y_p = |B| v_q + |A| v_p
       for (int e = ur0; e < ur1; ++e) {
         const int c = nt.u_col[e];
         yq = fma(mu[e], sv[c], yq); yp = fma(mu[e], sv[32 + c], yp);
@@ -230,7 +266,7 @@ __global__ void __launch_bounds__(128) k_slice_degrees(int n, int J, double dt, 
       for (int e = wr0; e < wr1; ++e) yp = fma(mw[e], sv[nt.w_col[e]], yp);
       sy[lane] = rq ? yq : 0.0; sy[32 + lane] = rp ? yp : 0.0;   // rows outside every role do not exist in the propagated system
       __syncwarp();
-      double tq = 0.0, tp = 0.0;                           // t = N^T y:  t_q = |A|^T y_q + |B|^T y_p,  t_p = |A|^T y_p
+      double tq = dmag * sy[lane], tp = dmag * sy[32 + lane];   // t = N^T y:  t_q = |A|^T y_q + |B|^T y_p,  t_p = |A|^T y_p
       for (int i = uc0; i < uc1; ++i) {
         const double m = mu[nt.u_ceid[i]];
         const int r = nt.u_crow[i];
@@ -375,7 +411,8 @@ int qocvl_launch_coefficients(qocvl_plan* p, const double* wave, cudaStream_t st
     k_slice_degrees<<<(d.n_slices + 3) / 4, 128, 0, st>>>(d.n, d.n_gen, d.dt, d.n_slices, p->d_coef, nt, p->d_mulmax,
                                                          p->d_addmax, p->qcap, p->taylor_tol(), p->d_qdeg, p->d_flag,
                                                          role_q ? p->duo.d_colrole : nullptr, role_q ? p->duo.nroles : 0,
-                                                         p->opt("duo_roleq", 2) >= 2 ? 1 : 0, p->duo.d_qdeg_role);
+                                                         p->opt("duo_roleq", 3) >= 2 ? 1 : 0, p->duo.d_qdeg_role,
+                                                         role_q && p->duo.shift_on ? p->duo.d_phi : nullptr);
     p->launches++;
   }
   QCUDA(cudaGetLastError());

@@ -278,7 +278,9 @@ def test_reduced_system_kernels_and_modes_agree(n_samples):
                 # one Taylor degree per slice for every role (default: every role -- an independent diagonal block of the
                 # propagated system -- runs the degree ITS OWN norm bound asks for)
                 ({"tp": 0, "duo_roleq": 0}, "reduced_duo"), ({"tp": 0, "duo_roleq": 0, "strong_chunks": 4}, "reduced_duo"),
-                ({"tp": 0, "duo_roleq": 1}, "reduced_duo")]     # ... from the role's 1-norm bound only (default: min with its 2-norm bound)
+                ({"tp": 0, "duo_roleq": 1}, "reduced_duo"),     # ... from the role's 1-norm bound only
+                ({"tp": 0, "duo_roleq": 2}, "reduced_duo"),     # ... min with its 2-norm bound, no phase shift (default: shifted)
+                ({"tp": 0, "duo_roleq": 2, "strong_chunks": 7}, "reduced_duo")]
     outs = []
     for kv, path in variants:
         with env(**kv):
@@ -292,7 +294,7 @@ def test_reduced_system_kernels_and_modes_agree(n_samples):
             assert abs(cost_only - outs[-1][0]) < 1e-14
             # per-role degrees: the {U psi, W psi} pair and U|11> get their own; never above the whole-system degree
             deg = prop._plan.role_degree_means()
-            if path == "reduced_duo" and not kv.get("duo_roleq", 2) == 0:
+            if path == "reduced_duo" and not kv.get("duo_roleq", 3) == 0:
                 assert len(deg["per_role"]) == 2 and min(deg["per_role"]) < max(deg["per_role"]) <= prop._plan.taylor_cap
             else:
                 assert deg["per_role"] == [] and deg["global"] >= 2
@@ -303,26 +305,30 @@ def test_reduced_system_kernels_and_modes_agree(n_samples):
 
 
 def test_per_role_taylor_degrees_are_rigorous_and_tighter():
-    """Every role (diagonal block of the propagated system) runs the Taylor degree its own norm bound asks for: 2-norm
-    bound (Collatz-Wielandt on the entrywise absolute values, model.cuh::qocvl_role_norms2) <= 1-norm bound <= the
-    whole-system bound, slice by slice; and the 2-norm bound really bounds the 2-norm of every member's role block
-    (computed here with NumPy from the oracle's generators), so the truncation rule  |X|^(q+1)/(q+1)! <= 2^-55  holds."""
+    """Every role (diagonal block of the propagated system) runs the Taylor degree its own norm bound asks for:
+    whole-system 1-norm ("duo_roleq" = 0) >= role's 1-norm (1) >= min with the role's 2-norm bound (2: Collatz-Wielandt
+    on the entrywise absolute values, k_slice_degrees) >= the same for the generator shifted by the role's phase
+    (3, the default: X - i phi I, phi = midpoint of the range of Im diag over the role's states), slice by slice; and the
+    bounds really bound the 2-norm of every member's (shifted) role block, computed here with NumPy from the oracle's
+    generators, so the truncation rule  |X|^(q+1)/(q+1)! <= 2^-55  holds."""
     from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL
     po, a, b, c = otq.notebook02_setup(seed=4, n_gauss=6, nt=77)
     args = (6, 77, po.padding, 50e6, po.delta_t, 0.0, po.Vint, po.Delta_i_val, po.Rabi_i_val, po.Rabi_r_val, otq.GAMMAS_CZ)
     dl, rs = ensemble.robust_cz_noise(9)
-    degs = {}
-    for mode in (0, 1, 2):
+    degs, outs = {}, {}
+    for mode in (0, 1, 2, 3):
         with env(tp=0, duo_roleq=mode):
             prop = PropagatorVL(*args)
             prop.set_ensemble(del_total=dl, rabi_scale=rs)
-            prop.cost_and_grad_packed(prop._pack(a, b, c))
+            outs[mode] = np_(prop.cost_and_grad_packed(prop._pack(a, b, c))).copy()
             prop._plan.check()
             degs[mode] = prop._plan.role_degrees()
-    assert degs[0].shape[0] == 1 and degs[1].shape == degs[2].shape == (2, degs[0].shape[1])
-    assert (degs[2] <= degs[1]).all() and (degs[1] <= degs[0]).all()
-    assert degs[2].sum() < degs[1].sum() < 2 * degs[0].sum()
-    # true 2-norms of the role blocks of every ensemble member
+    assert degs[0].shape[0] == 1 and degs[1].shape == degs[2].shape == degs[3].shape == (2, degs[0].shape[1])
+    assert (degs[3] <= degs[2]).all() and (degs[2] <= degs[1]).all() and (degs[1] <= degs[0]).all()
+    assert degs[3].sum() < degs[2].sum() < degs[1].sum() < 2 * degs[0].sum()
+    for mode in (1, 2, 3):
+        assert np.abs(outs[mode][:3] - outs[0][:3]).max() < 1e-13 and rel(outs[mode][3:], outs[0][3:]) < 1e-10
+    # true 2-norms of the role blocks of every ensemble member, unshifted and shifted
     from oracle import vector_model as vm
 
     def need(nrm, tol=2.0 ** -55):
@@ -334,9 +340,8 @@ def test_per_role_taylor_degrees_are_rigorous_and_tighter():
                 return q
         return 40
     r10, r11 = [4, 8, 12], [5, 6, 7, 9, 10, 11, 13, 14, 15]
-    worst = np.zeros_like(degs[2])
-    for d_, s_ in zip(dl, rs):
-        member, *_ = otq.notebook02_setup(seed=4, n_gauss=6, nt=77, del_total=float(d_), rabi_scale=float(s_))
+
+    def blocks(member):
         wave, _ = vm.pulse_map(member, a, b, c, "tq")
         coef, _ = vm.coefficients_tq(member, wave)
         gu, gw = vm.split_generators(np.asarray(member.VL_Generators_ansatz))
@@ -344,15 +349,29 @@ def test_per_role_taylor_degrees_are_rigorous_and_tighter():
             A = member.delta_t * np.tensordot(coef[k], gu, axes=[[0], [0]])
             B = member.delta_t * np.tensordot(coef[k], gw, axes=[[0], [0]])
             a0, b0 = A[np.ix_(r10, r10)], B[np.ix_(r10, r10)]
-            x0 = np.block([[a0, np.zeros_like(a0)], [b0, a0]])
-            x1 = A[np.ix_(r11, r11)]
-            n0, n1 = need(np.linalg.norm(x0, 2)), need(np.linalg.norm(x1, 2))
-            # (the engine numbers its roles by size: find which is which from the mean degrees)
-            worst[0, k], worst[1, k] = max(worst[0, k], n0), max(worst[1, k], n1)
+            yield k, np.block([[a0, np.zeros_like(a0)], [b0, a0]]), A[np.ix_(r11, r11)]
+    phis = np.zeros((2, degs[0].shape[1]))                       # the engine's shift rule, on the noise-free generator
+    for k, x0, x1 in blocks(po):
+        for r, x in enumerate((x0, x1)):
+            dg = np.diag(x).imag
+            phis[r, k] = 0.5 * (dg.max() + dg.min())
+    worst2, worst3, worst3_abs = np.zeros_like(degs[2]), np.zeros_like(degs[2]), np.zeros_like(degs[2])
+    for d_, s_ in zip(dl, rs):
+        member, *_ = otq.notebook02_setup(seed=4, n_gauss=6, nt=77, del_total=float(d_), rabi_scale=float(s_))
+        for k, x0, x1 in blocks(member):
+            for r, x in enumerate((x0, x1)):
+                worst2[r, k] = max(worst2[r, k], need(np.linalg.norm(x, 2)))
+                y = x - 1j * phis[r, k] * np.eye(x.shape[0])
+                worst3[r, k] = max(worst3[r, k], need(np.linalg.norm(y, 2)))
+                worst3_abs[r, k] = max(worst3_abs[r, k], need(np.linalg.norm(np.abs(y), 2)))
+    # (the engine numbers its roles by size: find which is which from the mean degrees)
     order = [0, 1] if degs[2][0].mean() < degs[2][1].mean() else [1, 0]
-    assert (degs[2][order[0]] >= worst[0]).all() and (degs[2][order[1]] >= worst[1]).all()
-    # ... and it is tight: within one degree of what the true 2-norm needs
-    assert (degs[2][order[0]] - worst[0]).max() <= 1 and (degs[2][order[1]] - worst[1]).max() <= 1
+    for r in (0, 1):
+        assert (degs[2][order[r]] >= worst2[r]).all() and (degs[3][order[r]] >= worst3[r]).all()
+        # ... and tight: within one degree of what the true 2-norm needs (shifted: of what the 2-norm of the entrywise
+        # absolute values needs -- the bound's first step; the shifted diagonal has both signs, which | . | forgets)
+        assert (degs[2][order[r]] - worst2[r]).max() <= 1 and (degs[3][order[r]] - worst3_abs[r]).max() <= 1
+        assert (degs[3][order[r]] - worst3[r]).max() <= 2
 
 
 @pytest.mark.parametrize("n_atoms", [2, 3, 4])
