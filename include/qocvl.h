@@ -145,7 +145,12 @@ int qocvl_set_shard(qocvl_plan* plan, int global_samples);
  * basis column of a chunk propagator), "duo_cols" (1 = three basis columns per work item of the chunk-propagator sweep instead of one),
  * "debug_sync" (1 = synchronise after every launch of the two-lane path and name the kernel that failed),
  * "duo_nolean" (1 = qocvl_cost_grad accumulates the gradient of every matrix entry,
- * also of those only a pulse channel that the model's pulse map discards would consume).
+ * also of those only a pulse channel that the model's pulse map discards would consume),
+ * "duo_roleq" (Taylor-degree rule of the two-lane kernels: 0 = one degree per slice from the whole system's 1-norm
+ * bound, 1 = per role from the role's 1-norm bound, 2 = min with the role's 2-norm bound, 3 [default] = the same for
+ * the generator shifted by the role's phase, see qocvl_role_degrees), "wide_norms" / "wide_shift" (0 = the samples-minor
+ * kernel without the 2-norm degree kernel / without the phase shift), "taylor_tol_exp" (e: Taylor remainder
+ * tolerance 2^-e instead of 2^-55 for complex128 / 2^-26 for complex64).
  * They exist so that every kernel path can be cross-checked against the others on the same plan API.
  * QOCVL_ERR_ARG for an unknown name. */
 int qocvl_set_option(qocvl_plan* plan, const char* name, int value);
@@ -154,8 +159,10 @@ int qocvl_set_option(qocvl_plan* plan, const char* name, int value);
  * itself runs complex128 only, jax_enable_x64 at TQ:1-12).  QOCVL_C64 runs the reduced stacked system
  * (qocvl_reduced_rows) with complex64 state, Taylor terms and matrix entries, Taylor remainder 2^-26; the pulse
  * map, the coefficients, the per-sample cost and the reduction of the gradient stay in fp64.  Stated bounds
- * against the complex128 result: cost 5e-5 absolute, gradient 1e-2 of its largest entry.  An evaluation whose
- * problem does not fit the reduced kernel returns QOCVL_ERR_UNSUPPORTED in this mode (no silent fp64 run). */
+ * against the complex128 result: cost 5e-5 absolute, gradient 1e-2 of its largest entry.  Large Hilbert spaces
+ * (blockade chains) run the complex64 instantiation of the samples-minor kernel (vectors, Taylor terms, HBM stream
+ * in fp32).  Only the cross-check fallback kernels have no complex64 form: an evaluation forced onto them returns
+ * QOCVL_ERR_UNSUPPORTED in this mode (no silent fp64 run). */
 enum { QOCVL_C128 = 0, QOCVL_C64 = 1 };
 int qocvl_set_precision(qocvl_plan* plan, int dtype);
 int qocvl_precision(const qocvl_plan* plan);
