@@ -150,7 +150,9 @@ int qocvl_set_shard(qocvl_plan* plan, int global_samples);
  * bound, 1 = per role from the role's 1-norm bound, 2 = min with the role's 2-norm bound, 3 [default] = the same for
  * the generator shifted by the role's phase, see qocvl_role_degrees), "wide_norms" / "wide_shift" (0 = the samples-minor
  * kernel without the 2-norm degree kernel / without the phase shift), "taylor_tol_exp" (e: Taylor remainder
- * tolerance 2^-e instead of 2^-55 for complex128 / 2^-26 for complex64).
+ * tolerance 2^-e instead of 2^-55 for complex128 / 2^-26 for complex64), "graph" (0 = qocvl_cost / qocvl_cost_grad
+ * always launch kernel by kernel; default: a caller that repeats the call with the same buffers gets the launch
+ * sequence replayed from a cached CUDA graph, bit-identical results).
  * They exist so that every kernel path can be cross-checked against the others on the same plan API.
  * QOCVL_ERR_ARG for an unknown name. */
 int qocvl_set_option(qocvl_plan* plan, const char* name, int value);

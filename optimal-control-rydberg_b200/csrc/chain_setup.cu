@@ -91,6 +91,7 @@ static double apriori_norm_bound(const qocvl_plan* p, const std::vector<double>&
 int qocvl_chain_configure(qocvl_plan* p) {
   if (!p->have_gens || !p->have_cost) return QOCVL_ERR_STATE;
   if (p->groups > 0) return QOCVL_OK;
+  p->cfg_epoch++;                                          // cached evaluation graphs (api.cu) are stale from here on
   const qocvl_desc& d = p->d;
   const int J = d.n_gen, n = d.n;
   p->use_big = (p->npad == 0);

@@ -270,6 +270,23 @@ struct qocvl_plan {
   cplx* d_blk_work = nullptr;                      // its per-batch workspace
   cplx* d_dense_a = nullptr;  // [M][2n][2n] ping
   cplx* d_dense_b = nullptr;  // [M/2+1][2n][2n] pong
+  // cached CUDA graphs of whole evaluations (api.cu): a caller that repeats qocvl_cost / qocvl_cost_grad with the same
+  // buffers -- an optimiser loop -- gets the ~15 launches of an evaluation replayed as one graph.  cfg_epoch counts the
+  // (re)configurations and every setter that changes what a launch would do; a graph is valid for one epoch only.
+  struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    int kind = 0;
+    const void* in = nullptr;
+    void* out = nullptr;
+    long long epoch = -1, launches = 0;
+  };
+  GraphSlot graphs[2][2];                 // [cost / cost + gradient][two buffer pairs: a caller whose output tensors ping-pong]
+  const void* recent_in[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // buffer pairs of the last two calls of each kind
+  void* recent_out[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  int recent_pos[2] = {0, 0}, graph_victim[2] = {0, 0};
+  cudaStream_t cap_stream = nullptr;
+  long long cfg_epoch = 0, evals_in_epoch = 0, evals_epoch = -1;
+  bool graph_failed = false;
   // optional kernel timing
   bool timing = false, timed_once = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -169,6 +169,8 @@ extern "C" int qocvl_plan_destroy(qocvl_plan* p) {
   }
   if (p->d_tring) cudaFree(p->d_tring);
   for (void* q : {(void*)p->d_gblk_u, (void*)p->d_gblk_w, (void*)p->d_blk_work}) if (q) cudaFree(q);
+  for (auto& row : p->graphs) for (auto& g : row) if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
   for (cudaEvent_t e : p->ev_stage) if (e) cudaEventDestroy(e);
@@ -248,6 +250,7 @@ extern "C" int qocvl_set_filter(qocvl_plan* p, const double* taps) {
   std::vector<double> h(taps, taps + p->d.n_slices);
   int rc = dev_upload(p, &p->d_taps, h);
   if (rc) return rc;
+  p->cfg_epoch++;
   p->have_filter = true;
   return QOCVL_OK;
 }
@@ -313,6 +316,7 @@ extern "C" int qocvl_set_symmetry(qocvl_plan* p, const int* perm) {
 extern "C" int qocvl_set_shard(qocvl_plan* p, int global_samples) {
   if (!p || global_samples < p->n_samples) return QOCVL_ERR_ARG;
   p->global_samples = global_samples;
+  p->cfg_epoch++;
   return QOCVL_OK;
 }
 
@@ -320,7 +324,7 @@ extern "C" int qocvl_set_shard(qocvl_plan* p, int global_samples) {
 // The library reads no environment variables: everything that changes a plan's behaviour is set on the plan.
 extern "C" int qocvl_set_option(qocvl_plan* p, const char* name, int value) {
   static const char* known[] = {"aug", "store", "spb", "nofold", "force_big", "qcap", "tp", "tp_chunk", "tlocal",
-                                "wide", "wide_store", "wide_spc", "wide_threads", "strong_chunks", "duo", "duo_wpc", "duo_nomirror", "duo_nolean", "duo_cols", "duo_roleq", "wide_norms", "wide_shift", "taylor_tol_exp", "debug_sync"};
+                                "wide", "wide_store", "wide_spc", "wide_threads", "strong_chunks", "duo", "duo_wpc", "duo_nomirror", "duo_nolean", "duo_cols", "duo_roleq", "wide_norms", "wide_shift", "taylor_tol_exp", "graph", "debug_sync"};
   if (!p || !name) return QOCVL_ERR_ARG;
   bool ok = false;
   for (const char* k : known) ok = ok || strcmp(k, name) == 0;

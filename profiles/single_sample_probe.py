@@ -27,9 +27,11 @@ for spec in (sys.argv[1:] or [""]):
         tq = TQ(10, 500, 15, 50e6, 648e-9 / 530, 0.0, 2 * np.pi * 10e6, 2 * np.pi * (-35.7e6), 2 * np.pi * 100e6,
                 2 * np.pi * 100e6, gam)
     ms1, k1, _, c1 = timed(st, a, b, c)
+    r1 = timed.last_repeat_ms
     rng = np.random.default_rng(0)
     a2, b2, c2 = rng.uniform(-1, 1, (10, 5)), rng.uniform(-1, 1, (10, 5)), rng.uniform(0, 0.5, (10, 5))
     ms2, k2, _, c2v = timed(tq, a2, b2, c2)
+    print(f"opts[{spec}] repeated calls with the same buffers (cached graph): cfg1 {r1:.3f} ms | cfg2 {timed.last_repeat_ms:.3f} ms")
     print(f"opts[{spec}] cfg1 {ms1:.3f} ms (chain {k1:.3f}, path {st._plan.chain_info()['path']}, chunks {st._plan.slice_chunks}, "
           f"cost {c1:.12f}) | cfg2 {ms2:.3f} ms (chain {k2:.3f}, path {tq._plan.chain_info()['path']}, chunks "
           f"{tq._plan.slice_chunks}, cost {c2v:.12f})", flush=True)

@@ -450,3 +450,45 @@ def test_device_side_lbfgs_matches_a_host_two_loop_recursion():
     assert np.array_equal(fc.cpu().numpy(), np.asarray(c, float))
     hist_gd, *_ = prop.optimize(a, b, c, num_iters=iters, lr=0.02, masks=masks)
     assert float(hist[-1]) < float(hist[0]) and float(hist[-1]) < float(hist_gd[-1])
+
+
+def test_repeated_evaluations_replay_a_cached_graph_bit_for_bit():
+    """qocvl_cost / qocvl_cost_grad called again and again with the same buffers (an optimiser loop updating its parameters
+    in place) capture the launch sequence once and replay it as one CUDA graph (api.cu::run_evaluation): same numbers bit
+    for bit as the launch-by-launch path ("graph" = 0), same launch count, and every change of the plan (ensemble,
+    precision) drops the graph."""
+    import qocvl
+    from quantum_optimal_control.two_qubit.propagator_vl import PropagatorVL
+    from oracle import ensemble
+    po, a, b, c = otq.notebook02_setup(seed=2, n_gauss=6, nt=77)
+    args = (6, 77, po.padding, 50e6, po.delta_t, 0.0, po.Vint, po.Delta_i_val, po.Rabi_i_val, po.Rabi_r_val, otq.GAMMAS_CZ)
+    runs = {}
+    for graph in (0, 1):
+        with qocvl.options(graph=graph):
+            prop = PropagatorVL(*args)
+        abc = prop._pack(a, b, c).clone()
+        out = torch.empty(3 + abc.numel(), dtype=torch.float64, device=abc.device)
+        hist = []
+        for it in range(6):                                  # plain gradient descent, parameters updated in place
+            prop.cost_and_grad_packed(abc, out)
+            hist.append(out.clone())
+            abc -= 0.02 * out[3:].view_as(abc)
+        costs = [float(prop._plan.cost(abc)[0]) for _ in range(4)]       # cost-only evaluations: their own graph
+        n0 = prop._plan.launches
+        prop.cost_and_grad_packed(abc, out)
+        per_eval = prop._plan.launches - n0
+        dl, rs = ensemble.robust_cz_noise(5)                 # a new ensemble: other kernels, other buffers
+        prop.set_ensemble(del_total=dl, rabi_scale=rs)
+        ens = [prop.cost_and_grad_packed(abc, out).clone() for _ in range(4)]
+        prop.set_precision("complex64")
+        c64 = [prop.cost_and_grad_packed(abc, out).clone() for _ in range(4)]
+        prop._plan.check()
+        runs[graph] = (torch.stack(hist), costs, per_eval, torch.stack(ens), torch.stack(c64))
+    for x, y in zip(runs[0], runs[1]):
+        if isinstance(x, torch.Tensor):
+            assert torch.equal(x, y)
+        else:
+            assert x == y
+    assert float(runs[1][0][-1, 0]) < float(runs[1][0][0, 0])                 # it descends
+    assert all(torch.equal(e, runs[1][3][0]) for e in runs[1][3])             # repeated evaluations: identical
+    assert not torch.equal(runs[1][3][0], runs[1][0][-1])                     # the ensemble changed the numbers
