@@ -166,8 +166,8 @@ static int wide_build(qocvl_plan* p, int spc_request, WideLayout& L, bool fwd = 
             }
             longest = std::max(longest, lists[r].size());
           }
-          const size_t lpad = (longest + 3) / 4 * 4;      // lists padded to whole 4-entry chunks
-          T.co[dir][(size_t)bi * T.ngroups + g] = make_int2((int)(lpad / 4), (int)T.col[dir].size());
+          const size_t lpad = (longest + WIDE_CHUNK - 1) / WIDE_CHUNK * WIDE_CHUNK;   // lists padded to whole chunks
+          T.co[dir][(size_t)bi * T.ngroups + g] = make_int2((int)(lpad / WIDE_CHUNK), (int)T.col[dir].size());
           for (int r = 0; r < T.rw; ++r) {
             const int own = std::max(0, T.grow[(size_t)g * T.rw + r]);
             for (size_t e = 0; e < lpad; ++e) {

@@ -6,7 +6,13 @@
 #define WIDE_THREADS 512
 #define WIDE_MAXB 2     // generator blocks with off-diagonal entries
 #define WIDE_MAXD 4     // generator blocks with diagonal entries
-static constexpr int kWideUnroll = 4;   // entries of a row list in flight per thread
+#ifndef WIDE_CHUNK
+#define WIDE_CHUNK 2    // entries per list chunk: one 4-byte (2) or 8-byte (4) load of 16-bit element offsets
+#endif
+#ifndef WIDE_GATHER_UNROLL
+#define WIDE_GATHER_UNROLL 1
+#endif
+constexpr int kWideGatherUnroll = WIDE_GATHER_UNROLL;   // list chunks in flight per thread
 #define WIDE_NVP 2      // propagated vectors: one moving start ket q and p = W psi
 
 struct WideArgs {
@@ -170,10 +176,13 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
       z[i][NV] = wide_from<CT>(P.tp_zc[((size_t)chunk * NVP + NV) * n + row[i]]);
     }
   }
-  // sum of the gathered elements of one list (4 pre-scaled 16-bit indices per 8-byte load): q and p, or q only
+  // sum of the gathered elements of one list (WIDE_CHUNK pre-scaled 16-bit indices per 4- or 8-byte load; lists are
+  // padded to whole chunks: 7.45 entries per row on the 12-atom chain with chunks of 2, 8.49 with chunks of 4, 6.94 real):
+  // q and p, or q only
   auto gather_sum = [&](const CT* ts, const unsigned short* list, int chunks, bool both, CT& sq, CT& sp) {
+#if WIDE_CHUNK == 4
     if (both) {
-#pragma unroll 2
+#pragma unroll kWideGatherUnroll
       for (int e = 0; e < chunks; ++e) {
         const uint2 c4 = *reinterpret_cast<const uint2*>(list + 4 * e);
         const CT* p0 = ts + (c4.x & 0xffffu); const CT* p1 = ts + (c4.x >> 16);
@@ -182,12 +191,29 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
         sp = cadd(sp, cadd(cadd(p0[SPC], p1[SPC]), cadd(p2[SPC], p3[SPC])));
       }
     } else {
-#pragma unroll 2
+#pragma unroll kWideGatherUnroll
       for (int e = 0; e < chunks; ++e) {
         const uint2 c4 = *reinterpret_cast<const uint2*>(list + 4 * e);
         sq = cadd(sq, cadd(cadd(ts[c4.x & 0xffffu], ts[c4.x >> 16]), cadd(ts[c4.y & 0xffffu], ts[c4.y >> 16])));
       }
     }
+#else
+    if (both) {
+#pragma unroll kWideGatherUnroll
+      for (int e = 0; e < chunks; ++e) {
+        const unsigned c2 = *reinterpret_cast<const unsigned*>(list + 2 * e);
+        const CT* p0 = ts + (c2 & 0xffffu); const CT* p1 = ts + (c2 >> 16);
+        sq = cadd(sq, cadd(p0[0], p1[0]));
+        sp = cadd(sp, cadd(p0[SPC], p1[SPC]));
+      }
+    } else {
+#pragma unroll kWideGatherUnroll
+      for (int e = 0; e < chunks; ++e) {
+        const unsigned c2 = *reinterpret_cast<const unsigned*>(list + 2 * e);
+        sq = cadd(sq, cadd(ts[c2 & 0xffffu], ts[c2 >> 16]));
+      }
+    }
+#endif
   };
   // one forward Taylor step of one owned row:  y = (X t)[row] / j
   auto forward_item = [&](int i, const CT* t, R invj, CT* y) {
@@ -198,7 +224,7 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
     if (SIMPLE) {          // one off-diagonal block, uniform value, acting on q and p (checked on the host)
       const int2 co = s_fco[g];
       CT sq = czero, sp = czero;
-      gather_sum(ts, s_fcol + co.y + rw * 4 * co.x, co.x, true, sq, sp);
+      gather_sum(ts, s_fcol + co.y + rw * WIDE_CHUNK * co.x, co.x, true, sq, sp);
       const CT c = cmul(csb[0], bvl[0]);
       accq = cfma(c, sq, accq);
       accp = cfma(c, sp, accp);
@@ -206,8 +232,8 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
 #pragma unroll
     for (int bb = 0; bb < NB; ++bb) {
       if (bb < P.nb) {
-        const int2 co = s_fco[bb * P.ngroups + g];            // {4-entry chunks per row, offset of the group's lists}
-        const unsigned short* list = s_fcol + co.y + rw * 4 * co.x;
+        const int2 co = s_fco[bb * P.ngroups + g];            // {chunks per row, offset of the group's lists}
+        const unsigned short* list = s_fcol + co.y + rw * WIDE_CHUNK * co.x;
         const bool both = (P.bfam[bb] == 0);     // u blocks act on q and p, w blocks map q into p
         CT sq = czero, sp = czero;
         if (P.buni[bb]) {                        // one common value: plain sums, scaled once
@@ -215,9 +241,9 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
           sq = cmul(bvl[bb], sq);
           sp = cmul(bvl[bb], sp);
         } else {
-          const cplx* ev = P.fwd_val + co.y + rw * 4 * co.x;
+          const cplx* ev = P.fwd_val + co.y + rw * WIDE_CHUNK * co.x;
 #pragma unroll 2
-          for (int e = 0; e < 4 * co.x; ++e) {
+          for (int e = 0; e < WIDE_CHUNK * co.x; ++e) {
             const CT val = wide_from<CT>(__ldg(&ev[e]));
             const int col = list[e];
             sq = cfma(val, ts[col], sq);
@@ -441,7 +467,7 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
         if (SIMPLE) {
           const int2 co = s_rco[g];
           CT sq = czero, sp = czero;
-          gather_sum(t + s, s_rcol + co.y + rw * 4 * co.x, co.x, true, sq, sp);
+          gather_sum(t + s, s_rcol + co.y + rw * WIDE_CHUNK * co.x, co.x, true, sq, sp);
           const CT vc = cconj(bvl[0]);
           sq = cmul(vc, sq);
           sp = cmul(vc, sp);
@@ -454,7 +480,7 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
           sqb[bb] = czero; spb[bb] = czero;
           if (bb < P.nb) {
             const int2 co = s_rco[bb * P.ngroups + g];
-            const unsigned short* list = s_rcol + co.y + rw * 4 * co.x;
+            const unsigned short* list = s_rcol + co.y + rw * WIDE_CHUNK * co.x;
             const bool both = (P.bfam[bb] == 0);   // w blocks: (G_w^dag tb_p)[c] feeds q
             CT sq = czero, sp = czero;
             if (P.buni[bb]) {
@@ -464,10 +490,10 @@ __global__ void __launch_bounds__(THREADS, (FWD && ITEMS <= 4) ? 2 : 1) k_chain_
               sq = cmul(vc, sq);
               sp = cmul(vc, sp);
             } else {
-              const cplx* ev = P.rev_val + co.y + rw * 4 * co.x;
+              const cplx* ev = P.rev_val + co.y + rw * WIDE_CHUNK * co.x;
               const CT* ts = t + s;
 #pragma unroll 2
-              for (int e = 0; e < 4 * co.x; ++e) {
+              for (int e = 0; e < WIDE_CHUNK * co.x; ++e) {
                 const CT val = wide_from<CT>(__ldg(&ev[e]));
                 const int a = list[e];
                 sp = cfma_conj(val, ts[a + SPC], sp);
