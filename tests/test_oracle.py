@@ -124,3 +124,56 @@ def test_chain_golden_fixture_reproduces(golden_dir):
     assert abs(mean[0] - float(gold["cost"])) < 1e-12 and abs(mean[1] - float(gold["infid"])) < 1e-12
     for mine, key in ((mean[3], "ga"), (mean[4], "gb"), (mean[5], "gc")):
         assert np.abs(mine - gold[key]).max() < 1e-10 * max(1.0, np.abs(gold[key]).max())
+
+
+def test_norm_aware_degree_rule_is_rigorous():
+    """oracle/norm_bounds.py (the NumPy twin of k_slice_degrees / k_wide_degrees): the Collatz-Wielandt bound never falls
+    below the true 2-norm whatever the iteration count or start vector, it is tight after five power steps, the phase
+    shift leaves exp(X) unchanged, and the degree it asks for really meets the truncation tolerance."""
+    from scipy.linalg import expm
+    from oracle import norm_bounds as nb
+    rng = np.random.default_rng(0)
+    for trial in range(40):
+        n = int(rng.integers(2, 12))
+        h = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))
+        h = (h + h.conj().T) * rng.uniform(0.01, 0.3) / n
+        h[rng.random((n, n)) < 0.5] = 0.0
+        h = np.triu(h) + np.triu(h, 1).conj().T
+        x = -1j * h - np.diag(rng.uniform(0, 0.01, n))          # X = -i dt (H - i Gamma / 2)
+        true2 = np.linalg.norm(x, 2)
+        for steps in (0, 1, 2, 5, 9):
+            assert nb.collatz_wielandt_two_norm(np.abs(x), steps) >= true2 * (1 - 1e-12)
+        assert nb.collatz_wielandt_two_norm(np.abs(x), 5) <= np.linalg.norm(np.abs(x), 2) * 1.05
+        phi = nb.phase_shift(x)
+        y = x - 1j * phi * np.eye(n)
+        assert np.abs(np.exp(1j * phi) * expm(y) - expm(x)).max() < 1e-14
+        q, _ = nb.block_degree(x)
+        z = rng.normal(size=n) + 1j * rng.normal(size=n)
+        z /= np.linalg.norm(z)
+        acc, term = z.copy(), z.copy()
+        for j in range(1, q + 1):
+            term = y @ term / j
+            acc = acc + term
+        assert np.linalg.norm(np.exp(1j * phi) * acc - expm(x) @ z) < 1e-14
+        q_plain, _ = nb.block_degree(x, shift=False)
+        assert q <= q_plain + 1                                  # (the shift never costs more than the |.| step can lose)
+    # the reference's CZ generator at notebook-02 pulses: per-role degrees below the whole-system 1-norm degree
+    vm = vector_model
+    prop, a, b, c = two_qubit.notebook02_setup(seed=0, n_gauss=6, nt=60)
+    wave, _ = vm.pulse_map(prop, a, b, c, "tq")
+    coef, _ = vm.coefficients_tq(prop, wave)
+    gu, gw = vm.split_generators(np.asarray(prop.VL_Generators_ansatz))
+    r10, r11 = [4, 8, 12], [5, 6, 7, 9, 10, 11, 13, 14, 15]
+    tot = np.zeros(3)
+    for k in range(coef.shape[0]):
+        a_k = prop.delta_t * np.tensordot(coef[k], gu, axes=[[0], [0]])
+        b_k = prop.delta_t * np.tensordot(coef[k], gw, axes=[[0], [0]])
+        whole = np.block([[a_k, b_k], [np.zeros_like(a_k), a_k]])
+        a0, b0 = a_k[np.ix_(r10, r10)], b_k[np.ix_(r10, r10)]
+        role0 = np.block([[a0, np.zeros_like(a0)], [b0, a0]])
+        role1 = a_k[np.ix_(r11, r11)]
+        q_whole = vm.taylor_degree(np.abs(whole).sum(axis=0).max(), 2.0 ** -55)
+        q0, q1 = nb.block_degree(role0)[0], nb.block_degree(role1)[0]
+        assert q0 <= q_whole and q1 <= q_whole
+        tot += (q_whole, q0, q1)
+    assert tot[1] < tot[2] < tot[0]
