@@ -22,6 +22,7 @@
 // stays as the fallback for problems this kernel does not take (several moving start kets, many generator blocks)
 // and as its cross-check (QOCVL_WIDE=0).
 #include "chain_wide.cuh"
+#include <cooperative_groups.h>
 #include <algorithm>
 #include <numeric>
 
@@ -243,7 +244,7 @@ static int wide_build(qocvl_plan* p, int spc_request, WideLayout& L, bool fwd = 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// time-parallel single-sample path: stitch the chunk propagators together (one CTA).
+// time-parallel single-sample path: stitch the chunk propagators together (one cluster of 8 CTAs).
 //   forward : z_{c+1} = (U_c q_c , U_c p_c + W_c q_c), boundary states zc[c]
 //   cost, terminal cotangents lc[n_chunks]
 //   backward: lam_c = (U_c^dag lq + W_c^dag lp , U_c^dag lp), boundary cotangents lc[c]
@@ -258,44 +259,56 @@ struct WideCombineArgs {
   double* sample_out;
 };
 
-__global__ void __launch_bounds__(1024) k_wide_combine(const WideCombineArgs A) {
+// A thread-block CLUSTER of WIDE_CC CTAs walks the chunks: every CTA keeps the whole current state (q, p) in its own shared
+// memory, multiplies its slice of the rows (forward) / columns (backward) of the chunk's blocks -- so the 2 n^2 block
+// entries of a chunk stream in through WIDE_CC SMs instead of one -- and writes its part of the next state into the shared
+// memory of all WIDE_CC CTAs (distributed shared memory), one cluster barrier per chunk.  (One CTA: 1.35 ms of cfg 4's 9.3.)
+#define WIDE_CC 8
+__global__ void __cluster_dims__(WIDE_CC, 1, 1) __launch_bounds__(1024) k_wide_combine(const WideCombineArgs A) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = A.n, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-  cplx* s_q = (cplx*)smem_raw;          // [n]
-  cplx* s_p = s_q + n;                  // [n]
-  cplx* s_part = s_p + n;               // [parts][2][n] partial sums of the forward products
-  const int parts = max(1, nt / n);     // thread (part, r): rows r, columns b = part, part + parts, ...
-  double* s_red = (double*)(s_part + (size_t)parts * 2 * n);   // [3][32]
+  const int rank = (int)cluster.block_rank();
+  const int per = (n + WIDE_CC - 1) / WIDE_CC, r0 = min(n, rank * per), r1 = min(n, r0 + per), nrows = r1 - r0;
+  cplx* s_state = (cplx*)smem_raw;             // [2 buffers][q | p][n]: the whole state, double buffered by chunk
+  cplx* s_part = s_state + 4 * n;              // [parts][2][per] partial sums of my rows
+  const int parts = max(1, nt / max(1, per));  // thread (part, rr): row r0 + rr, columns b = part, part + parts, ...
+  double* s_red = (double*)(s_part + (size_t)parts * 2 * per);   // [3][32]
   const cplx czero = cmake(0, 0);
-  for (int r = tid; r < n; r += nt) {
-    s_q[r] = A.starts[r]; s_p[r] = czero;
-    A.zc[r] = A.starts[r]; A.zc[n + r] = czero;
-  }
-  __syncthreads();
-  const int part = tid / n, r = tid % n;
+  for (int r = tid; r < n; r += nt) { s_state[r] = A.starts[r]; s_state[n + r] = czero; }
+  for (int r = r0 + tid; r < r1; r += nt) { A.zc[r] = A.starts[r]; A.zc[n + r] = czero; }
+  cluster.sync();                              // (every CTA of the cluster is running before anyone writes into it)
+  int cur = 0;
+  const int part = tid / max(1, per), rr = tid % max(1, per);
   for (int c = 0; c < A.n_chunks; ++c) {
     const cplx* U = A.uc + (size_t)c * n * n;
     const cplx* W = A.wc + (size_t)c * n * n;
-    if (part < parts) {
+    const cplx *s_q = s_state + cur * 2 * n, *s_p = s_q + n;
+    if (part < parts && rr < nrows) {
       cplx aq = czero, ap = czero;
       for (int b = part; b < n; b += parts) {
-        const cplx u = U[(size_t)b * n + r], w = W[(size_t)b * n + r], qb = s_q[b], pb = s_p[b];
+        const cplx u = U[(size_t)b * n + r0 + rr], w = W[(size_t)b * n + r0 + rr], qb = s_q[b], pb = s_p[b];
         aq = cfma(u, qb, aq);
         ap = cfma(w, qb, cfma(u, pb, ap));
       }
-      s_part[((size_t)part * 2 + 0) * n + r] = aq;
-      s_part[((size_t)part * 2 + 1) * n + r] = ap;
+      s_part[((size_t)part * 2 + 0) * per + rr] = aq;
+      s_part[((size_t)part * 2 + 1) * per + rr] = ap;
     }
     __syncthreads();
-    for (int i = tid; i < 2 * n; i += nt) {
+    for (int i = tid; i < 2 * nrows; i += nt) {          // i = v * nrows + rr: fixed summation order over the parts
+      const int v = i / nrows, r2 = i % nrows;
       cplx a = czero;
-      for (int pp = 0; pp < parts; ++pp) a = cadd(a, s_part[(size_t)pp * 2 * n + i]);
-      (i < n ? s_q[i] : s_p[i - n]) = a;
-      A.zc[(size_t)(c + 1) * 2 * n + i] = a;
+      for (int pp = 0; pp < parts; ++pp) a = cadd(a, s_part[((size_t)pp * 2 + v) * per + r2]);
+      const int dst = ((cur ^ 1) * 2 + v) * n + r0 + r2;
+      for (int k = 0; k < WIDE_CC; ++k) cluster.map_shared_rank(s_state, k)[dst] = a;
+      A.zc[(size_t)(c + 1) * 2 * n + v * n + r0 + r2] = a;
     }
-    __syncthreads();
+    cluster.sync();
+    cur ^= 1;
   }
-  // ---- cost
+  // ---- cost (every CTA holds the whole final state and evaluates it; rank 0 writes)
+  const cplx *s_q = s_state + cur * 2 * n, *s_p = s_q + n;
   double red[3] = {0, 0, 0};
   for (int i = tid; i < n; i += nt) {
     const cplx y = A.targets[i], zq = s_q[i], zp = s_p[i];
@@ -312,36 +325,40 @@ __global__ void __launch_bounds__(1024) k_wide_combine(const WideCombineArgs A) 
   for (int k = 0; k < 3; ++k)
     for (int w = 0; w < nwarps; ++w) tot[k] += s_red[k * 32 + w];
   const cplx dsum = cmake(tot[0] + A.d_const.x, tot[1] + A.d_const.y);
-  if (tid == 0) {
+  if (tid == 0 && rank == 0) {
     const double infid = 1.0 - (dsum.x * dsum.x + dsum.y * dsum.y) * A.inv_fid_norm;
     const double adiab = 1.0 - tot[2] * A.inv_duration;
     A.sample_out[0] = A.w_infid * infid + A.w_adiab * adiab;
     A.sample_out[1] = infid;
     A.sample_out[2] = adiab;
   }
-  if (!A.want_grad) return;
-  // ---- terminal cotangents
-  __syncthreads();
+  if (!A.want_grad) return;                    // (uniform over the cluster)
+  // ---- terminal cotangents into the other state buffer (local: every CTA computes all of them)
   const double ca = -0.5 * A.w_adiab * A.inv_duration * A.inv_samples;
   const double cf = -A.w_infid * A.inv_fid_norm * A.inv_samples;
-  cplx* s_lq = s_part;                  // reuse: [n], [n]
-  cplx* s_lp = s_part + n;
-  for (int i = tid; i < n; i += nt) {
-    const cplx lq = cadd(cscale(cmul(dsum, A.targets[i]), cf), cscale(s_p[i], ca));
-    const cplx lp = cscale(s_q[i], ca);
-    s_lq[i] = lq; s_lp[i] = lp;
-    A.lc[(size_t)A.n_chunks * 2 * n + i] = lq;
-    A.lc[(size_t)A.n_chunks * 2 * n + n + i] = lp;
+  {
+    cplx* s_l = s_state + (cur ^ 1) * 2 * n;
+    for (int i = tid; i < n; i += nt) {
+      const cplx lq = cadd(cscale(cmul(dsum, A.targets[i]), cf), cscale(s_p[i], ca));
+      const cplx lp = cscale(s_q[i], ca);
+      s_l[i] = lq; s_l[n + i] = lp;
+      if (i >= r0 && i < r1) {
+        A.lc[(size_t)A.n_chunks * 2 * n + i] = lq;
+        A.lc[(size_t)A.n_chunks * 2 * n + n + i] = lp;
+      }
+    }
   }
-  __syncthreads();
-  // ---- backward walk: one warp per output element b, lanes over the rows of column b
+  cur ^= 1;
+  cluster.sync();                              // nobody overwrites the final state while a neighbour still reads it
+  // ---- backward walk: my slice of the output elements b, one warp per element, lanes over the rows of column b
   for (int c = A.n_chunks - 1; c >= 0; --c) {
     const cplx* U = A.uc + (size_t)c * n * n;
     const cplx* W = A.wc + (size_t)c * n * n;
-    for (int b = warp; b < n; b += nwarps) {
+    const cplx *s_lq = s_state + cur * 2 * n, *s_lp = s_lq + n;
+    for (int b = r0 + warp; b < r1; b += nwarps) {
       cplx aq = czero, ap = czero;
-      for (int rr = lane; rr < n; rr += 32) {
-        const cplx u = U[(size_t)b * n + rr], w = W[(size_t)b * n + rr], lq = s_lq[rr], lp = s_lp[rr];
+      for (int r2 = lane; r2 < n; r2 += 32) {
+        const cplx u = U[(size_t)b * n + r2], w = W[(size_t)b * n + r2], lq = s_lq[r2], lp = s_lp[r2];
         aq = cfma_conj(w, lp, cfma_conj(u, lq, aq));
         ap = cfma_conj(u, lp, ap);
       }
@@ -349,15 +366,17 @@ __global__ void __launch_bounds__(1024) k_wide_combine(const WideCombineArgs A) 
         aq.x += __shfl_xor_sync(0xffffffffu, aq.x, off); aq.y += __shfl_xor_sync(0xffffffffu, aq.y, off);
         ap.x += __shfl_xor_sync(0xffffffffu, ap.x, off); ap.y += __shfl_xor_sync(0xffffffffu, ap.y, off);
       }
-      if (lane == 0) { s_q[b] = aq; s_p[b] = ap; }     // s_q / s_p are free after the cost
+      if (lane < WIDE_CC) {                    // lane k delivers the element to CTA k
+        cplx* dst = cluster.map_shared_rank(s_state, lane) + (cur ^ 1) * 2 * n;
+        dst[b] = aq; dst[n + b] = ap;
+      }
+      if (lane == 0) {
+        A.lc[(size_t)c * 2 * n + b] = aq;
+        A.lc[(size_t)c * 2 * n + n + b] = ap;
+      }
     }
-    __syncthreads();
-    for (int i = tid; i < n; i += nt) {
-      s_lq[i] = s_q[i]; s_lp[i] = s_p[i];
-      A.lc[(size_t)c * 2 * n + i] = s_q[i];
-      A.lc[(size_t)c * 2 * n + n + i] = s_p[i];
-    }
-    __syncthreads();
+    cluster.sync();
+    cur ^= 1;
   }
 }
 
@@ -701,10 +720,12 @@ int qocvl_wide_launch(qocvl_plan* p, bool want_grad, double* gwave, cudaStream_t
   c.inv_samples = a.inv_samples; c.d_const = a.d_const;
   c.uc = p->d_tp_uc; c.wc = p->d_tp_wc; c.starts = p->d_starts; c.targets = a.targets;
   c.zc = p->d_tp_zc; c.lc = p->d_tp_lc; c.sample_out = p->d_sample_out;
-  const int cthreads = 1024, parts = std::max(1, cthreads / p->d.n);
-  const size_t csmem = (size_t)(2 + 2 * parts) * p->d.n * sizeof(cplx) + 3 * 32 * sizeof(double);
+  const int per = (p->d.n + WIDE_CC - 1) / WIDE_CC;
+  const int cthreads = std::min(1024, std::max(128, (per * std::max(1, 512 / per) + 31) / 32 * 32));
+  const int parts = std::max(1, cthreads / per);
+  const size_t csmem = ((size_t)4 * p->d.n + (size_t)parts * 2 * per) * sizeof(cplx) + 3 * 32 * sizeof(double);
   if (csmem > 48 * 1024) QCUDA(cudaFuncSetAttribute(k_wide_combine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-  k_wide_combine<<<1, cthreads, csmem, st>>>(c);
+  k_wide_combine<<<WIDE_CC, cthreads, csmem, st>>>(c);
   p->launches += 2;
   if (want_grad) {
     a.mode = 2; a.tp_gwave = gwave;
