@@ -127,20 +127,34 @@ __global__ void __launch_bounds__(128) k_duo_combine(const DuoArgs Q, int dir) {
   const int myrow = li < 6 ? Q.srow[role * 6 + li] : -1;
   cplx z = cmake(0.0, 0.0);
   if (on && myrow >= 0) z = dir > 0 ? Q.starts[myrow] : Q.lam[(size_t)sm * Q.N + myrow];
+  // my six propagator entries of a chunk -- row li of P (forward) or column li (backward) -- are requested one chunk
+  // ahead: the walk is a chain of `chunks` dependent steps, and with the loads inside the step every step waited for six
+  // L2 round trips in a row (61 us of a 240 us single-sample evaluation for each of the two walks).
+  auto fetch = [&](int cc, cplx (&pe)[6]) {
+    const int c = dir > 0 ? cc : Q.chunks - 1 - cc;
+    const cplx* P = Q.prop + (((size_t)sm * Q.chunks + c) * Q.nroles + role) * 36;
+#pragma unroll
+    for (int l = 0; l < 6; ++l)
+      pe[l] = li < 6 ? (dir > 0 ? duo_pfull(Q, P, colof, role, li, l) : duo_pfull(Q, P, colof, role, l, li)) : cmake(0.0, 0.0);
+  };
+  cplx pe[6], pn[6];
+  fetch(0, pe);
   for (int cc = 0; cc < Q.chunks; ++cc) {
     const int c = dir > 0 ? cc : Q.chunks - 1 - cc;
+    if (cc + 1 < Q.chunks) fetch(cc + 1, pn);
     if (on && myrow >= 0) ((dir > 0 ? Q.zstart : Q.lamend) + ((size_t)sm * Q.chunks + c) * Q.N)[myrow] = z;
-    const cplx* P = Q.prop + (((size_t)sm * Q.chunks + c) * Q.nroles + role) * 36;
     cplx zn = cmake(0.0, 0.0);
 #pragma unroll
     for (int l = 0; l < 6; ++l) {
       const cplx zl = cmake(__shfl_sync(0xffffffffu, z.x, base + l), __shfl_sync(0xffffffffu, z.y, base + l));
-      if (li < 6) {
-        if (dir > 0) zn = cfma(duo_pfull(Q, P, colof, role, li, l), zl, zn);          // z'_li = sum_l P[li][l] z_l
-        else zn = cfma_conj(duo_pfull(Q, P, colof, role, l, li), zl, zn);           // lam'_li = sum_l conj(P[l][li]) lam_l
-      }
+      if (dir > 0) zn = cfma(pe[l], zl, zn);                 // z'_li = sum_l P[li][l] z_l
+      else zn = cfma_conj(pe[l], zl, zn);                    // lam'_li = sum_l conj(P[l][li]) lam_l
     }
     z = zn;
+    if (cc + 1 < Q.chunks) {
+#pragma unroll
+      for (int l = 0; l < 6; ++l) pe[l] = pn[l];
+    }
   }
   if (dir > 0 && on && myrow >= 0) Q.zfin[(size_t)sm * Q.N + myrow] = z;
 }
