@@ -140,7 +140,7 @@ __global__ void k_coefficients(ModelParams mp, int M, const double* __restrict__
 // Collatz-Wielandt bound), where N >= |Y(s)| entrywise for every noise sample:  N_e = |nominal entry| + the entrywise
 // deviation bound used above.  N is the non-negative image of [[A, 0], [B, A]] restricted to the role's (q, p) states
 // (colrole: [2][n] role masks of the q part and the p part; the states of a role are closed under the pattern, so the
-// roles are diagonal blocks and one iteration on the union serves them all).  A few power steps make v the Perron vector
+// roles are diagonal blocks and one iteration on the union serves them all).  Three power steps make v the Perron vector
 // and the bound tight: for the reference's models | |Y| |_2 = |Y|_2 to 3 digits and the bound is 0.78 of the 1-norm
 // (CZ: mean degree 9.9 -> 9.4 and 11.9 -> 11.0).  Rigorous for every v, so the iteration count only affects tightness.
 // One warp per slice, lane = basis state (n <= 32): the kernel also computes what k_coefficients computes serially for
@@ -149,7 +149,7 @@ __global__ void k_coefficients(ModelParams mp, int M, const double* __restrict__
 // column sums (1-norms) and t = N^T y run over the columns (CSC view), y = N v over the rows (CSR view) of the lane's state.
 #define QOCVL_N2_EMAX_U 160
 #define QOCVL_N2_EMAX_W 96
-#define QOCVL_N2_STEPS 5
+#define QOCVL_N2_STEPS 3
 __global__ void __launch_bounds__(128) k_slice_degrees(int n, int J, double dt, int M, cplx* __restrict__ coef,
                                                        NormTables nt, const double* __restrict__ mulmax,
                                                        const double* __restrict__ addmax, int qcap, double taylor_tol,
@@ -157,6 +157,12 @@ __global__ void __launch_bounds__(128) k_slice_degrees(int n, int J, double dt, 
                                                        const unsigned char* __restrict__ colrole, int nroles, int norm2,
                                                        int* __restrict__ qdeg_role, double* __restrict__ phi) {
   __shared__ double s_mu[4][QOCVL_N2_EMAX_U], s_mw[4][QOCVL_N2_EMAX_W], s_v[4][64], s_y[4][64];
+  // the index tables of the two sparse views, once per CTA (its four warps walk them in every pass of the iteration)
+  __shared__ int s_ucol[QOCVL_N2_EMAX_U], s_uceid[QOCVL_N2_EMAX_U], s_ucrow[QOCVL_N2_EMAX_U];
+  __shared__ int s_wcol[QOCVL_N2_EMAX_W], s_wceid[QOCVL_N2_EMAX_W], s_wcrow[QOCVL_N2_EMAX_W];
+  for (int i = threadIdx.x; i < nt.u_rowptr[n]; i += blockDim.x) { s_ucol[i] = nt.u_col[i]; s_uceid[i] = nt.u_ceid[i]; s_ucrow[i] = nt.u_crow[i]; }
+  for (int i = threadIdx.x; i < nt.w_rowptr[n]; i += blockDim.x) { s_wcol[i] = nt.w_col[i]; s_wceid[i] = nt.w_ceid[i]; s_wcrow[i] = nt.w_crow[i]; }
+  __syncthreads();
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, k = blockIdx.x * 4 + wl;
   if (k >= M) return;
   double *mu = s_mu[wl], *mw = s_mw[wl], *sv = s_v[wl], *sy = s_y[wl];
@@ -191,8 +197,8 @@ __global__ void __launch_bounds__(128) k_slice_degrees(int n, int J, double dt, 
   const int wc0 = on ? nt.w_colptr[lane] : 0, wc1 = on ? nt.w_colptr[lane + 1] : 0;
   // ---- 1-norm bounds: column n + b of [[A, B], [0, A]] sums |A_ab| + |B_ab| (qocvl_slice_norm_csr's bound, in parallel)
   double colsum = 0.0;
-  for (int i = uc0; i < uc1; ++i) colsum += mu[nt.u_ceid[i]];
-  for (int i = wc0; i < wc1; ++i) colsum += mw[nt.w_ceid[i]];
+  for (int i = uc0; i < uc1; ++i) colsum += mu[s_uceid[i]];
+  for (int i = wc0; i < wc1; ++i) colsum += mw[s_wceid[i]];
   double nrm = colsum;
   for (int off = 16; off > 0; off >>= 1) nrm = fmax(nrm, __shfl_xor_sync(0xffffffffu, nrm, off));
   const bool isnan_ = !(nrm == nrm) || !(co[0].x == co[0].x);
@@ -213,7 +219,7 @@ __global__ void __launch_bounds__(128) k_slice_degrees(int n, int J, double dt, 
   //      phi_r = midpoint of the range of Im diag(X) over the role's states (exp(X) = e^{i phi} exp(Y); the phases of
   //      all slices go into the role's target kets, k_duo_phase).  From here on the diagonal lives in `dmag`.
   int ed = -1;                                             // my state's diagonal entry in A
-  for (int e = ur0; e < ur1; ++e) if (nt.u_col[e] == lane) ed = e;
+  for (int e = ur0; e < ur1; ++e) if (s_ucol[e] == lane) ed = e;
   double dre = 0.0, dim = 0.0, ddev = 0.0;
   if (ed >= 0) {
     for (int c = 0; c < nt.u_kc; ++c) {
@@ -243,8 +249,8 @@ __global__ void __launch_bounds__(128) k_slice_degrees(int n, int J, double dt, 
   __syncwarp();
   const double dmag = sqrt(dre * dre + (dim - myphi) * (dim - myphi)) + ddev;
   colsum = dmag;                                           // column sums of the shifted generator
-  for (int i = uc0; i < uc1; ++i) colsum += mu[nt.u_ceid[i]];
-  for (int i = wc0; i < wc1; ++i) colsum += mw[nt.w_ceid[i]];
+  for (int i = uc0; i < uc1; ++i) colsum += mu[s_uceid[i]];
+  for (int i = wc0; i < wc1; ++i) colsum += mw[s_wceid[i]];
   double role_n1[4];
   for (int r = 0; r < nroles; ++r) {
     double v = (((rq | rp) >> r) & 1u) ? colsum : 0.0;
@@ -260,19 +266,19 @@ __global__ void __launch_bounds__(128) k_slice_degrees(int n, int J, double dt, 
       __syncwarp();
       double yq = dmag * vq, yp = dmag * vp;               // y = N v:  y_q = |A| v_q,  y_p = |B| v_q + |A| v_p
       for (int e = ur0; e < ur1; ++e) {
-        const int c = nt.u_col[e];
+        const int c = s_ucol[e];
         yq = fma(mu[e], sv[c], yq); yp = fma(mu[e], sv[32 + c], yp);
       }
-      for (int e = wr0; e < wr1; ++e) yp = fma(mw[e], sv[nt.w_col[e]], yp);
+      for (int e = wr0; e < wr1; ++e) yp = fma(mw[e], sv[s_wcol[e]], yp);
       sy[lane] = rq ? yq : 0.0; sy[32 + lane] = rp ? yp : 0.0;   // rows outside every role do not exist in the propagated system
       __syncwarp();
       double tq = dmag * sy[lane], tp = dmag * sy[32 + lane];   // t = N^T y:  t_q = |A|^T y_q + |B|^T y_p,  t_p = |A|^T y_p
       for (int i = uc0; i < uc1; ++i) {
-        const double m = mu[nt.u_ceid[i]];
-        const int r = nt.u_crow[i];
+        const double m = mu[s_uceid[i]];
+        const int r = s_ucrow[i];
         tq = fma(m, sy[r], tq); tp = fma(m, sy[32 + r], tp);
       }
-      for (int i = wc0; i < wc1; ++i) tq = fma(mw[nt.w_ceid[i]], sy[32 + nt.w_crow[i]], tq);
+      for (int i = wc0; i < wc1; ++i) tq = fma(mw[s_wceid[i]], sy[32 + s_wcrow[i]], tq);
       if (!rq) tq = 0.0;
       if (!rp) tp = 0.0;
       if (it == QOCVL_N2_STEPS) {
